@@ -1,0 +1,294 @@
+// phase.cuh -- stage A (f0 upsample + fp64 phase accumulation) and the standalone core ops
+// upsample / fo_to_rot / remove_above_fmax.
+//
+// Reference: ddsp/core.py:7-21 (upsample), :31-51 (fo_to_rot), :24-28 (remove_above_fmax);
+// callers ddsp/vocoder.py:391-393, 449-451, 515-517.
+#pragma once
+#include "common.cuh"
+
+namespace ddsp {
+
+// ---------------------------------------------------------------------------------------------
+// A1: per-hop totals.  One warp per hop: sum over the 512 upsampled fp32 f0 samples of the hop,
+// accumulated in fp64 (exact for any realistic f0: 24-bit mantissas, 512 terms).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hop_totals_kernel(const float* __restrict__ f0_frames, int64_t fB,
+                                                         int64_t fF, int B, int F,
+                                                         double* __restrict__ totals) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (warp >= (int64_t)B * F) return;
+    const int b = (int)(warp / F), h = (int)(warp % F);
+    const float* row = f0_frames + (int64_t)b * fB;
+    const float x0 = __ldg(row + (int64_t)h * fF);
+    const float x1 = __ldg(row + (int64_t)min(h + 1, F - 1) * fF);
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < kHop / 32; ++i) {
+        const float w1 = (float)(lane + 32 * i) * (1.0f / kHop);
+        s += (double)lerp_torch(x0, x1, w1);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(kFullMask, s, d);
+    if (lane == 0) totals[warp] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A2: per-clip exclusive scan of the hop totals (in place: totals -> prefix) and the frame-rate
+// phase  phase_frames[b,h] = fl32(2*pi) * wrap((prefix[h] + f0[h]) / sr + init/2/pi).
+// One CTA of 1024 threads per clip; each thread owns a contiguous chunk of hops.
+// ---------------------------------------------------------------------------------------------
+template <typename Acc>
+__device__ __forceinline__ Acc block_exclusive_scan(Acc v, Acc* smem /* >= 32 */, Acc& block_total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    Acc inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Acc t = __shfl_up_sync(kFullMask, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) smem[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        Acc w = (lane < nw) ? smem[lane] : Acc(0);
+        Acc winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const Acc t = __shfl_up_sync(kFullMask, winc, d);
+            if (lane >= d) winc += t;
+        }
+        smem[lane] = winc - w;            // exclusive warp offsets
+        if (lane == 31) smem[32] = winc;  // grand total
+    }
+    __syncthreads();
+    const Acc off = smem[wid];
+    block_total = smem[32];
+    __syncthreads();
+    return off + (inc - v);
+}
+
+__global__ void __launch_bounds__(1024) phase_scan_kernel(const float* __restrict__ f0_frames, int64_t fB,
+                                                          int64_t fF, int F, double inv_sr,
+                                                          const float* __restrict__ initial_phase,
+                                                          double* __restrict__ prefix /* in: totals */,
+                                                          float* __restrict__ phase_frames) {
+    __shared__ double sm[33];
+    const int b = blockIdx.x;
+    double* pf = prefix + (int64_t)b * F;
+    const float* row = f0_frames + (int64_t)b * fB;
+    const int per = (F + blockDim.x - 1) / blockDim.x;
+    const int h0 = min(F, (int)threadIdx.x * per), h1 = min(F, h0 + per);
+    double s = 0.0;
+    for (int h = h0; h < h1; ++h) s += pf[h];
+    double total;
+    double run = block_exclusive_scan<double>(s, sm, total);
+    const double init_rot = initial_phase ? ((double)initial_phase[b] / 2.0) / 3.14159265358979323846 : 0.0;
+    for (int h = h0; h < h1; ++h) {
+        const double t = pf[h];
+        pf[h] = run;
+        const double c = (run + (double)__ldg(row + (int64_t)h * fF)) * inv_sr + init_rot;
+        phase_frames[(int64_t)b * F + h] = __fmul_rn(DDSP_TWO_PI_F, wrap_rot(c));
+        run += t;
+    }
+}
+
+// Small-problem variant: one CTA per clip does A1 and A2 in one launch (streaming sizes).
+__global__ void __launch_bounds__(1024) phase_fused_kernel(const float* __restrict__ f0_frames, int64_t fB,
+                                                           int64_t fF, int F, double inv_sr,
+                                                           const float* __restrict__ initial_phase,
+                                                           double* __restrict__ prefix,
+                                                           float* __restrict__ phase_frames) {
+    __shared__ double sm[33];
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* pf = prefix + (int64_t)b * F;
+    const float* row = f0_frames + (int64_t)b * fB;
+    for (int h = wid; h < F; h += nw) {
+        const float x0 = __ldg(row + (int64_t)h * fF);
+        const float x1 = __ldg(row + (int64_t)min(h + 1, F - 1) * fF);
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < kHop / 32; ++i) s += (double)lerp_torch(x0, x1, (float)(lane + 32 * i) * (1.0f / kHop));
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(kFullMask, s, d);
+        if (lane == 0) pf[h] = s;
+    }
+    __syncthreads();
+    const int per = (F + blockDim.x - 1) / blockDim.x;
+    const int h0 = min(F, (int)threadIdx.x * per), h1 = min(F, h0 + per);
+    double s = 0.0;
+    for (int h = h0; h < h1; ++h) s += pf[h];
+    double total;
+    double run = block_exclusive_scan<double>(s, sm, total);
+    const double init_rot = initial_phase ? ((double)initial_phase[b] / 2.0) / 3.14159265358979323846 : 0.0;
+    for (int h = h0; h < h1; ++h) {
+        const double t = pf[h];
+        pf[h] = run;
+        const double c = (run + (double)__ldg(row + (int64_t)h * fF)) * inv_sr + init_rot;
+        phase_frames[(int64_t)b * F + h] = __fmul_rn(DDSP_TWO_PI_F, wrap_rot(c));
+        run += t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One hop of per-sample rotation, computed by a warp: lane owns 16 consecutive samples.
+// f[i] = upsampled f0, rot[i] = wrapped rotation (fp32) of sample 16*lane + i of hop h.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hop_rotation(float x0, float x1, double base, double inv_sr, double init_rot,
+                                             int lane, float (&f)[16], float (&rot)[16]) {
+    double sl[16];
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        f[i] = lerp_torch(x0, x1, (float)(16 * lane + i) * (1.0f / kHop));
+        s += (double)f[i];
+        sl[i] = s;
+    }
+    double inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double t = __shfl_up_sync(kFullMask, inc, d);
+        if (lane >= d) inc += t;
+    }
+    const double off = base + (inc - s);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) rot[i] = wrap_rot((off + sl[i]) * inv_sr + init_rot);
+}
+
+// A3 (Sins): full-rate phase = fl32(2*pi)*rot (vocoder.py:392), one warp per hop.
+__global__ void __launch_bounds__(256) phase_full_kernel(const float* __restrict__ f0_frames, int64_t fB,
+                                                         int64_t fF, int B, int F, double inv_sr,
+                                                         const float* __restrict__ initial_phase,
+                                                         const double* __restrict__ prefix,
+                                                         float* __restrict__ phase_full) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (warp >= (int64_t)B * F) return;
+    const int b = (int)(warp / F), h = (int)(warp % F);
+    const float* row = f0_frames + (int64_t)b * fB;
+    const float x0 = __ldg(row + (int64_t)h * fF);
+    const float x1 = __ldg(row + (int64_t)min(h + 1, F - 1) * fF);
+    const double init_rot = initial_phase ? ((double)initial_phase[b] / 2.0) / 3.14159265358979323846 : 0.0;
+    float f[16], rot[16];
+    hop_rotation(x0, x1, prefix[warp], inv_sr, init_rot, lane, f, rot);
+    float4* out = reinterpret_cast<float4*>(phase_full + warp * kHop + 16 * lane);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        out[i] = make_float4(__fmul_rn(DDSP_TWO_PI_F, rot[4 * i]), __fmul_rn(DDSP_TWO_PI_F, rot[4 * i + 1]),
+                             __fmul_rn(DDSP_TWO_PI_F, rot[4 * i + 2]), __fmul_rn(DDSP_TWO_PI_F, rot[4 * i + 3]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Standalone upsample (core.py:7-21): (B,F,C) strided -> (B,F*factor,C) contiguous.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample_kernel(const float* __restrict__ x, int64_t sB, int64_t sF,
+                                                       int64_t sC, int B, int F, int C, int factor,
+                                                       float rwidth, float* __restrict__ y) {
+    const int64_t total = (int64_t)B * F * factor * C;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        const int64_t bt = idx / C;
+        const int64_t t = bt % ((int64_t)F * factor);
+        const int b = (int)(bt / ((int64_t)F * factor));
+        // torch: w1r = rwidth * w2 (fp32), w1 = (int)w1r, lambda = w1r - w1      (UpSampleLinear1d.cu)
+        const float w1r = __fmul_rn(rwidth, (float)t);
+        int m = (int)w1r;
+        const float lam = __fsub_rn(w1r, (float)m);
+        const int m1 = min(m + 1, F - 1);          // x[F] := x[F-1] (core.py:17 hold-last)
+        m = min(m, F - 1);
+        const float* base = x + (int64_t)b * sB + (int64_t)c * sC;
+        y[idx] = lerp_torch(__ldg(base + (int64_t)m * sF), __ldg(base + (int64_t)m1 * sF), lam);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Standalone remove_above_fmax (core.py:24-28), bit-exact fp32.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) remove_above_fmax_kernel(const float* __restrict__ amp, int64_t aB,
+                                                                int64_t aF, const float* __restrict__ pitch,
+                                                                int64_t pB, int64_t pF, float fmax,
+                                                                int level_start, int B, int F, int K,
+                                                                float* __restrict__ out) {
+    const int64_t total = (int64_t)B * F * K;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % K);
+        const int64_t bf = idx / K;
+        const int f = (int)(bf % F), b = (int)(bf / F);
+        const float p = __ldg(pitch + (int64_t)b * pB + (int64_t)f * pF);
+        const float pk = __fmul_rn(p, (float)(k + level_start));
+        const float aa = __fadd_rn((pk < fmax) ? 1.0f : 0.0f, 1e-7f);
+        out[idx] = __fmul_rn(__ldg(amp + (int64_t)b * aB + (int64_t)f * aF + k), aa);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Standalone fo_to_rot (core.py:31-51) over an arbitrary (B,T) fp32 contour: three-kernel
+// chunked scan (chunk sums -> per-row scan of chunk sums -> apply).
+// ---------------------------------------------------------------------------------------------
+constexpr int kRotChunk = 2048;   // samples per CTA chunk (256 threads x 8)
+
+template <typename Acc>
+__global__ void __launch_bounds__(256) rot_chunk_sums_kernel(const float* __restrict__ fo, int64_t T,
+                                                             int nchunks, Acc sr, Acc* __restrict__ sums) {
+    __shared__ Acc sm[33];
+    const int b = blockIdx.y, ch = blockIdx.x;
+    const float* row = fo + (int64_t)b * T;
+    const int64_t t0 = (int64_t)ch * kRotChunk + (int64_t)threadIdx.x * 8;
+    Acc s = Acc(0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t t = t0 + i;
+        if (t < T) s += (Acc)row[t] / sr;
+    }
+    Acc total;
+    (void)block_exclusive_scan<Acc>(s, sm, total);
+    if (threadIdx.x == 0) sums[(int64_t)b * nchunks + ch] = total;
+}
+
+template <typename Acc>
+__global__ void __launch_bounds__(1024) rot_scan_sums_kernel(int nchunks, Acc* __restrict__ sums) {
+    __shared__ Acc sm[33];
+    Acc* row = sums + (int64_t)blockIdx.x * nchunks;
+    const int per = (nchunks + blockDim.x - 1) / blockDim.x;
+    const int c0 = min(nchunks, (int)threadIdx.x * per), c1 = min(nchunks, c0 + per);
+    Acc s = Acc(0);
+    for (int c = c0; c < c1; ++c) s += row[c];
+    Acc total;
+    Acc run = block_exclusive_scan<Acc>(s, sm, total);
+    for (int c = c0; c < c1; ++c) { const Acc t = row[c]; row[c] = run; run += t; }
+}
+
+template <typename Acc>
+__global__ void __launch_bounds__(256) rot_apply_kernel(const float* __restrict__ fo, int64_t T, int nchunks,
+                                                        Acc sr, const float* __restrict__ initial_phase,
+                                                        const Acc* __restrict__ sums, float* __restrict__ rot) {
+    __shared__ Acc sm[33];
+    const int b = blockIdx.y, ch = blockIdx.x;
+    const float* row = fo + (int64_t)b * T;
+    const int64_t t0 = (int64_t)ch * kRotChunk + (int64_t)threadIdx.x * 8;
+    Acc v[8];
+    Acc s = Acc(0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t t = t0 + i;
+        v[i] = (t < T) ? (Acc)row[t] / sr : Acc(0);     // core.py:43  _fo / sr
+        s += v[i];
+        v[i] = s;
+    }
+    Acc total;
+    const Acc off = block_exclusive_scan<Acc>(s, sm, total) + sums[(int64_t)b * nchunks + ch];
+    Acc init = Acc(0);
+    if (initial_phase) init = (Acc)initial_phase[b] / Acc(2) / Acc(3.14159265358979323846);   // core.py:45
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t t = t0 + i;
+        if (t < T) {
+            const Acc c = off + v[i] + init;
+            rot[(int64_t)b * T + t] = (float)(c - rint(c));   // core.py:46,49
+        }
+    }
+}
+
+}  // namespace ddsp

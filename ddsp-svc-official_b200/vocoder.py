@@ -1,0 +1,101 @@
+"""Drop-in synthesizer modules: same constructors, `forward` signature, return tuple and
+state_dict keys as the reference's `ddsp/vocoder.py:343-550`, with the DSP (everything except
+`Unit2Control`) running as hand-written sm_100a kernels.
+
+`unit2ctrl` (the control network, out of scope for this path) is the reference's own
+`ddsp.unit2control.Unit2Control` when the reference repo is importable, or any module passed as
+`unit2ctrl=` with the same call signature returning the dict of control tensors.
+"""
+import os
+
+import torch
+import yaml
+
+from . import core
+
+
+class DotDict(dict):
+    """Attribute access to nested config dicts (reference vocoder.py:335-341)."""
+
+    def __getattr__(*args):
+        val = dict.get(*args)
+        return DotDict(val) if type(val) is dict else val
+
+    __setattr__ = dict.__setitem__
+    __delattr__ = dict.__delitem__
+
+
+def _make_unit2ctrl(n_unit, n_spk, output_splits, c):
+    try:
+        from ddsp.unit2control import Unit2Control      # the reference's control network
+    except Exception as e:                               # pragma: no cover - depends on the host repo
+        raise ImportError(
+            'ddsp_b200 replaces the synthesizer DSP only; the control network `Unit2Control` is the '
+            'reference\'s (ddsp/unit2control.py). Put the reference repo on sys.path or pass '
+            '`unit2ctrl=<module>` to the constructor.') from e
+    return Unit2Control(n_unit, n_spk, output_splits, c)
+
+
+class _SynthBase(torch.nn.Module):
+    def __init__(self, sampling_rate, block_size):
+        super().__init__()
+        # same buffers as the reference (state_dict keys `sampling_rate`, `block_size`), plus
+        # python ints so that forward never syncs on `.item()` (18 syncs in the reference)
+        self.register_buffer('sampling_rate', torch.tensor(sampling_rate))
+        self.register_buffer('block_size', torch.tensor(block_size))
+        self._sr = int(sampling_rate)
+        self._hop = int(block_size)
+        self._noise_calls = 0
+
+    def _next_seed(self):
+        self._noise_calls += 1
+        return (torch.initial_seed() * 0x9E3779B1 + self._noise_calls) & ((1 << 62) - 1)
+
+    @staticmethod
+    def _forward_only(ctrls):
+        if torch.is_grad_enabled() and any(t.requires_grad for t in ctrls.values()):
+            raise RuntimeError('ddsp_b200 synthesizers are forward-only (no autograd): call under '
+                               'torch.no_grad() as main.py:145 / gui.py:125 / solver.py:28 do')
+
+
+class CombSubFast(_SynthBase):
+    """Reference: ddsp/vocoder.py:426-492."""
+
+    def __init__(self, sampling_rate, block_size, n_unit=256, n_spk=1, c: bool = False, unit2ctrl=None):
+        super().__init__(sampling_rate, block_size)
+        print(' [DDSP Model] Combtooth Subtractive Synthesiser (ddsp_b200)')
+        self.register_buffer('window', torch.sqrt(torch.hann_window(2 * block_size)))
+        splits = {'harmonic_magnitude': block_size + 1, 'harmonic_phase': block_size + 1,
+                  'noise_magnitude': block_size + 1}
+        self.unit2ctrl = unit2ctrl if unit2ctrl is not None else _make_unit2ctrl(n_unit, n_spk, splits, c)
+
+    def forward(self, units_frames, f0_frames, volume_frames, spk_id, spk_mix_dict=None, initial_phase=None,
+                infer=True, noise_u=None, **kwargs):
+        # stage A: vocoder.py:449-451
+        phase_frames, prefix, _ = core.phase_stage(f0_frames, self._hop, self._sr, initial_phase, infer)
+        # control network (reference PyTorch): vocoder.py:454
+        ctrls = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id, spk_mix_dict=spk_mix_dict)
+        self._forward_only(ctrls)
+        # stage B: vocoder.py:455-490
+        signal = core.combsubfast_stage(ctrls['harmonic_magnitude'], ctrls['harmonic_phase'], ctrls['noise_magnitude'],
+                                        f0_frames, prefix, self._hop, self._sr, initial_phase, noise_u=noise_u,
+                                        seed=self._next_seed(), window=self.window)
+        return signal, phase_frames.unsqueeze(-1), (signal, signal)      # vocoder.py:492
+
+
+def load_model(model_path, device='cuda'):
+    """Reference: ddsp/vocoder.py:343-369 (same config.yaml + checkpoint layout)."""
+    config_file = os.path.join(os.path.split(model_path)[0], 'config.yaml')
+    with open(config_file, 'r') as config:
+        args = DotDict(yaml.safe_load(config))
+    if args.model.type == 'CombSubFast':
+        model = CombSubFast(sampling_rate=args.data.sampling_rate, block_size=args.data.block_size,
+                            n_unit=args.data.encoder_out_channels, n_spk=args.model.n_spk, c=args.model.c)
+    else:
+        raise ValueError(f' [x] Unknown Model: {args.model.type}')
+    print(' [Loading] ' + model_path)
+    ckpt = torch.load(model_path, map_location=torch.device(device))
+    model.to(device)
+    model.load_state_dict(ckpt['model'])
+    model.eval()
+    return model, args

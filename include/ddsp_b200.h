@@ -1,0 +1,164 @@
+/*
+ * ddsp_b200.h -- C ABI of the B200-native DDSP-SVC synthesizer forward path.
+ *
+ * The reference (tarepan/DDSP-SVC-official) has no FFI: the path sits behind the Python
+ * `torch.nn.Module` classes `Sins` / `CombSub` / `CombSubFast` (ddsp/vocoder.py:372-550) and
+ * the functions of ddsp/core.py they call.  This header is the boundary a binding (ctypes,
+ * a TORCH_LIBRARY op, cffi ...) talks to; every entry point names the reference code it
+ * replaces.  See INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, strides (in ELEMENTS, not bytes); no C++/torch types.
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless stated otherwise.
+ *   - every function returns 0 on success or a negative ddsp_b200_status; nothing throws.
+ *   - nothing here allocates or frees device memory, and nothing synchronises: work is
+ *     enqueued on `stream` (a cudaStream_t passed as void*) and the call returns.
+ *   - re-entrant and thread-safe (no global mutable state besides immutable tables that are
+ *     uploaded lazily once per device under a lock).
+ *   - shapes: B clips, F frames per clip, hop = block_size samples per frame, T = F*hop.
+ */
+#ifndef DDSP_B200_H_
+#define DDSP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDSP_B200_ABI_VERSION 1
+
+typedef enum ddsp_b200_status {
+    DDSP_B200_OK = 0,
+    DDSP_B200_ERR_INVALID_ARGUMENT = -1,  /* null pointer, non-positive size, bad stride        */
+    DDSP_B200_ERR_UNSUPPORTED = -2,       /* e.g. hop != 512 or n_mag not in {256,512} on a fused path */
+    DDSP_B200_ERR_WORKSPACE = -3,         /* workspace too small                                  */
+    DDSP_B200_ERR_CUDA = -4,              /* a CUDA runtime call failed (see ddsp_b200_last_cuda_error) */
+    DDSP_B200_ERR_BATCH_MISMATCH = -5     /* core.py:212-213 ValueError                            */
+} ddsp_b200_status;
+
+/* filter window modes of ddsp/core.py:306-328 */
+#define DDSP_B200_WINDOW_NONE 0    /* hann_window=False           (core.py:324-326) */
+#define DDSP_B200_WINDOW_HANN 1    /* hann_window=True            (core.py:242-289) */
+#define DDSP_B200_WINDOW_DYNAMIC 2 /* half_width_frames != None   (core.py:292-303) */
+
+/* magnitude encodings accepted by ddsp_b200_frequency_filter */
+#define DDSP_B200_MAG_REAL 0        /* magnitudes are real >= 0: complex(m, 0)                  */
+#define DDSP_B200_MAG_EXP 1         /* control c -> exp(c) * scale (vocoder.py:399,475,522-523)  */
+#define DDSP_B200_MAG_ALLPASS_TANH 2 /* control c -> exp(j*cumsum(pi*tanh(c))) (vocoder.py:398,415,521,540) */
+#define DDSP_B200_MAG_COMPLEX 3     /* interleaved complex64 magnitudes                           */
+
+int ddsp_b200_version(void);                 /* DDSP_B200_ABI_VERSION of the loaded library */
+const char *ddsp_b200_strerror(int status);  /* static string                                */
+int ddsp_b200_last_cuda_error(void);         /* cudaError_t of the last failing call on this thread */
+
+/* ------------------------------------------------------------------------------------------
+ * Standalone ops of ddsp/core.py (used by callers outside the fused path and by the tests).
+ * ---------------------------------------------------------------------------------------- */
+
+/* upsample(signal, factor)                                        ddsp/core.py:7-21
+ * x: (B,F,C) with element strides (sB,sF,sC) -> y: (B,F*factor,C) contiguous.
+ * Bit-identical to torch's upsample_linear1d(align_corners=True) + hold-last. */
+int ddsp_b200_upsample(const float *x, int64_t sB, int64_t sF, int64_t sC, int B, int F, int C,
+                       int factor, float *y, void *stream);
+
+/* fo_to_rot(fo, sr, initial_phase, precise)                       ddsp/core.py:31-51
+ * fo: (B,T) contiguous -> rot: (B,T) contiguous, wrapped to [-0.5,0.5] (round-half-even).
+ * initial_phase: (B,) radians or NULL.  precise!=0: fp64 accumulation (inference),
+ * precise==0: fp32 accumulation (core.py:40).
+ * workspace: ddsp_b200_fo_to_rot_workspace_bytes(B,T) bytes. */
+size_t ddsp_b200_fo_to_rot_workspace_bytes(int B, int64_t T);
+int ddsp_b200_fo_to_rot(const float *fo, int B, int64_t T, double sr, const float *initial_phase,
+                        int precise, float *rot, void *workspace, size_t workspace_bytes,
+                        void *stream);
+
+/* remove_above_fmax(amplitudes, pitch, fmax, level_start)        ddsp/core.py:24-28
+ * amplitudes (B,F,K) strides (aB,aF,1); pitch (B,F) strides (pB,pF); out (B,F,K) contiguous.
+ * out = amp * ((pitch*k < fmax) + 1e-7), k = level_start..level_start+K-1, fp32, bit-exact. */
+int ddsp_b200_remove_above_fmax(const float *amplitudes, int64_t aB, int64_t aF, const float *pitch,
+                                int64_t pB, int64_t pF, float fmax, int level_start, int B, int F,
+                                int K, float *out, void *stream);
+
+/* frequency_filter(audio, magnitudes, hann_window, half_width_frames)   ddsp/core.py:331-336
+ * (= _frequency_impulse_response :306-328 + _fft_convolve :185-239).
+ * audio (B,T) contiguous, T = F*hop, hop must be 512; mags (B,F,n_mag) strides (mB,mF,1),
+ * n_mag in {256,512}; encoding per DDSP_B200_MAG_*; `mag_scale` multiplies MAG_EXP results;
+ * f0_frames (B,F) strides (fB,fF) only for DDSP_B200_WINDOW_DYNAMIC
+ * (half_width_frames = 1.5*sr/(f0+1e-3), vocoder.py:542); out (B,T) contiguous, must not alias
+ * audio.  `accumulate` != 0 adds into out instead of overwriting it. */
+size_t ddsp_b200_frequency_filter_workspace_bytes(int B, int F, int n_mag);
+int ddsp_b200_frequency_filter(const float *audio, const float *mags, int64_t mB, int64_t mF,
+                               int n_mag, int mag_encoding, float mag_scale, int window_mode,
+                               const float *f0_frames, int64_t fB, int64_t fF, double sr, int B,
+                               int F, int hop, float *out, int accumulate, void *workspace,
+                               size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage A of every synthesizer forward: f0 upsample + phase accumulation.
+ *   Sins.forward        vocoder.py:391-393      CombSubFast.forward  vocoder.py:449-451
+ *   CombSub.forward     vocoder.py:515-517      (upsample core.py:7-21, fo_to_rot core.py:31-51)
+ * f0_frames (B,F) strides (fB,fF).  Outputs: phase_frames (B,F) contiguous
+ * = fl32(2*pi)*rot[:, ::hop]; prefix (B,F) fp64 = sum of the upsampled fp32 f0 over all samples
+ * before each frame (consumed by stage B); phase_full (B,T) or NULL (Sins: 2*pi*rot at sample
+ * rate, vocoder.py:392).  hop must be 512.
+ * ---------------------------------------------------------------------------------------- */
+int ddsp_b200_phase(const float *f0_frames, int64_t fB, int64_t fF, int B, int F, int hop, double sr,
+                    const float *initial_phase, int precise, float *phase_frames, double *prefix,
+                    float *phase_full, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage B of CombSubFast.forward                               vocoder.py:455-492
+ * ctrl views harmonic_magnitude / harmonic_phase / noise_magnitude: three pointers into
+ * (B,F,513) views sharing strides (cB,cF,1) -- exactly what split_to_dict emits
+ * (unit2control.py:10-20).  noise_u: (B,T) uniform [0,1) tensor standing in for
+ * torch.rand_like (vocoder.py:461), or NULL to draw it in-kernel from (seed, clip, sample).
+ * window: the module's `window` buffer sqrt(hann_window(1024)) (vocoder.py:434; 1024 floats) or
+ * NULL for the exactly computed sin(pi*i/1024).  prefix: from ddsp_b200_phase.
+ * signal: (B,T) contiguous.
+ * ---------------------------------------------------------------------------------------- */
+int ddsp_b200_combsubfast(const float *harmonic_magnitude, const float *harmonic_phase,
+                          const float *noise_magnitude, int64_t cB, int64_t cF,
+                          const float *f0_frames, int64_t fB, int64_t fF, const double *prefix,
+                          const float *initial_phase, const float *noise_u, uint64_t seed,
+                          const float *window, int B, int F, int hop, double sr, float *signal,
+                          void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage B of CombSub.forward (old)                             vocoder.py:521-550
+ * ctrl views group_delay (n_mag_allpass), harmonic_magnitude (n_mag_harmonic),
+ * noise_magnitude (n_mag_noise) with common strides (cB,cF,1).  Outputs signal, harmonic,
+ * noise: (B,T) contiguous each.  workspace: ddsp_b200_combsub_workspace_bytes.
+ * ---------------------------------------------------------------------------------------- */
+size_t ddsp_b200_combsub_workspace_bytes(int B, int F, int n_mag_allpass, int n_mag_harmonic,
+                                         int n_mag_noise);
+int ddsp_b200_combsub(const float *group_delay, int n_mag_allpass, const float *harmonic_magnitude,
+                      int n_mag_harmonic, const float *noise_magnitude, int n_mag_noise, int64_t cB,
+                      int64_t cF, const float *f0_frames, int64_t fB, int64_t fF,
+                      const double *prefix, const float *initial_phase, const float *noise_u,
+                      uint64_t seed, int B, int F, int hop, double sr, float *signal,
+                      float *harmonic, float *noise, void *workspace, size_t workspace_bytes,
+                      void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage B of Sins.forward                                      vocoder.py:397-423
+ * ctrl views amplitudes (n_harmonics), group_delay (n_mag_allpass), noise_magnitude
+ * (n_mag_noise) with common strides (cB,cF,1).  phase_full: (B,T) from ddsp_b200_phase.
+ * ---------------------------------------------------------------------------------------- */
+size_t ddsp_b200_sins_workspace_bytes(int B, int F, int n_harmonics, int n_mag_allpass,
+                                      int n_mag_noise);
+int ddsp_b200_sins(const float *amplitudes, int n_harmonics, const float *group_delay,
+                   int n_mag_allpass, const float *noise_magnitude, int n_mag_noise, int64_t cB,
+                   int64_t cF, const float *f0_frames, int64_t fB, int64_t fF,
+                   const float *phase_full, const float *noise_u, uint64_t seed, int B, int F,
+                   int hop, double sr, float *signal, float *harmonic, float *noise,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* Number of kernel launches the last call of each entry point enqueued on this thread
+ * (bench.py reports it as gpu_launches). */
+int ddsp_b200_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDSP_B200_H_ */
