@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the DDSP-SVC synthesizer forward path (stage A + stage B, the
+control network excluded) on synthetic control frames, per BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--model combsubfast|combsub|sins] [--clips B] [--frames F]
+
+One "step" = one pass of the hot path over one batch of clips: B clips x F frames per GPU
+(default: config (2) of BASELINE.json, CombSubFast B=64 x 10 s, F=862, 44.1 kHz, hop 512).
+Clips are independent, so N GPUs each process their own B clips (weak scaling, no data-path
+collective); NCCL only reduces the timings.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SR, HOP = 44100, 512
+SPLITS = {'combsubfast': (513, 513, 513), 'combsub': (256, 512, 256), 'sins': (128, 256, 256)}
+# algorithmic bytes per frame: control rows + f0 in, returned tensors out
+ALG_BYTES_PER_FRAME = {'combsubfast': 3 * 513 * 4 + 4 + 512 * 4 + 4,
+                       'combsub': (256 + 512 + 256) * 4 + 4 + 3 * 2048 + 4,
+                       'sins': (128 + 256 + 256) * 4 + 4 + 3 * 2048 + 2048}
+METRIC = 'synthesized audio samples/sec'
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def recorded_traffic(model):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            return json.load(f).get(model)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.gpu), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == 'active'})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's CPU path on the host cores
+# --------------------------------------------------------------------------------------------
+def _oracle_clip(args):
+    model, F, seed = args
+    from oracle import ddsp_oracle as O
+    from ddsp_b200.synthetic import make_inputs
+    a, b, c = SPLITS[model]
+    d = make_inputs(1, F, a + b + c, seed=seed)
+    c0, c1, c2 = d['ctrl'][..., :a], d['ctrl'][..., a:a + b], d['ctrl'][..., a + b:]
+    t0 = time.perf_counter()
+    if model == 'combsubfast':
+        O.combsubfast_forward(c0, c1, c2, d['f0_frames'], d['U'], wd=np.float32)
+    elif model == 'combsub':
+        O.combsub_forward(c0, c1, c2, d['f0_frames'], d['U'], wd=np.float32)
+    else:
+        O.sins_forward(c0, c1, c2, d['f0_frames'], d['U'], wd=np.float32)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_throughput(model, F, clips, workers, repeats=1):
+    """samples/s of the oracle (numpy port of the reference's CPU path), `clips` clips of F frames
+    spread over `workers` processes (clips are independent)."""
+    from concurrent.futures import ProcessPoolExecutor
+    best = None
+    with ProcessPoolExecutor(max_workers=workers) as ex:
+        list(ex.map(_oracle_clip, [(model, 8, 1)] * workers))          # warm the workers (imports)
+        for r in range(repeats):
+            t0 = time.perf_counter()
+            list(ex.map(_oracle_clip, [(model, F, 100 + i) for i in range(clips)]))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return clips * F * HOP / best, best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    model = args.model
+    # bounded sample of the same workload: one 10 s clip per host core per step
+    clips = max(1, min(cores, args.clips))
+    from concurrent.futures import ProcessPoolExecutor
+    times = []
+    with ProcessPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(_oracle_clip, [(model, 8, 1)] * cores))
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            list(ex.map(_oracle_clip, [(model, args.frames, 100 + i) for i in range(clips)]))
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = clips * args.frames * HOP * args.steps / total
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'samples/s', 'x_realtime': value / SR,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, args.gpus),
+        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{clips} clips x {args.frames} frames per step (oracle numpy port of the '
+                                   f'reference CPU path, fp32, one clip per process)'},
+        'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n):
+    names = {'combsubfast': 'CombSubFast (configs/combsub.yaml)', 'combsub': 'CombSub-old (configs/combsub-old.yaml)',
+             'sins': 'Sins (configs/sins.yaml)'}
+    return {'workload': f'{names[args.model]} synthesizer forward (stage A + stage B, Unit2Control excluded), '
+                        f'{args.clips} clips x {args.frames * HOP / SR:.1f} s per GPU, 44.1 kHz, block_size 512',
+            'clips_per_gpu': args.clips, 'frames': args.frames, 'global_clips': args.clips * n,
+            'noise': 'in-kernel counter-based uniform' if not args.inject_noise else 'injected U tensor',
+            'parallelism': f'clips sharded over {n} GPU(s), no collective on the data path',
+            'l2': 'per-step inputs (control rows) exceed the 126 MB L2' if
+                  args.clips * args.frames * sum(SPLITS[args.model]) * 4 > 126e6 else
+                  'L2 flushed by a 256 MB write between timed steps'}
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from ddsp_b200 import core
+    from ddsp_b200.synthetic import make_inputs
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    model = args.model
+    if model != 'combsubfast':
+        raise SystemExit('bench: only --model combsubfast is wired in this build')
+    B, F = args.clips, args.frames
+    T = F * HOP
+    a, b_, c = SPLITS[model]
+    d = make_inputs(B, F, a + b_ + c, seed=1234 + rank, noise=args.inject_noise)
+    # host (pinned) copies for the end-to-end leg; device-resident copies for the kernel leg
+    h_ctrl = torch.from_numpy(d['ctrl']).pin_memory()
+    h_f0 = torch.from_numpy(d['f0_frames']).pin_memory()
+    h_u = torch.from_numpy(d['U']).pin_memory() if args.inject_noise else None
+    h_out = torch.empty((B, T), dtype=torch.float32).pin_memory()
+    g_ctrl = h_ctrl.to(dev)
+    g_f0 = h_f0.to(dev)[..., None]
+    g_u = h_u.to(dev) if h_u is not None else None
+    window = torch.sqrt(torch.hann_window(2 * HOP)).to(dev)
+    flush = None
+    if B * F * (a + b_ + c) * 4 <= 126e6:
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step(ctrl, f0, u, seed, ev=None):
+        hm, hp, nm = torch.split(ctrl, [a, b_, c], dim=-1)
+        pf, prefix, _ = core.phase_stage(f0, HOP, SR)
+        n_launch = core.last_launch_count()
+        if ev is not None:
+            ev[0].record()
+        sig = core.combsubfast_stage(hm, hp, nm, f0, prefix, HOP, SR, noise_u=u, seed=seed, window=window)
+        n_launch += core.last_launch_count()
+        if ev is not None:
+            ev[1].record()
+        return sig, pf, n_launch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel leg: inputs resident in HBM ----------------------------------------------
+    for i in range(args.warmup):
+        step(g_ctrl, g_f0, g_u, i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches = 0
+    flush_ms = 0.0
+    e_start.record()
+    for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(i & 0xff)
+        _, _, nl = step(g_ctrl, g_f0, g_u, 1000 + i, evs[i])
+        launches += nl
+    e_stop.record()
+    barrier()
+    elapsed_ms = e_start.elapsed_time(e_stop)
+    if flush is not None:       # measure the flush cost alone and take it out of the step time
+        f0e, f1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0e.record()
+        for i in range(args.steps):
+            flush.fill_(i & 0xff)
+        f1e.record()
+        torch.cuda.synchronize()
+        flush_ms = f0e.elapsed_time(f1e)
+        elapsed_ms = max(elapsed_ms - flush_ms, 1e-6)
+    kern_ms = float(np.mean([x.elapsed_time(y) for x, y in evs]))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end leg: host buffers, H2D + compute + D2H inside the timed region ---------
+    def e2e_step(seed):
+        ctrl = h_ctrl.to(dev, non_blocking=True)
+        f0 = h_f0.to(dev, non_blocking=True)[..., None]
+        u = h_u.to(dev, non_blocking=True) if h_u is not None else None
+        sig, pf, _ = step(ctrl, f0, u, seed)
+        h_out.copy_(sig, non_blocking=True)
+    e2e_steps = max(1, min(args.steps, 10))
+    for i in range(2):
+        e2e_step(i)
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    x0.record()
+    for i in range(e2e_steps):
+        e2e_step(2000 + i)
+    x1.record()
+    barrier()
+    e2e_ms = x0.elapsed_time(x1)
+
+    # ---- reduce over ranks: max time, sum of samples ----------------------------------------
+    t = torch.tensor([elapsed_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms, kern_ms = [float(x) for x in t.tolist()]
+    samples_per_step = B * T * world
+    value = samples_per_step * args.steps / (elapsed_ms * 1e-3)
+    e2e_value = samples_per_step * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        alg_bytes = ALG_BYTES_PER_FRAME[model] * B * F - 4 * B * F   # stage-B kernel: phase_frames belongs to stage A
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'samples/s', 'x_realtime': value / SR, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args, world),
+            'roofline': {'bound': 'hbm', 'kernel': 'combsubfast_kernel', 'achieved': achieved, 'peak': peak,
+                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': recorded_traffic(model),
+                         'peak_source': peak_src, 'kernel_ms': kern_ms, 'algorithmic_bytes_per_launch': alg_bytes,
+                         'step_frac_of_hbm_roofline': (ALG_BYTES_PER_FRAME[model] * B * F) /
+                         (elapsed_ms / args.steps * 1e-3) / 1e9 / peak},
+            'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': e2e_ms / e2e_steps,
+                    'h2d_bytes_per_step': int(h_ctrl.numel() * 4 + h_f0.numel() * 4 + (h_u.numel() * 4 if h_u is not None else 0)),
+                    'd2h_bytes_per_step': int(h_out.numel() * 4), 'steps': e2e_steps},
+            'gpu_launches': launches, 'clocks': clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = len(os.sched_getaffinity(0))
+            clips = max(1, min(cores, 8))
+            v, dt = cpu_reference_throughput(model, F, clips, min(cores, clips))
+            line['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': min(cores, clips), 'kind': 'port',
+                                    'sample': f'{clips} clips x {F} frames, oracle numpy port (fp32) of the reference '
+                                              f'CPU path, one clip per process, {dt:.1f} s'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--model', default='combsubfast', choices=list(SPLITS))
+    ap.add_argument('--clips', type=int, default=64, help='clips per GPU')
+    ap.add_argument('--frames', type=int, default=862, help='frames per clip (862 = 10 s)')
+    ap.add_argument('--inject-noise', action='store_true', help='read the noise excitation from a U tensor')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', '29517', os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

@@ -25,7 +25,7 @@ def make_f0(B, F, rng, zero_f0_fraction=0.0, f0_min=65.0, f0_max=800.0, sr=SR, h
     if zero_f0_fraction > 0:
         # unvoiced runs of 1..4 frames
         mask = rng.random((B, F)) < zero_f0_fraction / 2.5
-        for s in range(1, 4):
+        for s in range(1, min(4, F)):
             mask[:, s:] |= mask[:, :-s] & (rng.random((B, F - s)) < 0.5)
         f0 = np.where(mask, np.float32(0), f0)
     return f0

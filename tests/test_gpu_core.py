@@ -116,6 +116,14 @@ def test_remove_above_fmax_mask_values():
     assert np.array_equal(out, O.nyquist_mask(pitch, 128, F32(22050.0)))
 
 
+def _wrapped_err(a, b):
+    """Phase error modulo one rotation: when the fp64 rotation count lands within an ulp of k+0.5
+    (e.g. a constant 65 Hz contour reaches exactly 6.5 rotations at sample 4410) the half-to-even
+    wrap may fall on either side, +pi or -pi; both are the same phase."""
+    d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+    return np.minimum(d, np.abs(d - 2 * np.pi)).max()
+
+
 def test_phase_stage_vs_oracle():
     from ddsp_b200.synthetic import make_f0
     rng = np.random.default_rng(21)
@@ -130,9 +138,9 @@ def test_phase_stage_vs_oracle():
             hop_sums = f0_up.astype(np.float64).reshape(B, F, 512).sum(-1)
             ref_prefix = np.cumsum(hop_sums, 1) - hop_sums
             np.testing.assert_allclose(prefix.cpu().numpy(), ref_prefix, rtol=1e-14, atol=1e-9)
-            assert np.abs(pf.cpu().numpy() - pf_ref).max() <= 4e-7, (B, F)
+            assert _wrapped_err(pf.cpu().numpy(), pf_ref) <= 4e-7, (B, F)
             ref_full = (F32(2 * np.pi) * rot).astype(F32)
-            assert np.abs(full.cpu().numpy() - ref_full).max() <= 4e-7, (B, F)
+            assert _wrapped_err(full.cpu().numpy(), ref_full) <= 4e-7, (B, F)
             assert np.mean(full.cpu().numpy() == ref_full) > 0.995
 
 
@@ -143,4 +151,4 @@ def test_phase_stage_two_kernel_path_equals_fused():
     f0 = make_f0(2, 3000, rng)
     pf2, pre2, _ = core.phase_stage(dev(f0), 512, 44100)          # B=2, F=3000 -> spread path
     ref = O.stage_a(f0, 44100, 512)[2]
-    assert np.abs(pf2.cpu().numpy() - ref).max() <= 4e-7
+    assert _wrapped_err(pf2.cpu().numpy(), ref) <= 4e-7
