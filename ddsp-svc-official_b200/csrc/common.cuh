@@ -30,20 +30,41 @@ __host__ __device__ __forceinline__ uint32_t noise_key(uint64_t seed, uint32_t c
     z = z ^ (z >> 31);
     return (uint32_t)(z >> 32) ^ (uint32_t)z;
 }
-__host__ __device__ __forceinline__ float noise_uniform(uint32_t key, uint32_t t) {
+__host__ __device__ __forceinline__ uint32_t noise_bits(uint32_t key, uint32_t t) {
     uint32_t x = t * 0x9E3779B1u + key;
     x ^= x >> 16; x *= 0x7feb352du;
     x ^= x >> 15; x *= 0x846ca68bu;
     x ^= x >> 16;
-    return (float)(x >> 8) * 5.9604644775390625e-8f;   // 2^-24
+    return x;
+}
+__host__ __device__ __forceinline__ float noise_uniform(uint32_t key, uint32_t t) {
+    return (float)(noise_bits(key, t) >> 8) * 5.9604644775390625e-8f;   // 2^-24
 }
 
-// torch.sinc (1 at 0, sin(pi x)/(pi x)) evaluated from the fp32 argument; sinpif is exact-range-
-// reduced so large |x| (up to sr*0.5/f0) costs nothing extra.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// torch.sinc (1 at 0, sin(pi x)/(pi x)) evaluated from the fp32 argument.
+// x = n + r with n = rint(x), |r| <= 0.5 (exact in fp32):  sinc(x) = (-1)^n * (r/x) * S(r^2),
+// S(u) = sin(pi r)/(pi r) as a degree-4 interpolant in u = r^2 (|error| < 5e-9 on |r| <= 0.5).
+// For |x| < 0.5 the quotient r/x is exactly 1, so there is no cancellation at the pulse peak.
 __device__ __forceinline__ float sinc_f(float x) {
-    const float px = DDSP_PI_F * x;
-    const float s = sinpif(x);
-    return (x == 0.0f) ? 1.0f : __fdividef(s, px);
+    const float n = rintf(x);
+    const float r = x - n;
+    const float u = r * r;
+    float p = 0.024718644097447395f;
+    p = fmaf(p, u, -0.19044175744056702f);
+    p = fmaf(p, u, 0.8117148280143738f);
+    p = fmaf(p, u, -1.6449332237243652f);
+    p = fmaf(p, u, 1.0f);
+    // (-1)^n: n is an exactly representable integer; its parity is bit 0 of (int)n
+    const int odd = __float2int_rn(n) & 1;
+    const float q = (n == 0.0f) ? 1.0f : __fdividef(r, x);
+    const float v = p * q;
+    return odd ? -v : v;
 }
 
 // rot (fp32, wrapped to [-0.5,0.5], half-to-even) from an fp64 rotation count (core.py:46-49)

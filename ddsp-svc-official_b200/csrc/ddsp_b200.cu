@@ -42,16 +42,33 @@ int sm_count() {
     return cached[dev];
 }
 
-std::once_flag g_attr_once[64];
-int ensure_smem_attr() {
+// Immutable per-device tables (FFT twiddles + exact sqrt-Hann window), filled on first use.
+__device__ float g_tables[ddsp::kTableBytes / 4];
+
+std::mutex g_init_mutex;
+bool g_device_ready[64] = {false};
+const float* g_tables_ptr[64] = {nullptr};
+
+// One-time per-device setup: opt-in shared memory sizes and the constant tables.  This is the
+// only place the library synchronises (once per device, on the first call).
+int ensure_device_ready(cudaStream_t st, const float** tables) {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
-    cudaError_t err = cudaSuccess;
-    std::call_once(g_attr_once[dev], [&] {
-        err = cudaFuncSetAttribute(ddsp::combsubfast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   ddsp::kCsfSmemBytes);
-    });
-    return err == cudaSuccess ? 0 : cuda_fail(err);
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return DDSP_B200_ERR_UNSUPPORTED;
+    std::lock_guard<std::mutex> lock(g_init_mutex);
+    if (!g_device_ready[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(ddsp::combsubfast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      ddsp::kCsfSmemBytes));
+        float* ptr = nullptr;
+        CUDA_TRY(cudaGetSymbolAddress((void**)&ptr, g_tables));
+        ddsp::fft_tables_kernel<<<4, 256, 0, st>>>(reinterpret_cast<float2*>(ptr), ptr + 2048);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(st));
+        g_tables_ptr[dev] = ptr;
+        g_device_ready[dev] = true;
+    }
+    *tables = g_tables_ptr[dev];
+    return 0;
 }
 
 inline int64_t grid_for(int64_t total, int per_block, int64_t cap) {
@@ -180,8 +197,8 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
         return DDSP_B200_ERR_INVALID_ARGUMENT;
     if (hop != ddsp::kHop) return DDSP_B200_ERR_UNSUPPORTED;
     if ((int64_t)F * hop >= (1ll << 24)) return DDSP_B200_ERR_UNSUPPORTED;
-    if (int rc = ensure_smem_attr()) return rc;
     ddsp::CsfParams P;
+    if (int rc = ensure_device_ready((cudaStream_t)stream, &P.tables)) return rc;
     P.hm = harmonic_magnitude; P.hp = harmonic_phase; P.nm = noise_magnitude;
     P.cB = cB; P.cF = cF;
     P.f0_frames = f0_frames; P.fB = fB; P.fF = fF;
@@ -199,6 +216,12 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
     P.zero_unvoiced = 1;
     const int64_t runs = (int64_t)B * P.runs_per_clip;
     const unsigned grid = (unsigned)((runs + ddsp::kCsfWarps - 1) / ddsp::kCsfWarps);
+    if (P.runs_per_clip > 1) {
+        const int n_seams = B * (P.runs_per_clip - 1);
+        ddsp::csf_zero_seams_kernel<<<n_seams, 128, 0, (cudaStream_t)stream>>>(signal, F, P.run_len, P.runs_per_clip,
+                                                                                n_seams);
+        LAUNCH_CHECK();
+    }
     ddsp::combsubfast_kernel<<<grid, ddsp::kCsfThreads, ddsp::kCsfSmemBytes, (cudaStream_t)stream>>>(P);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
