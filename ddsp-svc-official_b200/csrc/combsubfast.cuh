@@ -45,11 +45,24 @@ struct CsfParams {
     int zero_unvoiced;                                    // CombSubFast: 1 (vocoder.py:460)
 };
 
+// Operands of one excitation hop, loaded a step ahead of their use so the DRAM latency is covered.
+struct HopIn { float x0, x1; double base; };
+
+__device__ __forceinline__ HopIn csf_load_hop(const CsfParams& P, int b, int h) {
+    HopIn in;
+    const int hc = min(max(h, 0), P.F - 1);
+    const float* row = P.f0_frames + (int64_t)b * P.fB;
+    in.x0 = __ldg(row + (int64_t)hc * P.fF);
+    in.x1 = __ldg(row + (int64_t)min(hc + 1, P.F - 1) * P.fF);
+    in.base = __ldg(P.prefix + (int64_t)b * P.F + hc);
+    return in;
+}
+
 // Generate excitation hop h of clip b into a ring slot (zeros outside [0,F)).
 // Lane l owns samples 16l..16l+15; the slot is padded by one word per 32 samples so that both
 // this write pattern and the FFT-order read (stride 32 across registers, lanes consecutive) are
 // bank-conflict free.
-__device__ __forceinline__ void csf_gen_hop(const CsfParams& P, int b, int h, float* __restrict__ slot,
+__device__ __forceinline__ void csf_gen_hop(const CsfParams& P, int h, const HopIn& in, float* __restrict__ slot,
                                             double init_rot, int lane) {
     float* dst = slot + 16 * lane + (lane >> 1);
     if (h < 0 || h >= P.F) {
@@ -57,12 +70,8 @@ __device__ __forceinline__ void csf_gen_hop(const CsfParams& P, int b, int h, fl
         for (int i = 0; i < 16; ++i) dst[i] = 0.0f;
         return;
     }
-    const float* row = P.f0_frames + (int64_t)b * P.fB;
-    const float x0 = __ldg(row + (int64_t)h * P.fF);
-    const float x1 = __ldg(row + (int64_t)min(h + 1, P.F - 1) * P.fF);
-    const double base = P.prefix[(int64_t)b * P.F + h];
     float f[16], rot[16];
-    hop_rotation(x0, x1, base, P.inv_sr, init_rot, lane, f, rot);
+    hop_rotation(in.x0, in.x1, in.base, P.inv_sr, init_rot, lane, f, rot);
     const bool zu = P.zero_unvoiced != 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -72,6 +81,10 @@ __device__ __forceinline__ void csf_gen_hop(const CsfParams& P, int b, int h, fl
         if (zu && f[i] <= 0.0f) c = 0.0f;                  // vocoder.py:460
         dst[i] = c;
     }
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // Zero the seam hops (first output hop of every run that does not start a clip).
@@ -119,9 +132,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
     const int F = P.F;
     const int64_t T = (int64_t)F * kHop;
     const double init_rot = P.initial_phase ? ((double)P.initial_phase[b] / 2.0) / 3.14159265358979323846 : 0.0;
-    const float* hm_b = P.hm + (int64_t)b * P.cB + lane;
-    const float* hp_b = P.hp + (int64_t)b * P.cB + lane;
-    const float* nm_b = P.nm + (int64_t)b * P.cB + lane;
+    const int64_t ctrl_b = (int64_t)b * P.cB + lane;       // element offset of this lane in the clip's rows
     const float* u_b = P.noise_u ? P.noise_u + (int64_t)b * T + lane : nullptr;
     const uint32_t key = noise_key(P.seed, (uint32_t)b);
     float* out_b = P.signal + (int64_t)b * T + lane;
@@ -130,9 +141,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
     const int k16 = lane0 ? 512 - 0 : 0;                    // bin 512 lives on lane 0 only; others read a dummy
 
     float re[32], im[32];
-    float carry[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) carry[q] = 0.0f;
+    HopIn hin = csf_load_hop(P, b, 2 * p_begin - 1);
 
     // steps per pair: s=0 frame 2p, s=1 frame 2p+1, s=2 inverse FFT of the pair + overlap-add.
     // s=-1 (first iteration only) just generates the first hop of the run.
@@ -142,9 +151,14 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
         const int fm = 2 * p + s;                           // frame handled by steps 0 and 1
         if (s < 2) {
             // ---- excitation hop fm (second half of frame fm; fm = 2p-1 on the priming step) ----
-            csf_gen_hop(P, b, fm, ring + (fm & 1) * kRingSlot, init_rot, lane);
+            csf_gen_hop(P, fm, hin, ring + (fm & 1) * kRingSlot, init_rot, lane);
+            hin = csf_load_hop(P, b, fm + 1);               // operands of the next hop (used one step later)
             __syncwarp();
             if (s < 0) { s = 0; continue; }
+            {   // pull this frame's three control rows into L2 while the FFT runs (lanes 0..16: one line each)
+                const int64_t ro = ctrl_b + (int64_t)min(fm, F - 1) * P.cF + 31 * lane;
+                if (lane <= 16) { prefetch_l2(P.hm + ro); prefetch_l2(P.hp + ro); prefetch_l2(P.nm + ro); }
+            }
             // ---- windowed frame: comb -> real part, noise -> imaginary part -------------------
             const float* slotA = ring + ((fm - 1) & 1) * kRingSlot + lane;   // hop fm-1
             const float* slotB = ring + (fm & 1) * kRingSlot + lane;         // hop fm
@@ -171,14 +185,26 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
 
         if (s < 2) {
             // ---- split the two real spectra, apply the filters (vocoder.py:472-481) ----------
-            const int mhat = min(fm, F - 1);                                  // last filter frame repeated (:473,476)
-            const float* hm_r = hm_b + (int64_t)mhat * P.cF;
-            const float* hp_r = hp_b + (int64_t)mhat * P.cF;
-            const float* nm_r = nm_b + (int64_t)mhat * P.cF;
+            const int64_t ro = ctrl_b + (int64_t)min(fm, F - 1) * P.cF;       // last filter frame repeated (:473,476)
+            const float* hm_r = P.hm + ro;
+            const float* hp_r = P.hp + ro;
+            const float* nm_r = P.nm + ro;
             float yr[17], yi[17];
+            // control loads run kLook bins ahead of their use (software pipeline over the unrolled loop)
+            constexpr int kLook = 4;
+            float chm[kLook], chp[kLook], cnm[kLook];
+#pragma unroll
+            for (int q = 0; q < kLook; ++q) {
+                chm[q] = __ldg(hm_r + 32 * q); chp[q] = __ldg(hp_r + 32 * q); cnm[q] = __ldg(nm_r + 32 * q);
+            }
 #pragma unroll
             for (int q = 0; q < 17; ++q) {
-                float a, bb, c, d, chm, chp, cnm;
+                float a, bb, c, d;
+                const float vhm = chm[q % kLook], vhp = chp[q % kLook], vnm = cnm[q % kLook];
+                if (q + kLook < 17) {
+                    const int off = (q + kLook < 16) ? 32 * (q + kLook) : k16;   // bin 512: lane 0 (others: dummy)
+                    chm[q % kLook] = __ldg(hm_r + off); chp[q % kLook] = __ldg(hp_r + off); cnm[q % kLook] = __ldg(nm_r + off);
+                }
                 if (q < 16) {
                     a = re[q]; bb = im[q];
                     c = __shfl_sync(kFullMask, re[31 - q], partner);
@@ -187,18 +213,16 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                     const float c0 = re[(32 - q) & 31], d0 = im[(32 - q) & 31];
                     c = lane0 ? c0 : c;
                     d = lane0 ? d0 : d;
-                    chm = __ldg(hm_r + 32 * q); chp = __ldg(hp_r + 32 * q); cnm = __ldg(nm_r + 32 * q);
                 } else {        // bin 512: lane 0, register 16, its own partner (other lanes: harmless dummy)
                     a = re[16]; bb = im[16]; c = a; d = bb;
-                    chm = __ldg(hm_r + k16); chp = __ldg(hp_r + k16); cnm = __ldg(nm_r + k16);
                 }
                 const float Cr = a + c, Ci = bb - d, Nr = bb + d, Ni = c - a;
                 // H = exp(hm + j*pi*hp) (vocoder.py:472), N = exp(nm)/128 (:475); the 1/2 of the
                 // split and the 1/1024 of irfft are folded in as exact powers of two.
-                const float g = ex2_approx(fmaf(chm, DDSP_LOG2E_F, -11.0f));
-                const float ang = DDSP_PI_F * chp;
+                const float g = ex2_approx(fmaf(vhm, DDSP_LOG2E_F, -11.0f));
+                const float ang = DDSP_PI_F * vhp;
                 const float Hr = g * __cosf(ang), Hi = g * __sinf(ang);
-                const float nf = ex2_approx(fmaf(cnm, DDSP_LOG2E_F, -18.0f));
+                const float nf = ex2_approx(fmaf(vnm, DDSP_LOG2E_F, -18.0f));
                 yr[q] = fmaf(Cr, Hr, fmaf(-Ci, Hi, Nr * nf));
                 yi[q] = fmaf(Cr, Hi, fmaf(Ci, Hr, Ni * nf));
             }
@@ -240,29 +264,41 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
         } else {
             // ---- window (vocoder.py:486), overlap-add (:485-487), crop (:490) -----------------
             // after the swapped FFT: im[] = Re v = frame 2p, re[] = Im v = frame 2p+1
-            const int hopA = 2 * p - 1, hopB = 2 * p;
-            const bool stA = hopA >= 0, stB = hopB < F;
-            const bool redA = seam_head && p == p_begin;
+            // Hop 2p-1 (shared with the previous pair) was left in the output buffer by that pair as a
+            // partial sum and is completed here by read-modify-write (same thread wrote it); at a run
+            // seam both sides use atomic adds onto zeros instead.
+            const int hopA = 2 * p - 1, hopB = 2 * p, hopC = 2 * p + 1;
+            const bool first = p == p_begin, last = p + 1 >= p_end;
             float* oA = out_b + (int64_t)hopA * kHop;
             float* oB = out_b + (int64_t)hopB * kHop;
+            float* oC = out_b + (int64_t)hopC * kHop;
+            if (first) {
+                if (seam_head) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const float wa = win[lane + 32 * q], wb = win[lane + 32 * q + kHop];
-                const float m_first = im[q] * wa, m_second = im[q + 16] * wb;
-                const float n_first = re[q] * wa;
-                if (redA) atomicAdd(oA + 32 * q, m_first);
-                else if (stA) oA[32 * q] = carry[q] + m_first;
-                if (stB) oB[32 * q] = m_second + n_first;
-                carry[q] = re[q + 16] * wb;
-            }
-            if (++p >= p_end) {
-                if (seam_tail) {
-                    float* oT = out_b + (int64_t)(2 * p - 1) * kHop;
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) atomicAdd(oT + 32 * q, carry[q]);
+                    for (int q = 0; q < 16; ++q) atomicAdd(oA + 32 * q, __fmul_rn(im[q], win[lane + 32 * q]));
                 }
-                break;
+            } else {
+                float prev[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) prev[q] = oA[32 * q];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) oA[32 * q] = __fadd_rn(prev[q], __fmul_rn(im[q], win[lane + 32 * q]));
             }
+            if (hopB < F) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    oB[32 * q] = __fadd_rn(__fmul_rn(im[q + 16], win[lane + 32 * q + kHop]), __fmul_rn(re[q], win[lane + 32 * q]));
+            }
+            if (hopC < F) {
+                if (!last) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) oC[32 * q] = __fmul_rn(re[q + 16], win[lane + 32 * q + kHop]);
+                } else if (seam_tail) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) atomicAdd(oC + 32 * q, __fmul_rn(re[q + 16], win[lane + 32 * q + kHop]));
+                }
+            }
+            if (++p >= p_end) break;
             s = 0;
         }
     }
