@@ -25,15 +25,15 @@ constexpr int kCsfWarps = 16;                       // warps per CTA (one CTA pe
 constexpr int kCsfThreads = kCsfWarps * 32;
 constexpr int kRingSlot = kHop + kHop / 32;         // 528 floats: one pad word per 32 samples
 constexpr int kStashFloat2 = 17 * 32;               // Y_m stash: 16 bins/lane (+ bin 512 on lane 0)
-constexpr int kCsfWarpBytes = kPlaneFloats * 4 + 2 * kRingSlot * 4 + kStashFloat2 * 8;
+constexpr int kCsfCtxInts = 8;                      // cold per-warp scalars parked in shared memory
+constexpr int kCsfWarpBytes = kPlaneFloats * 4 + 2 * kRingSlot * 4 + kStashFloat2 * 8 + kCsfCtxInts * 4;
 constexpr int kCsfSmemBytes = kTableBytes + kCsfWarps * kCsfWarpBytes;
 
 struct CsfParams {
     const float* hm; const float* hp; const float* nm;   // (B,F,513) views, strides (cB,cF,1)
     int64_t cB, cF;
     const float* f0_frames; int64_t fB, fF;              // (B,F)
-    const double* prefix;                                 // (B,F) from stage A
-    const float* initial_phase;                           // (B,) or null
+    const double* prefix;                                 // (B,F) from stage A (initial phase included)
     const float* noise_u;                                 // (B,T) or null
     const float* window;                                  // (1024,) module buffer or null
     const float* tables;                                  // device tables (twiddles + exact window)
@@ -63,7 +63,7 @@ __device__ __forceinline__ HopIn csf_load_hop(const CsfParams& P, int b, int h) 
 // this write pattern and the FFT-order read (stride 32 across registers, lanes consecutive) are
 // bank-conflict free.
 __device__ __forceinline__ void csf_gen_hop(const CsfParams& P, int h, const HopIn& in, float* __restrict__ slot,
-                                            double init_rot, int lane) {
+                                            int lane) {
     float* dst = slot + 16 * lane + (lane >> 1);
     if (h < 0 || h >= P.F) {
 #pragma unroll
@@ -71,12 +71,12 @@ __device__ __forceinline__ void csf_gen_hop(const CsfParams& P, int h, const Hop
         return;
     }
     float f[16], rot[16];
-    hop_rotation(in.x0, in.x1, in.base, P.inv_sr, init_rot, lane, f, rot);
+    hop_rotation(in.x0, in.x1, in.base, P.inv_sr, lane, f, rot);
     const bool zu = P.zero_unvoiced != 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         // vocoder.py:459  sinc(sr * rot / (f0 + 1e-3))
-        const float x = __fdividef(__fmul_rn(P.sr, rot[i]), __fadd_rn(f[i], 1e-3f));
+        const float x = __fmul_rn(P.sr, rot[i]) * rcp_approx(__fadd_rn(f[i], 1e-3f));
         float c = sinc_f(x);
         if (zu && f[i] <= 0.0f) c = 0.0f;                  // vocoder.py:460
         dst[i] = c;
@@ -120,43 +120,50 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
         }
     }
 
-    const int64_t run = (int64_t)blockIdx.x * kCsfWarps + wid;
-    if (run >= (int64_t)P.B * P.runs_per_clip) return;
-    const int b = (int)(run / P.runs_per_clip);
-    const int p_begin = (int)(run % P.runs_per_clip) * P.run_len;
-    const int p_end = min(P.pairs_per_clip, p_begin + P.run_len);
+    // Per-warp scalars that are needed only a few times per step live in shared memory (volatile
+    // reads) instead of registers: the FFT keeps 64 data registers live and anything else held
+    // across it would be spilled to local memory, whose reloads miss the (tiny) L1 here.
+    volatile int* ctx = reinterpret_cast<volatile int*>(stash + kStashFloat2);
+    {
+        const int64_t run = (int64_t)blockIdx.x * kCsfWarps + wid;
+        if (run >= (int64_t)P.B * P.runs_per_clip) return;
+        const int b0 = (int)(run / P.runs_per_clip);
+        const int pb = (int)(run % P.runs_per_clip) * P.run_len;
+        if (lane == 0) {
+            ctx[0] = b0;
+            ctx[1] = pb;                                        // p_begin
+            ctx[2] = min(P.pairs_per_clip, pb + P.run_len);     // p_end
+            ctx[3] = (int)noise_key(P.seed, (uint32_t)b0);
+        }
+        __syncwarp();
+    }
+#define CTX_B ctx[0]
+#define CTX_PBEGIN ctx[1]
+#define CTX_PEND ctx[2]
+#define CTX_KEY ((uint32_t)ctx[3])
     // Seams between runs: the hop shared by the last frame of run r-1 and the first frame of run r
     // receives one atomic add from each side onto zeros written by csf_zero_seams_kernel
     // (0 + a + b is the same fp32 number in either order, so the result does not depend on timing).
-    const bool seam_head = p_begin > 0, seam_tail = p_end < P.pairs_per_clip;
     const int F = P.F;
-    const int64_t T = (int64_t)F * kHop;
-    const double init_rot = P.initial_phase ? ((double)P.initial_phase[b] / 2.0) / 3.14159265358979323846 : 0.0;
-    const int64_t ctrl_b = (int64_t)b * P.cB + lane;       // element offset of this lane in the clip's rows
-    const float* u_b = P.noise_u ? P.noise_u + (int64_t)b * T + lane : nullptr;
-    const uint32_t key = noise_key(P.seed, (uint32_t)b);
-    float* out_b = P.signal + (int64_t)b * T + lane;
     const int partner = (32 - lane) & 31;
     const bool lane0 = lane == 0;
-    const int k16 = lane0 ? 512 - 0 : 0;                    // bin 512 lives on lane 0 only; others read a dummy
 
     float re[32], im[32];
-    HopIn hin = csf_load_hop(P, b, 2 * p_begin - 1);
 
     // steps per pair: s=0 frame 2p, s=1 frame 2p+1, s=2 inverse FFT of the pair + overlap-add.
     // s=-1 (first iteration only) just generates the first hop of the run.
-    int p = p_begin, s = -1;
+    int p = CTX_PBEGIN, s = -1;
 #pragma unroll 1
     for (;;) {
         const int fm = 2 * p + s;                           // frame handled by steps 0 and 1
         if (s < 2) {
             // ---- excitation hop fm (second half of frame fm; fm = 2p-1 on the priming step) ----
-            csf_gen_hop(P, fm, hin, ring + (fm & 1) * kRingSlot, init_rot, lane);
-            hin = csf_load_hop(P, b, fm + 1);               // operands of the next hop (used one step later)
+            // (f0 / prefix of consecutive hops share cache lines: after the first hop of a run these are L2 hits)
+            csf_gen_hop(P, fm, csf_load_hop(P, CTX_B, fm), ring + (fm & 1) * kRingSlot, lane);
             __syncwarp();
             if (s < 0) { s = 0; continue; }
             {   // pull this frame's three control rows into L2 while the FFT runs (lanes 0..16: one line each)
-                const int64_t ro = ctrl_b + (int64_t)min(fm, F - 1) * P.cF + 31 * lane;
+                const int64_t ro = (int64_t)CTX_B * P.cB + (int64_t)min(fm, F - 1) * P.cF + 32 * lane;
                 if (lane <= 16) { prefetch_l2(P.hm + ro); prefetch_l2(P.hp + ro); prefetch_l2(P.nm + ro); }
             }
             // ---- windowed frame: comb -> real part, noise -> imaginary part -------------------
@@ -167,6 +174,8 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             const bool vA = (fm >= 1) && (fm - 1 < F), vB = fm < F;
             const int64_t baseA = vA ? (int64_t)(fm - 1) * kHop : 0, baseB = vB ? (int64_t)fm * kHop : 0;
             const float okA = vA ? 1.0f : 0.0f, okB = vB ? 1.0f : 0.0f;
+            const uint32_t key = CTX_KEY;
+            const float* u_b = P.noise_u ? P.noise_u + (int64_t)CTX_B * F * kHop + lane : nullptr;
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1) {
                 const int j = 32 * (n1 & 15);                                 // sample in hop = j + lane
@@ -185,7 +194,9 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
 
         if (s < 2) {
             // ---- split the two real spectra, apply the filters (vocoder.py:472-481) ----------
-            const int64_t ro = ctrl_b + (int64_t)min(fm, F - 1) * P.cF;       // last filter frame repeated (:473,476)
+            // last filter frame repeated (:473,476)
+            const int64_t ro = (int64_t)CTX_B * P.cB + (int64_t)min(fm, F - 1) * P.cF + lane;
+            const int k16 = lane0 ? 512 : 0;                                  // bin 512 lives on lane 0 only; others read a dummy
             const float* hm_r = P.hm + ro;
             const float* hp_r = P.hp + ro;
             const float* nm_r = P.nm + ro;
@@ -221,7 +232,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                 // split and the 1/1024 of irfft are folded in as exact powers of two.
                 const float g = ex2_approx(fmaf(vhm, DDSP_LOG2E_F, -11.0f));
                 const float ang = DDSP_PI_F * vhp;
-                const float Hr = g * __cosf(ang), Hi = g * __sinf(ang);
+                const float Hr = g * cos_approx(ang), Hi = g * sin_approx(ang);
                 const float nf = ex2_approx(fmaf(vnm, DDSP_LOG2E_F, -18.0f));
                 yr[q] = fmaf(Cr, Hr, fmaf(-Ci, Hi, Nr * nf));
                 yi[q] = fmaf(Cr, Hi, fmaf(Ci, Hr, Ni * nf));
@@ -268,7 +279,10 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             // partial sum and is completed here by read-modify-write (same thread wrote it); at a run
             // seam both sides use atomic adds onto zeros instead.
             const int hopA = 2 * p - 1, hopB = 2 * p, hopC = 2 * p + 1;
+            const int p_begin = CTX_PBEGIN, p_end = CTX_PEND;
             const bool first = p == p_begin, last = p + 1 >= p_end;
+            const bool seam_head = p_begin > 0, seam_tail = p_end < P.pairs_per_clip;
+            float* out_b = P.signal + (int64_t)CTX_B * F * kHop + lane;
             float* oA = out_b + (int64_t)hopA * kHop;
             float* oB = out_b + (int64_t)hopB * kHop;
             float* oC = out_b + (int64_t)hopC * kHop;

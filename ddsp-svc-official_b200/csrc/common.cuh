@@ -41,9 +41,25 @@ __host__ __device__ __forceinline__ float noise_uniform(uint32_t key, uint32_t t
     return (float)(noise_bits(key, t) >> 8) * 5.9604644775390625e-8f;   // 2^-24
 }
 
+// Single-MUFU approximations (flush-to-zero forms: no denormal fix-up code around them).
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sin_approx(float x) {
+    float y;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float cos_approx(float x) {
+    float y;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
@@ -62,7 +78,7 @@ __device__ __forceinline__ float sinc_f(float x) {
     p = fmaf(p, u, 1.0f);
     // (-1)^n: n is an exactly representable integer; its parity is bit 0 of (int)n
     const int odd = __float2int_rn(n) & 1;
-    const float q = (n == 0.0f) ? 1.0f : __fdividef(r, x);
+    const float q = (n == 0.0f) ? 1.0f : r * rcp_approx(x);
     const float v = p * q;
     return odd ? -v : v;
 }

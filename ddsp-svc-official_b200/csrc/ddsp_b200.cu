@@ -202,7 +202,7 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
     P.hm = harmonic_magnitude; P.hp = harmonic_phase; P.nm = noise_magnitude;
     P.cB = cB; P.cF = cF;
     P.f0_frames = f0_frames; P.fB = fB; P.fF = fF;
-    P.prefix = prefix; P.initial_phase = initial_phase; P.noise_u = noise_u; P.window = window;
+    P.prefix = prefix; (void)initial_phase; P.noise_u = noise_u; P.window = window;
     P.signal = signal; P.seed = seed; P.B = B; P.F = F;
     P.pairs_per_clip = (F + 2) / 2;                 // frames 0..F in pairs
     const int64_t slots = (int64_t)sm_count() * ddsp::kCsfWarps;

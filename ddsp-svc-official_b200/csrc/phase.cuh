@@ -82,11 +82,12 @@ __global__ void __launch_bounds__(1024) phase_scan_kernel(const float* __restric
     for (int h = h0; h < h1; ++h) s += pf[h];
     double total;
     double run = block_exclusive_scan<double>(s, sm, total);
-    const double init_rot = initial_phase ? ((double)initial_phase[b] / 2.0) / 3.14159265358979323846 : 0.0;
+    // initial_phase/2/pi rotations (core.py:45), carried inside the prefix in Hz*samples
+    run += initial_phase ? (((double)initial_phase[b] / 2.0) / 3.14159265358979323846) / inv_sr : 0.0;
     for (int h = h0; h < h1; ++h) {
         const double t = pf[h];
         pf[h] = run;
-        const double c = (run + (double)__ldg(row + (int64_t)h * fF)) * inv_sr + init_rot;
+        const double c = (run + (double)__ldg(row + (int64_t)h * fF)) * inv_sr;
         phase_frames[(int64_t)b * F + h] = __fmul_rn(DDSP_TWO_PI_F, wrap_rot(c));
         run += t;
     }
@@ -120,11 +121,12 @@ __global__ void __launch_bounds__(1024) phase_fused_kernel(const float* __restri
     for (int h = h0; h < h1; ++h) s += pf[h];
     double total;
     double run = block_exclusive_scan<double>(s, sm, total);
-    const double init_rot = initial_phase ? ((double)initial_phase[b] / 2.0) / 3.14159265358979323846 : 0.0;
+    // initial_phase/2/pi rotations (core.py:45), carried inside the prefix in Hz*samples
+    run += initial_phase ? (((double)initial_phase[b] / 2.0) / 3.14159265358979323846) / inv_sr : 0.0;
     for (int h = h0; h < h1; ++h) {
         const double t = pf[h];
         pf[h] = run;
-        const double c = (run + (double)__ldg(row + (int64_t)h * fF)) * inv_sr + init_rot;
+        const double c = (run + (double)__ldg(row + (int64_t)h * fF)) * inv_sr;
         phase_frames[(int64_t)b * F + h] = __fmul_rn(DDSP_TWO_PI_F, wrap_rot(c));
         run += t;
     }
@@ -134,8 +136,8 @@ __global__ void __launch_bounds__(1024) phase_fused_kernel(const float* __restri
 // One hop of per-sample rotation, computed by a warp: lane owns 16 consecutive samples.
 // f[i] = upsampled f0, rot[i] = wrapped rotation (fp32) of sample 16*lane + i of hop h.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void hop_rotation(float x0, float x1, double base, double inv_sr, double init_rot,
-                                             int lane, float (&f)[16], float (&rot)[16]) {
+__device__ __forceinline__ void hop_rotation(float x0, float x1, double base, double inv_sr, int lane,
+                                             float (&f)[16], float (&rot)[16]) {
     double sl[16];
     double s = 0.0;
 #pragma unroll
@@ -152,7 +154,7 @@ __device__ __forceinline__ void hop_rotation(float x0, float x1, double base, do
     }
     const double off = base + (inc - s);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) rot[i] = wrap_rot((off + sl[i]) * inv_sr + init_rot);
+    for (int i = 0; i < 16; ++i) rot[i] = wrap_rot((off + sl[i]) * inv_sr);
 }
 
 // A3 (Sins): full-rate phase = fl32(2*pi)*rot (vocoder.py:392), one warp per hop.
@@ -168,9 +170,8 @@ __global__ void __launch_bounds__(256) phase_full_kernel(const float* __restrict
     const float* row = f0_frames + (int64_t)b * fB;
     const float x0 = __ldg(row + (int64_t)h * fF);
     const float x1 = __ldg(row + (int64_t)min(h + 1, F - 1) * fF);
-    const double init_rot = initial_phase ? ((double)initial_phase[b] / 2.0) / 3.14159265358979323846 : 0.0;
     float f[16], rot[16];
-    hop_rotation(x0, x1, prefix[warp], inv_sr, init_rot, lane, f, rot);
+    hop_rotation(x0, x1, prefix[warp], inv_sr, lane, f, rot);
     float4* out = reinterpret_cast<float4*>(phase_full + warp * kHop + 16 * lane);
 #pragma unroll
     for (int i = 0; i < 4; ++i)

@@ -137,6 +137,8 @@ def test_phase_stage_vs_oracle():
             # prefix = exclusive per-hop sums of the upsampled fp32 f0 (exact in fp64)
             hop_sums = f0_up.astype(np.float64).reshape(B, F, 512).sum(-1)
             ref_prefix = np.cumsum(hop_sums, 1) - hop_sums
+            if init is not None:      # the initial phase rides in the prefix, in Hz*samples
+                ref_prefix = ref_prefix + (init.astype(np.float64) / 2 / np.pi * 44100)[:, None]
             np.testing.assert_allclose(prefix.cpu().numpy(), ref_prefix, rtol=1e-14, atol=1e-9)
             assert _wrapped_err(pf.cpu().numpy(), pf_ref) <= 4e-7, (B, F)
             ref_full = (F32(2 * np.pi) * rot).astype(F32)
