@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(128) csf_zero_seams_kernel(float* __restrict__
 
 __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tw = reinterpret_cast<float2*>(smem_raw);
-    float* win = reinterpret_cast<float*>(smem_raw + 1024 * 8);
+    const float4* tw4 = reinterpret_cast<const float4*>(smem_raw);
+    float* win = reinterpret_cast<float*>(smem_raw + 512 * 16);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned char* wbase = smem_raw + kTableBytes + wid * kCsfWarpBytes;
     float* plane = reinterpret_cast<float*>(wbase);
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
     const int partner = (32 - lane) & 31;
     const bool lane0 = lane == 0;
 
-    float re[32], im[32];
+    Pts32 X;
 
     // steps per pair: s=0 frame 2p, s=1 frame 2p+1, s=2 inverse FFT of the pair + overlap-add.
     // s=-1 (first iteration only) just generates the first hop of the run.
@@ -184,13 +184,13 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                 const int64_t t = (n1 < 16 ? baseA : baseB) + j;
                 const float u = u_b ? __ldg(u_b + t) : noise_uniform(key, (uint32_t)t + (uint32_t)lane);
                 const float wn = w * (n1 < 16 ? okA : okB);
-                re[brev5(n1)] = w * c;
-                im[brev5(n1)] = fmaf(u, wn + wn, -wn);                        // w * (2u - 1)   (vocoder.py:461)
+                DDSP_RE(X, brev5(n1)) = w * c;
+                DDSP_IM(X, brev5(n1)) = fmaf(u, wn + wn, -wn);                        // w * (2u - 1)   (vocoder.py:461)
             }
         }
         // s == 2: re/im already hold the packed spectrum of the pair (swapped for the inverse)
 
-        warp_fft1024(re, im, plane, tw, lane);
+        warp_fft1024(X, plane, tw4, lane);
 
         if (s < 2) {
             // ---- split the two real spectra, apply the filters (vocoder.py:472-481) ----------
@@ -217,15 +217,15 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                     chm[q % kLook] = __ldg(hm_r + off); chp[q % kLook] = __ldg(hp_r + off); cnm[q % kLook] = __ldg(nm_r + off);
                 }
                 if (q < 16) {
-                    a = re[q]; bb = im[q];
-                    c = __shfl_sync(kFullMask, re[31 - q], partner);
-                    d = __shfl_sync(kFullMask, im[31 - q], partner);
+                    a = DDSP_RE(X, q); bb = DDSP_IM(X, q);
+                    c = __shfl_sync(kFullMask, DDSP_RE(X, 31 - q), partner);
+                    d = __shfl_sync(kFullMask, DDSP_IM(X, 31 - q), partner);
                     // lane 0 holds bins 32q: its partner 1024-32q sits in its own register 32-q
-                    const float c0 = re[(32 - q) & 31], d0 = im[(32 - q) & 31];
+                    const float c0 = DDSP_RE(X, (32 - q) & 31), d0 = DDSP_IM(X, (32 - q) & 31);
                     c = lane0 ? c0 : c;
                     d = lane0 ? d0 : d;
                 } else {        // bin 512: lane 0, register 16, its own partner (other lanes: harmless dummy)
-                    a = re[16]; bb = im[16]; c = a; d = bb;
+                    a = DDSP_RE(X, 16); bb = DDSP_IM(X, 16); c = a; d = bb;
                 }
                 const float Cr = a + c, Ci = bb - d, Nr = bb + d, Ni = c - a;
                 // H = exp(hm + j*pi*hp) (vocoder.py:472), N = exp(nm)/128 (:475); the 1/2 of the
@@ -252,8 +252,8 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                 for (int q = 0; q < 16; ++q) {
                     const float2 y = stash[q * 32 + lane];
                     // V[k] = (y.x - yi) + j (y.y + yr);  V[N-k] = (y.x + yi) + j (yr - y.y)
-                    re[brev5(q)] = y.y + yr[q];       // swapped: "real" input = Im V
-                    im[brev5(q)] = y.x - yi[q];
+                    DDSP_RE(X, brev5(q)) = y.y + yr[q];       // swapped: "real" input = Im V
+                    DDSP_IM(X, brev5(q)) = y.x - yi[q];
                     xr[q] = y.x + yi[q];              // Re V[N-k]
                     xi[q] = yr[q] - y.y;              // Im V[N-k]
                 }
@@ -267,14 +267,14 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                     const float ti0 = (q == 15) ? v512i : xi[(q + 1) & 15];
                     tr = lane0 ? tr0 : tr;
                     ti = lane0 ? ti0 : ti;
-                    re[brev5(31 - q)] = ti;            // swapped
-                    im[brev5(31 - q)] = tr;
+                    DDSP_RE(X, brev5(31 - q)) = ti;            // swapped
+                    DDSP_IM(X, brev5(31 - q)) = tr;
                 }
                 s = 2;
             }
         } else {
             // ---- window (vocoder.py:486), overlap-add (:485-487), crop (:490) -----------------
-            // after the swapped FFT: im[] = Re v = frame 2p, re[] = Im v = frame 2p+1
+            // after the swapped FFT: DDSP_IM(X, ) = Re v = frame 2p, DDSP_RE(X, ) = Im v = frame 2p+1
             // Hop 2p-1 (shared with the previous pair) was left in the output buffer by that pair as a
             // partial sum and is completed here by read-modify-write (same thread wrote it); at a run
             // seam both sides use atomic adds onto zeros instead.
@@ -289,27 +289,27 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             if (first) {
                 if (seam_head) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) atomicAdd(oA + 32 * q, __fmul_rn(im[q], win[lane + 32 * q]));
+                    for (int q = 0; q < 16; ++q) atomicAdd(oA + 32 * q, __fmul_rn(DDSP_IM(X, q), win[lane + 32 * q]));
                 }
             } else {
                 float prev[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) prev[q] = oA[32 * q];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) oA[32 * q] = __fadd_rn(prev[q], __fmul_rn(im[q], win[lane + 32 * q]));
+                for (int q = 0; q < 16; ++q) oA[32 * q] = __fadd_rn(prev[q], __fmul_rn(DDSP_IM(X, q), win[lane + 32 * q]));
             }
             if (hopB < F) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q)
-                    oB[32 * q] = __fadd_rn(__fmul_rn(im[q + 16], win[lane + 32 * q + kHop]), __fmul_rn(re[q], win[lane + 32 * q]));
+                    oB[32 * q] = __fadd_rn(__fmul_rn(DDSP_IM(X, q + 16), win[lane + 32 * q + kHop]), __fmul_rn(DDSP_RE(X, q), win[lane + 32 * q]));
             }
             if (hopC < F) {
                 if (!last) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) oC[32 * q] = __fmul_rn(re[q + 16], win[lane + 32 * q + kHop]);
+                    for (int q = 0; q < 16; ++q) oC[32 * q] = __fmul_rn(DDSP_RE(X, q + 16), win[lane + 32 * q + kHop]);
                 } else if (seam_tail) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) atomicAdd(oC + 32 * q, __fmul_rn(re[q + 16], win[lane + 32 * q + kHop]));
+                    for (int q = 0; q < 16; ++q) atomicAdd(oC + 32 * q, __fmul_rn(DDSP_RE(X, q + 16), win[lane + 32 * q + kHop]));
                 }
             }
             if (++p >= p_end) break;

@@ -43,7 +43,7 @@ int sm_count() {
 }
 
 // Immutable per-device tables (FFT twiddles + exact sqrt-Hann window), filled on first use.
-__device__ float g_tables[ddsp::kTableBytes / 4];
+__device__ __align__(16) float g_tables[ddsp::kTableBytes / 4];
 
 std::mutex g_init_mutex;
 bool g_device_ready[64] = {false};
@@ -61,7 +61,7 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
                                       ddsp::kCsfSmemBytes));
         float* ptr = nullptr;
         CUDA_TRY(cudaGetSymbolAddress((void**)&ptr, g_tables));
-        ddsp::fft_tables_kernel<<<4, 256, 0, st>>>(reinterpret_cast<float2*>(ptr), ptr + 2048);
+        ddsp::fft_tables_kernel<<<4, 256, 0, st>>>(reinterpret_cast<float4*>(ptr), ptr + 2048);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(st));
         g_tables_ptr[dev] = ptr;

@@ -1,5 +1,12 @@
 // fft32.cuh -- register-resident 32-point complex FFT and the warp-level 1024-point FFT
 // (32 x 32 four-step: each lane owns 32 points; one transpose through shared memory).
+//
+// The butterflies use Blackwell's packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2, sm_100+):
+// register-index r and r+16 of the 32-point transform share one 64-bit register pair, so the
+// stages with span 1, 2, 4, 8 process two butterflies per instruction (the twiddle is the same
+// for both halves and rides as a broadcast immediate); only the last stage (span 16) works
+// inside the pairs with scalar FFMAs.  The kernel is issue-bound, so halving the FP instruction
+// count of the FFT is worth more than anything the (identical) FLOP rate could give.
 #pragma once
 #include "common.cuh"
 
@@ -31,121 +38,170 @@ __device__ __forceinline__ constexpr float sin32(int j) {
          : 0.19509032201612826785f;
 }
 
-// One decimation-in-time stage (butterfly span `half`) on 32 register-resident points.
-// x0' = a + w b, x1' = a - w b = 2a - x0' : a general butterfly is 6 FFMA.
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }   // folds into an operand modifier
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }            // folds into a broadcast immediate
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return fma2(b, bc2(-1.0f), a); }
+
+// The 32 points of one lane: element with register-index r lives in R[r & 15] (.x for r < 16,
+// .y for r >= 16), real parts in R, imaginary parts in I.
+struct Pts32 {
+    float2 R[16], I[16];
+};
+#define DDSP_RE(P, r) ((r) < 16 ? (P).R[(r) & 15].x : (P).R[(r) & 15].y)
+#define DDSP_IM(P, r) ((r) < 16 ? (P).I[(r) & 15].x : (P).I[(r) & 15].y)
+
+// One decimation-in-time stage with butterfly span HALF in {1,2,4,8} on the 16 packed positions:
+// x0' = a + w b, x1' = a - w b, two butterflies per instruction.
 template <int HALF>
-__device__ __forceinline__ void dit_stage(float (&re)[32], float (&im)[32]) {
-    constexpr float R = 0.70710678118654752440f;
+__device__ __forceinline__ void dit_stage2(Pts32& P) {
+    constexpr float Rq = 0.70710678118654752440f;
     constexpr int tstep = 16 / HALF;
 #pragma unroll
-    for (int g = 0; g < 32; g += 2 * HALF) {
+    for (int g = 0; g < 16; g += 2 * HALF) {
 #pragma unroll
         for (int j = 0; j < HALF; ++j) {
             const int i0 = g + j, i1 = i0 + HALF;
-            const float ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
+            const float2 ar = P.R[i0], ai = P.I[i0], br = P.R[i1], bi = P.I[i1];
             const int tw = j * tstep;                 // w = W32^tw = cos - j sin
             if (tw == 0) {
-                re[i0] = ar + br; im[i0] = ai + bi; re[i1] = ar - br; im[i1] = ai - bi;
+                P.R[i0] = add2(ar, br); P.I[i0] = add2(ai, bi);
+                P.R[i1] = sub2(ar, br); P.I[i1] = sub2(ai, bi);
             } else if (tw == 8) {                      // w = -j : w b = (bi, -br)
-                re[i0] = ar + bi; im[i0] = ai - br; re[i1] = ar - bi; im[i1] = ai + br;
-            } else if (tw == 4) {                      // w = (1-j)/sqrt2 : w b = R(br+bi) + jR(bi-br)
-                const float t1 = br + bi, t2 = bi - br;
-                re[i0] = fmaf(R, t1, ar); im[i0] = fmaf(R, t2, ai);
-                re[i1] = fmaf(-R, t1, ar); im[i1] = fmaf(-R, t2, ai);
-            } else if (tw == 12) {                     // w = (-1-j)/sqrt2 : w b = R(bi-br) - jR(br+bi)
-                const float t1 = bi - br, t2 = br + bi;
-                re[i0] = fmaf(R, t1, ar); im[i0] = fmaf(-R, t2, ai);
-                re[i1] = fmaf(-R, t1, ar); im[i1] = fmaf(R, t2, ai);
+                P.R[i0] = add2(ar, bi); P.I[i0] = sub2(ai, br);
+                P.R[i1] = sub2(ar, bi); P.I[i1] = add2(ai, br);
+            } else if (tw == 4) {                      // w = (1-j)/sqrt2 : w b = q(br+bi) + j q(bi-br)
+                const float2 t1 = add2(br, bi), t2 = sub2(bi, br);
+                P.R[i0] = fma2(t1, bc2(Rq), ar); P.I[i0] = fma2(t2, bc2(Rq), ai);
+                P.R[i1] = fma2(t1, bc2(-Rq), ar); P.I[i1] = fma2(t2, bc2(-Rq), ai);
+            } else if (tw == 12) {                     // w = (-1-j)/sqrt2 : w b = q(bi-br) - j q(br+bi)
+                const float2 t1 = sub2(bi, br), t2 = add2(br, bi);
+                P.R[i0] = fma2(t1, bc2(Rq), ar); P.I[i0] = fma2(t2, bc2(-Rq), ai);
+                P.R[i1] = fma2(t1, bc2(-Rq), ar); P.I[i1] = fma2(t2, bc2(Rq), ai);
             } else {                                    // w b = (c br + s bi) + j(c bi - s br)
                 const float c = cos32(tw), s = sin32(tw);
-                const float xr = fmaf(c, br, fmaf(s, bi, ar));
-                const float xi = fmaf(c, bi, fmaf(-s, br, ai));
-                re[i0] = xr; im[i0] = xi;
-                re[i1] = fmaf(2.0f, ar, -xr); im[i1] = fmaf(2.0f, ai, -xi);
+                P.R[i0] = fma2(br, bc2(c), fma2(bi, bc2(s), ar));
+                P.I[i0] = fma2(bi, bc2(c), fma2(br, bc2(-s), ai));
+                P.R[i1] = fma2(br, bc2(-c), fma2(bi, bc2(-s), ar));
+                P.I[i1] = fma2(bi, bc2(-c), fma2(br, bc2(s), ai));
             }
         }
     }
 }
 
-// 32-point forward FFT, decimation in time: element n must sit in register brev5(n) on entry;
-// on exit register k holds X[k] (natural order).
-__device__ __forceinline__ void fft32_dit(float (&re)[32], float (&im)[32]) {
-    dit_stage<1>(re, im);
-    dit_stage<2>(re, im);
-    dit_stage<4>(re, im);
-    dit_stage<8>(re, im);
-    dit_stage<16>(re, im);
-}
-
-// Same, but element n (register brev5(n)) is first multiplied by the per-lane twiddle tw[n*32+lane];
-// the multiply is folded into the span-1 butterflies (10 ops per pair instead of 8 + 4).
-__device__ __forceinline__ void fft32_dit_twiddled(float (&re)[32], float (&im)[32],
-                                                   const float2* __restrict__ tw, int lane) {
+// Last stage (span 16): butterflies between the two halves of each pair, twiddle W32^r.
+__device__ __forceinline__ void dit_stage_last(Pts32& P) {
+    constexpr float Rq = 0.70710678118654752440f;
 #pragma unroll
-    for (int g = 0; g < 16; ++g) {
-        const int na = brev5(2 * g);                   // element index of register 2g (< 16)
-        const int i0 = 2 * g, i1 = 2 * g + 1;          // register 2g+1 holds element na + 16
-        float ar = re[i0], ai = im[i0];
-        if (na != 0) {
-            const float2 wa = tw[na * 32 + lane];
-            const float tr = fmaf(-ai, wa.y, ar * wa.x);
-            const float ti = fmaf(ar, wa.y, ai * wa.x);
-            ar = tr; ai = ti;
+    for (int r = 0; r < 16; ++r) {
+        const float ar = P.R[r].x, ai = P.I[r].x, br = P.R[r].y, bi = P.I[r].y;
+        if (r == 0) {
+            P.R[r] = make_float2(ar + br, ar - br); P.I[r] = make_float2(ai + bi, ai - bi);
+        } else if (r == 8) {
+            P.R[r] = make_float2(ar + bi, ar - bi); P.I[r] = make_float2(ai - br, ai + br);
+        } else if (r == 4) {
+            const float t1 = br + bi, t2 = bi - br;
+            P.R[r] = make_float2(fmaf(Rq, t1, ar), fmaf(-Rq, t1, ar));
+            P.I[r] = make_float2(fmaf(Rq, t2, ai), fmaf(-Rq, t2, ai));
+        } else if (r == 12) {
+            const float t1 = bi - br, t2 = br + bi;
+            P.R[r] = make_float2(fmaf(Rq, t1, ar), fmaf(-Rq, t1, ar));
+            P.I[r] = make_float2(fmaf(-Rq, t2, ai), fmaf(Rq, t2, ai));
+        } else {
+            const float c = cos32(r), s = sin32(r);
+            const float xr = fmaf(c, br, fmaf(s, bi, ar));
+            const float xi = fmaf(c, bi, fmaf(-s, br, ai));
+            P.R[r] = make_float2(xr, fmaf(2.0f, ar, -xr));
+            P.I[r] = make_float2(xi, fmaf(2.0f, ai, -xi));
         }
-        const float2 wb = tw[(na + 16) * 32 + lane];
-        const float br = re[i1], bi = im[i1];
-        const float xr = fmaf(br, wb.x, fmaf(-bi, wb.y, ar));
-        const float xi = fmaf(br, wb.y, fmaf(bi, wb.x, ai));
-        re[i0] = xr; im[i0] = xi;
-        re[i1] = fmaf(2.0f, ar, -xr); im[i1] = fmaf(2.0f, ai, -xi);
     }
-    dit_stage<2>(re, im);
-    dit_stage<4>(re, im);
-    dit_stage<8>(re, im);
-    dit_stage<16>(re, im);
 }
 
-constexpr int kPlaneStride = 33;                 // padded row stride of the transpose plane
-constexpr int kPlaneFloats = 32 * kPlaneStride;  // 1056 floats = 4224 B per warp
+// 32-point forward FFT, decimation in time: element n must sit at register-index brev5(n) on
+// entry; on exit register-index k holds X[k] (natural order).
+__device__ __forceinline__ void fft32_dit(Pts32& P) {
+    dit_stage2<1>(P);
+    dit_stage2<2>(P);
+    dit_stage2<4>(P);
+    dit_stage2<8>(P);
+    dit_stage_last(P);
+}
+
+// Same, but every element n is first multiplied by this lane's twiddle W1024^(n*lane).  The
+// packed position i holds elements (e, e+1), e = brev5(i); `tw4[(e/2)*32 + lane]` delivers
+// (cos e, cos e+1, -sin e, -sin e+1) in one 128-bit load.  The multiply is folded into the span-1
+// butterflies (12 packed ops per two butterflies).
+__device__ __forceinline__ void fft32_dit_twiddled(Pts32& P, const float4* __restrict__ tw4, int lane) {
+#pragma unroll
+    for (int i0 = 0; i0 < 16; i0 += 2) {
+        const int e = brev5(i0);                        // even, bit 4 clear; position i0+1 holds (e+16, e+17)
+        const float4 wa = tw4[(e >> 1) * 32 + lane];
+        const float4 wb = tw4[((e >> 1) + 8) * 32 + lane];
+        const float2 wax = make_float2(wa.x, wa.y), way = make_float2(wa.z, wa.w);
+        const float2 wbx = make_float2(wb.x, wb.y), wby = make_float2(wb.z, wb.w);
+        const float2 Ar = P.R[i0], Ai = P.I[i0], Br = P.R[i0 + 1], Bi = P.I[i0 + 1];
+        const float2 ar = fma2(neg2(Ai), way, mul2(Ar, wax));       // a = wa * A
+        const float2 ai = fma2(Ar, way, mul2(Ai, wax));
+        P.R[i0] = fma2(Br, wbx, fma2(neg2(Bi), wby, ar));           // a + wb * B
+        P.I[i0] = fma2(Br, wby, fma2(Bi, wbx, ai));
+        P.R[i0 + 1] = fma2(neg2(Br), wbx, fma2(Bi, wby, ar));       // a - wb * B
+        P.I[i0 + 1] = fma2(neg2(Br), wby, fma2(neg2(Bi), wbx, ai));
+    }
+    dit_stage2<2>(P);
+    dit_stage2<4>(P);
+    dit_stage2<8>(P);
+    dit_stage_last(P);
+}
+
+constexpr int kPlaneStride = 34;                 // even (64-bit reads) and conflict-free for both access patterns
+constexpr int kPlaneFloats = 32 * kPlaneStride;  // 1088 floats = 4352 B per warp
 
 // Forward complex FFT of 1024 points spread over one warp.
-//   in : re/im[brev5(n1)] = x[32*n1 + lane]          (bit-reversed register order)
-//   out: re/im[k2]        = X[lane + 32*k2]          (natural register order)
-// `plane` is this warp's private 32x33-float transpose buffer, `tw` the CTA-wide table
-// tw[a*32 + b] = (cos, -sin)(2*pi*a*b/1024).
-// The inverse transform is obtained by calling it with the two arrays swapped.
-__device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32], float* __restrict__ plane,
-                                             const float2* __restrict__ tw, int lane) {
-    fft32_dit(re, im);                               // register k1 = A[k1] for column n2 = lane
+//   in : element x[32*n1 + lane] at register-index brev5(n1)
+//   out: X[lane + 32*k2] at register-index k2 (natural order)
+// `plane` is this warp's private 32x34-float transpose buffer, `tw4` the CTA-wide twiddle table.
+// The inverse transform is obtained by calling it with real and imaginary parts swapped.
+__device__ __forceinline__ void warp_fft1024(Pts32& P, float* __restrict__ plane, const float4* __restrict__ tw4,
+                                             int lane) {
+    fft32_dit(P);                                    // register-index k1 = A[k1] for column n2 = lane
+    float* wr = plane + lane;
+    const float2* rd = reinterpret_cast<const float2*>(plane + lane * kPlaneStride);
 #pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) plane[k1 * kPlaneStride + lane] = re[k1];
+    for (int k1 = 0; k1 < 32; ++k1) wr[k1 * kPlaneStride] = DDSP_RE(P, k1);
     __syncwarp();
 #pragma unroll
-    for (int n2 = 0; n2 < 32; ++n2) re[brev5(n2)] = plane[lane * kPlaneStride + n2];
+    for (int i = 0; i < 16; ++i) P.R[i] = rd[brev5(i) >> 1];       // elements (e, e+1), e = brev5(i)
     __syncwarp();
 #pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) plane[k1 * kPlaneStride + lane] = im[k1];
+    for (int k1 = 0; k1 < 32; ++k1) wr[k1 * kPlaneStride] = DDSP_IM(P, k1);
     __syncwarp();
 #pragma unroll
-    for (int n2 = 0; n2 < 32; ++n2) im[brev5(n2)] = plane[lane * kPlaneStride + n2];
+    for (int i = 0; i < 16; ++i) P.I[i] = rd[brev5(i) >> 1];
     __syncwarp();
-    fft32_dit_twiddled(re, im, tw, lane);            // row k1 = lane: X[lane + 32*k2]
+    fft32_dit_twiddled(P, tw4, lane);                // row k1 = lane: X[lane + 32*k2]
 }
 
 // Device-wide constant tables (filled once per device by fft_tables_kernel):
-//   [0, 1024) float2 twiddles tw[a*32+b] = (cos, -sin)(2 pi a b / 1024)
+//   [0, 512) float4 twiddles tw4[(e/2)*32 + lane] = (cos(e l), cos((e+1) l), -sin(e l), -sin((e+1) l)),
+//            angles 2 pi e l / 1024, e even
 //   then 1024 floats sin(pi i / 1024) = sqrt(hann_periodic(1024))[i]
-constexpr int kTableBytes = 1024 * 8 + 1024 * 4;
+constexpr int kTableBytes = 512 * 16 + 1024 * 4;
 
-__global__ void fft_tables_kernel(float2* __restrict__ tw, float* __restrict__ win) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= 1024) return;
-    const int a = e >> 5, b = e & 31;
+__global__ void fft_tables_kernel(float4* __restrict__ tw4, float* __restrict__ win) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 1024) return;
     double s, c;
-    sincospi((double)(a * b) / 512.0, &s, &c);
-    tw[e] = make_float2((float)c, (float)(-s));
-    sincospi((double)e / 1024.0, &s, &c);
-    win[e] = (float)s;
+    if (t < 512) {
+        const int e = 2 * (t >> 5), l = t & 31;
+        double s1, c1;
+        sincospi((double)(e * l) / 512.0, &s, &c);
+        sincospi((double)((e + 1) * l) / 512.0, &s1, &c1);
+        tw4[t] = make_float4((float)c, (float)c1, (float)(-s), (float)(-s1));
+    }
+    sincospi((double)t / 1024.0, &s, &c);
+    win[t] = (float)s;
 }
 
 }  // namespace ddsp
