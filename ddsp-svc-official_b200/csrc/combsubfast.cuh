@@ -176,16 +176,24 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             const float okA = vA ? 1.0f : 0.0f, okB = vB ? 1.0f : 0.0f;
             const uint32_t key = CTX_KEY;
             const float* u_b = P.noise_u ? P.noise_u + (int64_t)CTX_B * F * kHop + lane : nullptr;
+            uint32_t stA = noise_seed(key, (uint32_t)(fm - 1), (uint32_t)lane);
+            uint32_t stB = noise_seed(key, (uint32_t)fm, (uint32_t)lane);
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1) {
                 const int j = 32 * (n1 & 15);                                 // sample in hop = j + lane
                 const float w = win[32 * n1 + lane];
                 const float c = (n1 < 16 ? slotA : slotB)[j + (n1 & 15)];
-                const int64_t t = (n1 < 16 ? baseA : baseB) + j;
-                const float u = u_b ? __ldg(u_b + t) : noise_uniform(key, (uint32_t)t + (uint32_t)lane);
+                float u;
+                if (u_b) {
+                    u = __ldg(u_b + (n1 < 16 ? baseA : baseB) + j);
+                } else {
+                    uint32_t& st = (n1 < 16) ? stA : stB;
+                    st = noise_next(st);
+                    u = (float)noise_u24(st) * 5.9604644775390625e-8f;
+                }
                 const float wn = w * (n1 < 16 ? okA : okB);
                 DDSP_RE(X, brev5(n1)) = w * c;
-                DDSP_IM(X, brev5(n1)) = fmaf(u, wn + wn, -wn);                        // w * (2u - 1)   (vocoder.py:461)
+                DDSP_IM(X, brev5(n1)) = fmaf(u, wn + wn, -wn);                // w * (2u - 1)   (vocoder.py:461)
             }
         }
         // s == 2: re/im already hold the packed spectrum of the pair (swapped for the inverse)

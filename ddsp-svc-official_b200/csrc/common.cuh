@@ -30,16 +30,19 @@ __host__ __device__ __forceinline__ uint32_t noise_key(uint64_t seed, uint32_t c
     z = z ^ (z >> 31);
     return (uint32_t)(z >> 32) ^ (uint32_t)z;
 }
-__host__ __device__ __forceinline__ uint32_t noise_bits(uint32_t key, uint32_t t) {
-    uint32_t x = t * 0x9E3779B1u + key;
+// Noise stream layout: the 16 samples {hop*512 + 32*i + lane, i = 0..15} that one lane feeds into
+// the FFT form one short LCG stream seeded by a strong hash of (clip key, hop, lane); one IMAD +
+// xorshift per sample instead of a full hash.
+__host__ __device__ __forceinline__ uint32_t noise_seed(uint32_t key, uint32_t hop, uint32_t lane) {
+    uint32_t x = (hop * 32u + lane) * 0x9E3779B1u + key;
     x ^= x >> 16; x *= 0x7feb352du;
     x ^= x >> 15; x *= 0x846ca68bu;
     x ^= x >> 16;
     return x;
 }
-__host__ __device__ __forceinline__ float noise_uniform(uint32_t key, uint32_t t) {
-    return (float)(noise_bits(key, t) >> 8) * 5.9604644775390625e-8f;   // 2^-24
-}
+__host__ __device__ __forceinline__ uint32_t noise_next(uint32_t state) { return state * 747796405u + 2891336453u; }
+// uniform integer in [0, 2^24) from an LCG state (top bits, xorshift-mixed); U = value * 2^-24
+__host__ __device__ __forceinline__ uint32_t noise_u24(uint32_t state) { return (state ^ (state >> 15)) >> 8; }
 
 // Single-MUFU approximations (flush-to-zero forms: no denormal fix-up code around them).
 __device__ __forceinline__ float ex2_approx(float x) {

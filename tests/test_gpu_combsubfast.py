@@ -109,17 +109,24 @@ def test_noise_generator_matches_host_restatement():
         z = z ^ (z >> 31)
         return ((z >> 32) ^ z) & 0xffffffff
 
-    def uniform(k, t):
-        x = (t.astype(np.uint64) * 0x9E3779B1 + k) & 0xffffffff
+    def hop_noise(k, hop):
+        """(512,) uniforms of one hop: lane l owns samples 32*i + l, an LCG stream seeded per (hop, lane)."""
+        lane = np.arange(32, dtype=np.uint64)
+        x = ((hop * 32 + lane) * 0x9E3779B1 + k) & 0xffffffff
         x ^= x >> 16; x = (x * 0x7feb352d) & 0xffffffff
         x ^= x >> 15; x = (x * 0x846ca68b) & 0xffffffff
         x ^= x >> 16
-        return ((x >> 8).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+        out = np.zeros(512, np.float32)
+        for i in range(16):
+            x = (x * 747796405 + 2891336453) & 0xffffffff
+            u24 = (x ^ (x >> 15)) >> 8
+            out[32 * i + np.arange(32)] = u24.astype(np.float32) * np.float32(2.0 ** -24)
+        return out
 
     B, F = 2, 9
     d = make_inputs(B, F, 1539, seed=10, noise=False)
     seed = 4242
-    U = np.stack([uniform(key(seed, b), np.arange(F * 512)) for b in range(B)])
+    U = np.stack([np.concatenate([hop_noise(key(seed, b), h) for h in range(F)]) for b in range(B)])
     a, _ = run_gpu(d['ctrl'], d['f0_frames'], None, seed=seed)
     b_, _ = run_gpu(d['ctrl'], d['f0_frames'], U)
     assert np.array_equal(a, b_)
