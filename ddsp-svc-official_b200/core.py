@@ -162,5 +162,116 @@ def combsubfast_stage(harmonic_magnitude, harmonic_phase, noise_magnitude, f0_fr
     return signal
 
 
+WINDOW_NONE, WINDOW_HANN, WINDOW_DYNAMIC = 0, 1, 2
+MAG_REAL, MAG_EXP, MAG_ALLPASS_TANH, MAG_COMPLEX = 0, 1, 2, 3
+
+
+def frequency_filter(audio, magnitudes, hann_window=True, half_width_frames=None, *, f0_frames=None,
+                     sampling_rate=44100, encoding=None, mag_scale=1.0):
+    """Apply a per-frame linear-phase LTV-FIR (reference ddsp/core.py:331-336).
+
+    audio (B,T) float32; magnitudes (B,F,n_mag) real float32 or complex64, n_mag in {256, 512},
+    T = 512*F.  `half_width_frames` (B,F,1) selects the dynamic cosine window exactly as in the
+    reference; it must be the synthesizer's `1.5*sr/(f0_frames+1e-3)` (vocoder.py:542) -- pass the
+    generating `f0_frames` instead and the kernel derives it.  `encoding`/`mag_scale` let the
+    synthesizer modules hand over raw control tensors (exp / all-pass) without materialising the
+    complex magnitudes.
+    """
+    audio = _need_cuda_f32(audio, 'audio').contiguous()
+    B, T = audio.shape
+    if magnitudes.shape[0] != B:
+        raise ValueError(f'Batch size of audio ({B}) and impulse response ({magnitudes.shape[0]}) must be the same.')
+    if encoding is None:
+        if magnitudes.is_complex():
+            magnitudes = torch.view_as_real(magnitudes.to(torch.complex64).contiguous()).reshape(
+                magnitudes.shape[0], magnitudes.shape[1], -1)
+            encoding, n_mag = MAG_COMPLEX, magnitudes.shape[-1] // 2
+        else:
+            encoding, n_mag = MAG_REAL, magnitudes.shape[-1]
+    else:
+        n_mag = magnitudes.shape[-1]
+    mags = _need_cuda_f32(magnitudes, 'magnitudes')
+    if mags.stride(-1) != 1:
+        mags = mags.contiguous()
+    F = mags.shape[1]
+    if T != F * 512:
+        raise _cabi.DDSPB200Error('frequency_filter: only hop = T/Frame = 512 is supported')
+    if not hann_window:
+        window = WINDOW_NONE
+    elif half_width_frames is None and f0_frames is None:
+        window = WINDOW_HANN
+    else:
+        window = WINDOW_DYNAMIC
+        if f0_frames is None:      # invert half_width = 1.5*sr/(f0+1e-3)
+            f0_frames = 1.5 * float(sampling_rate) / half_width_frames.reshape(B, F).to(torch.float32) - 1e-3
+    f0 = None if f0_frames is None else _f0_2d(f0_frames)
+    out = torch.empty_like(audio)
+    with torch.cuda.device(audio.device):
+        _cabi.check(_cabi.lib().ddsp_b200_frequency_filter(
+            audio.data_ptr(), mags.data_ptr(), mags.stride(0), mags.stride(1), n_mag, encoding, float(mag_scale),
+            window, _ptr(f0), 0 if f0 is None else f0.stride(0), 0 if f0 is None else f0.stride(1),
+            float(sampling_rate), B, F, 512, out.data_ptr(), 0, 0, 0, _stream()))
+    return out
+
+
+def _check_noise(noise_u, B, T):
+    if noise_u is None:
+        return None
+    noise_u = _need_cuda_f32(noise_u, 'noise_u').contiguous()
+    if tuple(noise_u.shape) != (B, T):
+        raise ValueError('noise_u must be (B, T)')
+    return noise_u
+
+
+def combsub_stage(group_delay, harmonic_magnitude, noise_magnitude, f0_frames, prefix, block_size, sampling_rate,
+                  noise_u=None, seed=0):
+    """Stage B of CombSub.forward (old) (vocoder.py:521-548) -> (signal, harmonic, noise), each (B,T)."""
+    gd, hm, nm = _common_views((group_delay, harmonic_magnitude, noise_magnitude),
+                               ('group_delay', 'harmonic_magnitude', 'noise_magnitude'))
+    f0 = _f0_2d(f0_frames)
+    B, F = f0.shape
+    hop = int(block_size)
+    dev = f0.device
+    T = F * hop
+    noise_u = _check_noise(noise_u, B, T)
+    L = _cabi.lib()
+    ws = torch.empty(L.ddsp_b200_combsub_workspace_bytes(B, F, gd.shape[-1], hm.shape[-1], nm.shape[-1]),
+                     dtype=torch.uint8, device=dev)
+    signal, harmonic, noise = (torch.empty((B, T), dtype=torch.float32, device=dev) for _ in range(3))
+    with torch.cuda.device(dev):
+        _cabi.check(L.ddsp_b200_combsub(
+            gd.data_ptr(), gd.shape[-1], hm.data_ptr(), hm.shape[-1], nm.data_ptr(), nm.shape[-1], gd.stride(0),
+            gd.stride(1), f0.data_ptr(), f0.stride(0), f0.stride(1), prefix.data_ptr(), 0, _ptr(noise_u),
+            int(seed) % _TWO62, B, F, hop, float(sampling_rate), signal.data_ptr(), harmonic.data_ptr(),
+            noise.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return signal, harmonic, noise
+
+
+def sins_stage(amplitudes, group_delay, noise_magnitude, f0_frames, phase, block_size, sampling_rate, noise_u=None,
+               seed=0):
+    """Stage B of Sins.forward (vocoder.py:397-421) -> (signal, harmonic, noise), each (B,T).
+    `phase` is the full-rate phase (B,T) from `phase_stage(..., full_rate=True)`."""
+    am, gd, nm = _common_views((amplitudes, group_delay, noise_magnitude),
+                               ('amplitudes', 'group_delay', 'noise_magnitude'))
+    f0 = _f0_2d(f0_frames)
+    B, F = f0.shape
+    hop = int(block_size)
+    dev = f0.device
+    T = F * hop
+    noise_u = _check_noise(noise_u, B, T)
+    phase = _need_cuda_f32(phase, 'phase').contiguous()
+    L = _cabi.lib()
+    ws = torch.empty(L.ddsp_b200_sins_workspace_bytes(B, F, am.shape[-1], gd.shape[-1], nm.shape[-1]),
+                     dtype=torch.uint8, device=dev)
+    signal, harmonic, noise = (torch.empty((B, T), dtype=torch.float32, device=dev) for _ in range(3))
+    with torch.cuda.device(dev):
+        _cabi.check(L.ddsp_b200_sins(
+            am.data_ptr(), am.shape[-1], gd.data_ptr(), gd.shape[-1], nm.data_ptr(), nm.shape[-1], am.stride(0),
+            am.stride(1), f0.data_ptr(), f0.stride(0), f0.stride(1), phase.data_ptr(), _ptr(noise_u),
+            int(seed) % _TWO62, B, F, hop, float(sampling_rate), signal.data_ptr(), harmonic.data_ptr(),
+            noise.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return signal, harmonic, noise
+
+
 def last_launch_count():
     return _cabi.lib().ddsp_b200_last_launch_count()

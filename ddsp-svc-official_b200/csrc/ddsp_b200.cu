@@ -7,6 +7,8 @@
 #include <mutex>
 
 #include "combsubfast.cuh"
+#include "excite.cuh"
+#include "ltvfir.cuh"
 #include "phase.cuh"
 
 namespace {
@@ -42,8 +44,11 @@ int sm_count() {
     return cached[dev];
 }
 
-// Immutable per-device tables (FFT twiddles + exact sqrt-Hann window), filled on first use.
+// Immutable per-device tables (FFT twiddles + exact sqrt-Hann window; Bluestein chirps for the
+// L=510 and L=1022 impulse responses), filled on first use.
 __device__ __align__(16) float g_tables[ddsp::kTableBytes / 4];
+__device__ __align__(16) float g_chirp[2][ddsp::kChirpFloats];
+const float* g_chirp_ptr[64][2] = {{nullptr, nullptr}};
 
 std::mutex g_init_mutex;
 bool g_device_ready[64] = {false};
@@ -63,6 +68,18 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
         CUDA_TRY(cudaGetSymbolAddress((void**)&ptr, g_tables));
         ddsp::fft_tables_kernel<<<4, 256, 0, st>>>(reinterpret_cast<float4*>(ptr), ptr + 2048);
         CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaFuncSetAttribute(ddsp::ltv_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      ddsp::kLtvSmemBytes));
+        float* cptr = nullptr;
+        CUDA_TRY(cudaGetSymbolAddress((void**)&cptr, g_chirp));
+        for (int v = 0; v < 2; ++v) {
+            const int L = v == 0 ? 510 : 1022, K = L / 2 + 1, n_out = v == 0 ? 510 : 512;
+            float* base = cptr + (size_t)v * ddsp::kChirpFloats;
+            ddsp::chirp_tables_kernel<<<4, 256, 0, st>>>(reinterpret_cast<float2*>(base),
+                                                         reinterpret_cast<float2*>(base) + 512, L, K, n_out);
+            CUDA_TRY(cudaGetLastError());
+            g_chirp_ptr[dev][v] = base;
+        }
         CUDA_TRY(cudaStreamSynchronize(st));
         g_tables_ptr[dev] = ptr;
         g_device_ready[dev] = true;
@@ -224,6 +241,173 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
     }
     ddsp::combsubfast_kernel<<<grid, ddsp::kCsfThreads, ddsp::kCsfSmemBytes, (cudaStream_t)stream>>>(P);
     LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// frequency_filter and the two synthesizers built on it
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+int launch_ltv(const float* audio, int audio_mode, uint64_t seed, const float* mags, int64_t mB, int64_t mF, int n_mag,
+               int encoding, float mag_scale, int window_mode, const float* f0_frames, int64_t fB, int64_t fF,
+               double sr, int B, int F, float* out, cudaStream_t st) {
+    if (n_mag != 256 && n_mag != 512) return DDSP_B200_ERR_UNSUPPORTED;
+    if (n_mag == 512 && (encoding == DDSP_B200_MAG_ALLPASS_TANH || encoding == DDSP_B200_MAG_COMPLEX))
+        return DDSP_B200_ERR_UNSUPPORTED;     // the L=1022 path assumes real magnitudes (symmetric IR)
+    if (window_mode == DDSP_B200_WINDOW_DYNAMIC && !f0_frames) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (audio_mode != 2 && (!audio || ((uintptr_t)audio & 7))) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    ddsp::LtvParams P;
+    if (int rc = ensure_device_ready(st, &P.tw_tables)) return rc;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    P.chirp = g_chirp_ptr[dev][n_mag == 256 ? 0 : 1];
+    P.audio = audio; P.audio_mode = audio_mode; P.seed = seed;
+    P.mags = mags; P.mB = mB; P.mF = mF; P.n_mag = n_mag; P.encoding = encoding; P.mag_scale = mag_scale;
+    P.window_mode = window_mode; P.f0_frames = f0_frames; P.fB = fB; P.fF = fF; P.sr15 = (float)(1.5 * sr);
+    P.out = out; P.B = B; P.F = F;
+    const int frames = F + 1;
+    const int64_t slots = (int64_t)sm_count() * ddsp::kLtvWarps;
+    int run_len = (int)(((int64_t)B * frames + slots - 1) / slots);
+    if (run_len < 4) run_len = frames < 4 ? frames : 4;     // keep the 3-hop seams a minority of the work
+    if (run_len > frames) run_len = frames;
+    P.run_len = run_len;
+    P.runs_per_clip = (frames + run_len - 1) / run_len;
+    if (P.runs_per_clip > 1) {
+        CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)B * F * ddsp::kHop * sizeof(float), st));
+        ++g_launches;
+    }
+    const int64_t runs = (int64_t)B * P.runs_per_clip;
+    const unsigned grid = (unsigned)((runs + ddsp::kLtvWarps - 1) / ddsp::kLtvWarps);
+    ddsp::ltv_filter_kernel<<<grid, ddsp::kLtvThreads, ddsp::kLtvSmemBytes, st>>>(P);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int launch_add(const float* a, const float* b, float* out, int64_t n, cudaStream_t st) {
+    if (n % 4) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    ddsp::add_kernel<<<(unsigned)grid_for(n / 4, 256, 148 * 16), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), reinterpret_cast<float4*>(out), n / 4);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t ddsp_b200_frequency_filter_workspace_bytes(int B, int F, int n_mag) {
+    (void)n_mag;
+    return (B > 0 && F > 0) ? (size_t)B * F * ddsp::kHop * sizeof(float) : 0;   // only used when accumulate != 0
+}
+
+int ddsp_b200_frequency_filter(const float* audio, const float* mags, int64_t mB, int64_t mF, int n_mag,
+                               int mag_encoding, float mag_scale, int window_mode, const float* f0_frames, int64_t fB,
+                               int64_t fF, double sr, int B, int F, int hop, float* out, int accumulate,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    if (!audio || !mags || !out || B <= 0 || F <= 0 || !(sr > 0) || audio == out) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (hop != ddsp::kHop) return DDSP_B200_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!accumulate)
+        return launch_ltv(audio, 0, 0, mags, mB, mF, n_mag, mag_encoding, mag_scale, window_mode, f0_frames, fB, fF, sr,
+                          B, F, out, st);
+    if (!workspace || workspace_bytes < ddsp_b200_frequency_filter_workspace_bytes(B, F, n_mag))
+        return DDSP_B200_ERR_WORKSPACE;
+    float* tmp = (float*)workspace;
+    if (int rc = launch_ltv(audio, 0, 0, mags, mB, mF, n_mag, mag_encoding, mag_scale, window_mode, f0_frames, fB, fF,
+                            sr, B, F, tmp, st))
+        return rc;
+    return launch_add(out, tmp, out, (int64_t)B * F * hop, st);
+}
+
+size_t ddsp_b200_combsub_workspace_bytes(int B, int F, int n_mag_allpass, int n_mag_harmonic, int n_mag_noise) {
+    (void)n_mag_allpass; (void)n_mag_harmonic; (void)n_mag_noise;
+    return (B > 0 && F > 0) ? (size_t)2 * B * F * ddsp::kHop * sizeof(float) : 0;   // combtooth + all-passed harmonic
+}
+
+int ddsp_b200_combsub(const float* group_delay, int n_mag_allpass, const float* harmonic_magnitude, int n_mag_harmonic,
+                      const float* noise_magnitude, int n_mag_noise, int64_t cB, int64_t cF, const float* f0_frames,
+                      int64_t fB, int64_t fF, const double* prefix, const float* initial_phase, const float* noise_u,
+                      uint64_t seed, int B, int F, int hop, double sr, float* signal, float* harmonic, float* noise,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    (void)initial_phase;   // carried by `prefix`
+    if (!group_delay || !harmonic_magnitude || !noise_magnitude || !f0_frames || !prefix || !signal || !harmonic ||
+        !noise || B <= 0 || F <= 0 || !(sr > 0))
+        return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (hop != ddsp::kHop) return DDSP_B200_ERR_UNSUPPORTED;
+    if ((int64_t)F * hop >= (1ll << 24)) return DDSP_B200_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < ddsp_b200_combsub_workspace_bytes(B, F, n_mag_allpass, n_mag_harmonic, n_mag_noise))
+        return DDSP_B200_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = (int64_t)B * F * hop;
+    float* comb = (float*)workspace;
+    float* h1 = comb + n;
+    int launches = 0;
+    // vocoder.py:539  combtooth (no unvoiced zeroing in the old CombSub)
+    ddsp::combtooth_kernel<<<(unsigned)(((int64_t)B * F + 7) / 8), 256, 0, st>>>(f0_frames, fB, fF, B, F, 1.0 / sr,
+                                                                                   (float)sr, prefix, 0, comb);
+    LAUNCH_CHECK();
+    launches += g_launches; g_launches = 0;
+    // :540  all-pass (group delay), no window
+    if (int rc = launch_ltv(comb, 0, 0, group_delay, cB, cF, n_mag_allpass, DDSP_B200_MAG_ALLPASS_TANH, 1.0f,
+                            DDSP_B200_WINDOW_NONE, nullptr, 0, 0, sr, B, F, h1, st)) return rc;
+    launches += g_launches; g_launches = 0;
+    // :541-542  harmonic magnitude filter with the f0-dependent window
+    if (int rc = launch_ltv(h1, 0, 0, harmonic_magnitude, cB, cF, n_mag_harmonic, DDSP_B200_MAG_EXP, 1.0f,
+                            DDSP_B200_WINDOW_DYNAMIC, f0_frames, fB, fF, sr, B, F, harmonic, st)) return rc;
+    launches += g_launches; g_launches = 0;
+    // :545-546  filtered noise
+    if (int rc = launch_ltv(noise_u, noise_u ? 1 : 2, seed, noise_magnitude, cB, cF, n_mag_noise, DDSP_B200_MAG_EXP,
+                            1.0f / 128.0f, DDSP_B200_WINDOW_HANN, nullptr, 0, 0, sr, B, F, noise, st)) return rc;
+    launches += g_launches; g_launches = 0;
+    // :548
+    if (int rc = launch_add(harmonic, noise, signal, n, st)) return rc;
+    g_launches += launches;
+    return DDSP_B200_OK;
+}
+
+size_t ddsp_b200_sins_workspace_bytes(int B, int F, int n_harmonics, int n_mag_allpass, int n_mag_noise) {
+    (void)n_harmonics; (void)n_mag_allpass; (void)n_mag_noise;
+    return (B > 0 && F > 0) ? (size_t)B * F * ddsp::kHop * sizeof(float) : 0;       // the sinusoid mix
+}
+
+int ddsp_b200_sins(const float* amplitudes, int n_harmonics, const float* group_delay, int n_mag_allpass,
+                   const float* noise_magnitude, int n_mag_noise, int64_t cB, int64_t cF, const float* f0_frames,
+                   int64_t fB, int64_t fF, const float* phase_full, const float* noise_u, uint64_t seed, int B, int F,
+                   int hop, double sr, float* signal, float* harmonic, float* noise, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    g_launches = 0;
+    if (!amplitudes || !group_delay || !noise_magnitude || !f0_frames || !phase_full || !signal || !harmonic || !noise ||
+        B <= 0 || F <= 0 || !(sr > 0) || n_harmonics <= 0)
+        return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (hop != ddsp::kHop || n_harmonics > ddsp::kSinsMaxHarm) return DDSP_B200_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < ddsp_b200_sins_workspace_bytes(B, F, n_harmonics, n_mag_allpass, n_mag_noise))
+        return DDSP_B200_ERR_WORKSPACE;
+    if ((int64_t)B * F > 0x7fffffffLL) return DDSP_B200_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = (int64_t)B * F * hop;
+    float* sinus = (float*)workspace;
+    int launches = 0;
+    // vocoder.py:397,402-412  oscillator bank with the Nyquist mask (fmax = sr/2)
+    ddsp::sins_osc_kernel<<<(unsigned)((int64_t)B * F), 128, 0, st>>>(amplitudes, cB, cF, n_harmonics, f0_frames, fB, fF,
+                                                                       F, (float)(sr / 2.0), phase_full, sinus);
+    LAUNCH_CHECK();
+    launches += g_launches; g_launches = 0;
+    // :415  all-pass
+    if (int rc = launch_ltv(sinus, 0, 0, group_delay, cB, cF, n_mag_allpass, DDSP_B200_MAG_ALLPASS_TANH, 1.0f,
+                            DDSP_B200_WINDOW_NONE, nullptr, 0, 0, sr, B, F, harmonic, st)) return rc;
+    launches += g_launches; g_launches = 0;
+    // :418-419  filtered noise
+    if (int rc = launch_ltv(noise_u, noise_u ? 1 : 2, seed, noise_magnitude, cB, cF, n_mag_noise, DDSP_B200_MAG_EXP,
+                            1.0f / 128.0f, DDSP_B200_WINDOW_HANN, nullptr, 0, 0, sr, B, F, noise, st)) return rc;
+    launches += g_launches; g_launches = 0;
+    // :421
+    if (int rc = launch_add(harmonic, noise, signal, n, st)) return rc;
+    g_launches += launches;
     return DDSP_B200_OK;
 }
 

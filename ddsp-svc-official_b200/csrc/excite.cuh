@@ -1,0 +1,107 @@
+// excite.cuh -- excitation generators that write a (B,T) buffer:
+//   * combtooth sinc pulse train            vocoder.py:539 (CombSub-old; no unvoiced zeroing)
+//   * Sins harmonic oscillator bank          vocoder.py:397,402-412 (+ core.py:24-28 Nyquist mask)
+//   * elementwise add                        vocoder.py:421,548
+#pragma once
+#include "fft32.cuh"
+#include "phase.cuh"
+
+namespace ddsp {
+
+// One warp per hop; lane owns 16 consecutive samples (128-bit stores).
+__global__ void __launch_bounds__(256) combtooth_kernel(const float* __restrict__ f0_frames, int64_t fB, int64_t fF,
+                                                        int B, int F, double inv_sr, float sr,
+                                                        const double* __restrict__ prefix, int zero_unvoiced,
+                                                        float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (warp >= (int64_t)B * F) return;
+    const int b = (int)(warp / F), h = (int)(warp % F);
+    const float* row = f0_frames + (int64_t)b * fB;
+    const float x0 = __ldg(row + (int64_t)h * fF);
+    const float x1 = __ldg(row + (int64_t)min(h + 1, F - 1) * fF);
+    float f[16], rot[16], c[16];
+    hop_rotation(x0, x1, prefix[warp], inv_sr, lane, f, rot);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float x = __fmul_rn(sr, rot[i]) * rcp_approx(__fadd_rn(f[i], 1e-3f));   // vocoder.py:539
+        c[i] = sinc_f(x);
+        if (zero_unvoiced && f[i] <= 0.0f) c[i] = 0.0f;
+    }
+    float4* dst = reinterpret_cast<float4*>(out + warp * kHop + 16 * lane);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
+}
+
+// Sins oscillator bank.  One CTA of 128 threads per hop (512 samples, 4 per thread).
+//   A[m,k] = fl(exp(a[m,k]) / 128) * ((f0[m]*k < sr/2) + 1e-7)            (vocoder.py:397,402)
+//   s[t]   = sum_k lerp(A[:,k])[t] * sin(k * theta[t])                     (vocoder.py:406-412)
+// sin(k*theta) comes from the complex rotation z_k = z_{k-1} * z_1 (z_1 = cis(theta), accurate
+// sincosf); two samples ride in one packed fp32x2 register pair.
+constexpr int kSinsMaxHarm = 512;
+
+__global__ void __launch_bounds__(128) sins_osc_kernel(const float* __restrict__ amp_ctrl, int64_t cB, int64_t cF,
+                                                       int n_harm, const float* __restrict__ f0_frames, int64_t fB,
+                                                       int64_t fF, int F, float fmax,
+                                                       const float* __restrict__ phase_full,
+                                                       float* __restrict__ out) {
+    __shared__ float4 amps[kSinsMaxHarm];      // (A0, A0, dA, dA) per harmonic
+    const int hop = blockIdx.x % F, b = blockIdx.x / F;
+    const int m1 = min(hop + 1, F - 1);         // hold-last (core.py:17)
+    const float f0a = __ldg(f0_frames + (int64_t)b * fB + (int64_t)hop * fF);
+    const float f0b = __ldg(f0_frames + (int64_t)b * fB + (int64_t)m1 * fF);
+    const float* ra = amp_ctrl + (int64_t)b * cB + (int64_t)hop * cF;
+    const float* rb = amp_ctrl + (int64_t)b * cB + (int64_t)m1 * cF;
+    for (int k = threadIdx.x; k < n_harm; k += blockDim.x) {
+        const float lvl = (float)(k + 1);
+        const float ma = __fadd_rn((__fmul_rn(f0a, lvl) < fmax) ? 1.0f : 0.0f, 1e-7f);     // core.py:26-27
+        const float mb = __fadd_rn((__fmul_rn(f0b, lvl) < fmax) ? 1.0f : 0.0f, 1e-7f);
+        const float A0 = __fmul_rn(__fmul_rn(expf(__ldg(ra + k)), 0.0078125f), ma);         // exp()/128 then mask
+        const float A1 = __fmul_rn(__fmul_rn(expf(__ldg(rb + k)), 0.0078125f), mb);
+        const float dA = A1 - A0;
+        amps[k] = make_float4(A0, A0, dA, dA);
+    }
+    __syncthreads();
+    const int64_t base = ((int64_t)b * F + hop) * kHop;
+    const int t = threadIdx.x;
+    float2 lam[2], c1[2], s1[2], c[2], s[2], acc[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int i0 = t + 256 * p, i1 = i0 + 128;
+        lam[p] = make_float2((float)i0 * (1.0f / kHop), (float)i1 * (1.0f / kHop));
+        float sa, ca, sb, cb;
+        sincosf(__ldg(phase_full + base + i0), &sa, &ca);
+        sincosf(__ldg(phase_full + base + i1), &sb, &cb);
+        c1[p] = make_float2(ca, cb); s1[p] = make_float2(sa, sb);
+        c[p] = make_float2(1.0f, 1.0f); s[p] = make_float2(0.0f, 0.0f);
+        acc[p] = make_float2(0.0f, 0.0f);
+    }
+#pragma unroll 4
+    for (int k = 0; k < n_harm; ++k) {
+        const float4 a = amps[k];
+        const float2 A0 = make_float2(a.x, a.y), dA = make_float2(a.z, a.w);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const float2 cn = fma2(neg2(s[p]), s1[p], mul2(c[p], c1[p]));     // z_k = z_{k-1} * z_1
+            const float2 sn = fma2(c[p], s1[p], mul2(s[p], c1[p]));
+            c[p] = cn; s[p] = sn;
+            const float2 amp = fma2(lam[p], dA, A0);
+            acc[p] = fma2(amp, sn, acc[p]);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        out[base + t + 256 * p] = acc[p].x;
+        out[base + t + 256 * p + 128] = acc[p].y;
+    }
+}
+
+__global__ void __launch_bounds__(256) add_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                  float4* __restrict__ out, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 x = __ldg(a + i), y = __ldg(b + i);
+        out[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    }
+}
+
+}  // namespace ddsp

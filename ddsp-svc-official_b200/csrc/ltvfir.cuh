@@ -1,0 +1,358 @@
+// ltvfir.cuh -- `frequency_filter` (ddsp/core.py:331-336): per-frame linear-phase LTV-FIR applied
+// through the frequency domain, as ONE kernel per filter:
+//
+//   _frequency_impulse_response  core.py:306-328   magnitudes -> irfft_L -> roll -> window
+//   _fft_convolve                core.py:185-239   Bartlett framing, FFT convolution, overlap-add,
+//                                                   crop with L//2 delay compensation
+//
+// A warp owns a run of consecutive frames of one clip and performs, per frame, five 1024-point
+// complex FFTs (all through the single warp_fft1024 instance of fft32.cuh):
+//   1. audio frame (1024 Bartlett-windowed samples, zero-padded to 2048): real FFT-2048 computed as
+//      the complex FFT-1024 of even/odd samples -> kept raw in shared memory;
+//   2./3. impulse response: the L-point inverse real DFT (L = 510 or 1022, NOT a power of two) is
+//      evaluated exactly with Bluestein's chirp-z identity as a 1024-point circular convolution
+//      (forward FFT, multiply with the precomputed chirp spectrum, inverse FFT); then the roll and
+//      the window (none / Hann / dynamic cosine) are applied while writing the taps to shared memory;
+//   4. the taps' real FFT-2048 (again as complex FFT-1024 of even/odd taps);
+//   5. spectra multiplied in the even/odd domain (so no second conjugate-pair exchange is needed)
+//      and one inverse FFT-1024 yields the 2048 output samples of the frame, which are overlap-added
+//      in a shared-memory ring; every frame retires 512 finished samples to HBM.
+// The reference's FFT size (1533 / 2045) only has to cover the linear convolution; 2048 gives the
+// identical result.
+#pragma once
+#include "fft32.cuh"
+
+namespace ddsp {
+
+constexpr int kLtvWarps = 10;                      // warps per CTA (smem-bound: 20.3 KB per warp)
+constexpr int kLtvThreads = kLtvWarps * 32;
+constexpr int kLtvStash = 1024;                    // float2: raw FFT of the audio frame
+constexpr int kLtvRing = 2048;                     // floats: overlap-add ring
+constexpr int kLtvWarpBytes = kPlaneFloats * 4 + kLtvStash * 8 + kLtvRing * 4;
+constexpr int kLtvSmemBytes = 512 * 16 + kLtvWarps * kLtvWarpBytes;
+
+// per-L chirp tables: c[m] = exp(i*pi*m^2/L), m < 512; dhat = FFT_1024 of the wrapped conjugate chirp
+constexpr int kChirpFloats = 512 * 2 + 1024 * 2;
+
+struct LtvParams {
+    const float* audio;                 // (B,T) contiguous, or U when audio_mode==1, unused when 2
+    int audio_mode;                     // 0: samples, 1: uniform U -> 2U-1 (vocoder.py:418,545), 2: in-kernel noise
+    uint64_t seed;
+    const float* mags; int64_t mB, mF;  // (B,F,n_mag) control / magnitude rows
+    int n_mag, encoding; float mag_scale;
+    int window_mode;
+    const float* f0_frames; int64_t fB, fF; float sr15;   // dynamic window: hw = 1.5*sr/(f0+1e-3)
+    const float* tw_tables;             // twiddles (fft32.cuh)
+    const float* chirp;                 // tables for this L
+    float* out;                         // (B,T)
+    int B, F, run_len, runs_per_clip;
+};
+
+__device__ __forceinline__ float bartlett1024(int i) {      // torch.bartlett_window(1024), periodic (core.py:221)
+    return (i <= 512) ? (float)i * (1.0f / 512.0f) : (float)(1024 - i) * (1.0f / 512.0f);
+}
+
+// Conjugate-symmetric partner of bin k = lane + 32 q of a 1024-point spectrum held in registers:
+// bin 1024-k lives in lane 32-l, register-index 31-q (lane 0: its own register (32-q)&31).
+#define LTV_PARTNER(X, q, outr, outi)                                              \
+    {                                                                              \
+        outr = __shfl_sync(kFullMask, DDSP_RE(X, 31 - (q)), partner);              \
+        outi = __shfl_sync(kFullMask, DDSP_IM(X, 31 - (q)), partner);              \
+        const float r0_ = DDSP_RE(X, (32 - (q)) & 31), i0_ = DDSP_IM(X, (32 - (q)) & 31); \
+        outr = lane0 ? r0_ : outr;                                                 \
+        outi = lane0 ? i0_ : outi;                                                 \
+    }
+
+__global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float4* tw4 = reinterpret_cast<const float4*>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char* wbase = smem_raw + 512 * 16 + wid * kLtvWarpBytes;
+    float* plane = reinterpret_cast<float*>(wbase);
+    float2* stash = reinterpret_cast<float2*>(plane + kPlaneFloats);
+    float* ring = reinterpret_cast<float*>(stash + kLtvStash);
+    {
+        const float4* src = reinterpret_cast<const float4*>(P.tw_tables);
+        float4* dst = reinterpret_cast<float4*>(smem_raw);
+        for (int e = threadIdx.x; e < 512; e += kLtvThreads) dst[e] = __ldg(src + e);
+        __syncthreads();
+    }
+    const int64_t run = (int64_t)blockIdx.x * kLtvWarps + wid;
+    if (run >= (int64_t)P.B * P.runs_per_clip) return;
+    const int b = (int)(run / P.runs_per_clip);
+    const int F = P.F;
+    const int m_begin = (int)(run % P.runs_per_clip) * P.run_len;
+    const int m_end = min(F + 1, m_begin + P.run_len);
+    const int64_t T = (int64_t)F * kHop;
+    const int n_mag = P.n_mag;
+    const int L = 2 * (n_mag - 1), D = L / 2;
+    const int n_out = (L == 510) ? 510 : 512;          // IR samples produced by the chirp convolution
+    const bool sym = L != 510;                          // L=1022: real magnitudes -> IR symmetric, mirror it
+    const int partner = (32 - lane) & 31;
+    const bool lane0 = lane == 0;
+    const float2* chirp_c = reinterpret_cast<const float2*>(P.chirp);
+    const float2* chirp_d = chirp_c + 512;
+    const float2 wl = make_float2(tw4[lane].y, tw4[lane].w);        // W1024^lane = (cos, -sin)
+    const uint32_t key = noise_key(P.seed, (uint32_t)b);
+
+    for (int i = lane; i < kLtvRing; i += 32) ring[i] = 0.0f;
+    __syncwarp();
+    int rs = 0;                                          // ring start (logical sample 0 of the current frame)
+
+    Pts32 X;
+    for (int m = m_begin; m < m_end; ++m) {
+        const int64_t t0 = (int64_t)(m - 1) * kHop;      // first input sample of the frame
+        const int mhat = min(m, F - 1);                  // last IR repeated (core.py:228)
+#pragma unroll 1
+        for (int phase = 0; phase < 5; ++phase) {
+            // ------------------------------ prologue ------------------------------------------
+            if (phase == 0) {
+                // z[n] = a[2n] + j a[2n+1], n = 32 n1 + lane < 512; a = bartlett * frame (core.py:218-222)
+                const bool vA = m >= 1, vB = m < F;
+                const float* src = P.audio + (int64_t)b * T;
+                uint32_t stA = noise_seed(key, (uint32_t)(m - 1), (uint32_t)lane);
+                uint32_t stB = noise_seed(key, (uint32_t)m, (uint32_t)lane);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    float v0 = 0.0f, v1 = 0.0f;
+                    if (n1 < 16) {
+                        const int i = 64 * n1 + 2 * lane;               // frame-relative sample index (even)
+                        const bool ok = (n1 < 8) ? vA : vB;
+                        if (P.audio_mode == 2) {
+                            uint32_t& st = (n1 < 8) ? stA : stB;
+                            st = noise_next(st); v0 = (float)noise_u24(st) * 5.9604644775390625e-8f;
+                            st = noise_next(st); v1 = (float)noise_u24(st) * 5.9604644775390625e-8f;
+                            v0 = ok ? fmaf(2.0f, v0, -1.0f) : 0.0f;
+                            v1 = ok ? fmaf(2.0f, v1, -1.0f) : 0.0f;
+                        } else if (ok) {
+                            const float2 x = __ldg(reinterpret_cast<const float2*>(src + t0 + i));
+                            v0 = x.x; v1 = x.y;
+                            if (P.audio_mode == 1) { v0 = fmaf(2.0f, v0, -1.0f); v1 = fmaf(2.0f, v1, -1.0f); }
+                        }
+                        v0 *= bartlett1024(i);
+                        v1 *= bartlett1024(i + 1);
+                    }
+                    DDSP_RE(X, brev5(n1)) = v0;
+                    DDSP_IM(X, brev5(n1)) = v1;
+                }
+            } else if (phase == 1) {
+                // a'[k] = w_k X[k] c[k] / (L*1024), k = 32 n1 + lane < n_mag   (irfft, core.py:316)
+                const float* row = P.mags + (int64_t)b * P.mB + (int64_t)mhat * P.mF;
+                const float scale = 1.0f / ((float)L * 1024.0f);
+                float carry = 0.0f;                                      // allpass: running phase in turns
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    float xr = 0.0f, xi = 0.0f;
+                    if (n1 * 32 < n_mag) {
+                        const int k = 32 * n1 + lane;
+                        if (P.encoding == DDSP_B200_MAG_ALLPASS_TANH) {
+                            // exp(j*cumsum(pi*tanh(c)))  (vocoder.py:398,415 / 521,540), phase kept in turns
+                            float g = 0.5f * tanhf(__ldg(row + k));
+#pragma unroll
+                            for (int d = 1; d < 32; d <<= 1) {
+                                const float t = __shfl_up_sync(kFullMask, g, d);
+                                if (lane >= d) g += t;
+                            }
+                            g += carry;
+                            carry = __shfl_sync(kFullMask, g, 31);
+                            carry -= rintf(carry);
+                            g -= rintf(g);
+                            xr = cos_approx(DDSP_TWO_PI_F * g);
+                            xi = sin_approx(DDSP_TWO_PI_F * g);
+                        } else if (P.encoding == DDSP_B200_MAG_EXP) {
+                            xr = expf(__ldg(row + k)) * P.mag_scale;     // vocoder.py:399,475,522-523
+                        } else if (P.encoding == DDSP_B200_MAG_COMPLEX) {
+                            const float2 v = __ldg(reinterpret_cast<const float2*>(row) + k);
+                            xr = v.x; xi = v.y;
+                        } else {
+                            xr = __ldg(row + k);
+                        }
+                        // DC and Nyquist: imaginary part ignored, weight 1; interior bins weight 2
+                        const bool edge = (k == 0) || (k == n_mag - 1);
+                        const float wgt = edge ? scale : 2.0f * scale;
+                        xi = edge ? 0.0f : xi;
+                        const float2 c = __ldg(chirp_c + k);
+                        const float ar = xr * wgt, ai = xi * wgt;
+                        xr = ar * c.x - ai * c.y;
+                        xi = ar * c.y + ai * c.x;
+                    }
+                    DDSP_RE(X, brev5(n1)) = xr;
+                    DDSP_IM(X, brev5(n1)) = xi;
+                }
+            } else if (phase == 3) {
+                // z[n] = h[2n] + j h[2n+1] from the taps in `plane`
+                const float2* h2 = reinterpret_cast<const float2*>(plane);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    float2 v = make_float2(0.0f, 0.0f);
+                    if (n1 < 16 && 32 * n1 < D + 1) v = h2[32 * n1 + lane];
+                    DDSP_RE(X, brev5(n1)) = v.x;
+                    DDSP_IM(X, brev5(n1)) = v.y;
+                }
+                __syncwarp();
+            }
+
+            warp_fft1024(X, plane, tw4, lane);
+
+            // ------------------------------ epilogue ------------------------------------------
+            if (phase == 0) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) stash[lane + 32 * q] = make_float2(DDSP_RE(X, q), DDSP_IM(X, q));
+            } else if (phase == 1) {
+                // times the chirp spectrum, then inverse FFT (real/imag swapped through the forward FFT)
+                float pr[32], pi[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const float2 dh = __ldg(chirp_d + lane + 32 * q);
+                    const float ur = DDSP_RE(X, q), ui = DDSP_IM(X, q);
+                    pr[q] = ur * dh.x - ui * dh.y;
+                    pi[q] = ur * dh.y + ui * dh.x;
+                }
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    DDSP_RE(X, brev5(q)) = pi[q];
+                    DDSP_IM(X, brev5(q)) = pr[q];
+                }
+            } else if (phase == 2) {
+                // conv[n] (Re in X.im, Im in X.re after the swapped FFT), n = lane + 32 q < n_out:
+                // ir_zero_phase[n] = Re(c[n] * conv[n]); causal form + window (core.py:242-303,326)
+                float hw_inv = 0.0f;
+                if (P.window_mode == DDSP_B200_WINDOW_DYNAMIC) {
+                    const float f0 = __ldg(P.f0_frames + (int64_t)b * P.fB + (int64_t)mhat * P.fF);
+                    hw_inv = __fdiv_rn(1.0f, __fdiv_rn(P.sr15, __fadd_rn(f0, 1e-3f)));
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int n = lane + 32 * q;
+                    if (n < n_out) {
+                        const float2 c = __ldg(chirp_c + n);
+                        const float ir = DDSP_IM(X, q) * c.x - DDSP_RE(X, q) * c.y;   // Re(c * conv)
+                        // tap positions: i = (n + D) mod L holds lag +n; for symmetric IRs also lag -n
+#pragma unroll
+                        for (int side = 0; side < 2; ++side) {
+                            int lag;
+                            if (side == 0) lag = (n <= L - D - 1) ? n : n - L;
+                            else {
+                                if (!sym || n == 0 || n >= D) continue;
+                                lag = -n;
+                            }
+                            const int i = lag + D;
+                            float w = 1.0f;
+                            if (P.window_mode == DDSP_B200_WINDOW_HANN) {
+                                w = 0.5f - 0.5f * cospif((float)(2 * i) / (float)L);
+                            } else if (P.window_mode == DDSP_B200_WINDOW_DYNAMIC) {
+                                float x = (float)lag * hw_inv;
+                                x = (x > 1.0f) ? 0.0f : x;                           // core.py:297 (only x>1 is cleared)
+                                w = 0.5f * (1.0f + cospif(x));
+                            }
+                            plane[i] = ir * w * (1.0f / 4096.0f);                    // 1/4 (even/odd split) * 1/1024 (inverse FFT)
+                        }
+                    }
+                }
+                if (lane < 2) plane[L + lane] = 0.0f;
+                __syncwarp();
+            } else if (phase == 3) {
+                // even/odd-domain product:  Zy = (Ea Eh + W1024^k Oa Oh) + j (Ea Oh + Oa Eh)
+                float zr[32], zi[32];
+#pragma unroll
+                for (int qq = 0; qq < 32; ++qq) {
+                    const int q = (qq & 1) ? 31 - (qq >> 1) : (qq >> 1);   // 0,31,1,30,...: registers die in pairs
+                    const int k = lane + 32 * q;
+                    float cr, ci;
+                    LTV_PARTNER(X, q, cr, ci);
+                    const float ar = DDSP_RE(X, q), ai = DDSP_IM(X, q);
+                    const float Ehr = ar + cr, Ehi = ai - ci, Ohr = ai + ci, Ohi = cr - ar;
+                    const float2 za = stash[k], zp = stash[(1024 - k) & 1023];
+                    const float Ear = za.x + zp.x, Eai = za.y - zp.y, Oar = za.y + zp.y, Oai = zp.x - za.x;
+                    // W1024^k = W1024^lane * W32^q
+                    const float cq = (q < 16) ? cos32(q & 15) : -cos32(q & 15);
+                    const float sq = (q < 16) ? -sin32(q & 15) : sin32(q & 15);      // W32^q = cq + j sq
+                    const float wr = wl.x * cq - wl.y * sq, wi = wl.x * sq + wl.y * cq;
+                    const float oor = Oar * Ohr - Oai * Ohi, ooi = Oar * Ohi + Oai * Ohr;
+                    const float eer = Ear * Ehr - Eai * Ehi, eei = Ear * Ehi + Eai * Ehr;
+                    const float eyr = eer + (wr * oor - wi * ooi), eyi = eei + (wr * ooi + wi * oor);
+                    const float oyr = (Ear * Ohr - Eai * Ohi) + (Oar * Ehr - Oai * Ehi);
+                    const float oyi = (Ear * Ohi + Eai * Ohr) + (Oar * Ehi + Oai * Ehr);
+                    zr[q] = eyr - oyi;          // Ey + j Oy
+                    zi[q] = eyi + oyr;
+                }
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    DDSP_RE(X, brev5(q)) = zi[q];      // swapped -> inverse
+                    DDSP_IM(X, brev5(q)) = zr[q];
+                }
+            } else if (phase == 4) {
+                // y[2n] = Re z'[n] = X.im, y[2n+1] = Im z'[n] = X.re, n = lane + 32 q; overlap-add (core.py:233-235)
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    float2* slot = reinterpret_cast<float2*>(ring + ((rs + 2 * lane + 64 * q) & (kLtvRing - 1)));
+                    float2 v = make_float2(DDSP_IM(X, q), DDSP_RE(X, q));
+                    if (q < 24) { const float2 o = *slot; v.x += o.x; v.y += o.y; }
+                    *slot = v;
+                }
+                __syncwarp();
+                // retire the first 512 samples of the window: output index t = 512(m-1) - D + j  (core.py:238,177-182)
+                const bool complete = (m - 3 >= m_begin) || (m_begin == 0);
+                float* ob = P.out + (int64_t)b * T;
+                const int64_t tb = t0 - D;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const int j = lane + 32 * r;
+                    const int64_t t = tb + j;
+                    if (t >= 0 && t < T) {
+                        const float v = ring[(rs + j) & (kLtvRing - 1)];
+                        if (complete) ob[t] = v; else atomicAdd(ob + t, v);
+                    }
+                }
+                __syncwarp();
+                rs = (rs + kHop) & (kLtvRing - 1);
+            }
+        }
+    }
+    // flush the three remaining hops of the ring
+    {
+        const int m_last = m_end - 1;
+        float* ob = P.out + (int64_t)b * T;
+        const int64_t tb = (int64_t)(m_last - 1) * kHop - D + kHop;       // rs already advanced past the retired hop
+        for (int c = 0; c < 3; ++c) {
+            const bool complete = (m_end == F + 1) && ((m_last - 2 + c >= m_begin) || (m_begin == 0));
+            for (int r = 0; r < 16; ++r) {
+                const int j = lane + 32 * r + kHop * c;
+                const int64_t t = tb + j;
+                if (t >= 0 && t < T) {
+                    const float v = ring[(rs + j) & (kLtvRing - 1)];
+                    if (complete) ob[t] = v; else atomicAdd(ob + t, v);
+                }
+            }
+        }
+    }
+}
+
+// Chirp tables for one L: c[m] = exp(i pi m^2 / L) (m < 512) and the 1024-point spectrum of the
+// wrapped conjugate chirp d[m] = exp(-i pi m^2 / L), m in [-(K-1), n_out-1].  Evaluated in double
+// with exact integer phase reduction (one-time setup; O(N^2) direct DFT on purpose).
+__global__ void chirp_tables_kernel(float2* __restrict__ c_out, float2* __restrict__ d_out, int L, int K, int n_out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 1024) return;
+    if (t < 512) {
+        const long long r = ((long long)t * t) % (2LL * L);
+        double s, c;
+        sincospi((double)r / (double)L, &s, &c);
+        c_out[t] = make_float2((float)c, (float)s);
+    }
+    double accr = 0.0, acci = 0.0;
+    for (int m = -(K - 1); m <= n_out - 1; ++m) {
+        const long long r = ((long long)m * m) % (2LL * L);
+        double ds, dc;
+        sincospi((double)r / (double)L, &ds, &dc);          // d = dc - i ds
+        const int idx = (m + 1024) & 1023;
+        const int e = (int)(((long long)idx * t) & 1023);   // exp(-2 pi i idx t / 1024)
+        double es, ec;
+        sincospi((double)e / 512.0, &es, &ec);              // = ec - i es
+        accr += dc * ec - ds * es;                          // (dc - i ds)(ec - i es)
+        acci += -(dc * es + ds * ec);
+    }
+    d_out[t] = make_float2((float)accr, (float)acci);
+}
+
+}  // namespace ddsp

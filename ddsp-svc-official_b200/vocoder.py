@@ -83,12 +83,66 @@ class CombSubFast(_SynthBase):
         return signal, phase_frames.unsqueeze(-1), (signal, signal)      # vocoder.py:492
 
 
+class CombSub(_SynthBase):
+    """Reference: ddsp/vocoder.py:495-550 (the "old" combtooth subtractive synthesiser)."""
+
+    def __init__(self, sampling_rate, block_size, n_mag_allpass, n_mag_harmonic, n_mag_noise, n_unit=256, n_spk=1,
+                 c: bool = False, unit2ctrl=None):
+        super().__init__(sampling_rate, block_size)
+        print(' [DDSP Model] Combtooth Subtractive Synthesiser (Old Version) (ddsp_b200)')
+        splits = {'group_delay': n_mag_allpass, 'harmonic_magnitude': n_mag_harmonic, 'noise_magnitude': n_mag_noise}
+        self.unit2ctrl = unit2ctrl if unit2ctrl is not None else _make_unit2ctrl(n_unit, n_spk, splits, c)
+
+    def forward(self, units_frames, f0_frames, volume_frames, spk_id, spk_mix_dict=None, initial_phase=None,
+                infer=True, noise_u=None, **kwargs):
+        phase_frames, prefix, _ = core.phase_stage(f0_frames, self._hop, self._sr, initial_phase, infer)   # :515-517
+        ctrls = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id, spk_mix_dict=spk_mix_dict)
+        self._forward_only(ctrls)
+        signal, harmonic, noise = core.combsub_stage(ctrls['group_delay'], ctrls['harmonic_magnitude'],
+                                                     ctrls['noise_magnitude'], f0_frames, prefix, self._hop, self._sr,
+                                                     noise_u=noise_u, seed=self._next_seed())                  # :521-548
+        return signal, phase_frames.unsqueeze(-1), (harmonic, noise)                                          # :550
+
+
+class Sins(_SynthBase):
+    """Reference: ddsp/vocoder.py:372-423 (sinusoids additive synthesiser)."""
+
+    def __init__(self, sampling_rate, block_size, n_harmonics, n_mag_allpass, n_mag_noise, n_unit=256, n_spk=1,
+                 c: bool = False, unit2ctrl=None):
+        super().__init__(sampling_rate, block_size)
+        print(' [DDSP Model] Sinusoids Additive Synthesiser (ddsp_b200)')
+        splits = {'amplitudes': n_harmonics, 'group_delay': n_mag_allpass, 'noise_magnitude': n_mag_noise}
+        self.unit2ctrl = unit2ctrl if unit2ctrl is not None else _make_unit2ctrl(n_unit, n_spk, splits, c)
+
+    def forward(self, units_frames, f0_frames, volume_frames, spk_id, spk_mix_dict=None, initial_phase=None,
+                infer=True, max_upsample_dim=32, noise_u=None):
+        # stage A with the full-rate phase (vocoder.py:391-393); `max_upsample_dim` only bounded the
+        # reference's (B,T,32) temporaries and has no effect here
+        phase_frames, _, phase = core.phase_stage(f0_frames, self._hop, self._sr, initial_phase, infer, full_rate=True)
+        ctrls = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id, spk_mix_dict=spk_mix_dict)
+        self._forward_only(ctrls)
+        signal, harmonic, noise = core.sins_stage(ctrls['amplitudes'], ctrls['group_delay'], ctrls['noise_magnitude'],
+                                                  f0_frames, phase, self._hop, self._sr, noise_u=noise_u,
+                                                  seed=self._next_seed())                                     # :397-421
+        return signal, phase.unsqueeze(-1), (harmonic, noise)                                                 # :423
+
+
 def load_model(model_path, device='cuda'):
     """Reference: ddsp/vocoder.py:343-369 (same config.yaml + checkpoint layout)."""
     config_file = os.path.join(os.path.split(model_path)[0], 'config.yaml')
     with open(config_file, 'r') as config:
         args = DotDict(yaml.safe_load(config))
-    if args.model.type == 'CombSubFast':
+    if args.model.type == 'Sins':
+        model = Sins(sampling_rate=args.data.sampling_rate, block_size=args.data.block_size,
+                     n_harmonics=args.model.n_harmonics, n_mag_allpass=args.model.n_mag_allpass,
+                     n_mag_noise=args.model.n_mag_noise, n_unit=args.data.encoder_out_channels,
+                     n_spk=args.model.n_spk, c=args.model.c)
+    elif args.model.type == 'CombSub':
+        model = CombSub(sampling_rate=args.data.sampling_rate, block_size=args.data.block_size,
+                        n_mag_allpass=args.model.n_mag_allpass, n_mag_harmonic=args.model.n_mag_harmonic,
+                        n_mag_noise=args.model.n_mag_noise, n_unit=args.data.encoder_out_channels,
+                        n_spk=args.model.n_spk, c=args.model.c)
+    elif args.model.type == 'CombSubFast':
         model = CombSubFast(sampling_rate=args.data.sampling_rate, block_size=args.data.block_size,
                             n_unit=args.data.encoder_out_channels, n_spk=args.model.n_spk, c=args.model.c)
     else:
