@@ -183,8 +183,6 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     model = args.model
-    if model != 'combsubfast':
-        raise SystemExit('bench: only --model combsubfast is wired in this build')
     B, F = args.clips, args.frames
     T = F * HOP
     a, b_, c = SPLITS[model]
@@ -203,12 +201,17 @@ def run_ours(args, rank, local_rank, world):
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def step(ctrl, f0, u, seed, ev=None):
-        hm, hp, nm = torch.split(ctrl, [a, b_, c], dim=-1)
-        pf, prefix, _ = core.phase_stage(f0, HOP, SR)
+        c0, c1, c2 = torch.split(ctrl, [a, b_, c], dim=-1)          # strided views, as Unit2Control emits them
+        pf, prefix, phase = core.phase_stage(f0, HOP, SR, full_rate=(model == 'sins'))
         n_launch = core.last_launch_count()
         if ev is not None:
             ev[0].record()
-        sig = core.combsubfast_stage(hm, hp, nm, f0, prefix, HOP, SR, noise_u=u, seed=seed, window=window)
+        if model == 'combsubfast':
+            sig = core.combsubfast_stage(c0, c1, c2, f0, prefix, HOP, SR, noise_u=u, seed=seed, window=window)
+        elif model == 'combsub':
+            sig = core.combsub_stage(c0, c1, c2, f0, prefix, HOP, SR, noise_u=u, seed=seed)[0]
+        else:
+            sig = core.sins_stage(c0, c1, c2, f0, phase, HOP, SR, noise_u=u, seed=seed)[0]
         n_launch += core.last_launch_count()
         if ev is not None:
             ev[1].record()
@@ -288,7 +291,9 @@ def run_ours(args, rank, local_rank, world):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(args, world),
-            'roofline': {'bound': 'hbm', 'kernel': 'combsubfast_kernel', 'achieved': achieved, 'peak': peak,
+            'roofline': {'bound': 'hbm', 'kernel': 'combsubfast_kernel' if model == 'combsubfast' else
+                         'stage B (ltv_filter_kernel x%d + excitation)' % (3 if model == 'combsub' else 2),
+                         'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': recorded_traffic(model),
                          'peak_source': peak_src, 'kernel_ms': kern_ms, 'algorithmic_bytes_per_launch': alg_bytes,
                          'step_frac_of_hbm_roofline': (ALG_BYTES_PER_FRAME[model] * B * F) /
@@ -300,14 +305,73 @@ def run_ours(args, rank, local_rank, world):
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))
-            clips = max(1, min(cores, 8))
-            v, dt = cpu_reference_throughput(model, F, clips, min(cores, clips))
-            line['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': min(cores, clips), 'kind': 'port',
+            clips = cores * (8 if model == 'combsubfast' else 2)     # ~5-20 s of host work
+            v, dt = cpu_reference_throughput(model, F, clips, cores)
+            line['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
                                     'sample': f'{clips} clips x {F} frames, oracle numpy port (fp32) of the reference '
                                               f'CPU path, one clip per process, {dt:.1f} s'}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_latency(args):
+    """Config (5): real-time streaming sizes, B=1, per-call latency p50/p99 (CUDA events around the
+    two-stage synth path replayed as a CUDA graph, and host wall clock around the eager calls)."""
+    import torch
+    from ddsp_b200 import core
+    from ddsp_b200.synthetic import make_inputs
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    model = args.model
+    a, b_, c = SPLITS[model]
+    window = torch.sqrt(torch.hann_window(2 * HOP)).to(dev)
+    rows = []
+    for F in [int(x) for x in args.latency_frames.split(',')]:
+        d = make_inputs(1, F, a + b_ + c, seed=99 + F, noise=False)
+        ctrl = torch.from_numpy(d['ctrl']).to(dev)
+        f0 = torch.from_numpy(d['f0_frames']).to(dev)[..., None]
+        c0, c1, c2 = torch.split(ctrl, [a, b_, c], dim=-1)
+
+        def synth():
+            pf, prefix, phase = core.phase_stage(f0, HOP, SR, full_rate=(model == 'sins'))
+            if model == 'combsubfast':
+                return core.combsubfast_stage(c0, c1, c2, f0, prefix, HOP, SR, seed=1, window=window)
+            if model == 'combsub':
+                return core.combsub_stage(c0, c1, c2, f0, prefix, HOP, SR, seed=1)[0]
+            return core.sins_stage(c0, c1, c2, f0, phase, HOP, SR, seed=1)[0]
+        for _ in range(10):
+            synth()
+        torch.cuda.synchronize()
+        # eager: host wall clock per call including the sync a realtime caller needs
+        wall = []
+        for _ in range(args.latency_iters):
+            t0 = time.perf_counter()
+            synth()
+            torch.cuda.synchronize()
+            wall.append((time.perf_counter() - t0) * 1e3)
+        # CUDA graph replay: device time per call
+        g = torch.cuda.CUDAGraph()
+        s_ = torch.cuda.Stream()
+        s_.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s_):
+            synth()
+            with torch.cuda.graph(g, stream=s_):
+                out = synth()
+        torch.cuda.synchronize()
+        devt = []
+        for _ in range(args.latency_iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            e1.synchronize()
+            devt.append(e0.elapsed_time(e1))
+        rows.append({'frames': F, 'audio_ms': F * HOP / SR * 1e3,
+                     'graph_device_ms_p50': float(np.percentile(devt, 50)), 'graph_device_ms_p99': float(np.percentile(devt, 99)),
+                     'eager_wall_ms_p50': float(np.percentile(wall, 50)), 'eager_wall_ms_p99': float(np.percentile(wall, 99))})
+    print(json.dumps({'metric': 'streaming synth latency per block', 'unit': 'ms', 'model': model, 'higher_is_better': False,
+                      'iters': args.latency_iters, 'rows': rows}), flush=True)
 
 
 def main():
@@ -321,7 +385,13 @@ def main():
     ap.add_argument('--frames', type=int, default=862, help='frames per clip (862 = 10 s)')
     ap.add_argument('--inject-noise', action='store_true', help='read the noise excitation from a U tensor')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--mode', default='throughput', choices=['throughput', 'latency'])
+    ap.add_argument('--latency-frames', default='9,18,26,130')
+    ap.add_argument('--latency-iters', type=int, default=1000)
     args = ap.parse_args()
+    if args.mode == 'latency':
+        run_latency(args)
+        return
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
