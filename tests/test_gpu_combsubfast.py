@@ -163,3 +163,46 @@ def test_rejects_cpu_tensors_and_bad_hop():
         core.phase_stage(torch.zeros(1, 4, 1), 512, 44100)
     with pytest.raises(_cabi.DDSPB200Error):
         core.phase_stage(torch.zeros(1, 4, 1).cuda(), 256, 44100)
+
+
+def test_long_form_five_minutes():
+    """Config (4): 5-minute clips (F=25840, T=13.2 M samples) stress the phase accumulation and the
+    overlap-add length.  One low-pitched (69-98 Hz) clip and one with unvoiced (f0=0) frames.
+
+    Arbiter: the oracle with an exact cumulative sum.  The reference's CPU path accumulates
+    `cumsum(f0/sr)` sequentially in fp64 and drifts by ~1e-5 rotations over 13 M samples; where f0
+    interpolates to 0 that drift is multiplied by sr/(f0+1e-3) inside the sinc argument
+    (vocoder.py:459), so the *sequential* CPU phase and any scan-based phase (torch's CUDA cumsum,
+    these kernels) disagree there by construction.  The phase itself is checked against torch's own
+    CUDA ops (the reference's stage A on this GPU)."""
+    F = 25840
+    d = make_inputs(2, F, 1539, seed=78, zero_f0_fraction=0.02)
+    t = np.arange(F) * (512 / 44100)
+    d['f0_frames'][0] = (82.0 * 2 ** (0.25 * np.sin(2 * np.pi * t / 7.0))).astype(np.float32)    # 69..98 Hz
+    sig, pf = run_gpu(d['ctrl'], d['f0_frames'], d['U'])
+    assert np.all(np.isfinite(sig))
+    # stage A against the reference's op sequence on this GPU (core.py:7-21,40-49 with torch CUDA ops)
+    f0 = dev(d['f0_frames'])[..., None]
+    _, _, full = core.phase_stage(f0, 512, 44100, full_rate=True)
+    xp = f0.permute(0, 2, 1)
+    up = torch.nn.functional.interpolate(torch.cat((xp, xp[:, :, -1:]), 2), size=F * 512 + 1, mode='linear',
+                                         align_corners=True)[:, 0, :-1]
+    rot = torch.cumsum(up.double() / 44100, axis=1)
+    rot = (rot - torch.round(rot)).float()
+    dphi = (full.double() - (2 * np.pi * rot).double()).abs()
+    dphi = torch.minimum(dphi, (dphi - 2 * np.pi).abs())
+    assert dphi.max().item() < 2e-6, dphi.max().item()
+    for b in range(2):
+        ref, pf_ref = O.combsubfast_forward(d['ctrl'][b:b + 1, :, :513], d['ctrl'][b:b + 1, :, 513:1026],
+                                            d['ctrl'][b:b + 1, :, 1026:], d['f0_frames'][b:b + 1], d['U'][b:b + 1],
+                                            exact_cumsum=True)
+        err, s = assert_waveform(sig[b:b + 1], ref, what=f'5-min clip {b}')
+        err_tail = np.abs(sig[b, -2_000_000:] - ref[0, -2_000_000:]).max()
+        assert err_tail <= 1e-4, err_tail
+        dp = np.abs(pf[b].astype(np.float64) - pf_ref[0])
+        assert np.minimum(dp, np.abs(dp - 2 * np.pi)).max() < 2e-6
+        print(f'5-min clip {b}: max-abs {err:.2e} snr {s:.1f} dB tail {err_tail:.2e}')
+    # the fully voiced clip also agrees with the sequential-cumsum (reference CPU) oracle
+    ref_seq, _ = O.combsubfast_forward(d['ctrl'][:1, :, :513], d['ctrl'][:1, :, 513:1026], d['ctrl'][:1, :, 1026:],
+                                       d['f0_frames'][:1], d['U'][:1])
+    assert_waveform(sig[:1], ref_seq, what='5-min voiced clip vs sequential-cumsum oracle')
