@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <initializer_list>
 #include <mutex>
 
 #include "combsubfast.cuh"
@@ -44,6 +45,29 @@ int sm_count() {
     return cached[dev];
 }
 
+using LtvKernel = void (*)(const ddsp::LtvParams);
+// Specialised instantiations for the combinations the synthesizers use + one generic fallback.
+LtvKernel ltv_select(int enc, int win, int amode) {
+    if (enc == DDSP_B200_MAG_ALLPASS_TANH && win == DDSP_B200_WINDOW_NONE && amode == 0)
+        return ddsp::ltv_filter_kernel<DDSP_B200_MAG_ALLPASS_TANH, DDSP_B200_WINDOW_NONE, 0>;
+    if (enc == DDSP_B200_MAG_EXP && win == DDSP_B200_WINDOW_DYNAMIC && amode == 0)
+        return ddsp::ltv_filter_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_DYNAMIC, 0>;
+    if (enc == DDSP_B200_MAG_EXP && win == DDSP_B200_WINDOW_HANN && amode == 1)
+        return ddsp::ltv_filter_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_HANN, 1>;
+    if (enc == DDSP_B200_MAG_EXP && win == DDSP_B200_WINDOW_HANN && amode == 2)
+        return ddsp::ltv_filter_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_HANN, 2>;
+    return ddsp::ltv_filter_kernel<-1, -1, -1>;
+}
+std::initializer_list<LtvKernel> ltv_kernels() {
+    static const std::initializer_list<LtvKernel> k = {
+        ddsp::ltv_filter_kernel<DDSP_B200_MAG_ALLPASS_TANH, DDSP_B200_WINDOW_NONE, 0>,
+        ddsp::ltv_filter_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_DYNAMIC, 0>,
+        ddsp::ltv_filter_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_HANN, 1>,
+        ddsp::ltv_filter_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_HANN, 2>,
+        ddsp::ltv_filter_kernel<-1, -1, -1>};
+    return k;
+}
+
 // Immutable per-device tables (FFT twiddles + exact sqrt-Hann window; Bluestein chirps for the
 // L=510 and L=1022 impulse responses), filled on first use.
 __device__ __align__(16) float g_tables[ddsp::kTableBytes / 4];
@@ -68,8 +92,8 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
         CUDA_TRY(cudaGetSymbolAddress((void**)&ptr, g_tables));
         ddsp::fft_tables_kernel<<<4, 256, 0, st>>>(reinterpret_cast<float4*>(ptr), ptr + 2048);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaFuncSetAttribute(ddsp::ltv_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      ddsp::kLtvSmemBytes));
+        for (auto fn : ltv_kernels())
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kLtvSmemBytes));
         float* cptr = nullptr;
         CUDA_TRY(cudaGetSymbolAddress((void**)&cptr, g_chirp));
         for (int v = 0; v < 2; ++v) {
@@ -281,7 +305,7 @@ int launch_ltv(const float* audio, int audio_mode, uint64_t seed, const float* m
     }
     const int64_t runs = (int64_t)B * P.runs_per_clip;
     const unsigned grid = (unsigned)((runs + ddsp::kLtvWarps - 1) / ddsp::kLtvWarps);
-    ddsp::ltv_filter_kernel<<<grid, ddsp::kLtvThreads, ddsp::kLtvSmemBytes, st>>>(P);
+    ltv_select(encoding, window_mode, audio_mode)<<<grid, ddsp::kLtvThreads, ddsp::kLtvSmemBytes, st>>>(P);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }

@@ -63,7 +63,13 @@ __device__ __forceinline__ float bartlett1024(int i) {      // torch.bartlett_wi
         outi = lane0 ? i0_ : outi;                                                 \
     }
 
+// ENC / WIN / AMODE >= 0 fix the magnitude encoding, window mode and audio source at compile time
+// (smaller code per instantiation: the kernel is instruction-fetch sensitive); -1 = read from P.
+template <int ENC, int WIN, int AMODE>
 __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvParams P) {
+    const int enc = ENC >= 0 ? ENC : P.encoding;
+    const int win_mode = WIN >= 0 ? WIN : P.window_mode;
+    const int amode = AMODE >= 0 ? AMODE : P.audio_mode;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float4* tw4 = reinterpret_cast<const float4*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -94,6 +100,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
     const float2* chirp_d = chirp_c + 512;
     const float2 wl = make_float2(tw4[lane].y, tw4[lane].w);        // W1024^lane = (cos, -sin)
     const uint32_t key = noise_key(P.seed, (uint32_t)b);
+    const float two_pi_over_L = DDSP_TWO_PI_F / (float)L;
 
     for (int i = lane; i < kLtvRing; i += 32) ring[i] = 0.0f;
     __syncwarp();
@@ -107,6 +114,10 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
         for (int phase = 0; phase < 5; ++phase) {
             // ------------------------------ prologue ------------------------------------------
             if (phase == 0) {
+                {   // pull this frame's magnitude row into L2 while the audio FFT runs
+                    const float* row = P.mags + (int64_t)b * P.mB + (int64_t)mhat * P.mF + 32 * lane;
+                    if (32 * lane < n_mag) asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+                }
                 // z[n] = a[2n] + j a[2n+1], n = 32 n1 + lane < 512; a = bartlett * frame (core.py:218-222)
                 const bool vA = m >= 1, vB = m < F;
                 const float* src = P.audio + (int64_t)b * T;
@@ -118,7 +129,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
                     if (n1 < 16) {
                         const int i = 64 * n1 + 2 * lane;               // frame-relative sample index (even)
                         const bool ok = (n1 < 8) ? vA : vB;
-                        if (P.audio_mode == 2) {
+                        if (amode == 2) {
                             uint32_t& st = (n1 < 8) ? stA : stB;
                             st = noise_next(st); v0 = (float)noise_u24(st) * 5.9604644775390625e-8f;
                             st = noise_next(st); v1 = (float)noise_u24(st) * 5.9604644775390625e-8f;
@@ -127,7 +138,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
                         } else if (ok) {
                             const float2 x = __ldg(reinterpret_cast<const float2*>(src + t0 + i));
                             v0 = x.x; v1 = x.y;
-                            if (P.audio_mode == 1) { v0 = fmaf(2.0f, v0, -1.0f); v1 = fmaf(2.0f, v1, -1.0f); }
+                            if (amode == 1) { v0 = fmaf(2.0f, v0, -1.0f); v1 = fmaf(2.0f, v1, -1.0f); }
                         }
                         v0 *= bartlett1024(i);
                         v1 *= bartlett1024(i + 1);
@@ -145,7 +156,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
                     float xr = 0.0f, xi = 0.0f;
                     if (n1 * 32 < n_mag) {
                         const int k = 32 * n1 + lane;
-                        if (P.encoding == DDSP_B200_MAG_ALLPASS_TANH) {
+                        if (enc == DDSP_B200_MAG_ALLPASS_TANH) {
                             // exp(j*cumsum(pi*tanh(c)))  (vocoder.py:398,415 / 521,540), phase kept in turns
                             float g = 0.5f * tanhf(__ldg(row + k));
 #pragma unroll
@@ -159,9 +170,9 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
                             g -= rintf(g);
                             xr = cos_approx(DDSP_TWO_PI_F * g);
                             xi = sin_approx(DDSP_TWO_PI_F * g);
-                        } else if (P.encoding == DDSP_B200_MAG_EXP) {
-                            xr = expf(__ldg(row + k)) * P.mag_scale;     // vocoder.py:399,475,522-523
-                        } else if (P.encoding == DDSP_B200_MAG_COMPLEX) {
+                        } else if (enc == DDSP_B200_MAG_EXP) {
+                            xr = ex2_approx(__ldg(row + k) * DDSP_LOG2E_F) * P.mag_scale;     // vocoder.py:399,475,522-523
+                        } else if (enc == DDSP_B200_MAG_COMPLEX) {
                             const float2 v = __ldg(reinterpret_cast<const float2*>(row) + k);
                             xr = v.x; xi = v.y;
                         } else {
@@ -217,7 +228,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
                 // conv[n] (Re in X.im, Im in X.re after the swapped FFT), n = lane + 32 q < n_out:
                 // ir_zero_phase[n] = Re(c[n] * conv[n]); causal form + window (core.py:242-303,326)
                 float hw_inv = 0.0f;
-                if (P.window_mode == DDSP_B200_WINDOW_DYNAMIC) {
+                if (win_mode == DDSP_B200_WINDOW_DYNAMIC) {
                     const float f0 = __ldg(P.f0_frames + (int64_t)b * P.fB + (int64_t)mhat * P.fF);
                     hw_inv = __fdiv_rn(1.0f, __fdiv_rn(P.sr15, __fadd_rn(f0, 1e-3f)));
                 }
@@ -238,12 +249,14 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
                             }
                             const int i = lag + D;
                             float w = 1.0f;
-                            if (P.window_mode == DDSP_B200_WINDOW_HANN) {
-                                w = 0.5f - 0.5f * cospif((float)(2 * i) / (float)L);
-                            } else if (P.window_mode == DDSP_B200_WINDOW_DYNAMIC) {
+                            if (win_mode == DDSP_B200_WINDOW_HANN) {
+                                // 0.5 - 0.5 cos(2 pi i / L) = 0.5 + 0.5 cos(2 pi i / L - pi), argument in [-pi, pi)
+                                w = fmaf(0.5f, cos_approx(fmaf((float)i, two_pi_over_L, -DDSP_PI_F)), 0.5f);
+                            } else if (win_mode == DDSP_B200_WINDOW_DYNAMIC) {
                                 float x = (float)lag * hw_inv;
                                 x = (x > 1.0f) ? 0.0f : x;                           // core.py:297 (only x>1 is cleared)
-                                w = 0.5f * (1.0f + cospif(x));
+                                x -= 2.0f * rintf(0.5f * x);                         // cos(pi x) has period 2: |x| <= 1
+                                w = fmaf(0.5f, cos_approx(DDSP_PI_F * x), 0.5f);
                             }
                             plane[i] = ir * w * (1.0f / 4096.0f);                    // 1/4 (even/odd split) * 1/1024 (inverse FFT)
                         }
