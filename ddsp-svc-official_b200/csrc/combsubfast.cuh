@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             const bool vA = (fm >= 1) && (fm - 1 < F), vB = fm < F;
             const int64_t baseA = vA ? (int64_t)(fm - 1) * kHop : 0, baseB = vB ? (int64_t)fm * kHop : 0;
             const float okA = vA ? 1.0f : 0.0f, okB = vB ? 1.0f : 0.0f;
+            const float sclA = okA * 1.1920928955078125e-7f, sclB = okB * 1.1920928955078125e-7f;   // 2^-23
             const uint32_t key = CTX_KEY;
             const float* u_b = P.noise_u ? P.noise_u + (int64_t)CTX_B * F * kHop + lane : nullptr;
             uint32_t stA = noise_seed(key, (uint32_t)(fm - 1), (uint32_t)lane);
@@ -183,17 +184,20 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                 const int j = 32 * (n1 & 15);                                 // sample in hop = j + lane
                 const float w = win[32 * n1 + lane];
                 const float c = (n1 < 16 ? slotA : slotB)[j + (n1 & 15)];
-                float u;
+                const float wc = w * c;
+                float wz;
                 if (u_b) {
-                    u = __ldg(u_b + (n1 < 16 ? baseA : baseB) + j);
+                    const float u = __ldg(u_b + (n1 < 16 ? baseA : baseB) + j);
+                    const float wn = w * (n1 < 16 ? okA : okB);
+                    wz = fmaf(u, wn + wn, -wn);                                   // w * (2u - 1)   (vocoder.py:461)
                 } else {
                     uint32_t& st = (n1 < 16) ? stA : stB;
                     st = noise_next(st);
-                    u = (float)noise_u24(st) * 5.9604644775390625e-8f;
+                    // 2u - 1 = v * 2^-23 with v the centred 24-bit draw; okA/okB carry the 2^-23 (or 0)
+                    wz = (float)noise_s24(st) * (w * (n1 < 16 ? sclA : sclB));
                 }
-                const float wn = w * (n1 < 16 ? okA : okB);
-                DDSP_RE(X, brev5(n1)) = w * c;
-                DDSP_IM(X, brev5(n1)) = fmaf(u, wn + wn, -wn);                // w * (2u - 1)   (vocoder.py:461)
+                DDSP_RE(X, brev5(n1)) = wc;
+                DDSP_IM(X, brev5(n1)) = wz;
             }
         }
         // s == 2: re/im already hold the packed spectrum of the pair (swapped for the inverse)

@@ -43,6 +43,10 @@ __host__ __device__ __forceinline__ uint32_t noise_seed(uint32_t key, uint32_t h
 __host__ __device__ __forceinline__ uint32_t noise_next(uint32_t state) { return state * 747796405u + 2891336453u; }
 // uniform integer in [0, 2^24) from an LCG state (top bits, xorshift-mixed); U = value * 2^-24
 __host__ __device__ __forceinline__ uint32_t noise_u24(uint32_t state) { return (state ^ (state >> 15)) >> 8; }
+// the same draw as a centred integer v = u24 - 2^23 in [-2^23, 2^23):  2U - 1 == v * 2^-23 exactly
+__host__ __device__ __forceinline__ int32_t noise_s24(uint32_t state) {
+    return (int32_t)(state ^ (state >> 15) ^ 0x80000000u) >> 8;
+}
 
 // Single-MUFU approximations (flush-to-zero forms: no denormal fix-up code around them).
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -71,19 +75,20 @@ __device__ __forceinline__ float cos_approx(float x) {
 // S(u) = sin(pi r)/(pi r) as a degree-4 interpolant in u = r^2 (|error| < 5e-9 on |r| <= 0.5).
 // For |x| < 0.5 the quotient r/x is exactly 1, so there is no cancellation at the pulse peak.
 __device__ __forceinline__ float sinc_f(float x) {
-    const float n = rintf(x);
-    const float r = x - n;
+    // n = rint(x) through the 1.5*2^23 magic constant: the low mantissa bit of t is the parity of n
+    // (exact for |x| < 2^22; beyond that sinc(x) < 8e-8 and the result stays below 1e-6).
+    const float xs = x + 1e-30f;                   // x == 0 -> tiny, so that r/x below is 1 instead of 0/0
+    const float t = xs + 12582912.0f;
+    const float n = t - 12582912.0f;
+    const float r = xs - n;
     const float u = r * r;
     float p = 0.024718644097447395f;
     p = fmaf(p, u, -0.19044175744056702f);
     p = fmaf(p, u, 0.8117148280143738f);
     p = fmaf(p, u, -1.6449332237243652f);
     p = fmaf(p, u, 1.0f);
-    // (-1)^n: n is an exactly representable integer; its parity is bit 0 of (int)n
-    const int odd = __float2int_rn(n) & 1;
-    const float q = (n == 0.0f) ? 1.0f : r * rcp_approx(x);
-    const float v = p * q;
-    return odd ? -v : v;
+    const float v = p * (r * rcp_approx(xs));
+    return __int_as_float(__float_as_int(v) ^ (__float_as_int(t) << 31));   // (-1)^n
 }
 
 // rot (fp32, wrapped to [-0.5,0.5], half-to-even) from an fp64 rotation count (core.py:46-49)

@@ -215,7 +215,8 @@ int ddsp_b200_phase(const float* f0_frames, int64_t fB, int64_t fF, int B, int F
         ddsp::phase_fused_kernel<<<B, 1024, 0, st>>>(f0_frames, fB, fF, F, inv_sr, initial_phase, prefix, phase_frames);
         LAUNCH_CHECK();
     } else {
-        ddsp::hop_totals_kernel<<<(unsigned)((hops + 7) / 8), 256, 0, st>>>(f0_frames, fB, fF, B, F, prefix);
+        ddsp::hop_totals_kernel<<<(unsigned)((hops + 8 * ddsp::kHopsPerWarp - 1) / (8 * ddsp::kHopsPerWarp)), 256, 0, st>>>(
+            f0_frames, fB, fF, B, F, prefix);
         LAUNCH_CHECK();
         ddsp::phase_scan_kernel<<<B, 1024, 0, st>>>(f0_frames, fB, fF, F, inv_sr, initial_phase, prefix, phase_frames);
         LAUNCH_CHECK();

@@ -12,25 +12,39 @@ namespace ddsp {
 // A1: per-hop totals.  One warp per hop: sum over the 512 upsampled fp32 f0 samples of the hop,
 // accumulated in fp64 (exact for any realistic f0: 24-bit mantissas, 512 terms).
 // ---------------------------------------------------------------------------------------------
+constexpr int kHopsPerWarp = 4;   // hops handled by one warp (amortises the interpolation weights)
+
 __global__ void __launch_bounds__(256) hop_totals_kernel(const float* __restrict__ f0_frames, int64_t fB,
                                                          int64_t fF, int B, int F,
                                                          double* __restrict__ totals) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (warp >= (int64_t)B * F) return;
-    const int b = (int)(warp / F), h = (int)(warp % F);
-    const float* row = f0_frames + (int64_t)b * fB;
-    const float x0 = __ldg(row + (int64_t)h * fF);
-    const float x1 = __ldg(row + (int64_t)min(h + 1, F - 1) * fF);
-    double s = 0.0;
+    const int64_t first = warp * kHopsPerWarp, n_hops = (int64_t)B * F;
+    if (first >= n_hops) return;
+    float w0[kHop / 32], w1[kHop / 32];
 #pragma unroll
     for (int i = 0; i < kHop / 32; ++i) {
-        const float w1 = (float)(lane + 32 * i) * (1.0f / kHop);
-        s += (double)lerp_torch(x0, x1, w1);
+        w1[i] = (float)(lane + 32 * i) * (1.0f / kHop);
+        w0[i] = __fsub_rn(1.0f, w1[i]);
+    }
+    // lane g (< kHopsPerWarp) fetches the two frame values of hop first+g
+    float x0 = 0.0f, x1 = 0.0f;
+    if (lane < kHopsPerWarp && first + lane < n_hops) {
+        const int b = (int)((first + lane) / F), h = (int)((first + lane) % F);
+        const float* row = f0_frames + (int64_t)b * fB;
+        x0 = __ldg(row + (int64_t)h * fF);
+        x1 = __ldg(row + (int64_t)min(h + 1, F - 1) * fF);
     }
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(kFullMask, s, d);
-    if (lane == 0) totals[warp] = s;
+    for (int g = 0; g < kHopsPerWarp; ++g) {
+        const float a = __shfl_sync(kFullMask, x0, g), c = __shfl_sync(kFullMask, x1, g);
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < kHop / 32; ++i) s += (double)__fmaf_rn(w0[i], a, __fmul_rn(w1[i], c));
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(kFullMask, s, d);
+        if (lane == 0 && first + g < n_hops) totals[first + g] = s;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -152,9 +166,9 @@ __device__ __forceinline__ void hop_rotation(float x0, float x1, double base, do
         const double t = __shfl_up_sync(kFullMask, inc, d);
         if (lane >= d) inc += t;
     }
-    const double off = base + (inc - s);
+    const double off = (base + (inc - s)) * inv_sr;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) rot[i] = wrap_rot((off + sl[i]) * inv_sr);
+    for (int i = 0; i < 16; ++i) rot[i] = wrap_rot(fma(sl[i], inv_sr, off));
 }
 
 // A3 (Sins): full-rate phase = fl32(2*pi)*rot (vocoder.py:392), one warp per hop.
