@@ -206,11 +206,13 @@ def frequency_filter(audio, magnitudes, hann_window=True, half_width_frames=None
             f0_frames = 1.5 * float(sampling_rate) / half_width_frames.reshape(B, F).to(torch.float32) - 1e-3
     f0 = None if f0_frames is None else _f0_2d(f0_frames)
     out = torch.empty_like(audio)
+    L = _cabi.lib()
+    ws = torch.empty(L.ddsp_b200_frequency_filter_workspace_bytes(B, F, n_mag), dtype=torch.uint8, device=audio.device)
     with torch.cuda.device(audio.device):
-        _cabi.check(_cabi.lib().ddsp_b200_frequency_filter(
+        _cabi.check(L.ddsp_b200_frequency_filter(
             audio.data_ptr(), mags.data_ptr(), mags.stride(0), mags.stride(1), n_mag, encoding, float(mag_scale),
             window, _ptr(f0), 0 if f0 is None else f0.stride(0), 0 if f0 is None else f0.stride(1),
-            float(sampling_rate), B, F, 512, out.data_ptr(), 0, 0, 0, _stream()))
+            float(sampling_rate), B, F, 512, out.data_ptr(), 0, ws.data_ptr(), ws.numel(), _stream()))
     return out
 
 

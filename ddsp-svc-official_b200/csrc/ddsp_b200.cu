@@ -46,26 +46,18 @@ int sm_count() {
 }
 
 using LtvKernel = void (*)(const ddsp::LtvParams);
-// Specialised instantiations for the combinations the synthesizers use + one generic fallback.
-LtvKernel ltv_select(int enc, int win, int amode) {
-    if (enc == DDSP_B200_MAG_ALLPASS_TANH && win == DDSP_B200_WINDOW_NONE && amode == 0)
-        return ddsp::ltv_filter_kernel<DDSP_B200_MAG_ALLPASS_TANH, DDSP_B200_WINDOW_NONE, 0>;
-    if (enc == DDSP_B200_MAG_EXP && win == DDSP_B200_WINDOW_DYNAMIC && amode == 0)
-        return ddsp::ltv_filter_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_DYNAMIC, 0>;
-    if (enc == DDSP_B200_MAG_EXP && win == DDSP_B200_WINDOW_HANN && amode == 1)
-        return ddsp::ltv_filter_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_HANN, 1>;
-    if (enc == DDSP_B200_MAG_EXP && win == DDSP_B200_WINDOW_HANN && amode == 2)
-        return ddsp::ltv_filter_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_HANN, 2>;
-    return ddsp::ltv_filter_kernel<-1, -1, -1>;
+// Specialised instantiations for the combinations the synthesizers use + generic fallbacks.
+LtvKernel ltv_ir_select(int enc, int win) {
+    if (enc == DDSP_B200_MAG_ALLPASS_TANH && win == DDSP_B200_WINDOW_NONE)
+        return ddsp::ltv_ir_kernel<DDSP_B200_MAG_ALLPASS_TANH, DDSP_B200_WINDOW_NONE>;
+    if (enc == DDSP_B200_MAG_EXP && win == DDSP_B200_WINDOW_DYNAMIC)
+        return ddsp::ltv_ir_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_DYNAMIC>;
+    if (enc == DDSP_B200_MAG_EXP && win == DDSP_B200_WINDOW_HANN)
+        return ddsp::ltv_ir_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_HANN>;
+    return ddsp::ltv_ir_kernel<-1, -1>;
 }
-std::initializer_list<LtvKernel> ltv_kernels() {
-    static const std::initializer_list<LtvKernel> k = {
-        ddsp::ltv_filter_kernel<DDSP_B200_MAG_ALLPASS_TANH, DDSP_B200_WINDOW_NONE, 0>,
-        ddsp::ltv_filter_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_DYNAMIC, 0>,
-        ddsp::ltv_filter_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_HANN, 1>,
-        ddsp::ltv_filter_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_HANN, 2>,
-        ddsp::ltv_filter_kernel<-1, -1, -1>};
-    return k;
+LtvKernel ltv_conv_select(int amode) {
+    return amode == 0 ? ddsp::ltv_conv_kernel<0> : amode == 1 ? ddsp::ltv_conv_kernel<1> : ddsp::ltv_conv_kernel<2>;
 }
 
 // Immutable per-device tables (FFT twiddles + exact sqrt-Hann window; Bluestein chirps for the
@@ -92,8 +84,13 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
         CUDA_TRY(cudaGetSymbolAddress((void**)&ptr, g_tables));
         ddsp::fft_tables_kernel<<<4, 256, 0, st>>>(reinterpret_cast<float4*>(ptr), ptr + 2048);
         CUDA_TRY(cudaGetLastError());
-        for (auto fn : ltv_kernels())
-            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kLtvSmemBytes));
+        for (LtvKernel fn : {ltv_ir_select(DDSP_B200_MAG_ALLPASS_TANH, DDSP_B200_WINDOW_NONE),
+                             ltv_ir_select(DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_DYNAMIC),
+                             ltv_ir_select(DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_HANN), ltv_ir_select(-1, -1)})
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kLtvIrSmemBytes));
+        for (int am = 0; am < 3; ++am)
+            CUDA_TRY(cudaFuncSetAttribute(ltv_conv_select(am), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          ddsp::kLtvConvSmemBytes));
         float* cptr = nullptr;
         CUDA_TRY(cudaGetSymbolAddress((void**)&cptr, g_chirp));
         for (int v = 0; v < 2; ++v) {
@@ -276,14 +273,17 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+size_t ltv_spec_bytes(int B, int F) { return (size_t)B * F * ddsp::kLtvSpecFloat2 * sizeof(float2); }
+
 int launch_ltv(const float* audio, int audio_mode, uint64_t seed, const float* mags, int64_t mB, int64_t mF, int n_mag,
                int encoding, float mag_scale, int window_mode, const float* f0_frames, int64_t fB, int64_t fF,
-               double sr, int B, int F, float* out, cudaStream_t st) {
+               double sr, int B, int F, float* out, void* spec_ws, cudaStream_t st) {
     if (n_mag != 256 && n_mag != 512) return DDSP_B200_ERR_UNSUPPORTED;
     if (n_mag == 512 && (encoding == DDSP_B200_MAG_ALLPASS_TANH || encoding == DDSP_B200_MAG_COMPLEX))
         return DDSP_B200_ERR_UNSUPPORTED;     // the L=1022 path assumes real magnitudes (symmetric IR)
     if (window_mode == DDSP_B200_WINDOW_DYNAMIC && !f0_frames) return DDSP_B200_ERR_INVALID_ARGUMENT;
     if (audio_mode != 2 && (!audio || ((uintptr_t)audio & 7))) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (!spec_ws || ((uintptr_t)spec_ws & 15)) return DDSP_B200_ERR_WORKSPACE;
     ddsp::LtvParams P;
     if (int rc = ensure_device_ready(st, &P.tw_tables)) return rc;
     int dev = 0;
@@ -292,7 +292,7 @@ int launch_ltv(const float* audio, int audio_mode, uint64_t seed, const float* m
     P.audio = audio; P.audio_mode = audio_mode; P.seed = seed;
     P.mags = mags; P.mB = mB; P.mF = mF; P.n_mag = n_mag; P.encoding = encoding; P.mag_scale = mag_scale;
     P.window_mode = window_mode; P.f0_frames = f0_frames; P.fB = fB; P.fF = fF; P.sr15 = (float)(1.5 * sr);
-    P.out = out; P.B = B; P.F = F;
+    P.spec = (float2*)spec_ws; P.out = out; P.B = B; P.F = F;
     const int frames = F + 1;
     const int64_t slots = (int64_t)sm_count() * ddsp::kLtvWarps;
     int run_len = (int)(((int64_t)B * frames + slots - 1) / slots);
@@ -300,13 +300,22 @@ int launch_ltv(const float* audio, int audio_mode, uint64_t seed, const float* m
     if (run_len > frames) run_len = frames;
     P.run_len = run_len;
     P.runs_per_clip = (frames + run_len - 1) / run_len;
+    // 1) impulse responses -> tap spectra (frames independent)
+    {
+        const int64_t n_frames = (int64_t)B * F;
+        int64_t grid = (n_frames + ddsp::kLtvWarps - 1) / ddsp::kLtvWarps;
+        if (grid > sm_count()) grid = sm_count();           // persistent: one CTA per SM, warps stride over frames
+        ltv_ir_select(encoding, window_mode)<<<(unsigned)grid, ddsp::kLtvThreads, ddsp::kLtvIrSmemBytes, st>>>(P);
+        LAUNCH_CHECK();
+    }
+    // 2) framing + convolution + overlap-add
     if (P.runs_per_clip > 1) {
         CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)B * F * ddsp::kHop * sizeof(float), st));
         ++g_launches;
     }
     const int64_t runs = (int64_t)B * P.runs_per_clip;
     const unsigned grid = (unsigned)((runs + ddsp::kLtvWarps - 1) / ddsp::kLtvWarps);
-    ltv_select(encoding, window_mode, audio_mode)<<<grid, ddsp::kLtvThreads, ddsp::kLtvSmemBytes, st>>>(P);
+    ltv_conv_select(audio_mode)<<<grid, ddsp::kLtvThreads, ddsp::kLtvConvSmemBytes, st>>>(P);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }
@@ -325,7 +334,9 @@ extern "C" {
 
 size_t ddsp_b200_frequency_filter_workspace_bytes(int B, int F, int n_mag) {
     (void)n_mag;
-    return (B > 0 && F > 0) ? (size_t)B * F * ddsp::kHop * sizeof(float) : 0;   // only used when accumulate != 0
+    if (B <= 0 || F <= 0) return 0;
+    // tap spectra (B,F,1024) complex  +  a (B,T) scratch that is only touched when accumulate != 0
+    return ltv_spec_bytes(B, F) + (size_t)B * F * ddsp::kHop * sizeof(float);
 }
 
 int ddsp_b200_frequency_filter(const float* audio, const float* mags, int64_t mB, int64_t mF, int n_mag,
@@ -335,22 +346,24 @@ int ddsp_b200_frequency_filter(const float* audio, const float* mags, int64_t mB
     g_launches = 0;
     if (!audio || !mags || !out || B <= 0 || F <= 0 || !(sr > 0) || audio == out) return DDSP_B200_ERR_INVALID_ARGUMENT;
     if (hop != ddsp::kHop) return DDSP_B200_ERR_UNSUPPORTED;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (!accumulate)
-        return launch_ltv(audio, 0, 0, mags, mB, mF, n_mag, mag_encoding, mag_scale, window_mode, f0_frames, fB, fF, sr,
-                          B, F, out, st);
     if (!workspace || workspace_bytes < ddsp_b200_frequency_filter_workspace_bytes(B, F, n_mag))
         return DDSP_B200_ERR_WORKSPACE;
-    float* tmp = (float*)workspace;
-    if (int rc = launch_ltv(audio, 0, 0, mags, mB, mF, n_mag, mag_encoding, mag_scale, window_mode, f0_frames, fB, fF,
-                            sr, B, F, tmp, st))
+    cudaStream_t st = (cudaStream_t)stream;
+    float* tmp = (float*)((char*)workspace + ltv_spec_bytes(B, F));
+    if (int rc = launch_ltv(audio, 0, 0, mags, mB, mF, n_mag, mag_encoding, mag_scale, window_mode, f0_frames, fB, fF, sr,
+                            B, F, accumulate ? tmp : out, workspace, st))
         return rc;
-    return launch_add(out, tmp, out, (int64_t)B * F * hop, st);
+    if (!accumulate) return DDSP_B200_OK;
+    const int l = g_launches;
+    if (int rc = launch_add(out, tmp, out, (int64_t)B * F * hop, st)) return rc;
+    g_launches += l;
+    return DDSP_B200_OK;
 }
 
 size_t ddsp_b200_combsub_workspace_bytes(int B, int F, int n_mag_allpass, int n_mag_harmonic, int n_mag_noise) {
     (void)n_mag_allpass; (void)n_mag_harmonic; (void)n_mag_noise;
-    return (B > 0 && F > 0) ? (size_t)2 * B * F * ddsp::kHop * sizeof(float) : 0;   // combtooth + all-passed harmonic
+    // combtooth + all-passed harmonic + tap spectra of the filter in flight
+    return (B > 0 && F > 0) ? (size_t)2 * B * F * ddsp::kHop * sizeof(float) + ltv_spec_bytes(B, F) : 0;
 }
 
 int ddsp_b200_combsub(const float* group_delay, int n_mag_allpass, const float* harmonic_magnitude, int n_mag_harmonic,
@@ -371,6 +384,7 @@ int ddsp_b200_combsub(const float* group_delay, int n_mag_allpass, const float* 
     const int64_t n = (int64_t)B * F * hop;
     float* comb = (float*)workspace;
     float* h1 = comb + n;
+    void* spec = (void*)(h1 + n);
     int launches = 0;
     // vocoder.py:539  combtooth (no unvoiced zeroing in the old CombSub)
     ddsp::combtooth_kernel<<<(unsigned)(((int64_t)B * F + 7) / 8), 256, 0, st>>>(f0_frames, fB, fF, B, F, 1.0 / sr,
@@ -379,15 +393,15 @@ int ddsp_b200_combsub(const float* group_delay, int n_mag_allpass, const float* 
     launches += g_launches; g_launches = 0;
     // :540  all-pass (group delay), no window
     if (int rc = launch_ltv(comb, 0, 0, group_delay, cB, cF, n_mag_allpass, DDSP_B200_MAG_ALLPASS_TANH, 1.0f,
-                            DDSP_B200_WINDOW_NONE, nullptr, 0, 0, sr, B, F, h1, st)) return rc;
+                            DDSP_B200_WINDOW_NONE, nullptr, 0, 0, sr, B, F, h1, spec, st)) return rc;
     launches += g_launches; g_launches = 0;
     // :541-542  harmonic magnitude filter with the f0-dependent window
     if (int rc = launch_ltv(h1, 0, 0, harmonic_magnitude, cB, cF, n_mag_harmonic, DDSP_B200_MAG_EXP, 1.0f,
-                            DDSP_B200_WINDOW_DYNAMIC, f0_frames, fB, fF, sr, B, F, harmonic, st)) return rc;
+                            DDSP_B200_WINDOW_DYNAMIC, f0_frames, fB, fF, sr, B, F, harmonic, spec, st)) return rc;
     launches += g_launches; g_launches = 0;
     // :545-546  filtered noise
     if (int rc = launch_ltv(noise_u, noise_u ? 1 : 2, seed, noise_magnitude, cB, cF, n_mag_noise, DDSP_B200_MAG_EXP,
-                            1.0f / 128.0f, DDSP_B200_WINDOW_HANN, nullptr, 0, 0, sr, B, F, noise, st)) return rc;
+                            1.0f / 128.0f, DDSP_B200_WINDOW_HANN, nullptr, 0, 0, sr, B, F, noise, spec, st)) return rc;
     launches += g_launches; g_launches = 0;
     // :548
     if (int rc = launch_add(harmonic, noise, signal, n, st)) return rc;
@@ -397,7 +411,7 @@ int ddsp_b200_combsub(const float* group_delay, int n_mag_allpass, const float* 
 
 size_t ddsp_b200_sins_workspace_bytes(int B, int F, int n_harmonics, int n_mag_allpass, int n_mag_noise) {
     (void)n_harmonics; (void)n_mag_allpass; (void)n_mag_noise;
-    return (B > 0 && F > 0) ? (size_t)B * F * ddsp::kHop * sizeof(float) : 0;       // the sinusoid mix
+    return (B > 0 && F > 0) ? (size_t)B * F * ddsp::kHop * sizeof(float) + ltv_spec_bytes(B, F) : 0;   // sinusoid mix + tap spectra
 }
 
 int ddsp_b200_sins(const float* amplitudes, int n_harmonics, const float* group_delay, int n_mag_allpass,
@@ -416,6 +430,7 @@ int ddsp_b200_sins(const float* amplitudes, int n_harmonics, const float* group_
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = (int64_t)B * F * hop;
     float* sinus = (float*)workspace;
+    void* spec = (void*)(sinus + n);
     int launches = 0;
     // vocoder.py:397,402-412  oscillator bank with the Nyquist mask (fmax = sr/2)
     ddsp::sins_osc_kernel<<<(unsigned)((int64_t)B * F), 128, 0, st>>>(amplitudes, cB, cF, n_harmonics, f0_frames, fB, fF,
@@ -424,11 +439,11 @@ int ddsp_b200_sins(const float* amplitudes, int n_harmonics, const float* group_
     launches += g_launches; g_launches = 0;
     // :415  all-pass
     if (int rc = launch_ltv(sinus, 0, 0, group_delay, cB, cF, n_mag_allpass, DDSP_B200_MAG_ALLPASS_TANH, 1.0f,
-                            DDSP_B200_WINDOW_NONE, nullptr, 0, 0, sr, B, F, harmonic, st)) return rc;
+                            DDSP_B200_WINDOW_NONE, nullptr, 0, 0, sr, B, F, harmonic, spec, st)) return rc;
     launches += g_launches; g_launches = 0;
     // :418-419  filtered noise
     if (int rc = launch_ltv(noise_u, noise_u ? 1 : 2, seed, noise_magnitude, cB, cF, n_mag_noise, DDSP_B200_MAG_EXP,
-                            1.0f / 128.0f, DDSP_B200_WINDOW_HANN, nullptr, 0, 0, sr, B, F, noise, st)) return rc;
+                            1.0f / 128.0f, DDSP_B200_WINDOW_HANN, nullptr, 0, 0, sr, B, F, noise, spec, st)) return rc;
     launches += g_launches; g_launches = 0;
     // :421
     if (int rc = launch_add(harmonic, noise, signal, n, st)) return rc;

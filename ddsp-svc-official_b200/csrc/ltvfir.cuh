@@ -5,8 +5,11 @@
 //   _fft_convolve                core.py:185-239   Bartlett framing, FFT convolution, overlap-add,
 //                                                   crop with L//2 delay compensation
 //
-// A warp owns a run of consecutive frames of one clip and performs, per frame, five 1024-point
-// complex FFTs (all through the single warp_fft1024 instance of fft32.cuh):
+// Two kernels per filter, five 1024-point complex FFTs per frame in total (all through the
+// warp_fft1024 of fft32.cuh).  `ltv_ir_kernel` (one warp per frame, frames independent) does steps
+// 2-4 and leaves the raw tap spectrum (1024 complex) in a workspace; `ltv_conv_kernel` (a warp owns
+// a run of consecutive frames of one clip) does steps 1 and 5.  Splitting keeps both kernels at 16
+// warps per SM (shared memory per warp 4.3 KB / 12.5 KB) and halves the code each warp walks through:
 //   1. audio frame (1024 Bartlett-windowed samples, zero-padded to 2048): real FFT-2048 computed as
 //      the complex FFT-1024 of even/odd samples -> kept raw in shared memory;
 //   2./3. impulse response: the L-point inverse real DFT (L = 510 or 1022, NOT a power of two) is
@@ -24,12 +27,13 @@
 
 namespace ddsp {
 
-constexpr int kLtvWarps = 10;                      // warps per CTA (smem-bound: 20.3 KB per warp)
+constexpr int kLtvWarps = 16;                      // warps per CTA, both kernels
 constexpr int kLtvThreads = kLtvWarps * 32;
-constexpr int kLtvStash = 1024;                    // float2: raw FFT of the audio frame
-constexpr int kLtvRing = 2048;                     // floats: overlap-add ring
-constexpr int kLtvWarpBytes = kPlaneFloats * 4 + kLtvStash * 8 + kLtvRing * 4;
-constexpr int kLtvSmemBytes = 512 * 16 + kLtvWarps * kLtvWarpBytes;
+constexpr int kLtvRing = 2048;                     // floats: overlap-add ring of the convolution kernel
+constexpr int kLtvIrSmemBytes = 512 * 16 + kLtvWarps * kPlaneFloats * 4;
+constexpr int kLtvConvWarpBytes = kPlaneFloats * 4 + kLtvRing * 4;
+constexpr int kLtvConvSmemBytes = 512 * 16 + kLtvWarps * kLtvConvWarpBytes;
+constexpr int kLtvSpecFloat2 = 1024;               // workspace per frame: raw FFT-1024 of the even/odd-packed taps
 
 // per-L chirp tables: c[m] = exp(i*pi*m^2/L), m < 512; dhat = FFT_1024 of the wrapped conjugate chirp
 constexpr int kChirpFloats = 512 * 2 + 1024 * 2;
@@ -44,6 +48,7 @@ struct LtvParams {
     const float* f0_frames; int64_t fB, fF; float sr15;   // dynamic window: hw = 1.5*sr/(f0+1e-3)
     const float* tw_tables;             // twiddles (fft32.cuh)
     const float* chirp;                 // tables for this L
+    float2* spec;                       // workspace (B,F,1024) complex: tap spectra
     float* out;                         // (B,T)
     int B, F, run_len, runs_per_clip;
 };
@@ -63,92 +68,42 @@ __device__ __forceinline__ float bartlett1024(int i) {      // torch.bartlett_wi
         outi = lane0 ? i0_ : outi;                                                 \
     }
 
-// ENC / WIN / AMODE >= 0 fix the magnitude encoding, window mode and audio source at compile time
-// (smaller code per instantiation: the kernel is instruction-fetch sensitive); -1 = read from P.
-template <int ENC, int WIN, int AMODE>
-__global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvParams P) {
+// ---------------------------------------------------------------------------------------------
+// Kernel 1: magnitudes -> windowed causal impulse response -> its spectrum.  One warp per frame.
+// ENC / WIN >= 0 fix the magnitude encoding / window mode at compile time (-1: read from P).
+// ---------------------------------------------------------------------------------------------
+template <int ENC, int WIN>
+__global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams P) {
     const int enc = ENC >= 0 ? ENC : P.encoding;
     const int win_mode = WIN >= 0 ? WIN : P.window_mode;
-    const int amode = AMODE >= 0 ? AMODE : P.audio_mode;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float4* tw4 = reinterpret_cast<const float4*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned char* wbase = smem_raw + 512 * 16 + wid * kLtvWarpBytes;
-    float* plane = reinterpret_cast<float*>(wbase);
-    float2* stash = reinterpret_cast<float2*>(plane + kPlaneFloats);
-    float* ring = reinterpret_cast<float*>(stash + kLtvStash);
+    float* plane = reinterpret_cast<float*>(smem_raw + 512 * 16) + wid * kPlaneFloats;
     {
         const float4* src = reinterpret_cast<const float4*>(P.tw_tables);
         float4* dst = reinterpret_cast<float4*>(smem_raw);
         for (int e = threadIdx.x; e < 512; e += kLtvThreads) dst[e] = __ldg(src + e);
         __syncthreads();
     }
-    const int64_t run = (int64_t)blockIdx.x * kLtvWarps + wid;
-    if (run >= (int64_t)P.B * P.runs_per_clip) return;
-    const int b = (int)(run / P.runs_per_clip);
     const int F = P.F;
-    const int m_begin = (int)(run % P.runs_per_clip) * P.run_len;
-    const int m_end = min(F + 1, m_begin + P.run_len);
-    const int64_t T = (int64_t)F * kHop;
     const int n_mag = P.n_mag;
     const int L = 2 * (n_mag - 1), D = L / 2;
     const int n_out = (L == 510) ? 510 : 512;          // IR samples produced by the chirp convolution
     const bool sym = L != 510;                          // L=1022: real magnitudes -> IR symmetric, mirror it
-    const int partner = (32 - lane) & 31;
-    const bool lane0 = lane == 0;
     const float2* chirp_c = reinterpret_cast<const float2*>(P.chirp);
     const float2* chirp_d = chirp_c + 512;
-    const float2 wl = make_float2(tw4[lane].y, tw4[lane].w);        // W1024^lane = (cos, -sin)
-    const uint32_t key = noise_key(P.seed, (uint32_t)b);
     const float two_pi_over_L = DDSP_TWO_PI_F / (float)L;
-
-    for (int i = lane; i < kLtvRing; i += 32) ring[i] = 0.0f;
-    __syncwarp();
-    int rs = 0;                                          // ring start (logical sample 0 of the current frame)
+    const int64_t n_frames = (int64_t)P.B * F;
 
     Pts32 X;
-    for (int m = m_begin; m < m_end; ++m) {
-        const int64_t t0 = (int64_t)(m - 1) * kHop;      // first input sample of the frame
-        const int mhat = min(m, F - 1);                  // last IR repeated (core.py:228)
+    for (int64_t fr = (int64_t)blockIdx.x * kLtvWarps + wid; fr < n_frames; fr += (int64_t)gridDim.x * kLtvWarps) {
+        const int b = (int)(fr / F), m = (int)(fr % F);
 #pragma unroll 1
-        for (int phase = 0; phase < 5; ++phase) {
-            // ------------------------------ prologue ------------------------------------------
+        for (int phase = 0; phase < 3; ++phase) {
             if (phase == 0) {
-                {   // pull this frame's magnitude row into L2 while the audio FFT runs
-                    const float* row = P.mags + (int64_t)b * P.mB + (int64_t)mhat * P.mF + 32 * lane;
-                    if (32 * lane < n_mag) asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
-                }
-                // z[n] = a[2n] + j a[2n+1], n = 32 n1 + lane < 512; a = bartlett * frame (core.py:218-222)
-                const bool vA = m >= 1, vB = m < F;
-                const float* src = P.audio + (int64_t)b * T;
-                uint32_t stA = noise_seed(key, (uint32_t)(m - 1), (uint32_t)lane);
-                uint32_t stB = noise_seed(key, (uint32_t)m, (uint32_t)lane);
-#pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    float v0 = 0.0f, v1 = 0.0f;
-                    if (n1 < 16) {
-                        const int i = 64 * n1 + 2 * lane;               // frame-relative sample index (even)
-                        const bool ok = (n1 < 8) ? vA : vB;
-                        if (amode == 2) {
-                            uint32_t& st = (n1 < 8) ? stA : stB;
-                            st = noise_next(st); v0 = (float)noise_u24(st) * 5.9604644775390625e-8f;
-                            st = noise_next(st); v1 = (float)noise_u24(st) * 5.9604644775390625e-8f;
-                            v0 = ok ? fmaf(2.0f, v0, -1.0f) : 0.0f;
-                            v1 = ok ? fmaf(2.0f, v1, -1.0f) : 0.0f;
-                        } else if (ok) {
-                            const float2 x = __ldg(reinterpret_cast<const float2*>(src + t0 + i));
-                            v0 = x.x; v1 = x.y;
-                            if (amode == 1) { v0 = fmaf(2.0f, v0, -1.0f); v1 = fmaf(2.0f, v1, -1.0f); }
-                        }
-                        v0 *= bartlett1024(i);
-                        v1 *= bartlett1024(i + 1);
-                    }
-                    DDSP_RE(X, brev5(n1)) = v0;
-                    DDSP_IM(X, brev5(n1)) = v1;
-                }
-            } else if (phase == 1) {
                 // a'[k] = w_k X[k] c[k] / (L*1024), k = 32 n1 + lane < n_mag   (irfft, core.py:316)
-                const float* row = P.mags + (int64_t)b * P.mB + (int64_t)mhat * P.mF;
+                const float* row = P.mags + (int64_t)b * P.mB + (int64_t)m * P.mF;
                 const float scale = 1.0f / ((float)L * 1024.0f);
                 float carry = 0.0f;                                      // allpass: running phase in turns
 #pragma unroll
@@ -171,7 +126,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
                             xr = cos_approx(DDSP_TWO_PI_F * g);
                             xi = sin_approx(DDSP_TWO_PI_F * g);
                         } else if (enc == DDSP_B200_MAG_EXP) {
-                            xr = ex2_approx(__ldg(row + k) * DDSP_LOG2E_F) * P.mag_scale;     // vocoder.py:399,475,522-523
+                            xr = ex2_approx(__ldg(row + k) * DDSP_LOG2E_F) * P.mag_scale;   // vocoder.py:399,475,522-523
                         } else if (enc == DDSP_B200_MAG_COMPLEX) {
                             const float2 v = __ldg(reinterpret_cast<const float2*>(row) + k);
                             xr = v.x; xi = v.y;
@@ -190,7 +145,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
                     DDSP_RE(X, brev5(n1)) = xr;
                     DDSP_IM(X, brev5(n1)) = xi;
                 }
-            } else if (phase == 3) {
+            } else if (phase == 2) {
                 // z[n] = h[2n] + j h[2n+1] from the taps in `plane`
                 const float2* h2 = reinterpret_cast<const float2*>(plane);
 #pragma unroll
@@ -205,11 +160,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
 
             warp_fft1024(X, plane, tw4, lane);
 
-            // ------------------------------ epilogue ------------------------------------------
             if (phase == 0) {
-#pragma unroll
-                for (int q = 0; q < 32; ++q) stash[lane + 32 * q] = make_float2(DDSP_RE(X, q), DDSP_IM(X, q));
-            } else if (phase == 1) {
                 // times the chirp spectrum, then inverse FFT (real/imag swapped through the forward FFT)
                 float pr[32], pi[32];
 #pragma unroll
@@ -224,12 +175,12 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
                     DDSP_RE(X, brev5(q)) = pi[q];
                     DDSP_IM(X, brev5(q)) = pr[q];
                 }
-            } else if (phase == 2) {
+            } else if (phase == 1) {
                 // conv[n] (Re in X.im, Im in X.re after the swapped FFT), n = lane + 32 q < n_out:
                 // ir_zero_phase[n] = Re(c[n] * conv[n]); causal form + window (core.py:242-303,326)
                 float hw_inv = 0.0f;
                 if (win_mode == DDSP_B200_WINDOW_DYNAMIC) {
-                    const float f0 = __ldg(P.f0_frames + (int64_t)b * P.fB + (int64_t)mhat * P.fF);
+                    const float f0 = __ldg(P.f0_frames + (int64_t)b * P.fB + (int64_t)m * P.fF);
                     hw_inv = __fdiv_rn(1.0f, __fdiv_rn(P.sr15, __fadd_rn(f0, 1e-3f)));
                 }
 #pragma unroll
@@ -264,7 +215,96 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
                 }
                 if (lane < 2) plane[L + lane] = 0.0f;
                 __syncwarp();
-            } else if (phase == 3) {
+            } else {
+                float2* dst = P.spec + fr * kLtvSpecFloat2 + lane;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) dst[32 * q] = make_float2(DDSP_RE(X, q), DDSP_IM(X, q));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 2: framing, FFT convolution with the stored tap spectra, overlap-add.  A warp owns a run
+// of consecutive frames of one clip.  AMODE >= 0 fixes the audio source at compile time.
+// ---------------------------------------------------------------------------------------------
+template <int AMODE>
+__global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParams P) {
+    const int amode = AMODE >= 0 ? AMODE : P.audio_mode;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float4* tw4 = reinterpret_cast<const float4*>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char* wbase = smem_raw + 512 * 16 + wid * kLtvConvWarpBytes;
+    float* plane = reinterpret_cast<float*>(wbase);
+    float* ring = plane + kPlaneFloats;
+    {
+        const float4* src = reinterpret_cast<const float4*>(P.tw_tables);
+        float4* dst = reinterpret_cast<float4*>(smem_raw);
+        for (int e = threadIdx.x; e < 512; e += kLtvThreads) dst[e] = __ldg(src + e);
+        __syncthreads();
+    }
+    const int64_t run = (int64_t)blockIdx.x * kLtvWarps + wid;
+    if (run >= (int64_t)P.B * P.runs_per_clip) return;
+    const int b = (int)(run / P.runs_per_clip);
+    const int F = P.F;
+    const int m_begin = (int)(run % P.runs_per_clip) * P.run_len;
+    const int m_end = min(F + 1, m_begin + P.run_len);
+    const int64_t T = (int64_t)F * kHop;
+    const int D = P.n_mag - 1;                          // L/2: delay compensation (core.py:177)
+    const int partner = (32 - lane) & 31;
+    const bool lane0 = lane == 0;
+    const float2 wl = make_float2(tw4[lane].y, tw4[lane].w);        // W1024^lane = (cos, -sin)
+    const uint32_t key = noise_key(P.seed, (uint32_t)b);
+
+    for (int i = lane; i < kLtvRing; i += 32) ring[i] = 0.0f;
+    __syncwarp();
+    int rs = 0;                                          // ring start (logical sample 0 of the current frame)
+
+    Pts32 X;
+    for (int m = m_begin; m < m_end; ++m) {
+        const int64_t t0 = (int64_t)(m - 1) * kHop;      // first input sample of the frame
+        const float2* zh = P.spec + ((int64_t)b * F + min(m, F - 1)) * kLtvSpecFloat2;   // last IR repeated (core.py:228)
+#pragma unroll 1
+        for (int phase = 0; phase < 2; ++phase) {
+            if (phase == 0) {
+                {   // pull this frame's tap spectrum (8 KB) into L2 while the audio FFT runs
+                    const char* pz = reinterpret_cast<const char*>(zh) + 128 * lane;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pz));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pz + 4096));
+                }
+                // z[n] = a[2n] + j a[2n+1], n = 32 n1 + lane < 512; a = bartlett * frame (core.py:218-222)
+                const bool vA = m >= 1, vB = m < F;
+                const float* src = P.audio + (int64_t)b * T;
+                uint32_t stA = noise_seed(key, (uint32_t)(m - 1), (uint32_t)lane);
+                uint32_t stB = noise_seed(key, (uint32_t)m, (uint32_t)lane);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    float v0 = 0.0f, v1 = 0.0f;
+                    if (n1 < 16) {
+                        const int i = 64 * n1 + 2 * lane;               // frame-relative sample index (even)
+                        const bool ok = (n1 < 8) ? vA : vB;
+                        if (amode == 2) {
+                            uint32_t& st = (n1 < 8) ? stA : stB;
+                            st = noise_next(st); v0 = (float)noise_s24(st) * 1.1920928955078125e-7f;
+                            st = noise_next(st); v1 = (float)noise_s24(st) * 1.1920928955078125e-7f;
+                            v0 = ok ? v0 : 0.0f;
+                            v1 = ok ? v1 : 0.0f;
+                        } else if (ok) {
+                            const float2 x = __ldg(reinterpret_cast<const float2*>(src + t0 + i));
+                            v0 = x.x; v1 = x.y;
+                            if (amode == 1) { v0 = fmaf(2.0f, v0, -1.0f); v1 = fmaf(2.0f, v1, -1.0f); }
+                        }
+                        v0 *= bartlett1024(i);
+                        v1 *= bartlett1024(i + 1);
+                    }
+                    DDSP_RE(X, brev5(n1)) = v0;
+                    DDSP_IM(X, brev5(n1)) = v1;
+                }
+            }
+
+            warp_fft1024(X, plane, tw4, lane);
+
+            if (phase == 0) {
                 // even/odd-domain product:  Zy = (Ea Eh + W1024^k Oa Oh) + j (Ea Oh + Oa Eh)
                 float zr[32], zi[32];
 #pragma unroll
@@ -274,9 +314,9 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
                     float cr, ci;
                     LTV_PARTNER(X, q, cr, ci);
                     const float ar = DDSP_RE(X, q), ai = DDSP_IM(X, q);
-                    const float Ehr = ar + cr, Ehi = ai - ci, Ohr = ai + ci, Ohi = cr - ar;
-                    const float2 za = stash[k], zp = stash[(1024 - k) & 1023];
-                    const float Ear = za.x + zp.x, Eai = za.y - zp.y, Oar = za.y + zp.y, Oai = zp.x - za.x;
+                    const float Ear = ar + cr, Eai = ai - ci, Oar = ai + ci, Oai = cr - ar;
+                    const float2 zk = __ldg(zh + k), zp = __ldg(zh + ((1024 - k) & 1023));
+                    const float Ehr = zk.x + zp.x, Ehi = zk.y - zp.y, Ohr = zk.y + zp.y, Ohi = zp.x - zk.x;
                     // W1024^k = W1024^lane * W32^q
                     const float cq = (q < 16) ? cos32(q & 15) : -cos32(q & 15);
                     const float sq = (q < 16) ? -sin32(q & 15) : sin32(q & 15);      // W32^q = cq + j sq
@@ -294,7 +334,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_filter_kernel(const LtvPar
                     DDSP_RE(X, brev5(q)) = zi[q];      // swapped -> inverse
                     DDSP_IM(X, brev5(q)) = zr[q];
                 }
-            } else if (phase == 4) {
+            } else {
                 // y[2n] = Re z'[n] = X.im, y[2n+1] = Im z'[n] = X.re, n = lane + 32 q; overlap-add (core.py:233-235)
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
