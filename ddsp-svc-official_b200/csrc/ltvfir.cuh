@@ -30,8 +30,9 @@ namespace ddsp {
 constexpr int kLtvWarps = 16;                      // warps per CTA, both kernels
 constexpr int kLtvThreads = kLtvWarps * 32;
 constexpr int kLtvRing = 2048;                     // floats: overlap-add ring of the convolution kernel
-constexpr int kLtvIrSmemBytes = 512 * 16 + kLtvWarps * kPlaneFloats * 4;
-constexpr int kLtvConvWarpBytes = kPlaneFloats * 4 + kLtvRing * 4;
+constexpr int kLtvCtxInts = 8;                     // cold per-warp scalars parked in shared memory (see combsubfast.cuh)
+constexpr int kLtvIrSmemBytes = 512 * 16 + kLtvWarps * (kPlaneFloats * 4 + kLtvCtxInts * 4);
+constexpr int kLtvConvWarpBytes = kPlaneFloats * 4 + kLtvRing * 4 + kLtvCtxInts * 4;
 constexpr int kLtvConvSmemBytes = 512 * 16 + kLtvWarps * kLtvConvWarpBytes;
 constexpr int kLtvSpecFloat2 = 1024;               // workspace per frame: raw FFT-1024 of the even/odd-packed taps
 
@@ -79,31 +80,30 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float4* tw4 = reinterpret_cast<const float4*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float* plane = reinterpret_cast<float*>(smem_raw + 512 * 16) + wid * kPlaneFloats;
+    float* plane = reinterpret_cast<float*>(smem_raw + 512 * 16) + wid * (kPlaneFloats + kLtvCtxInts);
+    volatile int* ctx = reinterpret_cast<volatile int*>(plane + kPlaneFloats);
     {
         const float4* src = reinterpret_cast<const float4*>(P.tw_tables);
         float4* dst = reinterpret_cast<float4*>(smem_raw);
         for (int e = threadIdx.x; e < 512; e += kLtvThreads) dst[e] = __ldg(src + e);
         __syncthreads();
     }
-    const int F = P.F;
-    const int n_mag = P.n_mag;
-    const int L = 2 * (n_mag - 1), D = L / 2;
-    const int n_out = (L == 510) ? 510 : 512;          // IR samples produced by the chirp convolution
-    const bool sym = L != 510;                          // L=1022: real magnitudes -> IR symmetric, mirror it
-    const float2* chirp_c = reinterpret_cast<const float2*>(P.chirp);
-    const float2* chirp_d = chirp_c + 512;
-    const float two_pi_over_L = DDSP_TWO_PI_F / (float)L;
-    const int64_t n_frames = (int64_t)P.B * F;
+#define IR_NMAG (P.n_mag)
+#define IR_L (2 * (P.n_mag - 1))
+#define IR_D (P.n_mag - 1)
+    const int64_t n_frames = (int64_t)P.B * P.F;
 
     Pts32 X;
-    for (int64_t fr = (int64_t)blockIdx.x * kLtvWarps + wid; fr < n_frames; fr += (int64_t)gridDim.x * kLtvWarps) {
-        const int b = (int)(fr / F), m = (int)(fr % F);
+    for (int64_t fr0 = (int64_t)blockIdx.x * kLtvWarps + wid; fr0 < n_frames; fr0 += (int64_t)gridDim.x * kLtvWarps) {
+        if (lane == 0) { ctx[0] = (int)(fr0 / P.F); ctx[1] = (int)(fr0 % P.F); }
+        __syncwarp();
 #pragma unroll 1
         for (int phase = 0; phase < 3; ++phase) {
             if (phase == 0) {
                 // a'[k] = w_k X[k] c[k] / (L*1024), k = 32 n1 + lane < n_mag   (irfft, core.py:316)
-                const float* row = P.mags + (int64_t)b * P.mB + (int64_t)m * P.mF;
+                const int n_mag = IR_NMAG, L = IR_L;
+                const float2* chirp_c = reinterpret_cast<const float2*>(P.chirp);
+                const float* row = P.mags + (int64_t)ctx[0] * P.mB + (int64_t)ctx[1] * P.mF;
                 const float scale = 1.0f / ((float)L * 1024.0f);
                 float carry = 0.0f;                                      // allpass: running phase in turns
 #pragma unroll
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
             } else if (phase == 2) {
                 // z[n] = h[2n] + j h[2n+1] from the taps in `plane`
                 const float2* h2 = reinterpret_cast<const float2*>(plane);
+                const int D = IR_D;
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) {
                     float2 v = make_float2(0.0f, 0.0f);
@@ -162,9 +163,11 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
 
             if (phase == 0) {
                 // times the chirp spectrum, then inverse FFT (real/imag swapped through the forward FFT)
+                const float2* chirp_d = reinterpret_cast<const float2*>(P.chirp) + 512;
                 float pr[32], pi[32];
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
+                    if ((q & 7) == 0) asm volatile("" ::: "memory");      // keep at most 8 table loads in flight (registers)
                     const float2 dh = __ldg(chirp_d + lane + 32 * q);
                     const float ur = DDSP_RE(X, q), ui = DDSP_IM(X, q);
                     pr[q] = ur * dh.x - ui * dh.y;
@@ -178,9 +181,14 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
             } else if (phase == 1) {
                 // conv[n] (Re in X.im, Im in X.re after the swapped FFT), n = lane + 32 q < n_out:
                 // ir_zero_phase[n] = Re(c[n] * conv[n]); causal form + window (core.py:242-303,326)
+                const int L = IR_L, D = IR_D;
+                const int n_out = (L == 510) ? 510 : 512;          // IR samples produced by the chirp convolution
+                const bool sym = L != 510;                          // L=1022: real magnitudes -> IR symmetric, mirror it
+                const float2* chirp_c = reinterpret_cast<const float2*>(P.chirp);
+                const float two_pi_over_L = DDSP_TWO_PI_F / (float)L;
                 float hw_inv = 0.0f;
                 if (win_mode == DDSP_B200_WINDOW_DYNAMIC) {
-                    const float f0 = __ldg(P.f0_frames + (int64_t)b * P.fB + (int64_t)m * P.fF);
+                    const float f0 = __ldg(P.f0_frames + (int64_t)ctx[0] * P.fB + (int64_t)ctx[1] * P.fF);
                     hw_inv = __fdiv_rn(1.0f, __fdiv_rn(P.sr15, __fadd_rn(f0, 1e-3f)));
                 }
 #pragma unroll
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
                 if (lane < 2) plane[L + lane] = 0.0f;
                 __syncwarp();
             } else {
-                float2* dst = P.spec + fr * kLtvSpecFloat2 + lane;
+                float2* dst = P.spec + ((int64_t)ctx[0] * P.F + ctx[1]) * kLtvSpecFloat2 + lane;
 #pragma unroll
                 for (int q = 0; q < 32; ++q) dst[32 * q] = make_float2(DDSP_RE(X, q), DDSP_IM(X, q));
             }
@@ -237,36 +245,44 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
     unsigned char* wbase = smem_raw + 512 * 16 + wid * kLtvConvWarpBytes;
     float* plane = reinterpret_cast<float*>(wbase);
     float* ring = plane + kPlaneFloats;
+    volatile int* ctx = reinterpret_cast<volatile int*>(ring + kLtvRing);
     {
         const float4* src = reinterpret_cast<const float4*>(P.tw_tables);
         float4* dst = reinterpret_cast<float4*>(smem_raw);
         for (int e = threadIdx.x; e < 512; e += kLtvThreads) dst[e] = __ldg(src + e);
         __syncthreads();
     }
-    const int64_t run = (int64_t)blockIdx.x * kLtvWarps + wid;
-    if (run >= (int64_t)P.B * P.runs_per_clip) return;
-    const int b = (int)(run / P.runs_per_clip);
+    {
+        const int64_t run = (int64_t)blockIdx.x * kLtvWarps + wid;
+        if (run >= (int64_t)P.B * P.runs_per_clip) return;
+        const int b0 = (int)(run / P.runs_per_clip);
+        const int mb = (int)(run % P.runs_per_clip) * P.run_len;
+        if (lane == 0) {
+            ctx[0] = b0; ctx[1] = mb; ctx[2] = min(P.F + 1, mb + P.run_len);
+            ctx[3] = (int)noise_key(P.seed, (uint32_t)b0);
+        }
+        __syncwarp();
+    }
+#define CV_B ctx[0]
+#define CV_MBEGIN ctx[1]
+#define CV_MEND ctx[2]
     const int F = P.F;
-    const int m_begin = (int)(run % P.runs_per_clip) * P.run_len;
-    const int m_end = min(F + 1, m_begin + P.run_len);
     const int64_t T = (int64_t)F * kHop;
     const int D = P.n_mag - 1;                          // L/2: delay compensation (core.py:177)
     const int partner = (32 - lane) & 31;
     const bool lane0 = lane == 0;
-    const float2 wl = make_float2(tw4[lane].y, tw4[lane].w);        // W1024^lane = (cos, -sin)
-    const uint32_t key = noise_key(P.seed, (uint32_t)b);
 
     for (int i = lane; i < kLtvRing; i += 32) ring[i] = 0.0f;
     __syncwarp();
     int rs = 0;                                          // ring start (logical sample 0 of the current frame)
 
     Pts32 X;
-    for (int m = m_begin; m < m_end; ++m) {
+    for (int m = CV_MBEGIN; m < CV_MEND; ++m) {
         const int64_t t0 = (int64_t)(m - 1) * kHop;      // first input sample of the frame
-        const float2* zh = P.spec + ((int64_t)b * F + min(m, F - 1)) * kLtvSpecFloat2;   // last IR repeated (core.py:228)
 #pragma unroll 1
         for (int phase = 0; phase < 2; ++phase) {
             if (phase == 0) {
+                const float2* zh = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2;
                 {   // pull this frame's tap spectrum (8 KB) into L2 while the audio FFT runs
                     const char* pz = reinterpret_cast<const char*>(zh) + 128 * lane;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(pz));
@@ -274,7 +290,8 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                 }
                 // z[n] = a[2n] + j a[2n+1], n = 32 n1 + lane < 512; a = bartlett * frame (core.py:218-222)
                 const bool vA = m >= 1, vB = m < F;
-                const float* src = P.audio + (int64_t)b * T;
+                const float* src = P.audio + (int64_t)CV_B * T;
+                const uint32_t key = (uint32_t)ctx[3];
                 uint32_t stA = noise_seed(key, (uint32_t)(m - 1), (uint32_t)lane);
                 uint32_t stB = noise_seed(key, (uint32_t)m, (uint32_t)lane);
 #pragma unroll
@@ -306,11 +323,14 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
 
             if (phase == 0) {
                 // even/odd-domain product:  Zy = (Ea Eh + W1024^k Oa Oh) + j (Ea Oh + Oa Eh)
+                const float2* zh = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2;   // last IR repeated (core.py:228)
+                const float2 wl = make_float2(tw4[lane].y, tw4[lane].w);        // W1024^lane = (cos, -sin)
                 float zr[32], zi[32];
 #pragma unroll
                 for (int qq = 0; qq < 32; ++qq) {
                     const int q = (qq & 1) ? 31 - (qq >> 1) : (qq >> 1);   // 0,31,1,30,...: registers die in pairs
                     const int k = lane + 32 * q;
+                    if ((qq & 3) == 0) asm volatile("" ::: "memory");       // bound the spectrum loads in flight (registers)
                     float cr, ci;
                     LTV_PARTNER(X, q, cr, ci);
                     const float ar = DDSP_RE(X, q), ai = DDSP_IM(X, q);
@@ -345,8 +365,9 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                 }
                 __syncwarp();
                 // retire the first 512 samples of the window: output index t = 512(m-1) - D + j  (core.py:238,177-182)
+                const int m_begin = CV_MBEGIN;
                 const bool complete = (m - 3 >= m_begin) || (m_begin == 0);
-                float* ob = P.out + (int64_t)b * T;
+                float* ob = P.out + (int64_t)CV_B * T;
                 const int64_t tb = t0 - D;
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
@@ -364,8 +385,9 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
     }
     // flush the three remaining hops of the ring
     {
+        const int m_begin = CV_MBEGIN, m_end = CV_MEND;
         const int m_last = m_end - 1;
-        float* ob = P.out + (int64_t)b * T;
+        float* ob = P.out + (int64_t)CV_B * T;
         const int64_t tb = (int64_t)(m_last - 1) * kHop - D + kHop;       // rs already advanced past the retired hop
         for (int c = 0; c < 3; ++c) {
             const bool complete = (m_end == F + 1) && ((m_last - 2 + c >= m_begin) || (m_begin == 0));
