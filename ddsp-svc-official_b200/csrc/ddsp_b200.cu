@@ -423,7 +423,7 @@ int ddsp_b200_sins(const float* amplitudes, int n_harmonics, const float* group_
     if (!amplitudes || !group_delay || !noise_magnitude || !f0_frames || !phase_full || !signal || !harmonic || !noise ||
         B <= 0 || F <= 0 || !(sr > 0) || n_harmonics <= 0)
         return DDSP_B200_ERR_INVALID_ARGUMENT;
-    if (hop != ddsp::kHop || n_harmonics > ddsp::kSinsMaxHarm) return DDSP_B200_ERR_UNSUPPORTED;
+    if (hop != ddsp::kHop || n_harmonics > ddsp::kSinsMaxHarm || (n_harmonics & 1)) return DDSP_B200_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < ddsp_b200_sins_workspace_bytes(B, F, n_harmonics, n_mag_allpass, n_mag_noise))
         return DDSP_B200_ERR_WORKSPACE;
     if ((int64_t)B * F > 0x7fffffffLL) return DDSP_B200_ERR_UNSUPPORTED;

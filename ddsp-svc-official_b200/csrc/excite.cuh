@@ -36,8 +36,8 @@ __global__ void __launch_bounds__(256) combtooth_kernel(const float* __restrict_
 // Sins oscillator bank.  One CTA of 128 threads per hop (512 samples, 4 per thread).
 //   A[m,k] = fl(exp(a[m,k]) / 128) * ((f0[m]*k < sr/2) + 1e-7)            (vocoder.py:397,402)
 //   s[t]   = sum_k lerp(A[:,k])[t] * sin(k * theta[t])                     (vocoder.py:406-412)
-// sin(k*theta) comes from the complex rotation z_k = z_{k-1} * z_1 (z_1 = cis(theta), accurate
-// sincosf); two samples ride in one packed fp32x2 register pair.
+// sin(k*theta) comes from a two-term recurrence (see below); two samples ride in one packed
+// fp32x2 register pair.  n_harm must be even.
 constexpr int kSinsMaxHarm = 512;
 
 __global__ void __launch_bounds__(128) sins_osc_kernel(const float* __restrict__ amp_ctrl, int64_t cB, int64_t cF,
@@ -64,35 +64,51 @@ __global__ void __launch_bounds__(128) sins_osc_kernel(const float* __restrict__
     __syncthreads();
     const int64_t base = ((int64_t)b * F + hop) * kHop;
     const int t = threadIdx.x;
-    float2 lam[2], c1[2], s1[2], c[2], s[2], acc[2];
+    // sin(k*theta) by Reinsch's stable recurrence:  d_{k+1} = d_k + delta*s_k,  s_{k+1} = s_k + d_{k+1},
+    // delta = -4 sin^2(phi/2), which needs |phi| <= pi/2: theta in the outer half of [-pi,pi] is shifted by
+    // +-pi, sin(k*theta) = (-1)^k sin(k*phi), i.e. the odd harmonics change sign (separate accumulators).
+    float2 lam[2], dl[2], sk[2], dk[2], acc_e[2], acc_o[2], sgn[2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
         const int i0 = t + 256 * p, i1 = i0 + 128;
         lam[p] = make_float2((float)i0 * (1.0f / kHop), (float)i1 * (1.0f / kHop));
-        float sa, ca, sb, cb;
-        sincosf(__ldg(phase_full + base + i0), &sa, &ca);
-        sincosf(__ldg(phase_full + base + i1), &sb, &cb);
-        c1[p] = make_float2(ca, cb); s1[p] = make_float2(sa, sb);
-        c[p] = make_float2(1.0f, 1.0f); s[p] = make_float2(0.0f, 0.0f);
-        acc[p] = make_float2(0.0f, 0.0f);
+        float th[2] = {__ldg(phase_full + base + i0), __ldg(phase_full + base + i1)};
+        float dv[2], sv[2], gv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const bool shift = fabsf(th[e]) > 0.5f * DDSP_PI_F;
+            const float phi = shift ? th[e] - copysignf(DDSP_PI_F, th[e]) : th[e];
+            float sh, ch;
+            sincosf(0.5f * phi, &sh, &ch);
+            dv[e] = -4.0f * sh * sh;
+            sv[e] = 2.0f * sh * ch;
+            gv[e] = shift ? -1.0f : 1.0f;
+        }
+        dl[p] = make_float2(dv[0], dv[1]);
+        sk[p] = make_float2(sv[0], sv[1]);       // s_1
+        dk[p] = sk[p];                            // d_1 = s_1 - s_0
+        sgn[p] = make_float2(gv[0], gv[1]);
+        acc_e[p] = make_float2(0.0f, 0.0f);
+        acc_o[p] = make_float2(0.0f, 0.0f);
     }
 #pragma unroll 4
-    for (int k = 0; k < n_harm; ++k) {
-        const float4 a = amps[k];
-        const float2 A0 = make_float2(a.x, a.y), dA = make_float2(a.z, a.w);
+    for (int k = 0; k < n_harm; k += 2) {        // k, k+1 are harmonics k+1 (odd) and k+2 (even); n_harm is even
+        const float4 a = amps[k], a2 = amps[k + 1];
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-            const float2 cn = fma2(neg2(s[p]), s1[p], mul2(c[p], c1[p]));     // z_k = z_{k-1} * z_1
-            const float2 sn = fma2(c[p], s1[p], mul2(s[p], c1[p]));
-            c[p] = cn; s[p] = sn;
-            const float2 amp = fma2(lam[p], dA, A0);
-            acc[p] = fma2(amp, sn, acc[p]);
+            acc_o[p] = fma2(fma2(lam[p], make_float2(a.z, a.w), make_float2(a.x, a.y)), sk[p], acc_o[p]);
+            dk[p] = fma2(dl[p], sk[p], dk[p]);
+            sk[p] = add2(sk[p], dk[p]);
+            acc_e[p] = fma2(fma2(lam[p], make_float2(a2.z, a2.w), make_float2(a2.x, a2.y)), sk[p], acc_e[p]);
+            dk[p] = fma2(dl[p], sk[p], dk[p]);
+            sk[p] = add2(sk[p], dk[p]);
         }
     }
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-        out[base + t + 256 * p] = acc[p].x;
-        out[base + t + 256 * p + 128] = acc[p].y;
+        const float2 r = fma2(sgn[p], acc_o[p], acc_e[p]);
+        out[base + t + 256 * p] = r.x;
+        out[base + t + 256 * p + 128] = r.y;
     }
 }
 
