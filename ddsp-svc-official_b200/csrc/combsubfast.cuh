@@ -42,7 +42,6 @@ struct CsfParams {
     int B, F;
     int pairs_per_clip, run_len, runs_per_clip;
     double inv_sr; float sr;
-    int zero_unvoiced;                                    // CombSubFast: 1 (vocoder.py:460)
 };
 
 // Operands of one excitation hop, loaded a step ahead of their use so the DRAM latency is covered.
@@ -72,13 +71,12 @@ __device__ __forceinline__ void csf_gen_hop(const CsfParams& P, int h, const Hop
     }
     float f[16], rot[16];
     hop_rotation(in.x0, in.x1, in.base, P.inv_sr, lane, f, rot);
-    const bool zu = P.zero_unvoiced != 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         // vocoder.py:459  sinc(sr * rot / (f0 + 1e-3))
         const float x = __fmul_rn(P.sr, rot[i]) * rcp_approx(__fadd_rn(f[i], 1e-3f));
         float c = sinc_f(x);
-        if (zu && f[i] <= 0.0f) c = 0.0f;                  // vocoder.py:460
+        if (f[i] <= 0.0f) c = 0.0f;                        // vocoder.py:460
         dst[i] = c;
     }
 }
@@ -99,6 +97,9 @@ __global__ void __launch_bounds__(128) csf_zero_seams_kernel(float* __restrict__
     dst[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// HAS_U: the noise excitation is read from the injected U tensor (parity mode) instead of being drawn
+// in-kernel; a compile-time switch so that neither variant carries the other's predicated-off code.
+template <bool HAS_U>
 __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float4* tw4 = reinterpret_cast<const float4*>(smem_raw);
@@ -176,9 +177,12 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             const float okA = vA ? 1.0f : 0.0f, okB = vB ? 1.0f : 0.0f;
             const float sclA = okA * 1.1920928955078125e-7f, sclB = okB * 1.1920928955078125e-7f;   // 2^-23
             const uint32_t key = CTX_KEY;
-            const float* u_b = P.noise_u ? P.noise_u + (int64_t)CTX_B * F * kHop + lane : nullptr;
-            uint32_t stA = noise_seed(key, (uint32_t)(fm - 1), (uint32_t)lane);
-            uint32_t stB = noise_seed(key, (uint32_t)fm, (uint32_t)lane);
+            const float* u_b = HAS_U ? P.noise_u + (int64_t)CTX_B * F * kHop + lane : nullptr;
+            uint32_t stA = 0, stB = 0;
+            if (!HAS_U) {
+                stA = noise_seed(key, (uint32_t)(fm - 1), (uint32_t)lane);
+                stB = noise_seed(key, (uint32_t)fm, (uint32_t)lane);
+            }
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1) {
                 const int j = 32 * (n1 & 15);                                 // sample in hop = j + lane
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                 const float c = (n1 < 16 ? slotA : slotB)[j + (n1 & 15)];
                 const float wc = w * c;
                 float wz;
-                if (u_b) {
+                if (HAS_U) {
                     const float u = __ldg(u_b + (n1 < 16 ? baseA : baseB) + j);
                     const float wn = w * (n1 < 16 ? okA : okB);
                     wz = fmaf(u, wn + wn, -wn);                                   // w * (2u - 1)   (vocoder.py:461)

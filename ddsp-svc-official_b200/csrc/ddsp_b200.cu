@@ -78,7 +78,9 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
     if (dev < 0 || dev >= 64) return DDSP_B200_ERR_UNSUPPORTED;
     std::lock_guard<std::mutex> lock(g_init_mutex);
     if (!g_device_ready[dev]) {
-        CUDA_TRY(cudaFuncSetAttribute(ddsp::combsubfast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(ddsp::combsubfast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      ddsp::kCsfSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(ddsp::combsubfast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       ddsp::kCsfSmemBytes));
         float* ptr = nullptr;
         CUDA_TRY(cudaGetSymbolAddress((void**)&ptr, g_tables));
@@ -252,7 +254,6 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
     P.run_len = run_len;
     P.runs_per_clip = (P.pairs_per_clip + run_len - 1) / run_len;
     P.inv_sr = 1.0 / sr; P.sr = (float)sr;
-    P.zero_unvoiced = 1;
     const int64_t runs = (int64_t)B * P.runs_per_clip;
     const unsigned grid = (unsigned)((runs + ddsp::kCsfWarps - 1) / ddsp::kCsfWarps);
     if (P.runs_per_clip > 1) {
@@ -261,7 +262,10 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
                                                                                 n_seams);
         LAUNCH_CHECK();
     }
-    ddsp::combsubfast_kernel<<<grid, ddsp::kCsfThreads, ddsp::kCsfSmemBytes, (cudaStream_t)stream>>>(P);
+    if (noise_u)
+        ddsp::combsubfast_kernel<true><<<grid, ddsp::kCsfThreads, ddsp::kCsfSmemBytes, (cudaStream_t)stream>>>(P);
+    else
+        ddsp::combsubfast_kernel<false><<<grid, ddsp::kCsfThreads, ddsp::kCsfSmemBytes, (cudaStream_t)stream>>>(P);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }
