@@ -106,14 +106,25 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
                 const float* row = P.mags + (int64_t)ctx[0] * P.mB + (int64_t)ctx[1] * P.mF;
                 const float scale = 1.0f / ((float)L * 1024.0f);
                 float carry = 0.0f;                                      // allpass: running phase in turns
+                // the whole control row first (all loads in flight at once), then the arithmetic
+                float craw[16];
+                float2 ccplx[16];
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    craw[n1] = 0.0f; ccplx[n1] = make_float2(0.0f, 0.0f);
+                    if (n1 * 32 < n_mag) {
+                        if (enc == DDSP_B200_MAG_COMPLEX) ccplx[n1] = __ldg(reinterpret_cast<const float2*>(row) + 32 * n1 + lane);
+                        else craw[n1] = __ldg(row + 32 * n1 + lane);
+                    }
+                }
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) {
                     float xr = 0.0f, xi = 0.0f;
-                    if (n1 * 32 < n_mag) {
+                    if (n1 < 16 && n1 * 32 < n_mag) {
                         const int k = 32 * n1 + lane;
                         if (enc == DDSP_B200_MAG_ALLPASS_TANH) {
                             // exp(j*cumsum(pi*tanh(c)))  (vocoder.py:398,415 / 521,540), phase kept in turns
-                            float g = 0.5f * tanhf(__ldg(row + k));
+                            float g = 0.5f * tanhf(craw[n1 & 15]);
 #pragma unroll
                             for (int d = 1; d < 32; d <<= 1) {
                                 const float t = __shfl_up_sync(kFullMask, g, d);
@@ -126,12 +137,11 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
                             xr = cos_approx(DDSP_TWO_PI_F * g);
                             xi = sin_approx(DDSP_TWO_PI_F * g);
                         } else if (enc == DDSP_B200_MAG_EXP) {
-                            xr = ex2_approx(__ldg(row + k) * DDSP_LOG2E_F) * P.mag_scale;   // vocoder.py:399,475,522-523
+                            xr = ex2_approx(craw[n1 & 15] * DDSP_LOG2E_F) * P.mag_scale;   // vocoder.py:399,475,522-523
                         } else if (enc == DDSP_B200_MAG_COMPLEX) {
-                            const float2 v = __ldg(reinterpret_cast<const float2*>(row) + k);
-                            xr = v.x; xi = v.y;
+                            xr = ccplx[n1 & 15].x; xi = ccplx[n1 & 15].y;
                         } else {
-                            xr = __ldg(row + k);
+                            xr = craw[n1 & 15];
                         }
                         // DC and Nyquist: imaginary part ignored, weight 1; interior bins weight 2
                         const bool edge = (k == 0) || (k == n_mag - 1);
@@ -330,7 +340,6 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                 for (int qq = 0; qq < 32; ++qq) {
                     const int q = (qq & 1) ? 31 - (qq >> 1) : (qq >> 1);   // 0,31,1,30,...: registers die in pairs
                     const int k = lane + 32 * q;
-                    if ((qq & 3) == 0) asm volatile("" ::: "memory");       // bound the spectrum loads in flight (registers)
                     float cr, ci;
                     LTV_PARTNER(X, q, cr, ci);
                     const float ar = DDSP_RE(X, q), ai = DDSP_IM(X, q);
