@@ -336,15 +336,28 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                 const float2* zh = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2;   // last IR repeated (core.py:228)
                 const float2 wl = make_float2(tw4[lane].y, tw4[lane].w);        // W1024^lane = (cos, -sin)
                 float zr[32], zi[32];
+                // tap-spectrum loads run kLook bins ahead of their use (software pipeline over the unrolled loop)
+                constexpr int kLook = 6;
+                float2 zkq[kLook], zpq[kLook];
+#pragma unroll
+                for (int qq = 0; qq < kLook; ++qq) {
+                    const int q = (qq & 1) ? 31 - (qq >> 1) : (qq >> 1);
+                    zkq[qq] = __ldg(zh + lane + 32 * q);
+                    zpq[qq] = __ldg(zh + ((1024 - (lane + 32 * q)) & 1023));
+                }
 #pragma unroll
                 for (int qq = 0; qq < 32; ++qq) {
                     const int q = (qq & 1) ? 31 - (qq >> 1) : (qq >> 1);   // 0,31,1,30,...: registers die in pairs
-                    const int k = lane + 32 * q;
+                    const float2 zk = zkq[qq % kLook], zp = zpq[qq % kLook];
+                    if (qq + kLook < 32) {
+                        const int qn = ((qq + kLook) & 1) ? 31 - ((qq + kLook) >> 1) : ((qq + kLook) >> 1);
+                        zkq[qq % kLook] = __ldg(zh + lane + 32 * qn);
+                        zpq[qq % kLook] = __ldg(zh + ((1024 - (lane + 32 * qn)) & 1023));
+                    }
                     float cr, ci;
                     LTV_PARTNER(X, q, cr, ci);
                     const float ar = DDSP_RE(X, q), ai = DDSP_IM(X, q);
                     const float Ear = ar + cr, Eai = ai - ci, Oar = ai + ci, Oai = cr - ar;
-                    const float2 zk = __ldg(zh + k), zp = __ldg(zh + ((1024 - k) & 1023));
                     const float Ehr = zk.x + zp.x, Ehi = zk.y - zp.y, Ohr = zk.y + zp.y, Ohi = zp.x - zk.x;
                     // W1024^k = W1024^lane * W32^q
                     const float cq = (q < 16) ? cos32(q & 15) : -cos32(q & 15);
