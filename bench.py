@@ -365,7 +365,7 @@ def run_ours(args, rank, local_rank, world):
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))
-            clips = cores * (8 if model == 'combsubfast' else 2)     # ~5-20 s of host work
+            clips = cores * {'combsubfast': 96, 'combsub': 24, 'sins': 4}[model]     # ~10-20 s of host work
             v, dt = cpu_reference_throughput(model, F, clips, cores)
             line['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
                                     'sample': f'{clips} clips x {F} frames, oracle numpy port (fp32) of the reference '
