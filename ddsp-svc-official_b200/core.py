@@ -26,6 +26,14 @@ def _need_cuda_f32(t, name):
     return t
 
 
+def as_f32(t):
+    """Module-level convenience: the reference accepts any floating dtype (AMP / fp64 experiments);
+    the kernels compute in fp32 (+fp64 phase), so other float dtypes are cast on the way in."""
+    if isinstance(t, torch.Tensor) and t.is_floating_point() and t.dtype != torch.float32:
+        return t.float()
+    return t
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 

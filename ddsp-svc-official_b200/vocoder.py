@@ -72,11 +72,13 @@ class CombSubFast(_SynthBase):
     def forward(self, units_frames, f0_frames, volume_frames, spk_id, spk_mix_dict=None, initial_phase=None,
                 infer=True, noise_u=None, **kwargs):
         # stage A: vocoder.py:449-451
+        f0_frames = core.as_f32(f0_frames)
         phase_frames, prefix, _ = core.phase_stage(f0_frames, self._hop, self._sr, initial_phase, infer)
         # control network (reference PyTorch): vocoder.py:454
         ctrls = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id, spk_mix_dict=spk_mix_dict)
         self._forward_only(ctrls)
         # stage B: vocoder.py:455-490
+        ctrls = {k: core.as_f32(v) for k, v in ctrls.items()}
         signal = core.combsubfast_stage(ctrls['harmonic_magnitude'], ctrls['harmonic_phase'], ctrls['noise_magnitude'],
                                         f0_frames, prefix, self._hop, self._sr, initial_phase, noise_u=noise_u,
                                         seed=self._next_seed(), window=self.window)
@@ -95,9 +97,11 @@ class CombSub(_SynthBase):
 
     def forward(self, units_frames, f0_frames, volume_frames, spk_id, spk_mix_dict=None, initial_phase=None,
                 infer=True, noise_u=None, **kwargs):
+        f0_frames = core.as_f32(f0_frames)
         phase_frames, prefix, _ = core.phase_stage(f0_frames, self._hop, self._sr, initial_phase, infer)   # :515-517
         ctrls = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id, spk_mix_dict=spk_mix_dict)
         self._forward_only(ctrls)
+        ctrls = {k: core.as_f32(v) for k, v in ctrls.items()}
         signal, harmonic, noise = core.combsub_stage(ctrls['group_delay'], ctrls['harmonic_magnitude'],
                                                      ctrls['noise_magnitude'], f0_frames, prefix, self._hop, self._sr,
                                                      noise_u=noise_u, seed=self._next_seed())                  # :521-548
@@ -118,9 +122,11 @@ class Sins(_SynthBase):
                 infer=True, max_upsample_dim=32, noise_u=None):
         # stage A with the full-rate phase (vocoder.py:391-393); `max_upsample_dim` only bounded the
         # reference's (B,T,32) temporaries and has no effect here
+        f0_frames = core.as_f32(f0_frames)
         phase_frames, _, phase = core.phase_stage(f0_frames, self._hop, self._sr, initial_phase, infer, full_rate=True)
         ctrls = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id, spk_mix_dict=spk_mix_dict)
         self._forward_only(ctrls)
+        ctrls = {k: core.as_f32(v) for k, v in ctrls.items()}
         signal, harmonic, noise = core.sins_stage(ctrls['amplitudes'], ctrls['group_delay'], ctrls['noise_magnitude'],
                                                   f0_frames, phase, self._hop, self._sr, noise_u=noise_u,
                                                   seed=self._next_seed())                                     # :397-421
