@@ -363,6 +363,8 @@ def run_ours(args, rank, local_rank, world):
                            'copies and compute of consecutive steps overlap on three streams'},
             'gpu_launches': launches, 'clocks': clocks,
         }
+        if args.torch_port and model == 'combsubfast':
+            line['torch_port'] = time_torch_port(g_ctrl, g_f0, g_u, window, args, dev)
         if world == 1 and not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))
             clips = cores * {'combsubfast': 96, 'combsub': 24, 'sins': 4}[model]     # ~10-20 s of host work
@@ -373,6 +375,30 @@ def run_ours(args, rank, local_rank, world):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_torch_port(g_ctrl, g_f0, g_u, window, args, dev):
+    """The same workload through stock PyTorch CUDA ops (oracle/torch_port.py, the reference's own op
+    sequence): the practical bar on this GPU."""
+    import torch
+    from oracle import torch_port as T
+    hm, hp, nm = torch.split(g_ctrl, [513, 513, 513], dim=-1)
+    steps = max(3, min(args.steps, 10))
+    with torch.no_grad():
+        for _ in range(3):
+            T.combsubfast_forward(hm, hp, nm, g_f0, window, noise_u=g_u)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            T.combsubfast_forward(hm, hp, nm, g_f0, window, noise_u=g_u)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    B, F = g_f0.shape[0], g_f0.shape[1]
+    return {'ms_per_step': ms, 'value': B * F * HOP / (ms * 1e-3), 'unit': 'samples/s', 'steps': steps,
+            'what': 'stock PyTorch CUDA ops in the reference order (F.interpolate, fp64 cumsum, sinc, unfold, '
+                    'rfft/irfft, Fold), fp32, same inputs, same GPU'}
 
 
 def run_latency(args):
@@ -445,6 +471,8 @@ def main():
     ap.add_argument('--frames', type=int, default=862, help='frames per clip (862 = 10 s)')
     ap.add_argument('--inject-noise', action='store_true', help='read the noise excitation from a U tensor')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--torch-port', action='store_true',
+                    help='also time the stock-PyTorch-ops restatement of the path on the same GPU (CombSubFast)')
     ap.add_argument('--mode', default='throughput', choices=['throughput', 'latency'])
     ap.add_argument('--latency-frames', default='9,18,26,130')
     ap.add_argument('--latency-iters', type=int, default=1000)

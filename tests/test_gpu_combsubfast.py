@@ -165,6 +165,21 @@ def test_rejects_cpu_tensors_and_bad_hop():
         core.phase_stage(torch.zeros(1, 4, 1).cuda(), 256, 44100)
 
 
+def test_vs_stock_pytorch_ops_on_the_same_gpu():
+    """fp32 reference of the same op sequence on the same device: the reference's forward restated
+    with torch CUDA ops (oracle/torch_port.py; bit-identical to the reference on CPU)."""
+    from oracle import torch_port as T
+    d = make_inputs(4, 200, 1539, seed=31, zero_f0_fraction=0.05)
+    sig, pf = run_gpu(d['ctrl'], d['f0_frames'], d['U'], window=torch_window())
+    hm, hp, nm = ctrl_views(d['ctrl'], 'combsubfast')
+    with torch.no_grad():
+        ref, pf_ref = T.combsubfast_forward(hm, hp, nm, dev(d['f0_frames'])[..., None], torch_window(), noise_u=dev(d['U']))
+    err, s = assert_waveform(sig, ref.cpu().numpy(), what='combsubfast vs torch CUDA ops')
+    assert err < 3e-5 and s > 80, (err, s)
+    dp = np.abs(pf.astype(np.float64) - pf_ref.cpu().numpy())
+    assert np.minimum(dp, np.abs(dp - 2 * np.pi)).max() < 1e-6
+
+
 def test_long_form_five_minutes():
     """Config (4): 5-minute clips (F=25840, T=13.2 M samples) stress the phase accumulation and the
     overlap-add length.  One low-pitched (69-98 Hz) clip and one with unvoiced (f0=0) frames.
