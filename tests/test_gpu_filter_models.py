@@ -199,3 +199,28 @@ def test_drop_in_modules_forward_signature():
         assert phase.shape == ((B, F * 512, 1) if cls is V.Sins else (B, F, 1))
         assert harm.shape == noise.shape == signal.shape
         signal *= 0.5        # callers mutate the result in place (main.py:159, gui.py:127)
+
+
+@pytest.mark.parametrize('model', ['combsub', 'sins'])
+def test_headline_shape_properties(model):
+    """B=64 x 10 s (F=862), the headline batch: a clip re-synthesised alone agrees to the last ulp or
+    two (clips are independent; the 4-frame overlap-add is associated per run, and the run length
+    depends on the batch size, so unlike CombSubFast the match is not bitwise), repeated runs are
+    bitwise identical, and one clip matches the oracle."""
+    B, F = 64, 862
+    run = run_combsub if model == 'combsub' else run_sins
+    d = make_inputs(B, F, sum(SPLITS[model]), seed=1234, zero_f0_fraction=0.02)
+    sig, _, harm, noise = run(d['ctrl'], d['f0_frames'], d['U'])
+    assert np.all(np.isfinite(sig))
+    sig2, *_ = run(d['ctrl'], d['f0_frames'], d['U'])
+    assert np.array_equal(sig, sig2)                       # deterministic (two-addend atomics at run seams)
+    for b in (0, 63):
+        one, *_ = run(d['ctrl'][b:b + 1], d['f0_frames'][b:b + 1], d['U'][b:b + 1])
+        assert np.abs(sig[b] - one[0]).max() < 2e-6, b
+    b = 17
+    a, c, e = SPLITS[model]
+    fwd = O.combsub_forward if model == 'combsub' else O.sins_forward
+    ref = fwd(d['ctrl'][b:b + 1, :, :a], d['ctrl'][b:b + 1, :, a:a + c], d['ctrl'][b:b + 1, :, a + c:],
+              d['f0_frames'][b:b + 1], d['U'][b:b + 1])
+    err, s = assert_waveform(sig[b:b + 1], ref[0], what=f'{model} headline clip 17')
+    assert err < 5e-5 and s > 75, (err, s)
