@@ -53,7 +53,10 @@ def lib():
     global _lib
     if _lib is None:
         path = _build.LIB
-        if not os.path.exists(path) or (_build.is_stale() and os.environ.get('DDSP_B200_NO_REBUILD') != '1'):
+        override = os.environ.get('DDSP_B200_LIB')           # experiments: load a differently built library
+        if override:
+            path = override
+        elif not os.path.exists(path) or (_build.is_stale() and os.environ.get('DDSP_B200_NO_REBUILD') != '1'):
             try:
                 path = _build.build()
             except Exception as e:                       # no nvcc on this box: use the shipped .so if any

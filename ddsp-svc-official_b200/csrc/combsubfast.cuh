@@ -150,6 +150,10 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
     const bool lane0 = lane == 0;
 
     Pts32 X;
+    // De-phase the four warps that share a scheduler (wid, wid+4, wid+8, wid+12) by 2 us each so that
+    // their FMA-heavy FFT phases do not start in lockstep (measured: -2 % on the 12-pairs-per-warp
+    // headline launch); skipped for short runs where it would only add latency.
+    if (P.run_len >= 4) __nanosleep((unsigned)(wid >> 2) * 2000u);
 
     // steps per pair: s=0 frame 2p, s=1 frame 2p+1, s=2 inverse FFT of the pair + overlap-add.
     // s=-1 (first iteration only) just generates the first hop of the run.
