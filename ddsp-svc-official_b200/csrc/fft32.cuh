@@ -82,10 +82,11 @@ __device__ __forceinline__ void dit_stage2(Pts32& P) {
                 P.R[i1] = fma2(t1, bc2(-Rq), ar); P.I[i1] = fma2(t2, bc2(Rq), ai);
             } else {                                    // w b = (c br + s bi) + j(c bi - s br)
                 const float c = cos32(tw), s = sin32(tw);
-                P.R[i0] = fma2(br, bc2(c), fma2(bi, bc2(s), ar));
-                P.I[i0] = fma2(bi, bc2(c), fma2(br, bc2(-s), ai));
-                P.R[i1] = fma2(br, bc2(-c), fma2(bi, bc2(-s), ar));
-                P.I[i1] = fma2(bi, bc2(-c), fma2(br, bc2(s), ai));
+                const float2 xr = fma2(br, bc2(c), fma2(bi, bc2(s), ar));
+                const float2 xi = fma2(bi, bc2(c), fma2(br, bc2(-s), ai));
+                P.R[i0] = xr; P.I[i0] = xi;
+                P.R[i1] = fma2(ar, bc2(2.0f), neg2(xr));      // a - w b = 2a - (a + w b)
+                P.I[i1] = fma2(ai, bc2(2.0f), neg2(xi));
             }
         }
     }
@@ -132,7 +133,7 @@ __device__ __forceinline__ void fft32_dit(Pts32& P) {
 // Same, but every element n is first multiplied by this lane's twiddle W1024^(n*lane).  The
 // packed position i holds elements (e, e+1), e = brev5(i); `tw4[(e/2)*32 + lane]` delivers
 // (cos e, cos e+1, -sin e, -sin e+1) in one 128-bit load.  The multiply is folded into the span-1
-// butterflies (12 packed ops per two butterflies).
+// butterflies (10 packed ops per two butterflies).
 __device__ __forceinline__ void fft32_dit_twiddled(Pts32& P, const float4* __restrict__ tw4, int lane) {
 #pragma unroll
     for (int i0 = 0; i0 < 16; i0 += 2) {
@@ -144,10 +145,12 @@ __device__ __forceinline__ void fft32_dit_twiddled(Pts32& P, const float4* __res
         const float2 Ar = P.R[i0], Ai = P.I[i0], Br = P.R[i0 + 1], Bi = P.I[i0 + 1];
         const float2 ar = fma2(neg2(Ai), way, mul2(Ar, wax));       // a = wa * A
         const float2 ai = fma2(Ar, way, mul2(Ai, wax));
-        P.R[i0] = fma2(Br, wbx, fma2(neg2(Bi), wby, ar));           // a + wb * B
-        P.I[i0] = fma2(Br, wby, fma2(Bi, wbx, ai));
-        P.R[i0 + 1] = fma2(neg2(Br), wbx, fma2(Bi, wby, ar));       // a - wb * B
-        P.I[i0 + 1] = fma2(neg2(Br), wby, fma2(neg2(Bi), wbx, ai));
+        const float2 xr = fma2(Br, wbx, fma2(neg2(Bi), wby, ar));   // a + wb * B
+        const float2 xi = fma2(Br, wby, fma2(Bi, wbx, ai));
+        P.R[i0] = xr;
+        P.I[i0] = xi;
+        P.R[i0 + 1] = fma2(ar, bc2(2.0f), neg2(xr));                // a - wb * B = 2a - (a + wb * B)
+        P.I[i0 + 1] = fma2(ai, bc2(2.0f), neg2(xi));
     }
     dit_stage2<2>(P);
     dit_stage2<4>(P);
