@@ -52,9 +52,9 @@ def recorded_traffic(model):
 
 
 # FP32 work of the CombSubFast kernel: FMA-pipe operations per frame pair counted from the ncu source
-# page (profiles/r01_ncu_combsubfast_v6.txt): scalar FFMA+FMUL+FADD 2253 + IMAD 134 + packed fp32x2
-# 1128 (each occupies the pipe like two scalar ops) = 4643 warp-level FMA-pipe slots per pair.
-CSF_FMA_SLOTS_PER_PAIR = 4643
+# page (profiles/r01_ncu_combsubfast_v8.txt): scalar FFMA+FMUL+FADD 2003 + IMAD 130 + packed fp32x2
+# 1032 (each occupies the pipe like two scalar ops) = 4197 warp-level FMA-pipe slots per pair.
+CSF_FMA_SLOTS_PER_PAIR = 4197
 
 
 def fp32_roofline(model, B, F, kern_ms, clocks):
@@ -67,7 +67,7 @@ def fp32_roofline(model, B, F, kern_ms, clocks):
     return {'fp32_pipe_frac': ach / peak_slots,
             'fp32_tflops_fma2': ach * 32 * 2 / 1e12, 'fp32_peak_tflops': peak_slots * 32 * 2 / 1e12,
             'note': 'the kernel is FP32-pipe / issue bound, not HBM bound: at 100 % FP32-pipe utilisation it would '
-                    'reach ~0.6 of the HBM roofline'}
+                    'reach ~0.67 of the HBM roofline'}
 
 
 class ClockSampler:
