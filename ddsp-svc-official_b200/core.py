@@ -283,5 +283,22 @@ def sins_stage(amplitudes, group_delay, noise_magnitude, f0_frames, phase, block
     return signal, harmonic, noise
 
 
+def apply_frame_mask_(signal, mask_frames, block_size=512):
+    """In place `signal *= upsample(mask_frames, block_size).squeeze(-1)` -- the silence-mask epilogue of
+    main.py:112-116,159 and gui.py:108-112,127 -- in one pass, without the (B,T) mask tensor.
+    signal (B,T) fp32 contiguous; mask_frames (B,F) or (B,F,1)."""
+    signal = _need_cuda_f32(signal, 'signal')
+    if not signal.is_contiguous():
+        raise ValueError('signal must be contiguous (it is modified in place)')
+    m = _f0_2d(mask_frames)
+    B, F = m.shape
+    if tuple(signal.shape) != (B, F * int(block_size)):
+        raise ValueError('signal must be (B, Frame*block_size)')
+    with torch.cuda.device(signal.device):
+        _cabi.check(_cabi.lib().ddsp_b200_apply_frame_mask(signal.data_ptr(), m.data_ptr(), m.stride(0), m.stride(1),
+                                                           B, F, int(block_size), _stream()))
+    return signal
+
+
 def last_launch_count():
     return _cabi.lib().ddsp_b200_last_launch_count()

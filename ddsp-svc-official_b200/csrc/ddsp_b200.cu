@@ -336,6 +336,18 @@ int launch_add(const float* a, const float* b, float* out, int64_t n, cudaStream
 
 extern "C" {
 
+int ddsp_b200_apply_frame_mask(float* signal, const float* mask_frames, int64_t mB, int64_t mF, int B, int F, int hop,
+                               void* stream) {
+    g_launches = 0;
+    if (!signal || !mask_frames || B <= 0 || F <= 0 || ((uintptr_t)signal & 15)) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (hop != ddsp::kHop) return DDSP_B200_ERR_UNSUPPORTED;
+    const int64_t n4 = (int64_t)B * F * (hop / 4);
+    ddsp::apply_frame_mask_kernel<<<(unsigned)grid_for(n4, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4*>(signal), mask_frames, mB, mF, B, F);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
 size_t ddsp_b200_frequency_filter_workspace_bytes(int B, int F, int n_mag) {
     (void)n_mag;
     if (B <= 0 || F <= 0) return 0;

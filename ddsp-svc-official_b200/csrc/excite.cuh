@@ -112,6 +112,27 @@ __global__ void __launch_bounds__(128) sins_osc_kernel(const float* __restrict__
     }
 }
 
+// Caller-side epilogue of main.py:116,159 / gui.py:112,127 fused:  signal *= upsample(mask_frames, hop)
+// without materialising the (B,T) mask.  One thread per 4 consecutive samples (same frame).
+__global__ void __launch_bounds__(256) apply_frame_mask_kernel(float4* __restrict__ signal,
+                                                               const float* __restrict__ mask_frames, int64_t mB,
+                                                               int64_t mF, int B, int F) {
+    const int64_t n4 = (int64_t)B * F * (kHop / 4);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t hop_id = i / (kHop / 4);
+        const int j = (int)(i % (kHop / 4)) * 4;
+        const int b = (int)(hop_id / F), h = (int)(hop_id % F);
+        const float* row = mask_frames + (int64_t)b * mB;
+        const float x0 = __ldg(row + (int64_t)h * mF), x1 = __ldg(row + (int64_t)min(h + 1, F - 1) * mF);
+        float4 v = signal[i];
+        v.x = __fmul_rn(v.x, lerp_torch(x0, x1, (float)(j + 0) * (1.0f / kHop)));
+        v.y = __fmul_rn(v.y, lerp_torch(x0, x1, (float)(j + 1) * (1.0f / kHop)));
+        v.z = __fmul_rn(v.z, lerp_torch(x0, x1, (float)(j + 2) * (1.0f / kHop)));
+        v.w = __fmul_rn(v.w, lerp_torch(x0, x1, (float)(j + 3) * (1.0f / kHop)));
+        signal[i] = v;
+    }
+}
+
 __global__ void __launch_bounds__(256) add_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                                   float4* __restrict__ out, int64_t n4) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {

@@ -154,6 +154,14 @@ int ddsp_b200_sins(const float *amplitudes, int n_harmonics, const float *group_
                    int hop, double sr, float *signal, float *harmonic, float *noise,
                    void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Caller-side epilogue, fused:  signal *= upsample(mask_frames, hop)   main.py:116,159  gui.py:112,127
+ * signal (B,T) contiguous, modified in place; mask_frames (B,F) strides (mB,mF).  Bit-identical to
+ * `signal * upsample(mask)[...,0]` of the reference without materialising the (B,T) mask.
+ * ---------------------------------------------------------------------------------------- */
+int ddsp_b200_apply_frame_mask(float *signal, const float *mask_frames, int64_t mB, int64_t mF, int B,
+                               int F, int hop, void *stream);
+
 /* Number of kernel launches the last call of each entry point enqueued on this thread
  * (bench.py reports it as gpu_launches). */
 int ddsp_b200_last_launch_count(void);

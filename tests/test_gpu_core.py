@@ -154,3 +154,18 @@ def test_phase_stage_two_kernel_path_equals_fused():
     pf2, pre2, _ = core.phase_stage(dev(f0), 512, 44100)          # B=2, F=3000 -> spread path
     ref = O.stage_a(f0, 44100, 512)[2]
     assert _wrapped_err(pf2.cpu().numpy(), ref) <= 4e-7
+
+
+def test_apply_frame_mask_bit_exact():
+    """signal *= upsample(mask) (main.py:116,159) fused: bit-identical to the two-op reference form."""
+    g = torch.Generator().manual_seed(9)
+    B, F = 3, 41
+    sig = torch.randn(B, F * 512, generator=g).cuda()
+    mask = (torch.rand(B, F, generator=g) > 0.4).float().cuda()
+    ref = sig * core.upsample(mask[..., None], 512)[..., 0]
+    out = core.apply_frame_mask_(sig.clone(), mask[..., None])
+    assert torch.equal(out, ref)
+    xp = mask[:, None, :]
+    up = torch.nn.functional.interpolate(torch.cat((xp, xp[:, :, -1:]), 2), size=F * 512 + 1, mode='linear',
+                                         align_corners=True)[:, 0, :-1]
+    assert torch.equal(out, sig * up)
