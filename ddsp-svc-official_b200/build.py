@@ -33,21 +33,36 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
-    """Compile if the library is missing or older than its sources.  Returns the .so path."""
+    """Compile if the library is missing or older than its sources.  Returns the .so path.
+
+    Safe under concurrent callers (e.g. 8 torchrun ranks importing at once): an flock serialises
+    the builders, late comers re-check staleness, and the library is moved into place atomically."""
     if not force and not is_stale():
         return LIB
+    import fcntl
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-           '-Xcompiler', '-fPIC', '-shared', '-Xptxas', '-v', '-I', INCLUDE,
-           '-o', LIB, os.path.join(CSRC, 'ddsp_b200.cu')]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    with open(os.path.join(LIBDIR, 'build.log'), 'w') as f:
-        f.write(' '.join(cmd) + '\n' + log)
-    if res.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + log)
-    if verbose:
-        print(log)
+    with open(os.path.join(LIBDIR, '.build.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():
+                return LIB
+            tmp = f'{LIB}.tmp.{os.getpid()}'
+            cmd = [_nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+                   '-Xcompiler', '-fPIC', '-shared', '-Xptxas', '-v', '-I', INCLUDE,
+                   '-o', tmp, os.path.join(CSRC, 'ddsp_b200.cu')]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            log = res.stdout + res.stderr
+            with open(os.path.join(LIBDIR, 'build.log'), 'w') as f:
+                f.write(' '.join(cmd) + '\n' + log)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError('nvcc failed:\n' + log)
+            os.replace(tmp, LIB)
+            if verbose:
+                print(log)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
