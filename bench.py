@@ -460,6 +460,53 @@ def run_latency(args):
                       'iters': args.latency_iters, 'rows': rows}), flush=True)
 
 
+def run_forward(args):
+    """Whole-module forward (stage A -> Unit2Control -> stage B) with the PyTorch control network of
+    ddsp_b200.control (random init): throughput at the headline batch and CUDA-graph replay latency
+    at the streaming sizes.  Reported beside the synth-only numbers; the control network is stock
+    PyTorch ops (SURVEY §8f rank 1 is the next row)."""
+    import torch
+    from ddsp_b200 import vocoder
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    torch.manual_seed(1234)
+    model = vocoder.CombSubFast(SR, HOP, n_unit=256, n_spk=100).to(dev).eval()
+    rows = []
+    for (B, F, iters) in [(1, 9, 300), (1, 26, 300), (1, 130, 300), (64, 862, 10)]:
+        units = torch.randn(B, F, 256, device=dev)
+        f0 = torch.rand(B, F, 1, device=dev) * 300 + 100
+        vol = torch.rand(B, F, device=dev)
+        spk = torch.ones(B, 1, dtype=torch.long, device=dev)
+        with torch.no_grad():
+            for _ in range(3):
+                model(units, f0, vol, spk)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                model(units, f0, vol, spk)
+            e1.record()
+            torch.cuda.synchronize()
+            eager_ms = e0.elapsed_time(e1) / iters
+            g = torch.cuda.CUDAGraph()
+            s_ = torch.cuda.Stream()
+            s_.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_):
+                model(units, f0, vol, spk)
+                with torch.cuda.graph(g, stream=s_):
+                    out = model(units, f0, vol, spk)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(iters):
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); g.replay(); b_.record(); b_.synchronize()
+                ts.append(a.elapsed_time(b_))
+        rows.append({'clips': B, 'frames': F, 'eager_ms': eager_ms, 'graph_ms_p50': float(np.percentile(ts, 50)),
+                     'graph_ms_p99': float(np.percentile(ts, 99)), 'samples_per_s_graph': B * F * HOP / (np.percentile(ts, 50) * 1e-3)})
+    print(json.dumps({'metric': 'full forward (stage A + PyTorch Unit2Control + stage B)', 'model': 'combsubfast',
+                      'rows': rows}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -473,12 +520,15 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--torch-port', action='store_true',
                     help='also time the stock-PyTorch-ops restatement of the path on the same GPU (CombSubFast)')
-    ap.add_argument('--mode', default='throughput', choices=['throughput', 'latency'])
+    ap.add_argument('--mode', default='throughput', choices=['throughput', 'latency', 'forward'])
     ap.add_argument('--latency-frames', default='9,18,26,130')
     ap.add_argument('--latency-iters', type=int, default=1000)
     args = ap.parse_args()
     if args.mode == 'latency':
         run_latency(args)
+        return
+    if args.mode == 'forward':
+        run_forward(args)
         return
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))

@@ -1,0 +1,178 @@
+"""Control network (first step): a plain-PyTorch `Unit2Control` that is
+state_dict-compatible with the reference's `ddsp/unit2control.py` + `ddsp/pcmer.py`, so that the
+drop-in synthesizer modules are usable (and reference checkpoints load with `strict=True`) without
+the reference repo and its un-vendored dependencies (`extorch`, `pytorch-fast-transformers`).
+
+This is NOT part of the hand-written hot path: it runs stock PyTorch ops (cuBLAS / cuDNN), exactly
+like the reference's own control network, and exists so that the full `forward` can be measured
+and CUDA-graphed end to end.  Only the non-causal configuration (`c: false`, the value in every
+shipped config) is implemented.
+
+Structure (the module / parameter names are dictated by the checkpoint layout):
+    unit_prenet : T - Conv1d(k3) - GroupNorm(4) - LeakyReLU - Conv1d(k3) - T        unit2control.py:38-45
+    f0/phase/volume_embed : Linear(1, 256);  spk_embed : Embedding                  :50-53
+    dec_post    : PCmer(3 layers, 8 heads) - LayerNorm - weight_norm(Linear)         :56-62
+    PCmer layer : x + Attn(LN(x));  x + ConvModule(x)                                pcmer.py:20-37
+    Attn        : Performer (FAVOR+) softmax-kernel linear attention, 266 features   pcmer.py:69-78,124-160,191-251
+    ConvModule  : LN - T - Conv1x1(256->1024) - GLU - depthwise Conv(k31) - SiLU - Conv1x1(512->256) - T   pcmer.py:41-63
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn.utils import weight_norm
+
+_DIM = 256
+_HEADS = 8
+_DIM_HEAD = 64
+
+
+class _Swap(nn.Module):
+    """(B, T, C) <-> (B, C, T); parameter-free, occupies a slot in the Sequential like the reference's Transpose."""
+
+    def __init__(self, a, b):
+        super().__init__()
+        self.a, self.b = a, b
+
+    def forward(self, x):
+        return x.transpose(self.a, self.b)
+
+
+def _orthogonal_gaussian_features(n_rows, n_cols):
+    """Random-feature matrix for FAVOR+: stacked Q factors of Gaussian blocks, rows rescaled to the
+    norms of Gaussian vectors (pcmer.py:80-120 with scaling=0).  Only used for fresh initialisation;
+    checkpoints carry their own `projection_matrix` buffer."""
+    blocks, left = [], n_rows
+    while left > 0:
+        q, _ = torch.linalg.qr(torch.randn(n_cols, n_cols), mode='reduced')
+        blocks.append(q.t()[:min(left, n_cols)])
+        left -= n_cols
+    mat = torch.cat(blocks)
+    return torch.randn(n_rows, n_cols).norm(dim=1).unsqueeze(1) * mat
+
+
+def _softmax_features(x, proj, is_query, eps=1e-4):
+    """Positive random features approximating the softmax kernel (pcmer.py:124-160).  x: (B,H,N,D)."""
+    d = x.shape[-1]
+    scale = d ** -0.25
+    ratio = proj.shape[0] ** -0.5
+    dash = torch.einsum('bhnd,jd->bhnj', scale * x, proj.to(x.dtype))
+    diag = (x * x).sum(dim=-1, keepdim=True) * (0.5 * scale * scale)
+    if is_query:
+        return ratio * (torch.exp(dash - diag - dash.amax(dim=-1, keepdim=True)) + eps)
+    return ratio * torch.exp(dash - diag + eps)
+
+
+class _FastAttention(nn.Module):
+    def __init__(self, dim_head):
+        super().__init__()
+        n_features = int(dim_head * math.log(dim_head))
+        self.register_buffer('projection_matrix', _orthogonal_gaussian_features(n_features, dim_head))
+
+    def forward(self, q, k, v):
+        q = _softmax_features(q, self.projection_matrix, True)
+        k = _softmax_features(k, self.projection_matrix, False)
+        # non-causal linear attention (pcmer.py:69-78)
+        k_sum = k.sum(dim=-2)
+        d_inv = 1.0 / (torch.einsum('bhnj,bhj->bhn', q, k_sum) + 1e-8)
+        context = torch.einsum('bhnj,bhne->bhje', k, v)
+        return torch.einsum('bhje,bhnj,bhn->bhne', context, q, d_inv)
+
+
+class _SelfAttention(nn.Module):
+    def __init__(self, dim, heads):
+        super().__init__()
+        inner = _DIM_HEAD * heads
+        self.heads = heads
+        self.fast_attention = _FastAttention(_DIM_HEAD)
+        self.to_q = nn.Linear(dim, inner)
+        self.to_k = nn.Linear(dim, inner)
+        self.to_v = nn.Linear(dim, inner)
+        self.to_out = nn.Linear(inner, dim)
+
+    def forward(self, x):
+        b, n, _ = x.shape
+        split = lambda t: t.view(b, n, self.heads, _DIM_HEAD).transpose(1, 2)      # noqa: E731
+        out = self.fast_attention(split(self.to_q(x)), split(self.to_k(x)), split(self.to_v(x)))
+        return self.to_out(out.transpose(1, 2).reshape(b, n, self.heads * _DIM_HEAD))
+
+
+class _ConvModule(nn.Module):
+    def __init__(self, dim, expansion=2, kernel_size=31):
+        super().__init__()
+        inner = dim * expansion
+        self.net = nn.Sequential(
+            nn.LayerNorm(dim),
+            _Swap(1, 2),
+            nn.Conv1d(dim, inner * 2, 1),
+            nn.GLU(dim=1),
+            nn.Conv1d(inner, inner, kernel_size, padding='same', groups=inner),
+            nn.SiLU(),
+            nn.Conv1d(inner, dim, 1),
+            _Swap(1, 2),
+            nn.Dropout(0.0),
+        )
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class _EncoderLayer(nn.Module):
+    def __init__(self, heads, dim):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.attn = _SelfAttention(dim, heads)
+        self.local_mixer = _ConvModule(dim)
+
+    def forward(self, x):
+        x = x + self.attn(self.norm(x))
+        return x + self.local_mixer(x)
+
+
+class PCmer(nn.Module):
+    def __init__(self, num_layers, num_heads, dim_model):
+        super().__init__()
+        self.net = nn.Sequential(*[_EncoderLayer(num_heads, dim_model) for _ in range(num_layers)])
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class Unit2Control(nn.Module):
+    """`Unit2Control(n_unit, n_spk, output_splits, c=False)` -- same call signature and return value
+    (dict of strided `torch.split` views of one (B, Frame, sum K) tensor) as unit2control.py:23-101."""
+
+    def __init__(self, ndim_feat_i, n_spk, output_splits, c=False):
+        super().__init__()
+        if c:
+            raise NotImplementedError('causal control network (c: true) is not implemented; no shipped config uses it')
+        self.unit_prenet = nn.Sequential(
+            _Swap(1, 2),
+            nn.Conv1d(ndim_feat_i, _DIM, 3, padding='same'),
+            nn.GroupNorm(4, _DIM),
+            nn.LeakyReLU(),
+            nn.Conv1d(_DIM, _DIM, 3, padding='same'),
+            _Swap(1, 2),
+        )
+        self.f0_embed = nn.Linear(1, _DIM)
+        self.phase_embed = nn.Linear(1, _DIM)
+        self.volume_embed = nn.Linear(1, _DIM)
+        self.spk_embed = nn.Embedding(n_spk, _DIM)
+        n_out = sum(output_splits.values())
+        self.dec_post = nn.Sequential(PCmer(3, _HEADS, _DIM), nn.LayerNorm(_DIM), weight_norm(nn.Linear(_DIM, n_out)))
+        self.output_splits = dict(output_splits)
+
+    def forward(self, units, f0, phase, volume, spk_id, spk_mix_dict=None):
+        x = self.unit_prenet(units)
+        x = x + self.f0_embed((1 + f0 / 700).log()) + self.phase_embed(phase.unsqueeze(-1) / math.pi) \
+            + self.volume_embed(volume.unsqueeze(-1))
+        if spk_mix_dict is not None:                     # weighted mix of speaker embeddings (unit2control.py:89-93)
+            for k, v in spk_mix_dict.items():
+                idx = torch.tensor([[int(k) - 1]], dtype=torch.long, device=units.device)
+                x = x + v * self.spk_embed(idx)
+        else:
+            x = x + self.spk_embed(spk_id - 1)
+        e = self.dec_post(x)
+        names, sizes = list(self.output_splits), list(self.output_splits.values())
+        return dict(zip(names, torch.split(e, sizes, dim=-1)))

@@ -2,9 +2,10 @@
 state_dict keys as the reference's `ddsp/vocoder.py:343-550`, with the DSP (everything except
 `Unit2Control`) running as hand-written sm_100a kernels.
 
-`unit2ctrl` (the control network, out of scope for this path) is the reference's own
-`ddsp.unit2control.Unit2Control` when the reference repo is importable, or any module passed as
-`unit2ctrl=` with the same call signature returning the dict of control tensors.
+`unit2ctrl` (the control network, not part of the hand-written path) is the reference's own
+`ddsp.unit2control.Unit2Control` when the reference repo is importable, else the state_dict-compatible
+PyTorch re-statement `ddsp_b200.control.Unit2Control`, or any module passed as `unit2ctrl=` with the
+same call signature returning the dict of control tensors.
 """
 import os
 
@@ -26,13 +27,13 @@ class DotDict(dict):
 
 
 def _make_unit2ctrl(n_unit, n_spk, output_splits, c):
+    """The control network is the reference's own `ddsp.unit2control.Unit2Control` when the reference
+    repo (and its extorch / fast-transformers dependencies) is importable; otherwise the
+    state_dict-compatible plain-PyTorch re-statement in `ddsp_b200.control`."""
     try:
         from ddsp.unit2control import Unit2Control      # the reference's control network
-    except Exception as e:                               # pragma: no cover - depends on the host repo
-        raise ImportError(
-            'ddsp_b200 replaces the synthesizer DSP only; the control network `Unit2Control` is the '
-            'reference\'s (ddsp/unit2control.py). Put the reference repo on sys.path or pass '
-            '`unit2ctrl=<module>` to the constructor.') from e
+    except Exception:
+        from .control import Unit2Control
     return Unit2Control(n_unit, n_spk, output_splits, c)
 
 

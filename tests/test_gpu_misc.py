@@ -114,3 +114,26 @@ def test_state_dict_keys_and_load_model(tmp_path):
         cfg = tmp_path / 'config.yaml'
         cfg.write_text('data:\n  sampling_rate: 44100\n  block_size: 512\n  encoder_out_channels: 4\nmodel:\n  type: Nope\n  n_spk: 1\n  c: false\n')
         vocoder.load_model(str(tmp_path / 'model_0.pt'))
+
+
+def test_full_module_forward_with_builtin_control_network():
+    """CombSubFast with the PyTorch control network of ddsp_b200.control: the synthesizer output must
+    equal the stock-PyTorch op sequence fed with the same control tensors (captured by a hook)."""
+    from oracle import torch_port as T
+    torch.manual_seed(5)
+    model = vocoder.CombSubFast(44100, 512, n_unit=32, n_spk=3).cuda().eval()
+    assert type(model.unit2ctrl).__module__.endswith('control')
+    B, F = 2, 40
+    units = torch.randn(B, F, 32).cuda()
+    f0 = (torch.rand(B, F, 1) * 300 + 100).cuda()
+    vol = torch.rand(B, F).cuda()
+    spk = torch.tensor([[1], [3]]).cuda()
+    U = torch.rand(B, F * 512).cuda()
+    cap = {}
+    model.unit2ctrl.register_forward_hook(lambda m, i, o: cap.update(o))
+    with torch.no_grad():
+        sig, pf, _ = model(units, f0, vol, spk, noise_u=U)
+        ref, pf_ref = T.combsubfast_forward(cap['harmonic_magnitude'], cap['harmonic_phase'], cap['noise_magnitude'],
+                                            f0, model.window, noise_u=U)
+    assert (sig - ref).abs().max().item() < 3e-5
+    assert (pf[..., 0] - pf_ref).abs().max().item() < 1e-6
