@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
         float4* dst = reinterpret_cast<float4*>(smem_raw);
         for (int e = threadIdx.x; e < kTableBytes / 16; e += kCsfThreads) dst[e] = __ldg(src + e);
         __syncthreads();
+        cudaGridDependencySynchronize();      // launched with programmatic stream serialisation (see ddsp_b200.cu)
         if (P.window) {
             for (int e = threadIdx.x; e < 1024; e += kCsfThreads) win[e] = __ldg(P.window + e);
             __syncthreads();

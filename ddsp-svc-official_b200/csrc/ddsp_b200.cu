@@ -262,10 +262,18 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
                                                                                 n_seams);
         LAUNCH_CHECK();
     }
-    if (noise_u)
-        ddsp::combsubfast_kernel<true><<<grid, ddsp::kCsfThreads, ddsp::kCsfSmemBytes, (cudaStream_t)stream>>>(P);
-    else
-        ddsp::combsubfast_kernel<false><<<grid, ddsp::kCsfThreads, ddsp::kCsfSmemBytes, (cudaStream_t)stream>>>(P);
+    // Programmatic dependent launch: the CTAs may be scheduled and stage their tables while the
+    // preceding kernel (seam zeroing / stage A) drains; they wait in cudaGridDependencySynchronize()
+    // before touching anything a previous kernel wrote.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(ddsp::kCsfThreads);
+    cfg.dynamicSmemBytes = ddsp::kCsfSmemBytes; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (noise_u) CUDA_TRY(cudaLaunchKernelEx(&cfg, ddsp::combsubfast_kernel<true>, P));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, ddsp::combsubfast_kernel<false>, P));
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }
