@@ -14,8 +14,27 @@ from . import _cabi
 _TWO62 = 1 << 62
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+class _OnDevice:
+    """`with _OnDevice(dev) as stream:` -- makes `dev` current only when it is not already (the
+    torch.cuda.device context manager and torch.cuda.current_stream() cost ~15 us per call, more than
+    a streaming-size synthesis itself) and yields the raw handle of torch's current stream on it."""
+    __slots__ = ('idx', 'prev')
+
+    def __init__(self, dev):
+        self.idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.prev = -1
+
+    def __enter__(self):
+        cur = torch._C._cuda_getDevice()
+        if cur != self.idx:
+            self.prev = cur
+            torch._C._cuda_setDevice(self.idx)
+        return torch._C._cuda_getCurrentRawStream(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch._C._cuda_setDevice(self.prev)
+        return False
 
 
 def _need_cuda_f32(t, name):
@@ -47,9 +66,9 @@ def upsample(signal, factor):
     B, F, Cc = signal.shape
     factor = int(factor)
     y = torch.empty((B, F * factor, Cc), dtype=torch.float32, device=signal.device)
-    with torch.cuda.device(signal.device):
+    with _OnDevice(signal.device) as _st:
         _cabi.check(_cabi.lib().ddsp_b200_upsample(signal.data_ptr(), signal.stride(0), signal.stride(1),
-                                                   signal.stride(2), B, F, Cc, factor, y.data_ptr(), _stream()))
+                                                   signal.stride(2), B, F, Cc, factor, y.data_ptr(), _st))
     return y
 
 
@@ -61,9 +80,9 @@ def fo_to_rot(fo, sr, initial_phase=None, precise=False):
     ws = torch.empty(max(1, L.ddsp_b200_fo_to_rot_workspace_bytes(B, T)), dtype=torch.uint8, device=fo.device)
     ip = None if initial_phase is None else _need_cuda_f32(initial_phase.to(fo.device, torch.float32), 'initial_phase').contiguous()
     rot = torch.empty_like(fo)
-    with torch.cuda.device(fo.device):
+    with _OnDevice(fo.device) as _st:
         _cabi.check(L.ddsp_b200_fo_to_rot(fo.data_ptr(), B, T, float(sr), _ptr(ip), int(bool(precise)),
-                                          rot.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+                                          rot.data_ptr(), ws.data_ptr(), ws.numel(), _st))
     return rot
 
 
@@ -76,10 +95,10 @@ def remove_above_fmax(amplitudes, pitch, fmax, level_start=1):
     B, F, K = amplitudes.shape
     p2 = pitch.reshape(B, F)
     out = torch.empty((B, F, K), dtype=torch.float32, device=amplitudes.device)
-    with torch.cuda.device(amplitudes.device):
+    with _OnDevice(amplitudes.device) as _st:
         _cabi.check(_cabi.lib().ddsp_b200_remove_above_fmax(
             amplitudes.data_ptr(), amplitudes.stride(0), amplitudes.stride(1), p2.data_ptr(), p2.stride(0),
-            p2.stride(1), float(fmax), int(level_start), B, F, K, out.data_ptr(), _stream()))
+            p2.stride(1), float(fmax), int(level_start), B, F, K, out.data_ptr(), _st))
     return out
 
 
@@ -119,11 +138,11 @@ def phase_stage(f0_frames, block_size, sampling_rate, initial_phase=None, infer=
     prefix = torch.empty((B, F), dtype=torch.float64, device=dev)
     phase_full = torch.empty((B, F * hop), dtype=torch.float32, device=dev) if full_rate else None
     ip = _init_phase(initial_phase, B, dev)
-    with torch.cuda.device(dev):
+    with _OnDevice(dev) as _st:
         _cabi.check(_cabi.lib().ddsp_b200_phase(f0.data_ptr(), f0.stride(0), f0.stride(1), B, F, hop,
                                                 float(sampling_rate), _ptr(ip), int(bool(infer)),
                                                 phase_frames.data_ptr(), prefix.data_ptr(), _ptr(phase_full),
-                                                _stream()))
+                                                _st))
     return phase_frames, prefix, phase_full
 
 
@@ -162,11 +181,11 @@ def combsubfast_stage(harmonic_magnitude, harmonic_phase, noise_magnitude, f0_fr
             raise ValueError('window must have 2*block_size entries')
     ip = _init_phase(initial_phase, B, dev)
     signal = out if out is not None else torch.empty((B, T), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _OnDevice(dev) as _st:
         _cabi.check(_cabi.lib().ddsp_b200_combsubfast(
             hm.data_ptr(), hp.data_ptr(), nm.data_ptr(), hm.stride(0), hm.stride(1), f0.data_ptr(), f0.stride(0),
             f0.stride(1), prefix.data_ptr(), _ptr(ip), _ptr(noise_u), int(seed) % _TWO62, _ptr(window), B, F, hop,
-            float(sampling_rate), signal.data_ptr(), _stream()))
+            float(sampling_rate), signal.data_ptr(), _st))
     return signal
 
 
@@ -216,11 +235,11 @@ def frequency_filter(audio, magnitudes, hann_window=True, half_width_frames=None
     out = torch.empty_like(audio)
     L = _cabi.lib()
     ws = torch.empty(L.ddsp_b200_frequency_filter_workspace_bytes(B, F, n_mag), dtype=torch.uint8, device=audio.device)
-    with torch.cuda.device(audio.device):
+    with _OnDevice(audio.device) as _st:
         _cabi.check(L.ddsp_b200_frequency_filter(
             audio.data_ptr(), mags.data_ptr(), mags.stride(0), mags.stride(1), n_mag, encoding, float(mag_scale),
             window, _ptr(f0), 0 if f0 is None else f0.stride(0), 0 if f0 is None else f0.stride(1),
-            float(sampling_rate), B, F, 512, out.data_ptr(), 0, ws.data_ptr(), ws.numel(), _stream()))
+            float(sampling_rate), B, F, 512, out.data_ptr(), 0, ws.data_ptr(), ws.numel(), _st))
     return out
 
 
@@ -248,12 +267,12 @@ def combsub_stage(group_delay, harmonic_magnitude, noise_magnitude, f0_frames, p
     ws = torch.empty(L.ddsp_b200_combsub_workspace_bytes(B, F, gd.shape[-1], hm.shape[-1], nm.shape[-1]),
                      dtype=torch.uint8, device=dev)
     signal, harmonic, noise = (torch.empty((B, T), dtype=torch.float32, device=dev) for _ in range(3))
-    with torch.cuda.device(dev):
+    with _OnDevice(dev) as _st:
         _cabi.check(L.ddsp_b200_combsub(
             gd.data_ptr(), gd.shape[-1], hm.data_ptr(), hm.shape[-1], nm.data_ptr(), nm.shape[-1], gd.stride(0),
             gd.stride(1), f0.data_ptr(), f0.stride(0), f0.stride(1), prefix.data_ptr(), 0, _ptr(noise_u),
             int(seed) % _TWO62, B, F, hop, float(sampling_rate), signal.data_ptr(), harmonic.data_ptr(),
-            noise.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+            noise.data_ptr(), ws.data_ptr(), ws.numel(), _st))
     return signal, harmonic, noise
 
 
@@ -274,12 +293,12 @@ def sins_stage(amplitudes, group_delay, noise_magnitude, f0_frames, phase, block
     ws = torch.empty(L.ddsp_b200_sins_workspace_bytes(B, F, am.shape[-1], gd.shape[-1], nm.shape[-1]),
                      dtype=torch.uint8, device=dev)
     signal, harmonic, noise = (torch.empty((B, T), dtype=torch.float32, device=dev) for _ in range(3))
-    with torch.cuda.device(dev):
+    with _OnDevice(dev) as _st:
         _cabi.check(L.ddsp_b200_sins(
             am.data_ptr(), am.shape[-1], gd.data_ptr(), gd.shape[-1], nm.data_ptr(), nm.shape[-1], am.stride(0),
             am.stride(1), f0.data_ptr(), f0.stride(0), f0.stride(1), phase.data_ptr(), _ptr(noise_u),
             int(seed) % _TWO62, B, F, hop, float(sampling_rate), signal.data_ptr(), harmonic.data_ptr(),
-            noise.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+            noise.data_ptr(), ws.data_ptr(), ws.numel(), _st))
     return signal, harmonic, noise
 
 
@@ -294,9 +313,9 @@ def apply_frame_mask_(signal, mask_frames, block_size=512):
     B, F = m.shape
     if tuple(signal.shape) != (B, F * int(block_size)):
         raise ValueError('signal must be (B, Frame*block_size)')
-    with torch.cuda.device(signal.device):
+    with _OnDevice(signal.device) as _st:
         _cabi.check(_cabi.lib().ddsp_b200_apply_frame_mask(signal.data_ptr(), m.data_ptr(), m.stride(0), m.stride(1),
-                                                           B, F, int(block_size), _stream()))
+                                                           B, F, int(block_size), _st))
     return signal
 
 
