@@ -71,43 +71,52 @@ def fp32_roofline(model, B, F, kern_ms, clocks):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
-        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    """Samples SM clock, power and throttle reasons through NVML from a thread while the timed
+    region runs (every ~2 ms; nvidia-smi is too slow to start for a 50 ms region)."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+        self.sm, self.pw, self.bits = [], [], 0
+        self.stop_flag = False
+        self.t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; NVML enumerates physical devices
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(',')) else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.pw.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.gpu), '-lms', '100'], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+        if self.nv is None:
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == 'active'})
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+        if self.nv is None or self.t is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable']}
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        reasons = sorted(n for b, n in self.REASONS.items() if self.bits & b)
+        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.max_sm,
+                'power_w_max': max(self.pw) if self.pw else None, 'reasons': reasons, 'samples': len(self.sm)}
 
 
 # --------------------------------------------------------------------------------------------
