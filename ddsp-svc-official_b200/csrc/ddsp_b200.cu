@@ -63,8 +63,8 @@ LtvKernel ltv_conv_select(int amode) {
 // Immutable per-device tables (FFT twiddles + exact sqrt-Hann window; Bluestein chirps for the
 // L=510 and L=1022 impulse responses), filled on first use.
 __device__ __align__(16) float g_tables[ddsp::kTableBytes / 4];
-__device__ __align__(16) float g_chirp[2][ddsp::kChirpFloats];
-const float* g_chirp_ptr[64][2] = {{nullptr, nullptr}};
+__device__ __align__(16) float g_chirp[3][ddsp::kChirpFloats];     // L=510, L=1022, L=510 dual (K=510)
+const float* g_chirp_ptr[64][3] = {{nullptr, nullptr, nullptr}};
 
 std::mutex g_init_mutex;
 bool g_device_ready[64] = {false};
@@ -95,8 +95,10 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
                                           ddsp::kLtvConvSmemBytes));
         float* cptr = nullptr;
         CUDA_TRY(cudaGetSymbolAddress((void**)&cptr, g_chirp));
-        for (int v = 0; v < 2; ++v) {
-            const int L = v == 0 ? 510 : 1022, K = L / 2 + 1, n_out = v == 0 ? 510 : 512;
+        CUDA_TRY(cudaFuncSetAttribute(ddsp::ltv_ir_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      ddsp::kLtvDualSmemBytes));
+        for (int v = 0; v < 3; ++v) {
+            const int L = v == 1 ? 1022 : 510, K = v == 2 ? 510 : L / 2 + 1, n_out = v == 1 ? 512 : 510;
             float* base = cptr + (size_t)v * ddsp::kChirpFloats;
             ddsp::chirp_tables_kernel<<<4, 256, 0, st>>>(reinterpret_cast<float2*>(base),
                                                          reinterpret_cast<float2*>(base) + 512, L, K, n_out);
@@ -287,16 +289,16 @@ namespace {
 
 size_t ltv_spec_bytes(int B, int F) { return (size_t)B * F * ddsp::kLtvSpecFloat2 * sizeof(float2); }
 
-int launch_ltv(const float* audio, int audio_mode, uint64_t seed, const float* mags, int64_t mB, int64_t mF, int n_mag,
-               int encoding, float mag_scale, int window_mode, const float* f0_frames, int64_t fB, int64_t fF,
-               double sr, int B, int F, float* out, void* spec_ws, cudaStream_t st) {
+// Fill the parameter block shared by the IR and the convolution kernels of one filter.
+int ltv_params(ddsp::LtvParams& P, const float* audio, int audio_mode, uint64_t seed, const float* mags, int64_t mB,
+               int64_t mF, int n_mag, int encoding, float mag_scale, int window_mode, const float* f0_frames,
+               int64_t fB, int64_t fF, double sr, int B, int F, float* out, void* spec_ws, cudaStream_t st) {
     if (n_mag != 256 && n_mag != 512) return DDSP_B200_ERR_UNSUPPORTED;
     if (n_mag == 512 && (encoding == DDSP_B200_MAG_ALLPASS_TANH || encoding == DDSP_B200_MAG_COMPLEX))
         return DDSP_B200_ERR_UNSUPPORTED;     // the L=1022 path assumes real magnitudes (symmetric IR)
     if (window_mode == DDSP_B200_WINDOW_DYNAMIC && !f0_frames) return DDSP_B200_ERR_INVALID_ARGUMENT;
     if (audio_mode != 2 && (!audio || ((uintptr_t)audio & 7))) return DDSP_B200_ERR_INVALID_ARGUMENT;
     if (!spec_ws || ((uintptr_t)spec_ws & 15)) return DDSP_B200_ERR_WORKSPACE;
-    ddsp::LtvParams P;
     if (int rc = ensure_device_ready(st, &P.tw_tables)) return rc;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -312,23 +314,74 @@ int launch_ltv(const float* audio, int audio_mode, uint64_t seed, const float* m
     if (run_len > frames) run_len = frames;
     P.run_len = run_len;
     P.runs_per_clip = (frames + run_len - 1) / run_len;
-    // 1) impulse responses -> tap spectra (frames independent)
-    {
-        const int64_t n_frames = (int64_t)B * F;
-        int64_t grid = (n_frames + ddsp::kLtvWarps - 1) / ddsp::kLtvWarps;
-        if (grid > sm_count()) grid = sm_count();           // persistent: one CTA per SM, warps stride over frames
-        ltv_ir_select(encoding, window_mode)<<<(unsigned)grid, ddsp::kLtvThreads, ddsp::kLtvIrSmemBytes, st>>>(P);
-        LAUNCH_CHECK();
-    }
-    // 2) framing + convolution + overlap-add
+    return DDSP_B200_OK;
+}
+
+unsigned ltv_ir_grid(int B, int F) {
+    int64_t grid = ((int64_t)B * F + ddsp::kLtvWarps - 1) / ddsp::kLtvWarps;
+    if (grid > sm_count()) grid = sm_count();               // persistent: one CTA per SM, warps stride over frames
+    return (unsigned)grid;
+}
+
+// 1) impulse responses -> tap spectra (frames independent)
+int launch_ltv_ir(const ddsp::LtvParams& P, cudaStream_t st) {
+    ltv_ir_select(P.encoding, P.window_mode)<<<ltv_ir_grid(P.B, P.F), ddsp::kLtvThreads, ddsp::kLtvIrSmemBytes, st>>>(P);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+// 2) framing + convolution + overlap-add
+int launch_ltv_conv(const ddsp::LtvParams& P, cudaStream_t st) {
     if (P.runs_per_clip > 1) {
-        CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)B * F * ddsp::kHop * sizeof(float), st));
+        CUDA_TRY(cudaMemsetAsync(P.out, 0, (size_t)P.B * P.F * ddsp::kHop * sizeof(float), st));
         ++g_launches;
     }
-    const int64_t runs = (int64_t)B * P.runs_per_clip;
+    const int64_t runs = (int64_t)P.B * P.runs_per_clip;
     const unsigned grid = (unsigned)((runs + ddsp::kLtvWarps - 1) / ddsp::kLtvWarps);
-    ltv_conv_select(audio_mode)<<<grid, ddsp::kLtvThreads, ddsp::kLtvConvSmemBytes, st>>>(P);
+    ltv_conv_select(P.audio_mode)<<<grid, ddsp::kLtvThreads, ddsp::kLtvConvSmemBytes, st>>>(P);
     LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int launch_ltv(const float* audio, int audio_mode, uint64_t seed, const float* mags, int64_t mB, int64_t mF, int n_mag,
+               int encoding, float mag_scale, int window_mode, const float* f0_frames, int64_t fB, int64_t fF,
+               double sr, int B, int F, float* out, void* spec_ws, cudaStream_t st) {
+    ddsp::LtvParams P;
+    if (int rc = ltv_params(P, audio, audio_mode, seed, mags, mB, mF, n_mag, encoding, mag_scale, window_mode, f0_frames,
+                            fB, fF, sr, B, F, out, spec_ws, st)) return rc;
+    if (int rc = launch_ltv_ir(P, st)) return rc;
+    return launch_ltv_conv(P, st);
+}
+
+// All-pass (group delay) + noise impulse responses of a frame from one shared Bluestein pass (both L=510),
+// followed by the two convolutions.  `between` (optional) runs after the all-pass convolution: CombSub's
+// harmonic filter consumes its output.
+int launch_allpass_and_noise(const float* allpass_in, float* allpass_out, const float* group_delay,
+                             const float* noise_u, uint64_t seed, const float* noise_magnitude, int64_t cB, int64_t cF,
+                             double sr, int B, int F, float* noise_out, void* spec_a, void* spec_n, cudaStream_t st,
+                             int (*between)(void*), void* between_arg) {
+    ddsp::LtvParams Pa, Pn;
+    if (int rc = ltv_params(Pa, allpass_in, 0, 0, group_delay, cB, cF, 256, DDSP_B200_MAG_ALLPASS_TANH, 1.0f,
+                            DDSP_B200_WINDOW_NONE, nullptr, 0, 0, sr, B, F, allpass_out, spec_a, st)) return rc;
+    if (int rc = ltv_params(Pn, noise_u, noise_u ? 1 : 2, seed, noise_magnitude, cB, cF, 256, DDSP_B200_MAG_EXP,
+                            1.0f / 128.0f, DDSP_B200_WINDOW_HANN, nullptr, 0, 0, sr, B, F, noise_out, spec_n, st)) return rc;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    ddsp::LtvDualParams D;
+    D.gd = group_delay; D.nm = noise_magnitude; D.mB = cB; D.mF = cF; D.noise_scale = 1.0f / 128.0f;
+    D.tw_tables = Pa.tw_tables; D.chirp_c = g_chirp_ptr[dev][0]; D.chirp_d_dual = g_chirp_ptr[dev][2] + 1024;
+    D.spec_a = (float2*)spec_a; D.spec_n = (float2*)spec_n; D.B = B; D.F = F;
+    ddsp::ltv_ir_dual_kernel<<<ltv_ir_grid(B, F), ddsp::kLtvThreads, ddsp::kLtvDualSmemBytes, st>>>(D);
+    LAUNCH_CHECK();
+    int launches = g_launches; g_launches = 0;
+    if (int rc = launch_ltv_conv(Pa, st)) return rc;
+    launches += g_launches; g_launches = 0;
+    if (between) {
+        if (int rc = between(between_arg)) return rc;
+        launches += g_launches; g_launches = 0;
+    }
+    if (int rc = launch_ltv_conv(Pn, st)) return rc;
+    g_launches += launches;
     return DDSP_B200_OK;
 }
 
@@ -387,7 +440,7 @@ int ddsp_b200_frequency_filter(const float* audio, const float* mags, int64_t mB
 size_t ddsp_b200_combsub_workspace_bytes(int B, int F, int n_mag_allpass, int n_mag_harmonic, int n_mag_noise) {
     (void)n_mag_allpass; (void)n_mag_harmonic; (void)n_mag_noise;
     // combtooth + all-passed harmonic + tap spectra of the filter in flight
-    return (B > 0 && F > 0) ? (size_t)2 * B * F * ddsp::kHop * sizeof(float) + ltv_spec_bytes(B, F) : 0;
+    return (B > 0 && F > 0) ? (size_t)2 * B * F * ddsp::kHop * sizeof(float) + 2 * ltv_spec_bytes(B, F) : 0;
 }
 
 int ddsp_b200_combsub(const float* group_delay, int n_mag_allpass, const float* harmonic_magnitude, int n_mag_harmonic,
@@ -415,18 +468,35 @@ int ddsp_b200_combsub(const float* group_delay, int n_mag_allpass, const float* 
                                                                                    (float)sr, prefix, 0, comb);
     LAUNCH_CHECK();
     launches += g_launches; g_launches = 0;
-    // :540  all-pass (group delay), no window
-    if (int rc = launch_ltv(comb, 0, 0, group_delay, cB, cF, n_mag_allpass, DDSP_B200_MAG_ALLPASS_TANH, 1.0f,
-                            DDSP_B200_WINDOW_NONE, nullptr, 0, 0, sr, B, F, h1, spec, st)) return rc;
-    launches += g_launches; g_launches = 0;
-    // :541-542  harmonic magnitude filter with the f0-dependent window
-    if (int rc = launch_ltv(h1, 0, 0, harmonic_magnitude, cB, cF, n_mag_harmonic, DDSP_B200_MAG_EXP, 1.0f,
-                            DDSP_B200_WINDOW_DYNAMIC, f0_frames, fB, fF, sr, B, F, harmonic, spec, st)) return rc;
-    launches += g_launches; g_launches = 0;
-    // :545-546  filtered noise
-    if (int rc = launch_ltv(noise_u, noise_u ? 1 : 2, seed, noise_magnitude, cB, cF, n_mag_noise, DDSP_B200_MAG_EXP,
-                            1.0f / 128.0f, DDSP_B200_WINDOW_HANN, nullptr, 0, 0, sr, B, F, noise, spec, st)) return rc;
-    launches += g_launches; g_launches = 0;
+    void* spec_n = (void*)((char*)spec + ltv_spec_bytes(B, F));
+    if (n_mag_allpass == 256 && n_mag_noise == 256) {
+        // :540 all-pass and :545-546 noise impulse responses share one Bluestein pass; the harmonic
+        // filter (:541-542, f0-dependent window) runs between the two convolutions on the all-pass output
+        struct Mid { const float* h1; const float* hm; int n_mag; int64_t cB, cF; const float* f0; int64_t fB, fF;
+                     double sr; int B, F; float* harmonic; void* spec; cudaStream_t st; } mid = {
+            h1, harmonic_magnitude, n_mag_harmonic, cB, cF, f0_frames, fB, fF, sr, B, F, harmonic, spec, st};
+        auto between = [](void* a) -> int {
+            Mid* m = (Mid*)a;
+            return launch_ltv(m->h1, 0, 0, m->hm, m->cB, m->cF, m->n_mag, DDSP_B200_MAG_EXP, 1.0f, DDSP_B200_WINDOW_DYNAMIC,
+                              m->f0, m->fB, m->fF, m->sr, m->B, m->F, m->harmonic, m->spec, m->st);
+        };
+        if (int rc = launch_allpass_and_noise(comb, h1, group_delay, noise_u, seed, noise_magnitude, cB, cF, sr, B, F,
+                                              noise, spec, spec_n, st, between, &mid)) return rc;
+        launches += g_launches; g_launches = 0;
+    } else {
+        // :540  all-pass (group delay), no window
+        if (int rc = launch_ltv(comb, 0, 0, group_delay, cB, cF, n_mag_allpass, DDSP_B200_MAG_ALLPASS_TANH, 1.0f,
+                                DDSP_B200_WINDOW_NONE, nullptr, 0, 0, sr, B, F, h1, spec, st)) return rc;
+        launches += g_launches; g_launches = 0;
+        // :541-542  harmonic magnitude filter with the f0-dependent window
+        if (int rc = launch_ltv(h1, 0, 0, harmonic_magnitude, cB, cF, n_mag_harmonic, DDSP_B200_MAG_EXP, 1.0f,
+                                DDSP_B200_WINDOW_DYNAMIC, f0_frames, fB, fF, sr, B, F, harmonic, spec, st)) return rc;
+        launches += g_launches; g_launches = 0;
+        // :545-546  filtered noise
+        if (int rc = launch_ltv(noise_u, noise_u ? 1 : 2, seed, noise_magnitude, cB, cF, n_mag_noise, DDSP_B200_MAG_EXP,
+                                1.0f / 128.0f, DDSP_B200_WINDOW_HANN, nullptr, 0, 0, sr, B, F, noise, spec, st)) return rc;
+        launches += g_launches; g_launches = 0;
+    }
     // :548
     if (int rc = launch_add(harmonic, noise, signal, n, st)) return rc;
     g_launches += launches;
@@ -435,7 +505,7 @@ int ddsp_b200_combsub(const float* group_delay, int n_mag_allpass, const float* 
 
 size_t ddsp_b200_sins_workspace_bytes(int B, int F, int n_harmonics, int n_mag_allpass, int n_mag_noise) {
     (void)n_harmonics; (void)n_mag_allpass; (void)n_mag_noise;
-    return (B > 0 && F > 0) ? (size_t)B * F * ddsp::kHop * sizeof(float) + ltv_spec_bytes(B, F) : 0;   // sinusoid mix + tap spectra
+    return (B > 0 && F > 0) ? (size_t)B * F * ddsp::kHop * sizeof(float) + 2 * ltv_spec_bytes(B, F) : 0;   // sinusoid mix + 2 tap spectra
 }
 
 int ddsp_b200_sins(const float* amplitudes, int n_harmonics, const float* group_delay, int n_mag_allpass,
@@ -461,14 +531,22 @@ int ddsp_b200_sins(const float* amplitudes, int n_harmonics, const float* group_
                                                                        F, (float)(sr / 2.0), phase_full, sinus);
     LAUNCH_CHECK();
     launches += g_launches; g_launches = 0;
-    // :415  all-pass
-    if (int rc = launch_ltv(sinus, 0, 0, group_delay, cB, cF, n_mag_allpass, DDSP_B200_MAG_ALLPASS_TANH, 1.0f,
-                            DDSP_B200_WINDOW_NONE, nullptr, 0, 0, sr, B, F, harmonic, spec, st)) return rc;
-    launches += g_launches; g_launches = 0;
-    // :418-419  filtered noise
-    if (int rc = launch_ltv(noise_u, noise_u ? 1 : 2, seed, noise_magnitude, cB, cF, n_mag_noise, DDSP_B200_MAG_EXP,
-                            1.0f / 128.0f, DDSP_B200_WINDOW_HANN, nullptr, 0, 0, sr, B, F, noise, spec, st)) return rc;
-    launches += g_launches; g_launches = 0;
+    void* spec_n = (void*)((char*)spec + ltv_spec_bytes(B, F));
+    if (n_mag_allpass == 256 && n_mag_noise == 256) {
+        // :415 all-pass and :418-419 noise: impulse responses from one shared Bluestein pass
+        if (int rc = launch_allpass_and_noise(sinus, harmonic, group_delay, noise_u, seed, noise_magnitude, cB, cF, sr, B,
+                                              F, noise, spec, spec_n, st, nullptr, nullptr)) return rc;
+        launches += g_launches; g_launches = 0;
+    } else {
+        // :415  all-pass
+        if (int rc = launch_ltv(sinus, 0, 0, group_delay, cB, cF, n_mag_allpass, DDSP_B200_MAG_ALLPASS_TANH, 1.0f,
+                                DDSP_B200_WINDOW_NONE, nullptr, 0, 0, sr, B, F, harmonic, spec, st)) return rc;
+        launches += g_launches; g_launches = 0;
+        // :418-419  filtered noise
+        if (int rc = launch_ltv(noise_u, noise_u ? 1 : 2, seed, noise_magnitude, cB, cF, n_mag_noise, DDSP_B200_MAG_EXP,
+                                1.0f / 128.0f, DDSP_B200_WINDOW_HANN, nullptr, 0, 0, sr, B, F, noise, spec, st)) return rc;
+        launches += g_launches; g_launches = 0;
+    }
     // :421
     if (int rc = launch_add(harmonic, noise, signal, n, st)) return rc;
     g_launches += launches;

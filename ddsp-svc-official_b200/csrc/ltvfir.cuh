@@ -243,6 +243,156 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Kernel 1b: the all-pass (group delay, no window) and the noise (exp/128, Hann) impulse responses
+// of one frame -- both L = 510 -- from ONE Bluestein pass.  With the full Hermitian extension of
+// both spectra, V[k] = Xa[k] + j Xn[k] (k = 0..509) has the real inverse DFT  ir_a[n] + j ir_n[n],
+// and 510 + 510 - 1 <= 1024 still fits the circular convolution.  4 FFTs for two filters instead
+// of 6.  Used by CombSub (vocoder.py:540,545-546) and Sins (:415,418-419).
+// ---------------------------------------------------------------------------------------------
+constexpr int kLtvDualWarpFloats = kPlaneFloats + 512 + kLtvCtxInts;     // plane + second tap set + ctx
+constexpr int kLtvDualSmemBytes = 512 * 16 + kLtvWarps * kLtvDualWarpFloats * 4;
+
+struct LtvDualParams {
+    const float* gd; const float* nm; int64_t mB, mF;   // group_delay / noise_magnitude control rows (B,F,256)
+    float noise_scale;                                   // 1/128
+    const float* tw_tables; const float* chirp_c;        // c[m], m < 512 (L = 510)
+    const float* chirp_d_dual;                           // FFT_1024 of the wrapped conjugate chirp, m in [-509, 509]
+    float2* spec_a; float2* spec_n;                      // (B,F,1024) complex each
+    int B, F;
+};
+
+__global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_dual_kernel(const LtvDualParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float4* tw4 = reinterpret_cast<const float4*>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* plane = reinterpret_cast<float*>(smem_raw + 512 * 16) + wid * kLtvDualWarpFloats;
+    float* tap2 = plane + kPlaneFloats;                  // 512 floats: noise taps while the all-pass taps are transformed
+    volatile int* ctx = reinterpret_cast<volatile int*>(tap2 + 512);
+    {
+        const float4* src = reinterpret_cast<const float4*>(P.tw_tables);
+        float4* dst = reinterpret_cast<float4*>(smem_raw);
+        for (int e = threadIdx.x; e < 512; e += kLtvThreads) dst[e] = __ldg(src + e);
+        __syncthreads();
+    }
+    constexpr int L = 510, D = 255, NM = 256;
+    const float2* chirp_c = reinterpret_cast<const float2*>(P.chirp_c);
+    const float2* chirp_d = reinterpret_cast<const float2*>(P.chirp_d_dual);
+    const int64_t n_frames = (int64_t)P.B * P.F;
+
+    Pts32 X;
+    for (int64_t fr0 = (int64_t)blockIdx.x * kLtvWarps + wid; fr0 < n_frames; fr0 += (int64_t)gridDim.x * kLtvWarps) {
+        if (lane == 0) { ctx[0] = (int)(fr0 / P.F); ctx[1] = (int)(fr0 % P.F); }
+        __syncwarp();
+#pragma unroll 1
+        for (int phase = 0; phase < 4; ++phase) {
+            if (phase == 0) {
+                const int64_t ro = (int64_t)ctx[0] * P.mB + (int64_t)ctx[1] * P.mF;
+                const float* rg = P.gd + ro;
+                const float* rn = P.nm + ro;
+                float cg[8], cn[8];
+#pragma unroll
+                for (int n1 = 0; n1 < 8; ++n1) { cg[n1] = __ldg(rg + 32 * n1 + lane); cn[n1] = __ldg(rn + 32 * n1 + lane); }
+                // lower half k = 32 n1 + lane < 256: all-pass phase by inclusive scan (in turns), noise magnitude;
+                // both are parked in `plane` (as float2 (theta, mag)) for the mirrored upper half
+                float2* park = reinterpret_cast<float2*>(plane);
+                float carry = 0.0f;
+#pragma unroll
+                for (int n1 = 0; n1 < 8; ++n1) {
+                    float g = 0.5f * tanhf(cg[n1]);
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const float t = __shfl_up_sync(kFullMask, g, d);
+                        if (lane >= d) g += t;
+                    }
+                    g += carry;
+                    carry = __shfl_sync(kFullMask, g, 31);
+                    carry -= rintf(carry);
+                    g -= rintf(g);
+                    park[32 * n1 + lane] = make_float2(g, ex2_approx(cn[n1] * DDSP_LOG2E_F) * P.noise_scale);
+                }
+                __syncwarp();
+                const float scale = 1.0f / ((float)L * 1024.0f);
+                float vr[16], vi[16];
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    const int k = 32 * n1 + lane;
+                    vr[n1] = 0.0f; vi[n1] = 0.0f;
+                    if (k < L) {
+                        const int km = (k < NM) ? k : L - k;              // Hermitian mirror (1..254 for k >= 256)
+                        const float2 pm = park[km];
+                        float xr = cos_approx(DDSP_TWO_PI_F * pm.x), xi = sin_approx(DDSP_TWO_PI_F * pm.x);
+                        if (k >= NM) xi = -xi;                            // conj
+                        if (k == 0 || k == NM - 1) xi = 0.0f;             // irfft ignores Im of DC / Nyquist
+                        // V = Xa + j Xn  (Xn real)
+                        const float ar = xr * scale, ai = (xi + pm.y) * scale;
+                        const float2 c = __ldg(chirp_c + k);
+                        vr[n1] = ar * c.x - ai * c.y;
+                        vi[n1] = ar * c.y + ai * c.x;
+                    }
+                }
+                __syncwarp();                                            // park (plane) is dead before the FFT reuses it
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    DDSP_RE(X, brev5(n1)) = (n1 < 16) ? vr[n1 & 15] : 0.0f;
+                    DDSP_IM(X, brev5(n1)) = (n1 < 16) ? vi[n1 & 15] : 0.0f;
+                }
+            } else if (phase >= 2) {
+                const float2* h2 = reinterpret_cast<const float2*>(phase == 2 ? plane : tap2);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    float2 v = make_float2(0.0f, 0.0f);
+                    if (n1 < 8) v = h2[32 * n1 + lane];
+                    DDSP_RE(X, brev5(n1)) = v.x;
+                    DDSP_IM(X, brev5(n1)) = v.y;
+                }
+                __syncwarp();
+            }
+
+            warp_fft1024(X, plane, tw4, lane);
+
+            if (phase == 0) {
+                float pr[32], pi[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const float2 dh = __ldg(chirp_d + lane + 32 * q);
+                    const float ur = DDSP_RE(X, q), ui = DDSP_IM(X, q);
+                    pr[q] = ur * dh.x - ui * dh.y;
+                    pi[q] = ur * dh.y + ui * dh.x;
+                }
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    DDSP_RE(X, brev5(q)) = pi[q];
+                    DDSP_IM(X, brev5(q)) = pr[q];
+                }
+            } else if (phase == 1) {
+                // S[n] = c[n] * conv[n] = ir_allpass[n] + j ir_noise[n]  (zero-phase form), n = lane + 32 q < 510
+                const float two_pi_over_L = DDSP_TWO_PI_F / (float)L;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int n = lane + 32 * q;
+                    if (n < L) {
+                        const float2 c = __ldg(chirp_c + n);
+                        const float cr = DDSP_IM(X, q), ci = DDSP_RE(X, q);      // conv = cr + j ci (swapped FFT)
+                        const float sa = cr * c.x - ci * c.y, sn = cr * c.y + ci * c.x;
+                        const int lag = (n <= L - D - 1) ? n : n - L;
+                        const int i = lag + D;
+                        const float w = fmaf(0.5f, cos_approx(fmaf((float)i, two_pi_over_L, -DDSP_PI_F)), 0.5f);   // Hann (core.py:262)
+                        plane[i] = sa * (1.0f / 4096.0f);                        // all-pass: no window (core.py:326)
+                        tap2[i] = sn * w * (1.0f / 4096.0f);
+                    }
+                }
+                if (lane < 2) { plane[L + lane] = 0.0f; tap2[L + lane] = 0.0f; }
+                __syncwarp();
+            } else {
+                float2* dst = (phase == 2 ? P.spec_a : P.spec_n) + ((int64_t)ctx[0] * P.F + ctx[1]) * kLtvSpecFloat2 + lane;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) dst[32 * q] = make_float2(DDSP_RE(X, q), DDSP_IM(X, q));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Kernel 2: framing, FFT convolution with the stored tap spectra, overlap-add.  A warp owns a run
 // of consecutive frames of one clip.  AMODE >= 0 fixes the audio source at compile time.
 // ---------------------------------------------------------------------------------------------

@@ -45,7 +45,7 @@ def test_strerror_and_argument_validation_without_gpu():
     p = ctypes.addressof(buf)
     assert lib.ddsp_b200_phase(p, 4, 1, 1, 4, 256, 44100.0, 0, 1, p, p, 0, 0) == -2      # hop != 512
     assert lib.ddsp_b200_fo_to_rot_workspace_bytes(2, 5000) == 2 * 3 * 8
-    assert lib.ddsp_b200_combsub_workspace_bytes(2, 10, 256, 512, 256) == 2 * 2 * 10 * 512 * 4 + 2 * 10 * 1024 * 8
+    assert lib.ddsp_b200_combsub_workspace_bytes(2, 10, 256, 512, 256) == 2 * 2 * 10 * 512 * 4 + 2 * 2 * 10 * 1024 * 8
     with pytest.raises(ValueError):
         _cabi.check(-5)
     with pytest.raises(_cabi.DDSPB200Error):
