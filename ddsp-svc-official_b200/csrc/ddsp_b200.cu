@@ -253,6 +253,9 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
     int run_len = (int)((total_pairs + slots - 1) / slots);
     if (run_len < 1) run_len = 1;
     if (run_len > P.pairs_per_clip) run_len = P.pairs_per_clip;
+    // one resident wave: grow the run until all runs fit the warp slots of the chip (the per-clip
+    // remainder run can otherwise push the count over and cost a second, nearly empty wave)
+    while (run_len < P.pairs_per_clip && (int64_t)B * ((P.pairs_per_clip + run_len - 1) / run_len) > slots) ++run_len;
     P.run_len = run_len;
     P.runs_per_clip = (P.pairs_per_clip + run_len - 1) / run_len;
     P.inv_sr = 1.0 / sr; P.sr = (float)sr;
@@ -312,6 +315,7 @@ int ltv_params(ddsp::LtvParams& P, const float* audio, int audio_mode, uint64_t 
     int run_len = (int)(((int64_t)B * frames + slots - 1) / slots);
     if (run_len < 4) run_len = frames < 4 ? frames : 4;     // keep the 3-hop seams a minority of the work
     if (run_len > frames) run_len = frames;
+    while (run_len < frames && (int64_t)B * ((frames + run_len - 1) / run_len) > slots) ++run_len;   // one resident wave
     P.run_len = run_len;
     P.runs_per_clip = (frames + run_len - 1) / run_len;
     return DDSP_B200_OK;
