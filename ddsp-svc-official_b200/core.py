@@ -189,6 +189,41 @@ def combsubfast_stage(harmonic_magnitude, harmonic_phase, noise_magnitude, f0_fr
     return signal
 
 
+def combsubfast_backward_stage(grad_signal, harmonic_magnitude, harmonic_phase, noise_magnitude, f0_frames, prefix,
+                               block_size, sampling_rate, noise_u=None, seed=0, window=None):
+    """Gradient of `combsubfast_stage` w.r.t. the three control tensors (what autograd derives for
+    vocoder.py:455-492).  All other arguments must be those of the forward call.  Returns three
+    (B,F,513) views of one (B,F,1539) tensor, in the order of the inputs."""
+    hm, hp, nm = _common_views((harmonic_magnitude, harmonic_phase, noise_magnitude),
+                               ('harmonic_magnitude', 'harmonic_phase', 'noise_magnitude'))
+    f0 = _f0_2d(f0_frames)
+    B, F = f0.shape
+    hop = int(block_size)
+    for t in (hm, hp, nm):
+        if tuple(t.shape) != (B, F, hop + 1):
+            raise ValueError(f'control tensors must be (B, Frame, {hop + 1}); got {tuple(t.shape)}')
+    grad_signal = _need_cuda_f32(grad_signal, 'grad_signal').contiguous()
+    if tuple(grad_signal.shape) != (B, F * hop):
+        raise ValueError('grad_signal must be (B, T)')
+    if noise_u is not None:
+        noise_u = _need_cuda_f32(noise_u, 'noise_u').contiguous()
+        if tuple(noise_u.shape) != (B, F * hop):
+            raise ValueError('noise_u must be (B, T)')
+    if window is not None:
+        window = _need_cuda_f32(window, 'window').contiguous()
+        if window.numel() != 2 * hop:
+            raise ValueError('window must have 2*block_size entries')
+    grads = torch.empty((B, F, 3 * (hop + 1)), dtype=torch.float32, device=f0.device)
+    ghm, ghp, gnm = torch.split(grads, hop + 1, dim=-1)
+    with _OnDevice(f0.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_combsubfast_backward(
+            hm.data_ptr(), hp.data_ptr(), nm.data_ptr(), hm.stride(0), hm.stride(1), f0.data_ptr(), f0.stride(0),
+            f0.stride(1), prefix.data_ptr(), _ptr(noise_u), int(seed) % _TWO62, _ptr(window), grad_signal.data_ptr(),
+            B, F, hop, float(sampling_rate), ghm.data_ptr(), ghp.data_ptr(), gnm.data_ptr(), ghm.stride(0),
+            ghm.stride(1), _st))
+    return ghm, ghp, gnm
+
+
 WINDOW_NONE, WINDOW_HANN, WINDOW_DYNAMIC = 0, 1, 2
 MAG_REAL, MAG_EXP, MAG_ALLPASS_TANH, MAG_COMPLEX = 0, 1, 2, 3
 

@@ -97,6 +97,48 @@ __global__ void __launch_bounds__(128) csf_zero_seams_kernel(float* __restrict__
     dst[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// Windowed frame fm of clip b in FFT input order: comb excitation (ring slots of hops fm-1, fm)
+// -> real part, noise excitation (injected U or the in-kernel stream) -> imaginary part.
+template <bool HAS_U>
+__device__ __forceinline__ void csf_load_frame(const CsfParams& P, Pts32& X, const float* __restrict__ ring,
+                                               const float* __restrict__ win, int fm, int b, uint32_t key, int lane) {
+    const int F = P.F;
+    const float* slotA = ring + ((fm - 1) & 1) * kRingSlot + lane;   // hop fm-1
+    const float* slotB = ring + (fm & 1) * kRingSlot + lane;         // hop fm
+    // hops outside [0,F) are zero padding (vocoder.py:463-464): their noise weight is 0 and
+    // the (unused) noise sample is read from the start of the clip to stay in bounds
+    const bool vA = (fm >= 1) && (fm - 1 < F), vB = fm < F;
+    const int64_t baseA = vA ? (int64_t)(fm - 1) * kHop : 0, baseB = vB ? (int64_t)fm * kHop : 0;
+    const float okA = vA ? 1.0f : 0.0f, okB = vB ? 1.0f : 0.0f;
+    const float sclA = okA * 1.1920928955078125e-7f, sclB = okB * 1.1920928955078125e-7f;   // 2^-23
+    const float* u_b = HAS_U ? P.noise_u + (int64_t)b * F * kHop + lane : nullptr;
+    uint32_t stA = 0, stB = 0;
+    if (!HAS_U) {
+        stA = noise_seed(key, (uint32_t)(fm - 1), (uint32_t)lane);
+        stB = noise_seed(key, (uint32_t)fm, (uint32_t)lane);
+    }
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1) {
+        const int j = 32 * (n1 & 15);                                 // sample in hop = j + lane
+        const float w = win[32 * n1 + lane];
+        const float c = (n1 < 16 ? slotA : slotB)[j + (n1 & 15)];
+        const float wc = w * c;
+        float wz;
+        if (HAS_U) {
+            const float u = __ldg(u_b + (n1 < 16 ? baseA : baseB) + j);
+            const float wn = w * (n1 < 16 ? okA : okB);
+            wz = fmaf(u, wn + wn, -wn);                                   // w * (2u - 1)   (vocoder.py:461)
+        } else {
+            uint32_t& st = (n1 < 16) ? stA : stB;
+            st = noise_next(st);
+            // 2u - 1 = v * 2^-23 with v the centred 24-bit draw; sclA/sclB carry the 2^-23 (or 0)
+            wz = (float)noise_s24(st) * (w * (n1 < 16 ? sclA : sclB));
+        }
+        DDSP_RE(X, brev5(n1)) = wc;
+        DDSP_IM(X, brev5(n1)) = wz;
+    }
+}
+
 // HAS_U: the noise excitation is read from the injected U tensor (parity mode) instead of being drawn
 // in-kernel; a compile-time switch so that neither variant carries the other's predicated-off code.
 template <bool HAS_U>
@@ -154,7 +196,10 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
     // De-phase the four warps that share a scheduler (wid, wid+4, wid+8, wid+12) by 2 us each so that
     // their FMA-heavy FFT phases do not start in lockstep (measured: -2 % on the 12-pairs-per-warp
     // headline launch); skipped for short runs where it would only add latency.
-    if (P.run_len >= 4) __nanosleep((unsigned)(wid >> 2) * 2000u);
+#ifndef CSF_STAGGER_NS
+#define CSF_STAGGER_NS 2000u
+#endif
+    if (P.run_len >= 4) __nanosleep((unsigned)(wid >> 2) * CSF_STAGGER_NS);
 
     // steps per pair: s=0 frame 2p, s=1 frame 2p+1, s=2 inverse FFT of the pair + overlap-add.
     // s=-1 (first iteration only) just generates the first hop of the run.
@@ -172,42 +217,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                 const int64_t ro = (int64_t)CTX_B * P.cB + (int64_t)min(fm, F - 1) * P.cF + 32 * lane;
                 if (lane <= 16) { prefetch_l2(P.hm + ro); prefetch_l2(P.hp + ro); prefetch_l2(P.nm + ro); }
             }
-            // ---- windowed frame: comb -> real part, noise -> imaginary part -------------------
-            const float* slotA = ring + ((fm - 1) & 1) * kRingSlot + lane;   // hop fm-1
-            const float* slotB = ring + (fm & 1) * kRingSlot + lane;         // hop fm
-            // hops outside [0,F) are zero padding (vocoder.py:463-464): their noise weight is 0 and
-            // the (unused) noise sample is read from the start of the clip to stay in bounds
-            const bool vA = (fm >= 1) && (fm - 1 < F), vB = fm < F;
-            const int64_t baseA = vA ? (int64_t)(fm - 1) * kHop : 0, baseB = vB ? (int64_t)fm * kHop : 0;
-            const float okA = vA ? 1.0f : 0.0f, okB = vB ? 1.0f : 0.0f;
-            const float sclA = okA * 1.1920928955078125e-7f, sclB = okB * 1.1920928955078125e-7f;   // 2^-23
-            const uint32_t key = CTX_KEY;
-            const float* u_b = HAS_U ? P.noise_u + (int64_t)CTX_B * F * kHop + lane : nullptr;
-            uint32_t stA = 0, stB = 0;
-            if (!HAS_U) {
-                stA = noise_seed(key, (uint32_t)(fm - 1), (uint32_t)lane);
-                stB = noise_seed(key, (uint32_t)fm, (uint32_t)lane);
-            }
-#pragma unroll
-            for (int n1 = 0; n1 < 32; ++n1) {
-                const int j = 32 * (n1 & 15);                                 // sample in hop = j + lane
-                const float w = win[32 * n1 + lane];
-                const float c = (n1 < 16 ? slotA : slotB)[j + (n1 & 15)];
-                const float wc = w * c;
-                float wz;
-                if (HAS_U) {
-                    const float u = __ldg(u_b + (n1 < 16 ? baseA : baseB) + j);
-                    const float wn = w * (n1 < 16 ? okA : okB);
-                    wz = fmaf(u, wn + wn, -wn);                                   // w * (2u - 1)   (vocoder.py:461)
-                } else {
-                    uint32_t& st = (n1 < 16) ? stA : stB;
-                    st = noise_next(st);
-                    // 2u - 1 = v * 2^-23 with v the centred 24-bit draw; okA/okB carry the 2^-23 (or 0)
-                    wz = (float)noise_s24(st) * (w * (n1 < 16 ? sclA : sclB));
-                }
-                DDSP_RE(X, brev5(n1)) = wc;
-                DDSP_IM(X, brev5(n1)) = wz;
-            }
+            csf_load_frame<HAS_U>(P, X, ring, win, fm, CTX_B, CTX_KEY, lane);
         }
         // s == 2: re/im already hold the packed spectrum of the pair (swapped for the inverse)
 
@@ -223,7 +233,10 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             const float* nm_r = P.nm + ro;
             float yr[17], yi[17];
             // control loads run kLook bins ahead of their use (software pipeline over the unrolled loop)
-            constexpr int kLook = 4;
+#ifndef CSF_LOOK
+#define CSF_LOOK 4
+#endif
+            constexpr int kLook = CSF_LOOK;
             float chm[kLook], chp[kLook], cnm[kLook];
 #pragma unroll
             for (int q = 0; q < kLook; ++q) {

@@ -8,6 +8,7 @@
 #include <mutex>
 
 #include "combsubfast.cuh"
+#include "combsubfast_bwd.cuh"
 #include "excite.cuh"
 #include "ltvfir.cuh"
 #include "phase.cuh"
@@ -82,6 +83,10 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
                                       ddsp::kCsfSmemBytes));
         CUDA_TRY(cudaFuncSetAttribute(ddsp::combsubfast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       ddsp::kCsfSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(ddsp::combsubfast_backward_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kCsbSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(ddsp::combsubfast_backward_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kCsbSmemBytes));
         float* ptr = nullptr;
         CUDA_TRY(cudaGetSymbolAddress((void**)&ptr, g_tables));
         ddsp::fft_tables_kernel<<<4, 256, 0, st>>>(reinterpret_cast<float4*>(ptr), ptr + 2048);
@@ -279,6 +284,53 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (noise_u) CUDA_TRY(cudaLaunchKernelEx(&cfg, ddsp::combsubfast_kernel<true>, P));
     else CUDA_TRY(cudaLaunchKernelEx(&cfg, ddsp::combsubfast_kernel<false>, P));
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int ddsp_b200_combsubfast_backward(const float* harmonic_magnitude, const float* harmonic_phase,
+                                   const float* noise_magnitude, int64_t cB, int64_t cF, const float* f0_frames,
+                                   int64_t fB, int64_t fF, const double* prefix, const float* noise_u, uint64_t seed,
+                                   const float* window, const float* grad_signal, int B, int F, int hop, double sr,
+                                   float* grad_harmonic_magnitude, float* grad_harmonic_phase,
+                                   float* grad_noise_magnitude, int64_t gB, int64_t gF, void* stream) {
+    g_launches = 0;
+    if (!harmonic_magnitude || !harmonic_phase || !noise_magnitude || !f0_frames || !prefix || !grad_signal ||
+        !grad_harmonic_magnitude || !grad_harmonic_phase || !grad_noise_magnitude || B <= 0 || F <= 0 || !(sr > 0))
+        return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (hop != ddsp::kHop) return DDSP_B200_ERR_UNSUPPORTED;
+    if ((int64_t)F * hop >= (1ll << 24)) return DDSP_B200_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    ddsp::CsbParams PB;
+    ddsp::CsfParams& P = PB.fwd;
+    if (int rc = ensure_device_ready(st, &P.tables)) return rc;
+    P.hm = harmonic_magnitude; P.hp = harmonic_phase; P.nm = noise_magnitude;
+    P.cB = cB; P.cF = cF;
+    P.f0_frames = f0_frames; P.fB = fB; P.fF = fF;
+    P.prefix = prefix; P.noise_u = noise_u; P.window = window;
+    P.signal = nullptr; P.seed = seed; P.B = B; P.F = F;
+    P.pairs_per_clip = (F + 2) / 2;
+    const int64_t slots = (int64_t)sm_count() * ddsp::kCsbWarps;
+    const int64_t total_pairs = (int64_t)B * P.pairs_per_clip;
+    int run_len = (int)((total_pairs + slots - 1) / slots);
+    if (run_len < 1) run_len = 1;
+    if (run_len > P.pairs_per_clip) run_len = P.pairs_per_clip;
+    while (run_len < P.pairs_per_clip && (int64_t)B * ((P.pairs_per_clip + run_len - 1) / run_len) > slots) ++run_len;
+    P.run_len = run_len;
+    P.runs_per_clip = (P.pairs_per_clip + run_len - 1) / run_len;
+    P.inv_sr = 1.0 / sr; P.sr = (float)sr;
+    PB.grad_signal = grad_signal;
+    PB.ghm = grad_harmonic_magnitude; PB.ghp = grad_harmonic_phase; PB.gnm = grad_noise_magnitude;
+    PB.gB = gB; PB.gF = gF;
+    // Filter row F-1 serves frames F-1 and F (vocoder.py:473,476): its gradient is the sum of two
+    // atomic adds onto zeros; every other row is written exactly once.
+    for (float* g : {PB.ghm, PB.ghp, PB.gnm})
+        CUDA_TRY(cudaMemset2DAsync(g + (int64_t)(F - 1) * gF, (size_t)gB * sizeof(float), 0,
+                                   (size_t)(hop + 1) * sizeof(float), (size_t)B, st));
+    const int64_t runs = (int64_t)B * P.runs_per_clip;
+    const unsigned grid = (unsigned)((runs + ddsp::kCsbWarps - 1) / ddsp::kCsbWarps);
+    if (noise_u) ddsp::combsubfast_backward_kernel<true><<<grid, ddsp::kCsbThreads, ddsp::kCsbSmemBytes, st>>>(PB);
+    else ddsp::combsubfast_backward_kernel<false><<<grid, ddsp::kCsbThreads, ddsp::kCsbSmemBytes, st>>>(PB);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }

@@ -55,8 +55,31 @@ class _SynthBase(torch.nn.Module):
     @staticmethod
     def _forward_only(ctrls):
         if torch.is_grad_enabled() and any(t.requires_grad for t in ctrls.values()):
-            raise RuntimeError('ddsp_b200 synthesizers are forward-only (no autograd): call under '
+            raise RuntimeError('this ddsp_b200 synthesizer is forward-only (only CombSubFast has a backward): call under '
                                'torch.no_grad() as main.py:145 / gui.py:125 / solver.py:28 do')
+
+
+class _CombSubFastStageB(torch.autograd.Function):
+    """Stage B of CombSubFast with its hand-written gradient, so that the drop-in module trains
+    (solver.py:111-113: `model(..., infer=False)` -> loss -> `backward()`).  Gradients flow to the three
+    control tensors only; f0 / phase / noise are data, as in the reference graph."""
+
+    @staticmethod
+    def forward(ctx, hm, hp, nm, f0_frames, prefix, hop, sr, initial_phase, noise_u, seed, window):
+        signal = core.combsubfast_stage(hm, hp, nm, f0_frames, prefix, hop, sr, initial_phase, noise_u=noise_u,
+                                        seed=seed, window=window)
+        ctx.save_for_backward(hm, hp, nm, f0_frames, prefix, noise_u, window)
+        ctx.cfg = (hop, sr, seed)
+        return signal
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_signal):
+        hm, hp, nm, f0_frames, prefix, noise_u, window = ctx.saved_tensors
+        hop, sr, seed = ctx.cfg
+        ghm, ghp, gnm = core.combsubfast_backward_stage(grad_signal, hm, hp, nm, f0_frames, prefix, hop, sr,
+                                                        noise_u=noise_u, seed=seed, window=window)
+        return ghm, ghp, gnm, None, None, None, None, None, None, None, None
 
 
 class CombSubFast(_SynthBase):
@@ -77,12 +100,14 @@ class CombSubFast(_SynthBase):
         phase_frames, prefix, _ = core.phase_stage(f0_frames, self._hop, self._sr, initial_phase, infer)
         # control network (reference PyTorch): vocoder.py:454
         ctrls = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id, spk_mix_dict=spk_mix_dict)
-        self._forward_only(ctrls)
         # stage B: vocoder.py:455-490
         ctrls = {k: core.as_f32(v) for k, v in ctrls.items()}
-        signal = core.combsubfast_stage(ctrls['harmonic_magnitude'], ctrls['harmonic_phase'], ctrls['noise_magnitude'],
-                                        f0_frames, prefix, self._hop, self._sr, initial_phase, noise_u=noise_u,
-                                        seed=self._next_seed(), window=self.window)
+        args = (ctrls['harmonic_magnitude'], ctrls['harmonic_phase'], ctrls['noise_magnitude'], f0_frames, prefix,
+                self._hop, self._sr, initial_phase)
+        if torch.is_grad_enabled() and any(t.requires_grad for t in ctrls.values()):
+            signal = _CombSubFastStageB.apply(*args, noise_u, self._next_seed(), self.window)
+        else:
+            signal = core.combsubfast_stage(*args, noise_u=noise_u, seed=self._next_seed(), window=self.window)
         return signal, phase_frames.unsqueeze(-1), (signal, signal)      # vocoder.py:492
 
 

@@ -125,6 +125,22 @@ int ddsp_b200_combsubfast(const float *harmonic_magnitude, const float *harmonic
                           void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Gradient of stage B of CombSubFast.forward with respect to the three control tensors -- what
+ * autograd derives for vocoder.py:455-492 when the module is trained (solver.py:111,113).
+ * Inputs are those of the forward call (same noise_u or seed, same window, same prefix) plus
+ * grad_signal (B,T) contiguous = dL/dsignal.  Outputs: three (B,F,513) views sharing strides
+ * (gB,gF,1), fully overwritten.  f0 / phase receive no gradient.
+ * ---------------------------------------------------------------------------------------- */
+int ddsp_b200_combsubfast_backward(const float *harmonic_magnitude, const float *harmonic_phase,
+                                   const float *noise_magnitude, int64_t cB, int64_t cF,
+                                   const float *f0_frames, int64_t fB, int64_t fF,
+                                   const double *prefix, const float *noise_u, uint64_t seed,
+                                   const float *window, const float *grad_signal, int B, int F,
+                                   int hop, double sr, float *grad_harmonic_magnitude,
+                                   float *grad_harmonic_phase, float *grad_noise_magnitude,
+                                   int64_t gB, int64_t gF, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Stage B of CombSub.forward (old)                             vocoder.py:521-550
  * ctrl views group_delay (n_mag_allpass), harmonic_magnitude (n_mag_harmonic),
  * noise_magnitude (n_mag_noise) with common strides (cB,cF,1).  Outputs signal, harmonic,

@@ -194,3 +194,21 @@ def test_sins_vs_reference(golden_dir, tag):
     ph_ref = d['phase32'][..., 0]
     step = phase.shape[1] // ph_ref.shape[1]
     np.testing.assert_allclose(phase[:, ::step], ph_ref, atol=1e-6)
+
+
+@pytest.mark.parametrize('tag', ['small', 'even', 'one'])
+def test_port_autograd_matches_reference_gradients(golden_dir, tag):
+    """The stock-PyTorch restatement differentiates to the same control-tensor gradients as the
+    reference module itself (tests/golden/make_golden_grad.py) -- it is the gradient oracle of the
+    GPU backward tests at sizes without a committed fixture."""
+    import torch
+    from oracle import torch_port as TP
+    d = dict(np.load(os.path.join(golden_dir, f'combsubfast_grad_{tag}.npz')))
+    ct = torch.from_numpy(d['ctrl']).double().requires_grad_(True)
+    hm, hp, nm = torch.split(ct, 513, dim=-1)
+    win = torch.sqrt(torch.hann_window(1024)).double()          # the module buffer is built in fp32 (vocoder.py:434)
+    sig, _ = TP.combsubfast_forward(hm, hp, nm, torch.from_numpy(d['f0_frames']).double()[..., None], win,
+                                    torch.from_numpy(d['U']).double())
+    (sig * torch.from_numpy(d['R']).double()).sum().backward()
+    g = ct.grad.numpy()
+    assert np.abs(g - d['grad64']).max() <= 2e-6 * np.abs(d['grad64']).max()
