@@ -510,6 +510,61 @@ def run_forward(args):
                       'rows': rows}), flush=True)
 
 
+def run_train(args):
+    """Synthesizer part of one training step (solver.py:111-113): stage A + stage B forward, then the
+    gradient of the three control tensors for a given dL/dsignal -- our kernels vs autograd through
+    the stock-PyTorch restatement (oracle/torch_port.py) on the same GPU.  Shapes: the training batch
+    of configs/combsub.yaml (24 clips x 2 s) and the headline inference batch."""
+    import torch
+    from ddsp_b200 import core
+    from ddsp_b200.synthetic import make_inputs
+    from oracle import torch_port
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    rows = []
+    for (B, F, iters) in [(24, 173, 200), (64, 862, 30)]:
+        d = make_inputs(B, F, 1539, seed=1234)
+        ctrl = torch.from_numpy(d['ctrl']).to(dev)
+        hm, hp, nm = torch.split(ctrl, 513, dim=-1)
+        f0 = torch.from_numpy(d['f0_frames']).to(dev)[..., None]
+        U = torch.from_numpy(d['U']).to(dev)
+        R = torch.randn(B, F * HOP, device=dev)
+        win = torch.sqrt(torch.hann_window(2 * HOP, device=dev))
+
+        def ours():
+            _, prefix, _ = core.phase_stage(f0, HOP, SR, None, True)
+            core.combsubfast_stage(hm, hp, nm, f0, prefix, HOP, SR, None, noise_u=U, window=win)
+            return core.combsubfast_backward_stage(R, hm, hp, nm, f0, prefix, HOP, SR, noise_u=U, window=win)
+
+        def port():
+            c = ctrl.detach().requires_grad_(True)
+            a, b_, c_ = torch.split(c, 513, dim=-1)
+            sig, _ = torch_port.combsubfast_forward(a, b_, c_, f0, win, U)
+            sig.backward(R)
+            return c.grad
+
+        res = {}
+        for name, fn, n in (('ours', ours, iters), ('torch_autograd', port, max(3, iters // 10))):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            res[name] = e0.elapsed_time(e1) / n
+        g_ours = torch.cat(ours(), dim=-1)
+        g_ref = port()
+        rel = ((g_ours - g_ref).abs().max() / g_ref.abs().max()).item()
+        rows.append({'clips': B, 'frames': F, 'ours_fwd_bwd_ms': res['ours'], 'torch_autograd_fwd_bwd_ms': res['torch_autograd'],
+                     'speedup': res['torch_autograd'] / res['ours'], 'samples_per_s': B * F * HOP / (res['ours'] * 1e-3),
+                     'grad_max_rel_diff': rel})
+    print(json.dumps({'metric': 'synth training step (stage A + stage B forward + control-tensor gradient)',
+                      'model': 'combsubfast', 'rows': rows}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -523,7 +578,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--torch-port', action='store_true',
                     help='also time the stock-PyTorch-ops restatement of the path on the same GPU (CombSubFast)')
-    ap.add_argument('--mode', default='throughput', choices=['throughput', 'latency', 'forward'])
+    ap.add_argument('--mode', default='throughput', choices=['throughput', 'latency', 'forward', 'train'])
     ap.add_argument('--latency-frames', default='9,18,26,130')
     ap.add_argument('--latency-iters', type=int, default=1000)
     args = ap.parse_args()
@@ -532,6 +587,9 @@ def main():
         return
     if args.mode == 'forward':
         run_forward(args)
+        return
+    if args.mode == 'train':
+        run_train(args)
         return
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
