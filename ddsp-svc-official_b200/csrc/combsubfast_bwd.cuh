@@ -92,6 +92,10 @@ __global__ void __launch_bounds__(kCsbThreads, 1) combsubfast_backward_kernel(co
             csf_gen_hop(P, fm, csf_load_hop(P, b, fm), ring + (fm & 1) * kRingSlot, lane);
             __syncwarp();
             if (s < 0) { s = 0; continue; }
+            {   // pull this frame's three control rows into L2 while the FFT runs (lanes 0..16: one line each)
+                const int64_t rp = (int64_t)b * P.cB + (int64_t)min(fm, F - 1) * P.cF + 32 * lane;
+                if (lane <= 16) { prefetch_l2(P.hm + rp); prefetch_l2(P.hp + rp); prefetch_l2(P.nm + rp); }
+            }
             csf_load_frame<HAS_U>(P, X, ring, win, fm, b, (uint32_t)ctx[3], lane);
         } else {
             // ---- q_2p -> real part, q_2p+1 -> imaginary part --------------------------------------
@@ -118,40 +122,69 @@ __global__ void __launch_bounds__(kCsbThreads, 1) combsubfast_backward_kernel(co
 
         // ---- split the packed spectrum into the two real-input spectra (x2) ---------------------
         // first = spectrum of the real part, second = spectrum of the imaginary part
-        const int row = min(fm, F - 1);
-        const int64_t ro = (int64_t)b * P.cB + (int64_t)row * P.cF + lane;
-        const int64_t go = (int64_t)b * PB.gB + (int64_t)row * PB.gF + lane;
-        const bool store = (s != 0) && fm <= F;
-        const bool shared_row = fm >= F - 1;                 // row F-1 also serves frame F
-        const float2* Qs = stash + (s == 2 ? kStashFloat2 : 0);
+        if (s == 0) {
+            // gradient spectra of frames 2p / 2p+1 -> the two parked slots; bins 0 and 512 (lane 0,
+            // q = 0 / 16) drop their imaginary part (irfft ignores it, so it has no gradient)
 #pragma unroll
-        for (int q = 0; q < 17; ++q) {
-            float a, bb, c, d;
-            if (q < 16) {
-                a = DDSP_RE(X, q); bb = DDSP_IM(X, q);
-                c = __shfl_sync(kFullMask, DDSP_RE(X, 31 - q), partner);
-                d = __shfl_sync(kFullMask, DDSP_IM(X, 31 - q), partner);
+            for (int q = 0; q < 16; ++q) {
+                const float a = DDSP_RE(X, q), bb = DDSP_IM(X, q);
+                float c = __shfl_sync(kFullMask, DDSP_RE(X, 31 - q), partner);
+                float d = __shfl_sync(kFullMask, DDSP_IM(X, 31 - q), partner);
                 const float c0 = DDSP_RE(X, (32 - q) & 31), d0 = DDSP_IM(X, (32 - q) & 31);
                 c = lane0 ? c0 : c;
                 d = lane0 ? d0 : d;
-            } else {
-                a = DDSP_RE(X, 16); bb = DDSP_IM(X, 16); c = a; d = bb;
+                const bool edge = lane0 && q == 0;
+                stash[q * 32 + lane] = make_float2(a + c, edge ? 0.0f : bb - d);
+                stash[kStashFloat2 + q * 32 + lane] = make_float2(bb + d, edge ? 0.0f : c - a);
             }
-            const float Cr = a + c, Ci = bb - d, Nr = bb + d, Ni = c - a;
-            // bins 0 and 512 (lane 0, q = 0 / 16): weight 1 instead of 2, imaginary gradient ignored
-            const bool edge = lane0 && (q == 0 || q == 16);
-            if (s == 0) {
-                const int slot = (q < 16) ? q * 32 + lane : 16 * 32;
-                if (q < 16 || lane0) {
-                    stash[slot] = make_float2(Cr, edge ? 0.0f : Ci);
-                    stash[kStashFloat2 + slot] = make_float2(Nr, edge ? 0.0f : Ni);
+            if (lane0) {
+                stash[16 * 32] = make_float2(2.0f * DDSP_RE(X, 16), 0.0f);
+                stash[kStashFloat2 + 16 * 32] = make_float2(2.0f * DDSP_IM(X, 16), 0.0f);
+            }
+            s = 1;
+            continue;
+        }
+        if (fm <= F) {          // (frame F+1 of an odd-length pair list does not exist)
+            const int row = min(fm, F - 1);
+            const float* hm_r = P.hm + ((int64_t)b * P.cB + (int64_t)row * P.cF + lane);
+            const float* hp_r = P.hp + ((int64_t)b * P.cB + (int64_t)row * P.cF + lane);
+            const float* nm_r = P.nm + ((int64_t)b * P.cB + (int64_t)row * P.cF + lane);
+            float* ghm_r = PB.ghm + ((int64_t)b * PB.gB + (int64_t)row * PB.gF + lane);
+            float* ghp_r = PB.ghp + ((int64_t)b * PB.gB + (int64_t)row * PB.gF + lane);
+            float* gnm_r = PB.gnm + ((int64_t)b * PB.gB + (int64_t)row * PB.gF + lane);
+            const bool shared_row = fm >= F - 1;             // row F-1 also serves frame F
+            const float2* Qs = stash + (s == 2 ? kStashFloat2 : 0);
+            // control loads run kLook bins ahead of their use (bin 512 lives on lane 0 only; others read a dummy)
+            constexpr int kLook = 4;
+            const int k16 = lane0 ? 512 : 0;
+            float chm[kLook], chp[kLook], cnm[kLook];
+#pragma unroll
+            for (int q = 0; q < kLook; ++q) {
+                chm[q] = __ldg(hm_r + 32 * q); chp[q] = __ldg(hp_r + 32 * q); cnm[q] = __ldg(nm_r + 32 * q);
+            }
+#pragma unroll
+            for (int q = 0; q < 17; ++q) {
+                const float vhm = chm[q % kLook], vhp = chp[q % kLook], vnm = cnm[q % kLook];
+                if (q + kLook < 17) {
+                    const int offn = (q + kLook < 16) ? 32 * (q + kLook) : k16;
+                    chm[q % kLook] = __ldg(hm_r + offn); chp[q % kLook] = __ldg(hp_r + offn); cnm[q % kLook] = __ldg(nm_r + offn);
                 }
-            } else if (q < 16 || lane0) {
-                const int off = (q < 16) ? 32 * q : 512;
-                const float vhm = __ldg(P.hm + ro + off), vhp = __ldg(P.hp + ro + off), vnm = __ldg(P.nm + ro + off);
+                float a, bb, c, d;
+                if (q < 16) {
+                    a = DDSP_RE(X, q); bb = DDSP_IM(X, q);
+                    c = __shfl_sync(kFullMask, DDSP_RE(X, 31 - q), partner);
+                    d = __shfl_sync(kFullMask, DDSP_IM(X, 31 - q), partner);
+                    const float c0 = DDSP_RE(X, (32 - q) & 31), d0 = DDSP_IM(X, (32 - q) & 31);
+                    c = lane0 ? c0 : c;
+                    d = lane0 ? d0 : d;
+                } else {
+                    a = DDSP_RE(X, 16); bb = DDSP_IM(X, 16); c = a; d = bb;
+                }
+                const float Cr = a + c, Ci = bb - d, Nr = bb + d, Ni = c - a;
                 const float2 G = Qs[(q < 16) ? q * 32 + lane : 16 * 32];
-                // 1/2 (split of C) * 1/2 (split of Q) * c_k/1024 folded into the exponentials
-                const float esh = edge ? 1.0f : 0.0f;
+                // 1/2 (split of C) * 1/2 (split of Q) * c_k/1024 folded into the exponentials;
+                // c_k = 1 instead of 2 for bins 0 and 512 (lane 0, q = 0 / 16)
+                const float esh = (lane0 && (q == 0 || q == 16)) ? 1.0f : 0.0f;
                 const float gmag = ex2_approx(fmaf(vhm, DDSP_LOG2E_F, -11.0f - esh));
                 const float ang = DDSP_PI_F * vhp;
                 const float Hr = gmag * cos_approx(ang), Hi = gmag * sin_approx(ang);
@@ -160,15 +193,16 @@ __global__ void __launch_bounds__(kCsbThreads, 1) combsubfast_backward_kernel(co
                 const float d_hm = fmaf(G.x, Ar, G.y * Ai);
                 const float d_hp = DDSP_PI_F * fmaf(G.y, Ar, -G.x * Ai);
                 const float d_nm = nf * fmaf(G.x, Nr, G.y * Ni);
-                if (store) {
+                if (q < 16 || lane0) {
+                    const int off = (q < 16) ? 32 * q : 512;
                     if (shared_row) {
-                        atomicAdd(PB.ghm + go + off, d_hm);
-                        atomicAdd(PB.ghp + go + off, d_hp);
-                        atomicAdd(PB.gnm + go + off, d_nm);
+                        atomicAdd(ghm_r + off, d_hm);
+                        atomicAdd(ghp_r + off, d_hp);
+                        atomicAdd(gnm_r + off, d_nm);
                     } else {
-                        PB.ghm[go + off] = d_hm;
-                        PB.ghp[go + off] = d_hp;
-                        PB.gnm[go + off] = d_nm;
+                        ghm_r[off] = d_hm;
+                        ghp_r[off] = d_hp;
+                        gnm_r[off] = d_nm;
                     }
                 }
             }
@@ -178,7 +212,7 @@ __global__ void __launch_bounds__(kCsbThreads, 1) combsubfast_backward_kernel(co
             if (++p >= ctx[2]) break;
             s = 0;
         } else {
-            ++s;
+            s = 2;
         }
     }
 }
