@@ -504,8 +504,22 @@ def run_forward(args):
                 a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(); g.replay(); b_.record(); b_.synchronize()
                 ts.append(a.elapsed_time(b_))
+            tf32_ms = None
+            if hasattr(model.unit2ctrl, 'matmul_tf32'):      # opt-in TF32 GEMMs in the control network
+                model.unit2ctrl.matmul_tf32 = True
+                for _ in range(3):
+                    model(units, f0, vol, spk)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(iters):
+                    model(units, f0, vol, spk)
+                e1.record()
+                torch.cuda.synchronize()
+                tf32_ms = e0.elapsed_time(e1) / iters
+                model.unit2ctrl.matmul_tf32 = False
         rows.append({'clips': B, 'frames': F, 'eager_ms': eager_ms, 'graph_ms_p50': float(np.percentile(ts, 50)),
-                     'graph_ms_p99': float(np.percentile(ts, 99)), 'samples_per_s_graph': B * F * HOP / (np.percentile(ts, 50) * 1e-3)})
+                     'graph_ms_p99': float(np.percentile(ts, 99)), 'samples_per_s_graph': B * F * HOP / (np.percentile(ts, 50) * 1e-3),
+                     'eager_ms_tf32_gemm_opt_in': tf32_ms})
     print(json.dumps({'metric': 'full forward (stage A + PyTorch Unit2Control + stage B)', 'model': 'combsubfast',
                       'rows': rows}), flush=True)
 

@@ -3,9 +3,11 @@ state_dict-compatible with the reference's `ddsp/unit2control.py` + `ddsp/pcmer.
 drop-in synthesizer modules are usable (and reference checkpoints load with `strict=True`) without
 the reference repo and its un-vendored dependencies (`extorch`, `pytorch-fast-transformers`).
 
-This is NOT part of the hand-written hot path: it runs stock PyTorch ops (cuBLAS / cuDNN), exactly
-like the reference's own control network, and exists so that the full `forward` can be measured
-and CUDA-graphed end to end.  Only the non-causal configuration (`c: false`, the value in every
+This is NOT part of the hand-written synthesizer path: the GEMMs and convolutions are stock PyTorch
+ops (cuBLAS / cuDNN), exactly like the reference's own control network.  Under `torch.no_grad()` on
+CUDA the memory-bound chains between the GEMMs run as two fused kernels of `csrc/control.cuh`
+(FAVOR+ feature map; GLU -> depthwise conv -> SiLU in channels-last layout); with autograd enabled or
+on CPU the plain ops below run.  Only the non-causal configuration (`c: false`, the value in every
 shipped config) is implemented.
 
 Structure (the module / parameter names are dictated by the checkpoint layout):
@@ -64,6 +66,12 @@ def _softmax_features(x, proj, is_query, eps=1e-4):
     return ratio * torch.exp(dash - diag + eps)
 
 
+def _fused_ok(x):
+    """The fused CUDA stages (csrc/control.cuh) are inference-only and fp32-only; everything else --
+    CPU tensors, autograd, other dtypes -- takes the plain PyTorch ops below."""
+    return x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
+
+
 class _FastAttention(nn.Module):
     def __init__(self, dim_head):
         super().__init__()
@@ -73,6 +81,10 @@ class _FastAttention(nn.Module):
     def forward(self, q, k, v):
         q = _softmax_features(q, self.projection_matrix, True)
         k = _softmax_features(k, self.projection_matrix, False)
+        return self.attend(q, k, v)
+
+    @staticmethod
+    def attend(q, k, v):
         # non-causal linear attention (pcmer.py:69-78)
         k_sum = k.sum(dim=-2)
         d_inv = 1.0 / (torch.einsum('bhnj,bhj->bhn', q, k_sum) + 1e-8)
@@ -94,6 +106,15 @@ class _SelfAttention(nn.Module):
     def forward(self, x):
         b, n, _ = x.shape
         split = lambda t: t.view(b, n, self.heads, _DIM_HEAD).transpose(1, 2)      # noqa: E731
+        if _fused_ok(x):
+            from . import core
+            proj_t = self.fast_attention.projection_matrix.t()
+            q, k = self.to_q(x), self.to_k(x)
+            scale = _DIM_HEAD ** -0.25
+            feats = [core.performer_features(torch.matmul((scale * t).view(-1, _DIM_HEAD), proj_t), t, self.heads, is_q)
+                     for t, is_q in ((q, True), (k, False))]
+            out = self.fast_attention.attend(feats[0], feats[1], split(self.to_v(x)))
+            return self.to_out(out.transpose(1, 2).reshape(b, n, self.heads * _DIM_HEAD))
         out = self.fast_attention(split(self.to_q(x)), split(self.to_k(x)), split(self.to_v(x)))
         return self.to_out(out.transpose(1, 2).reshape(b, n, self.heads * _DIM_HEAD))
 
@@ -115,6 +136,11 @@ class _ConvModule(nn.Module):
         )
 
     def forward(self, x):
+        if _fused_ok(x):
+            from . import core
+            ln, _, pw1, _, dw, _, pw2, _, _ = self.net
+            u = F.linear(ln(x), pw1.weight.squeeze(-1), pw1.bias)                  # channels last: no transposes
+            return F.linear(core.glu_dwconv_silu(u, dw.weight, dw.bias), pw2.weight.squeeze(-1), pw2.bias)
         return self.net(x)
 
 
@@ -163,7 +189,22 @@ class Unit2Control(nn.Module):
         self.dec_post = nn.Sequential(PCmer(3, _HEADS, _DIM), nn.LayerNorm(_DIM), weight_norm(nn.Linear(_DIM, n_out)))
         self.output_splits = dict(output_splits)
 
+    # Opt-in: run the fp32 GEMMs of the network on the TF32 tensor cores (the reference's cuDNN
+    # convolutions already do by PyTorch default; its Linear layers do not).  Off by default so that the
+    # control rows match the reference's fp32 Linear arithmetic.
+    matmul_tf32 = False
+
     def forward(self, units, f0, phase, volume, spk_id, spk_mix_dict=None):
+        if self.matmul_tf32 and units.is_cuda:
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True
+            try:
+                return self._forward(units, f0, phase, volume, spk_id, spk_mix_dict)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+        return self._forward(units, f0, phase, volume, spk_id, spk_mix_dict)
+
+    def _forward(self, units, f0, phase, volume, spk_id, spk_mix_dict=None):
         x = self.unit_prenet(units)
         x = x + self.f0_embed((1 + f0 / 700).log()) + self.phase_embed(phase.unsqueeze(-1) / math.pi) \
             + self.volume_embed(volume.unsqueeze(-1))

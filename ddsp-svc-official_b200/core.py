@@ -356,3 +356,39 @@ def apply_frame_mask_(signal, mask_frames, block_size=512):
 
 def last_launch_count():
     return _cabi.lib().ddsp_b200_last_launch_count()
+
+
+# ------------------------------------------------------------------------------------------------
+# fused elementwise stages of the control network (not on the synthesizer path)
+def performer_features(dash, x, heads, is_query, eps=1e-4):
+    """FAVOR+ softmax-kernel features (pcmer.py:124-160).  dash (B,N,H*M) or (B,N,H,M) =
+    (64^-0.25 * x) @ projection^T, x (B,N,H*64) -> (B,H,N,M)."""
+    dash = _need_cuda_f32(dash, 'dash').contiguous()
+    x = _need_cuda_f32(x, 'x').contiguous()
+    B, N = x.shape[0], x.shape[1]
+    H = int(heads)
+    if x.numel() != B * N * H * 64 or dash.numel() % (B * N * H):
+        raise ValueError('x must be (B, N, heads*64) and dash (B, N, heads, M)')
+    M = dash.numel() // (B * N * H)
+    out = torch.empty((B, H, N, M), dtype=torch.float32, device=x.device)
+    with _OnDevice(x.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_performer_features(dash.data_ptr(), x.data_ptr(), B, N, H, M, int(bool(is_query)),
+                                                             float(eps), out.data_ptr(), _st))
+    return out
+
+
+def glu_dwconv_silu(u, weight, bias):
+    """GLU -> depthwise Conv1d(k=31, 'same') -> SiLU in channels-last layout (pcmer.py:53-55).
+    u (B,T,2C), weight (C,1,31) or (C,31), bias (C) -> (B,T,C)."""
+    u = _need_cuda_f32(u, 'u').contiguous()
+    B, T, C2 = u.shape
+    C = C2 // 2
+    weight = _need_cuda_f32(weight, 'weight').reshape(C, -1).contiguous()
+    if weight.shape[1] != 31:
+        raise ValueError('depthwise kernel size must be 31')
+    bias = _need_cuda_f32(bias, 'bias').contiguous()
+    out = torch.empty((B, T, C), dtype=torch.float32, device=u.device)
+    with _OnDevice(u.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_glu_dwconv_silu(u.data_ptr(), weight.data_ptr(), bias.data_ptr(), B, T, C,
+                                                          out.data_ptr(), _st))
+    return out

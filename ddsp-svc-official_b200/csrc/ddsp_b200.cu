@@ -9,6 +9,7 @@
 
 #include "combsubfast.cuh"
 #include "combsubfast_bwd.cuh"
+#include "control.cuh"
 #include "excite.cuh"
 #include "ltvfir.cuh"
 #include "phase.cuh"
@@ -461,6 +462,35 @@ int ddsp_b200_apply_frame_mask(float* signal, const float* mask_frames, int64_t 
     const int64_t n4 = (int64_t)B * F * (hop / 4);
     ddsp::apply_frame_mask_kernel<<<(unsigned)grid_for(n4, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<float4*>(signal), mask_frames, mB, mF, B, F);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int ddsp_b200_performer_features(const float* dash, const float* x, int B, int N, int H, int M, int is_query, float eps,
+                                 float* out, void* stream) {
+    g_launches = 0;
+    if (!dash || !x || !out || B <= 0 || N <= 0 || H <= 0 || M <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (M > 384 || ((uintptr_t)x & 7)) return DDSP_B200_ERR_UNSUPPORTED;
+    const int64_t rows = (int64_t)B * N * H;
+    const unsigned grid = (unsigned)grid_for(rows, 8, (int64_t)sm_count() * 32);
+    const float ratio = 1.0f / sqrtf((float)M);
+    if (is_query)
+        ddsp::performer_features_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(dash, x, out, B, N, H, M, 0.0625f,
+                                                                                     ratio, eps);
+    else
+        ddsp::performer_features_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dash, x, out, B, N, H, M, 0.0625f,
+                                                                                      ratio, eps);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int ddsp_b200_glu_dwconv_silu(const float* u, const float* weight, const float* bias, int B, int T, int C, float* out,
+                              void* stream) {
+    g_launches = 0;
+    if (!u || !weight || !bias || !out || B <= 0 || T <= 0 || C <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (B > 65535) return DDSP_B200_ERR_UNSUPPORTED;
+    const dim3 grid((C + ddsp::kDwTileC - 1) / ddsp::kDwTileC, (T + ddsp::kDwTileT - 1) / ddsp::kDwTileT, B);
+    ddsp::glu_dwconv_silu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(u, weight, bias, out, B, T, C);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }

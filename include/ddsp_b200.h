@@ -178,6 +178,23 @@ int ddsp_b200_sins(const float *amplitudes, int n_harmonics, const float *group_
 int ddsp_b200_apply_frame_mask(float *signal, const float *mask_frames, int64_t mB, int64_t mF, int B,
                                int F, int hop, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Control network (ddsp/unit2control.py, ddsp/pcmer.py) -- fused elementwise stages between the
+ * library GEMMs.  Not part of the synthesizer path; see DESIGN.md section 7.
+ *
+ * FAVOR+ softmax-kernel feature map                               pcmer.py:124-160
+ *   dash (B,N,H,M) contiguous = (64^-0.25 * x) @ projection^T;  x (B,N,H,64) contiguous (to_q / to_k
+ *   output before the head split);  out (B,H,N,M) contiguous:
+ *   query: M^-0.5 * (exp(dash - |x|^2/16 - max_j dash) + eps);  key: M^-0.5 * exp(dash - |x|^2/16 + eps).
+ *   M <= 384.
+ * GLU -> depthwise Conv1d(k=31, padding 'same') -> SiLU          pcmer.py:53-55, channels last
+ *   u (B,T,2C) contiguous, weight (C,31), bias (C), out (B,T,C) contiguous.
+ * ---------------------------------------------------------------------------------------- */
+int ddsp_b200_performer_features(const float *dash, const float *x, int B, int N, int H, int M,
+                                 int is_query, float eps, float *out, void *stream);
+int ddsp_b200_glu_dwconv_silu(const float *u, const float *weight, const float *bias, int B, int T,
+                              int C, float *out, void *stream);
+
 /* Number of kernel launches the last call of each entry point enqueued on this thread
  * (bench.py reports it as gpu_launches). */
 int ddsp_b200_last_launch_count(void);

@@ -1,0 +1,86 @@
+"""Fused stages of the control network (csrc/control.cuh) against the plain PyTorch ops they replace
+(ddsp_b200/control.py, itself checked against the reference modules in tests/test_control.py)."""
+import numpy as np
+import pytest
+
+from tests.gpu_util import HAS_CUDA, torch
+
+pytestmark = pytest.mark.gpu
+
+if HAS_CUDA:
+    import torch.nn.functional as F
+    from ddsp_b200 import core
+    from ddsp_b200.control import Unit2Control, _softmax_features
+
+
+@pytest.mark.parametrize('B,N,H', [(1, 1, 8), (2, 37, 8), (3, 130, 4)])
+@pytest.mark.parametrize('is_query', [True, False])
+def test_performer_features(B, N, H, is_query):
+    torch.manual_seed(B * 100 + N)
+    x = torch.randn(B, N, H * 64, device='cuda') * 1.5
+    proj = torch.randn(266, 64, device='cuda')
+    ref = _softmax_features(x.view(B, N, H, 64).transpose(1, 2), proj, is_query)        # (B,H,N,266)
+    dash = torch.matmul((64 ** -0.25 * x).view(-1, 64), proj.t())
+    out = core.performer_features(dash, x, H, is_query)
+    assert out.shape == ref.shape
+    assert torch.isfinite(out).all()
+    assert ((out - ref).abs() <= 1e-4 * ref.abs() + 1e-9).all(), (out - ref).abs().max().item()   # exp() of args up to ~20
+
+
+@pytest.mark.parametrize('B,T,C', [(1, 5, 512), (2, 64, 512), (2, 131, 512), (1, 300, 96)])
+def test_glu_dwconv_silu(B, T, C):
+    torch.manual_seed(T)
+    u = torch.randn(B, T, 2 * C, device='cuda')
+    w = torch.randn(C, 1, 31, device='cuda') * 0.2
+    b = torch.randn(C, device='cuda')
+    ref = F.silu(F.conv1d(F.glu(u.transpose(1, 2).double(), dim=1), w.double(), b.double(), padding=15, groups=C))
+    out = core.glu_dwconv_silu(u, w, b)
+    assert out.shape == (B, T, C)
+    assert (out.double() - ref.transpose(1, 2)).abs().max().item() < 5e-6
+
+
+@pytest.mark.parametrize('B,F_', [(1, 9), (2, 130), (3, 77)])
+def test_unit2control_fused_matches_plain_ops(B, F_):
+    """no_grad on CUDA takes the fused stages; under enable_grad the same module runs stock ops."""
+    torch.manual_seed(7)
+    splits = {'harmonic_magnitude': 513, 'harmonic_phase': 513, 'noise_magnitude': 513}
+    net = Unit2Control(32, 3, splits).cuda().eval()
+    units = torch.randn(B, F_, 32, device='cuda')
+    f0 = torch.rand(B, F_, 1, device='cuda') * 500 + 80
+    ph = (torch.rand(B, F_, device='cuda') - 0.5) * 6
+    vol = torch.rand(B, F_, device='cuda')
+    spk = torch.full((B, 1), 2, dtype=torch.long, device='cuda')
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the stock 1x1 convs would otherwise run in TF32
+    try:
+        with torch.enable_grad():
+            ref = net(units, f0, ph, vol, spk)
+        with torch.no_grad():
+            out = net(units, f0, ph, vol, spk)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    for k in splits:
+        assert out[k].shape == ref[k].shape and not out[k].requires_grad
+        assert (out[k] - ref[k].detach()).abs().max().item() < 5e-5, k
+    # views of one tensor, as the reference's split_to_dict emits
+    assert out['harmonic_phase'].data_ptr() == out['harmonic_magnitude'].data_ptr() + 513 * 4
+
+
+def test_fused_forward_is_graph_capturable():
+    torch.manual_seed(8)
+    net = Unit2Control(16, 1, {'a': 513, 'b': 513, 'c': 513}).cuda().eval()
+    args = (torch.randn(1, 26, 16, device='cuda'), torch.rand(1, 26, 1, device='cuda') * 300 + 100,
+            torch.rand(1, 26, device='cuda'), torch.rand(1, 26, device='cuda'),
+            torch.ones(1, 1, dtype=torch.long, device='cuda'))
+    with torch.no_grad():
+        eager = net(*args)['a'].clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            net(*args)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                out = net(*args)
+        g.replay()
+        torch.cuda.synchronize()
+    assert np.allclose(out['a'].cpu().numpy(), eager.cpu().numpy(), atol=1e-6)
