@@ -99,14 +99,16 @@ def test_state_dict_keys_and_load_model(tmp_path):
     keys = set(m.state_dict().keys())
     assert {'sampling_rate', 'block_size', 'window', 'unit2ctrl.lin.weight', 'unit2ctrl.lin.bias'} == keys
     assert m.state_dict()['window'].shape == (1024,) and m.state_dict()['sampling_rate'].dtype == torch.int64
-    # a control network that requires grad must be refused outside no_grad (forward-only path)
+    # outside no_grad CombSubFast records its hand-written backward (tests/test_gpu_backward.py)
     m = m.cuda()
     units = torch.randn(1, 6, 4).cuda()
     f0 = torch.full((1, 6, 1), 220.0).cuda()
     vol = torch.zeros(1, 6).cuda()
     spk = torch.ones(1, 1, dtype=torch.long).cuda()
-    with pytest.raises(RuntimeError):
-        m(units, f0, vol, spk)
+    sig, _, _ = m(units, f0, vol, spk)
+    assert sig.requires_grad
+    sig.square().mean().backward()
+    assert m.unit2ctrl.lin.weight.grad is not None and torch.isfinite(m.unit2ctrl.lin.weight.grad).all()
     with torch.no_grad():
         sig, ph, (h, n) = m(units, f0, vol, spk)
     assert sig.shape == (1, 6 * 512) and h is sig and n is sig          # vocoder.py:492 returns the same tensor thrice
