@@ -28,6 +28,7 @@ from torch.nn.utils import weight_norm
 _DIM = 256
 _HEADS = 8
 _DIM_HEAD = 64
+_FUSED_PROJECTION_MIN_ROWS = 1 << 16      # (batch x frames x heads) above which the fused projection kernel wins
 
 
 class _Swap(nn.Module):
@@ -108,12 +109,18 @@ class _SelfAttention(nn.Module):
         split = lambda t: t.view(b, n, self.heads, _DIM_HEAD).transpose(1, 2)      # noqa: E731
         if _fused_ok(x):
             from . import core
-            proj_t = self.fast_attention.projection_matrix.t()
+            proj = self.fast_attention.projection_matrix
             q, k = self.to_q(x), self.to_k(x)
-            scale = _DIM_HEAD ** -0.25
-            feats = [core.performer_features(torch.matmul((scale * t).view(-1, _DIM_HEAD), proj_t), t, self.heads, is_q)
-                     for t, is_q in ((q, True), (k, False))]
-            out = self.fast_attention.attend(feats[0], feats[1], split(self.to_v(x)))
+            if b * n * self.heads >= _FUSED_PROJECTION_MIN_ROWS:
+                # large batches: projection fused into the feature kernel, the (B,N,H,266) products stay on chip
+                q = core.performer_project_features(q, proj, self.heads, True)
+                k = core.performer_project_features(k, proj, self.heads, False)
+            else:
+                # streaming blocks: a library GEMM + the one-pass feature kernel has the lower latency
+                scale = _DIM_HEAD ** -0.25
+                q, k = [core.performer_features(torch.matmul((scale * t).view(-1, _DIM_HEAD), proj.t()), t, self.heads, is_q)
+                        for t, is_q in ((q, True), (k, False))]
+            out = self.fast_attention.attend(q, k, split(self.to_v(x)))
             return self.to_out(out.transpose(1, 2).reshape(b, n, self.heads * _DIM_HEAD))
         out = self.fast_attention(split(self.to_q(x)), split(self.to_k(x)), split(self.to_v(x)))
         return self.to_out(out.transpose(1, 2).reshape(b, n, self.heads * _DIM_HEAD))

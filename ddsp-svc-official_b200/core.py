@@ -377,6 +377,23 @@ def performer_features(dash, x, heads, is_query, eps=1e-4):
     return out
 
 
+def performer_project_features(x, projection, heads, is_query, eps=1e-4):
+    """`performer_features` with the random-feature projection fused: x (B,N,H*64), projection (M,64)
+    -> (B,H,N,M); the (B,N,H,M) projections never touch HBM."""
+    x = _need_cuda_f32(x, 'x').contiguous()
+    projection = _need_cuda_f32(projection, 'projection').contiguous()
+    B, N = x.shape[0], x.shape[1]
+    H = int(heads)
+    if x.numel() != B * N * H * 64 or projection.dim() != 2 or projection.shape[1] != 64:
+        raise ValueError('x must be (B, N, heads*64) and projection (M, 64)')
+    M = projection.shape[0]
+    out = torch.empty((B, H, N, M), dtype=torch.float32, device=x.device)
+    with _OnDevice(x.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_performer_project_features(x.data_ptr(), projection.data_ptr(), B, N, H, M,
+                                                                     int(bool(is_query)), float(eps), out.data_ptr(), _st))
+    return out
+
+
 def glu_dwconv_silu(u, weight, bias):
     """GLU -> depthwise Conv1d(k=31, 'same') -> SiLU in channels-last layout (pcmer.py:53-55).
     u (B,T,2C), weight (C,1,31) or (C,31), bias (C) -> (B,T,C)."""

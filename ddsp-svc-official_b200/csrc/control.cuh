@@ -66,6 +66,105 @@ __global__ void __launch_bounds__(256) performer_features_kernel(const float* __
     }
 }
 
+// Projection + feature map in one kernel: dash never touches HBM.
+//   x    : (B, N, H, 64) contiguous;  proj : (M, 64) random-feature matrix (pcmer.py:80-120 buffer)
+//   out  : (B, H, N, M)
+// dash[r][j] = sum_d fl(normalizer * x[r][d]) * proj[j][d]  (fp32 FMA chain over d), then the feature
+// map above.  A CTA keeps proj^T (64 x 288, zero padded) in shared memory; a warp owns kPpfRows rows
+// at a time (72 accumulators per lane: 8 rows x 9 column groups), x is staged per warp in shared
+// memory and read back as broadcast float4s: 9 + 2 shared loads per 72 FMAs.
+constexpr int kPpfRows = 8, kPpfCols = 288, kPpfWarps = 8;
+constexpr int kPpfSmemBytes = (kPerfDim * kPpfCols + kPpfWarps * kPpfRows * kPerfDim) * 4;
+
+template <bool IS_QUERY>
+__global__ void __launch_bounds__(kPpfWarps * 32, 2) performer_project_features_kernel(
+    const float* __restrict__ x, const float* __restrict__ proj, float* __restrict__ out, int B, int N, int H, int M,
+    float normalizer, float normalizer2_half, float ratio, float eps) {
+    extern __shared__ __align__(16) float ppf_smem[];
+    float* PT = ppf_smem;                                       // [64][288]: PT[d][j] = proj[j][d]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* xs = ppf_smem + kPerfDim * kPpfCols + wid * (kPpfRows * kPerfDim);   // [8][64] scaled rows of this warp
+    for (int e = threadIdx.x; e < kPerfDim * kPpfCols; e += kPpfWarps * 32) {
+        const int j = e / kPerfDim, d = e % kPerfDim;           // read proj row-major (coalesced), write transposed
+        PT[d * kPpfCols + j] = (j < M) ? __ldg(proj + (int64_t)j * kPerfDim + d) : 0.0f;
+    }
+    __syncthreads();
+    const int64_t rows = (int64_t)B * N * H;
+    const int64_t groups = (rows + kPpfRows - 1) / kPpfRows;
+    for (int64_t g = (int64_t)blockIdx.x * kPpfWarps + wid; g < groups; g += (int64_t)gridDim.x * kPpfWarps) {
+        const int64_t r0 = g * kPpfRows;
+        // stage 8 rows (512 floats): lane holds 16 consecutive floats = a quarter of row lane/4
+        float ss = 0.0f;
+        {
+            const int64_t row = r0 + (lane >> 2);
+            const float4* src = reinterpret_cast<const float4*>(x + row * kPerfDim) + (lane & 3) * 4;
+            float4* dst = reinterpret_cast<float4*>(xs + (lane >> 2) * kPerfDim) + (lane & 3) * 4;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < rows) t = __ldg(src + v);
+                ss = fmaf(t.x, t.x, fmaf(t.y, t.y, fmaf(t.z, t.z, fmaf(t.w, t.w, ss))));
+                dst[v] = make_float4(normalizer * t.x, normalizer * t.y, normalizer * t.z, normalizer * t.w);
+            }
+            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 2);           // lanes 4r..4r+3 hold |x_r|^2
+        }
+        __syncwarp();
+        float acc[kPpfRows][9];
+#pragma unroll
+        for (int r = 0; r < kPpfRows; ++r)
+#pragma unroll
+            for (int i = 0; i < 9; ++i) acc[r][i] = 0.0f;
+#pragma unroll 1
+        for (int d4 = 0; d4 < kPerfDim; d4 += 4) {
+            float4 xv[kPpfRows];
+#pragma unroll
+            for (int r = 0; r < kPpfRows; ++r) xv[r] = *reinterpret_cast<const float4*>(xs + r * kPerfDim + d4);
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) {
+                float pv[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) pv[i] = PT[(d4 + dd) * kPpfCols + lane + 32 * i];
+#pragma unroll
+                for (int r = 0; r < kPpfRows; ++r) {
+                    const float xr = dd == 0 ? xv[r].x : dd == 1 ? xv[r].y : dd == 2 ? xv[r].z : xv[r].w;
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) acc[r][i] = fmaf(xr, pv[i], acc[r][i]);
+                }
+            }
+        }
+        __syncwarp();                                            // xs is rewritten by the next group
+#pragma unroll
+        for (int r = 0; r < kPpfRows; ++r) {
+            const int64_t row = r0 + r;
+            const float diag = __shfl_sync(0xffffffffu, ss, 4 * r) * normalizer2_half;
+            float mx = -INFINITY;
+            if (IS_QUERY) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) mx = fmaxf(mx, (lane + 32 * i < M) ? acc[r][i] : -INFINITY);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            if (row < rows) {
+                const int h = (int)(row % H);
+                const int64_t bn = row / H;
+                const int n = (int)(bn % N), b = (int)(bn / N);
+                float* orow = out + (((int64_t)b * H + h) * N + n) * M;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) {
+                    const int j = lane + 32 * i;
+                    if (j < M) {
+                        float y;
+                        if (IS_QUERY) y = ratio * (expf(acc[r][i] - diag - mx) + eps);
+                        else y = ratio * expf(acc[r][i] - diag + eps);
+                        orow[j] = y;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // GLU + depthwise conv (k=31, zero 'same' padding) + SiLU, channels last.
 //   u   : (B, T, 2C) contiguous (output of the first pointwise conv, bias included)
 //   w   : (C, 31) depthwise taps (Conv1d weight (C,1,31)), bias (C)

@@ -88,6 +88,10 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kCsbSmemBytes));
         CUDA_TRY(cudaFuncSetAttribute(ddsp::combsubfast_backward_kernel<true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kCsbSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(ddsp::performer_project_features_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kPpfSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(ddsp::performer_project_features_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kPpfSmemBytes));
         float* ptr = nullptr;
         CUDA_TRY(cudaGetSymbolAddress((void**)&ptr, g_tables));
         ddsp::fft_tables_kernel<<<4, 256, 0, st>>>(reinterpret_cast<float4*>(ptr), ptr + 2048);
@@ -480,6 +484,27 @@ int ddsp_b200_performer_features(const float* dash, const float* x, int B, int N
     else
         ddsp::performer_features_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dash, x, out, B, N, H, M, 0.0625f,
                                                                                       ratio, eps);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int ddsp_b200_performer_project_features(const float* x, const float* projection, int B, int N, int H, int M,
+                                         int is_query, float eps, float* out, void* stream) {
+    g_launches = 0;
+    if (!x || !projection || !out || B <= 0 || N <= 0 || H <= 0 || M <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (M > ddsp::kPpfCols || ((uintptr_t)x & 15)) return DDSP_B200_ERR_UNSUPPORTED;
+    const float* tables = nullptr;
+    if (int rc = ensure_device_ready((cudaStream_t)stream, &tables)) return rc;     // shared-memory opt-in
+    const int64_t groups = ((int64_t)B * N * H + ddsp::kPpfRows - 1) / ddsp::kPpfRows;
+    const unsigned grid = (unsigned)grid_for(groups, ddsp::kPpfWarps, (int64_t)sm_count() * 2);
+    const float normalizer = 0.35355339059327373f;             // 64^-0.25 (pcmer.py:137)
+    const float ratio = 1.0f / sqrtf((float)M);
+    if (is_query)
+        ddsp::performer_project_features_kernel<true><<<grid, ddsp::kPpfWarps * 32, ddsp::kPpfSmemBytes, (cudaStream_t)stream>>>(
+            x, projection, out, B, N, H, M, normalizer, 0.0625f, ratio, eps);
+    else
+        ddsp::performer_project_features_kernel<false><<<grid, ddsp::kPpfWarps * 32, ddsp::kPpfSmemBytes, (cudaStream_t)stream>>>(
+            x, projection, out, B, N, H, M, normalizer, 0.0625f, ratio, eps);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }

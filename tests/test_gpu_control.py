@@ -27,6 +27,18 @@ def test_performer_features(B, N, H, is_query):
     assert ((out - ref).abs() <= 1e-4 * ref.abs() + 1e-9).all(), (out - ref).abs().max().item()   # exp() of args up to ~20
 
 
+@pytest.mark.parametrize('B,N,H', [(1, 1, 8), (2, 37, 8), (3, 131, 4), (64, 100, 8)])
+@pytest.mark.parametrize('is_query', [True, False])
+def test_performer_project_features(B, N, H, is_query):
+    torch.manual_seed(B * 100 + N + 1)
+    x = torch.randn(B, N, H * 64, device='cuda') * 1.5
+    proj = torch.randn(266, 64, device='cuda')
+    ref = _softmax_features(x.view(B, N, H, 64).transpose(1, 2).double(), proj.double(), is_query)
+    out = core.performer_project_features(x, proj, H, is_query)
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert ((out.double() - ref).abs() <= 1e-4 * ref.abs() + 1e-9).all(), (out.double() - ref).abs().max().item()
+
+
 @pytest.mark.parametrize('B,T,C', [(1, 5, 512), (2, 64, 512), (2, 131, 512), (1, 300, 96)])
 def test_glu_dwconv_silu(B, T, C):
     torch.manual_seed(T)
@@ -39,7 +51,7 @@ def test_glu_dwconv_silu(B, T, C):
     assert (out.double() - ref.transpose(1, 2)).abs().max().item() < 5e-6
 
 
-@pytest.mark.parametrize('B,F_', [(1, 9), (2, 130), (3, 77)])
+@pytest.mark.parametrize('B,F_', [(1, 9), (2, 130), (3, 77), (16, 520)])       # the last one takes the fused projection
 def test_unit2control_fused_matches_plain_ops(B, F_):
     """no_grad on CUDA takes the fused stages; under enable_grad the same module runs stock ops."""
     torch.manual_seed(7)
