@@ -58,7 +58,9 @@ LtvKernel ltv_ir_select(int enc, int win) {
         return ddsp::ltv_ir_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_HANN>;
     return ddsp::ltv_ir_kernel<-1, -1>;
 }
-LtvKernel ltv_conv_select(int amode) {
+LtvKernel ltv_conv_select(int amode, int n_mag = 512) {
+    if (n_mag == 256)      // L = 510: packed half-frame convolution (ltv_conv510_kernel)
+        return amode == 0 ? ddsp::ltv_conv510_kernel<0> : amode == 1 ? ddsp::ltv_conv510_kernel<1> : ddsp::ltv_conv510_kernel<2>;
     return amode == 0 ? ddsp::ltv_conv_kernel<0> : amode == 1 ? ddsp::ltv_conv_kernel<1> : ddsp::ltv_conv_kernel<2>;
 }
 
@@ -101,8 +103,9 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
                              ltv_ir_select(DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_HANN), ltv_ir_select(-1, -1)})
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kLtvIrSmemBytes));
         for (int am = 0; am < 3; ++am)
-            CUDA_TRY(cudaFuncSetAttribute(ltv_conv_select(am), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          ddsp::kLtvConvSmemBytes));
+            for (int nm : {256, 512})
+                CUDA_TRY(cudaFuncSetAttribute(ltv_conv_select(am, nm), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              ddsp::kLtvConvSmemBytes));
         float* cptr = nullptr;
         CUDA_TRY(cudaGetSymbolAddress((void**)&cptr, g_chirp));
         CUDA_TRY(cudaFuncSetAttribute(ddsp::ltv_ir_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -399,7 +402,7 @@ int launch_ltv_conv(const ddsp::LtvParams& P, cudaStream_t st) {
     }
     const int64_t runs = (int64_t)P.B * P.runs_per_clip;
     const unsigned grid = (unsigned)((runs + ddsp::kLtvWarps - 1) / ddsp::kLtvWarps);
-    ltv_conv_select(P.audio_mode)<<<grid, ddsp::kLtvThreads, ddsp::kLtvConvSmemBytes, st>>>(P);
+    ltv_conv_select(P.audio_mode, P.n_mag)<<<grid, ddsp::kLtvThreads, ddsp::kLtvConvSmemBytes, st>>>(P);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }

@@ -156,15 +156,25 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
                     DDSP_IM(X, brev5(n1)) = xi;
                 }
             } else if (phase == 2) {
-                // z[n] = h[2n] + j h[2n+1] from the taps in `plane`
-                const float2* h2 = reinterpret_cast<const float2*>(plane);
                 const int D = IR_D;
+                if (IR_L == 510) {
+                    // L = 510: z[n] = h[n] (n < 512, imaginary part 0) -> the stored spectrum is H[k] itself,
+                    // which ltv_conv510_kernel multiplies with the packed half-frames (no even/odd split)
 #pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    float2 v = make_float2(0.0f, 0.0f);
-                    if (n1 < 16 && 32 * n1 < D + 1) v = h2[32 * n1 + lane];
-                    DDSP_RE(X, brev5(n1)) = v.x;
-                    DDSP_IM(X, brev5(n1)) = v.y;
+                    for (int n1 = 0; n1 < 32; ++n1) {
+                        DDSP_RE(X, brev5(n1)) = (n1 < 16) ? plane[32 * (n1 & 15) + lane] : 0.0f;
+                        DDSP_IM(X, brev5(n1)) = 0.0f;
+                    }
+                } else {
+                    // z[n] = h[2n] + j h[2n+1] from the taps in `plane`
+                    const float2* h2 = reinterpret_cast<const float2*>(plane);
+#pragma unroll
+                    for (int n1 = 0; n1 < 32; ++n1) {
+                        float2 v = make_float2(0.0f, 0.0f);
+                        if (n1 < 16 && 32 * n1 < D + 1) v = h2[32 * n1 + lane];
+                        DDSP_RE(X, brev5(n1)) = v.x;
+                        DDSP_IM(X, brev5(n1)) = v.y;
+                    }
                 }
                 __syncwarp();
             }
@@ -227,7 +237,8 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
                                 x -= 2.0f * rintf(0.5f * x);                         // cos(pi x) has period 2: |x| <= 1
                                 w = fmaf(0.5f, cos_approx(DDSP_PI_F * x), 0.5f);
                             }
-                            plane[i] = ir * w * (1.0f / 4096.0f);                    // 1/4 (even/odd split) * 1/1024 (inverse FFT)
+                            // L=1022: 1/4 (even/odd split) * 1/1024 (inverse FFT); L=510: 1/1024 only
+                            plane[i] = ir * w * (sym ? (1.0f / 4096.0f) : (1.0f / 1024.0f));
                         }
                     }
                 }
@@ -246,10 +257,10 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
 // Kernel 1b: the all-pass (group delay, no window) and the noise (exp/128, Hann) impulse responses
 // of one frame -- both L = 510 -- from ONE Bluestein pass.  With the full Hermitian extension of
 // both spectra, V[k] = Xa[k] + j Xn[k] (k = 0..509) has the real inverse DFT  ir_a[n] + j ir_n[n],
-// and 510 + 510 - 1 <= 1024 still fits the circular convolution.  4 FFTs for two filters instead
-// of 6.  Used by CombSub (vocoder.py:540,545-546) and Sins (:415,418-419).
+// and 510 + 510 - 1 <= 1024 still fits the circular convolution; the two real tap sets then share ONE 1024-point FFT
+// (packed as real / imaginary part and split by conjugate symmetry).  3 FFTs for two filters instead of 6.  Used by CombSub (vocoder.py:540,545-546) and Sins (:415,418-419).
 // ---------------------------------------------------------------------------------------------
-constexpr int kLtvDualWarpFloats = kPlaneFloats + 512 + kLtvCtxInts;     // plane + second tap set + ctx
+constexpr int kLtvDualWarpFloats = kPlaneFloats + kLtvCtxInts;           // plane (also holds the packed taps) + ctx
 constexpr int kLtvDualSmemBytes = 512 * 16 + kLtvWarps * kLtvDualWarpFloats * 4;
 
 struct LtvDualParams {
@@ -266,8 +277,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_dual_kernel(const LtvDu
     const float4* tw4 = reinterpret_cast<const float4*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float* plane = reinterpret_cast<float*>(smem_raw + 512 * 16) + wid * kLtvDualWarpFloats;
-    float* tap2 = plane + kPlaneFloats;                  // 512 floats: noise taps while the all-pass taps are transformed
-    volatile int* ctx = reinterpret_cast<volatile int*>(tap2 + 512);
+    volatile int* ctx = reinterpret_cast<volatile int*>(plane + kPlaneFloats);
     {
         const float4* src = reinterpret_cast<const float4*>(P.tw_tables);
         float4* dst = reinterpret_cast<float4*>(smem_raw);
@@ -284,7 +294,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_dual_kernel(const LtvDu
         if (lane == 0) { ctx[0] = (int)(fr0 / P.F); ctx[1] = (int)(fr0 % P.F); }
         __syncwarp();
 #pragma unroll 1
-        for (int phase = 0; phase < 4; ++phase) {
+        for (int phase = 0; phase < 3; ++phase) {
             if (phase == 0) {
                 const int64_t ro = (int64_t)ctx[0] * P.mB + (int64_t)ctx[1] * P.mF;
                 const float* rg = P.gd + ro;
@@ -336,12 +346,12 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_dual_kernel(const LtvDu
                     DDSP_RE(X, brev5(n1)) = (n1 < 16) ? vr[n1 & 15] : 0.0f;
                     DDSP_IM(X, brev5(n1)) = (n1 < 16) ? vi[n1 & 15] : 0.0f;
                 }
-            } else if (phase >= 2) {
-                const float2* h2 = reinterpret_cast<const float2*>(phase == 2 ? plane : tap2);
+            } else if (phase == 2) {
+                const float2* h2 = reinterpret_cast<const float2*>(plane);
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) {
                     float2 v = make_float2(0.0f, 0.0f);
-                    if (n1 < 8) v = h2[32 * n1 + lane];
+                    if (n1 < 16) v = h2[32 * n1 + lane];
                     DDSP_RE(X, brev5(n1)) = v.x;
                     DDSP_IM(X, brev5(n1)) = v.y;
                 }
@@ -377,16 +387,27 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_dual_kernel(const LtvDu
                         const int lag = (n <= L - D - 1) ? n : n - L;
                         const int i = lag + D;
                         const float w = fmaf(0.5f, cos_approx(fmaf((float)i, two_pi_over_L, -DDSP_PI_F)), 0.5f);   // Hann (core.py:262)
-                        plane[i] = sa * (1.0f / 4096.0f);                        // all-pass: no window (core.py:326)
-                        tap2[i] = sn * w * (1.0f / 4096.0f);
+                        // packed taps z[i] = h_allpass[i] + j h_noise[i]; 1/1024 (inverse FFT of the convolution)
+                        // * 1/2 (split of the two spectra below).  All-pass: no window (core.py:326)
+                        reinterpret_cast<float2*>(plane)[i] = make_float2(sa * (1.0f / 2048.0f), sn * w * (1.0f / 2048.0f));
                     }
                 }
-                if (lane < 2) { plane[L + lane] = 0.0f; tap2[L + lane] = 0.0f; }
+                if (lane < 2) reinterpret_cast<float2*>(plane)[L + lane] = make_float2(0.0f, 0.0f);
                 __syncwarp();
             } else {
-                float2* dst = (phase == 2 ? P.spec_a : P.spec_n) + ((int64_t)ctx[0] * P.F + ctx[1]) * kLtvSpecFloat2 + lane;
+                // one FFT carried both real tap sets: H_a[k] = Z[k] + conj Z[N-k],  H_n[k] = (Z[k] - conj Z[N-k]) / j
+                const int partner = (32 - lane) & 31;
+                const bool lane0 = lane == 0;
+                float2* da = P.spec_a + ((int64_t)ctx[0] * P.F + ctx[1]) * kLtvSpecFloat2 + lane;
+                float2* dn = P.spec_n + ((int64_t)ctx[0] * P.F + ctx[1]) * kLtvSpecFloat2 + lane;
 #pragma unroll
-                for (int q = 0; q < 32; ++q) dst[32 * q] = make_float2(DDSP_RE(X, q), DDSP_IM(X, q));
+                for (int q = 0; q < 32; ++q) {
+                    float c, d;
+                    LTV_PARTNER(X, q, c, d);
+                    const float a = DDSP_RE(X, q), b = DDSP_IM(X, q);
+                    da[32 * q] = make_float2(a + c, b - d);
+                    dn[32 * q] = make_float2(b + d, c - a);
+                }
             }
         }
     }
@@ -563,6 +584,165 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
         const int64_t tb = (int64_t)(m_last - 1) * kHop - D + kHop;       // rs already advanced past the retired hop
         for (int c = 0; c < 3; ++c) {
             const bool complete = (m_end == F + 1) && ((m_last - 2 + c >= m_begin) || (m_begin == 0));
+            for (int r = 0; r < 16; ++r) {
+                const int j = lane + 32 * r + kHop * c;
+                const int64_t t = tb + j;
+                if (t >= 0 && t < T) {
+                    const float v = ring[(rs + j) & (kLtvRing - 1)];
+                    if (complete) ob[t] = v; else atomicAdd(ob + t, v);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 2b: the convolution for L = 510 filters (n_mag = 256: all-pass and noise filters).
+// The Bartlett-windowed 1024-sample frame is the sum of its rising half (samples of hop m-1) and
+// its falling half (hop m, placed 512 later); each half convolved with 510 taps spans 1021 <= 1024
+// samples, and both halves meet the SAME real impulse response, so they travel as real and
+// imaginary part of one complex FFT-1024: ifft(FFT(up + j*down) . H) = up*h + j (down*h) with no
+// conjugate-pair exchange and no even/odd twiddles -- the spectral product is 32 plain complex
+// multiplies per lane.  The frame's output spans 1536 samples (3 hops) of the ring.
+// ---------------------------------------------------------------------------------------------
+template <int AMODE>
+__global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvParams P) {
+    const int amode = AMODE >= 0 ? AMODE : P.audio_mode;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float4* tw4 = reinterpret_cast<const float4*>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char* wbase = smem_raw + 512 * 16 + wid * kLtvConvWarpBytes;
+    float* plane = reinterpret_cast<float*>(wbase);
+    float* ring = plane + kPlaneFloats;
+    volatile int* ctx = reinterpret_cast<volatile int*>(ring + kLtvRing);
+    {
+        const float4* src = reinterpret_cast<const float4*>(P.tw_tables);
+        float4* dst = reinterpret_cast<float4*>(smem_raw);
+        for (int e = threadIdx.x; e < 512; e += kLtvThreads) dst[e] = __ldg(src + e);
+        __syncthreads();
+    }
+    {
+        const int64_t run = (int64_t)blockIdx.x * kLtvWarps + wid;
+        if (run >= (int64_t)P.B * P.runs_per_clip) return;
+        const int b0 = (int)(run / P.runs_per_clip);
+        const int mb = (int)(run % P.runs_per_clip) * P.run_len;
+        if (lane == 0) {
+            ctx[0] = b0; ctx[1] = mb; ctx[2] = min(P.F + 1, mb + P.run_len);
+            ctx[3] = (int)noise_key(P.seed, (uint32_t)b0);
+        }
+        __syncwarp();
+    }
+    const int F = P.F;
+    const int64_t T = (int64_t)F * kHop;
+    constexpr int D = 255;                               // L/2: delay compensation (core.py:177)
+
+    for (int i = lane; i < kLtvRing; i += 32) ring[i] = 0.0f;
+    __syncwarp();
+    int rs = 0;
+
+    Pts32 X;
+    for (int m = CV_MBEGIN; m < CV_MEND; ++m) {
+        const int64_t t0 = (int64_t)(m - 1) * kHop;
+#pragma unroll 1
+        for (int phase = 0; phase < 2; ++phase) {
+            if (phase == 0) {
+                const float2* zh = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2;
+                {   // pull this frame's tap spectrum (8 KB) into L2 while the audio FFT runs
+                    const char* pz = reinterpret_cast<const char*>(zh) + 128 * lane;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pz));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pz + 4096));
+                }
+                // z[n] = up[n] + j down[n], n = 32 n1 + lane < 512:
+                //   up[n] = x[t0 + n] * n/512, down[n] = x[t0 + 512 + n] * (512 - n)/512   (core.py:218-222)
+                const bool vA = m >= 1, vB = m < F;
+                const float* src = P.audio + (int64_t)CV_B * T + lane;
+                const uint32_t key = (uint32_t)ctx[3];
+                uint32_t stA = noise_seed(key, (uint32_t)(m - 1), (uint32_t)lane);
+                uint32_t stB = noise_seed(key, (uint32_t)m, (uint32_t)lane);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    float v0 = 0.0f, v1 = 0.0f;
+                    if (n1 < 16) {
+                        const int n = 32 * n1 + lane;
+                        if (amode == 2) {
+                            // lane l draws the samples 32 i + l of a hop, i = 0..15, from its (hop, lane) stream
+                            stA = noise_next(stA); v0 = (float)noise_s24(stA) * 1.1920928955078125e-7f;
+                            stB = noise_next(stB); v1 = (float)noise_s24(stB) * 1.1920928955078125e-7f;
+                            v0 = vA ? v0 : 0.0f;
+                            v1 = vB ? v1 : 0.0f;
+                        } else {
+                            if (vA) v0 = __ldg(src + t0 + 32 * n1);
+                            if (vB) v1 = __ldg(src + t0 + kHop + 32 * n1);
+                            if (amode == 1) { v0 = vA ? fmaf(2.0f, v0, -1.0f) : 0.0f; v1 = vB ? fmaf(2.0f, v1, -1.0f) : 0.0f; }
+                        }
+                        v0 *= (float)n * (1.0f / 512.0f);
+                        v1 *= (float)(512 - n) * (1.0f / 512.0f);
+                    }
+                    DDSP_RE(X, brev5(n1)) = v0;
+                    DDSP_IM(X, brev5(n1)) = v1;
+                }
+            }
+
+            warp_fft1024(X, plane, tw4, lane);
+
+            if (phase == 0) {
+                const float2* zh = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2 + lane;   // last IR repeated (core.py:228)
+                constexpr int kLook = 8;
+                float2 hq[kLook];
+#pragma unroll
+                for (int q = 0; q < kLook; ++q) hq[q] = __ldg(zh + 32 * q);
+                float yr[32], yi[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const float2 h = hq[q % kLook];
+                    if (q + kLook < 32) hq[q % kLook] = __ldg(zh + 32 * (q + kLook));
+                    const float ar = DDSP_RE(X, q), ai = DDSP_IM(X, q);
+                    yr[q] = ar * h.x - ai * h.y;
+                    yi[q] = ar * h.y + ai * h.x;
+                }
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    DDSP_RE(X, brev5(q)) = yi[q];      // swapped -> inverse
+                    DDSP_IM(X, brev5(q)) = yr[q];
+                }
+            } else {
+                // after the swapped FFT: X.im = up*h, X.re = down*h, sample n = lane + 32 q.
+                // ring[rs + n] += up*h;  ring[rs + 512 + n] (+)= down*h -- its last 512 samples open a fresh hop
+#pragma unroll
+                for (int q = 0; q < 32; ++q) ring[(rs + lane + 32 * q) & (kLtvRing - 1)] += DDSP_IM(X, q);
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    float* slot = ring + ((rs + kHop + lane + 32 * q) & (kLtvRing - 1));
+                    *slot = (q < 16) ? *slot + DDSP_RE(X, q) : DDSP_RE(X, q);
+                }
+                __syncwarp();
+                // retire the first 512 samples of the window: output index t = 512(m-1) - D + j  (core.py:238,177-182)
+                const int m_begin = CV_MBEGIN;
+                const bool complete = (m - 2 >= m_begin) || (m_begin == 0);
+                float* ob = P.out + (int64_t)CV_B * T;
+                const int64_t tb = t0 - D;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const int j = lane + 32 * r;
+                    const int64_t t = tb + j;
+                    if (t >= 0 && t < T) {
+                        const float v = ring[(rs + j) & (kLtvRing - 1)];
+                        if (complete) ob[t] = v; else atomicAdd(ob + t, v);
+                    }
+                }
+                __syncwarp();
+                rs = (rs + kHop) & (kLtvRing - 1);
+            }
+        }
+    }
+    // flush the two remaining hops of the ring
+    {
+        const int m_begin = CV_MBEGIN, m_end = CV_MEND;
+        const int m_last = m_end - 1;
+        float* ob = P.out + (int64_t)CV_B * T;
+        const int64_t tb = (int64_t)(m_last - 1) * kHop - D + kHop;       // rs already advanced past the retired hop
+        for (int c = 0; c < 2; ++c) {
+            const bool complete = (m_end == F + 1) && ((m_last - 1 + c >= m_begin) || (m_begin == 0));
             for (int r = 0; r < 16; ++r) {
                 const int j = lane + 32 * r + kHop * c;
                 const int64_t t = tb + j;
