@@ -22,6 +22,9 @@
 //      in a shared-memory ring; every frame retires 512 finished samples to HBM.
 // The reference's FFT size (1533 / 2045) only has to cover the linear convolution; 2048 gives the
 // identical result.
+// L = 510 filters take a shorter route on the convolution side (ltv_conv510_kernel below): the two
+// halves of the Bartlett frame ride as real/imaginary part of one FFT-1024 and the taps' spectrum is
+// stored as H[k] itself.
 #pragma once
 #include "fft32.cuh"
 
