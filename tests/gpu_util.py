@@ -46,3 +46,34 @@ def assert_waveform(out, ref, max_abs=MAX_ABS_TOL, snr=SNR_TOL_DB, what=''):
     assert err <= max_abs, f'{what}: max-abs {err:.3e} > {max_abs:.1e} (snr {s:.1f} dB)'
     assert s >= snr, f'{what}: snr {s:.1f} dB < {snr} (max-abs {err:.3e})'
     return err, s
+
+
+# ---- host restatement of the in-kernel counter-based noise (csrc/common.cuh: noise_key / noise_seed /
+# noise_next / noise_u24).  Integer work, so the comparison with the kernels is bit-exact.
+def noise_key(seed, clip):
+    m = (1 << 64) - 1
+    z = (seed + 0x9E3779B97F4A7C15 * (clip + 1)) & m
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+    z = z ^ (z >> 31)
+    return ((z >> 32) ^ z) & 0xffffffff
+
+
+def hop_noise(k, hop):
+    """(512,) uniforms of one hop: lane l owns samples 32*i + l, an LCG stream seeded per (hop, lane)."""
+    lane = np.arange(32, dtype=np.uint64)
+    x = ((hop * 32 + lane) * 0x9E3779B1 + k) & 0xffffffff
+    x ^= x >> 16; x = (x * 0x7feb352d) & 0xffffffff
+    x ^= x >> 15; x = (x * 0x846ca68b) & 0xffffffff
+    x ^= x >> 16
+    out = np.zeros(512, np.float32)
+    for i in range(16):
+        x = (x * 747796405 + 2891336453) & 0xffffffff
+        u24 = (x ^ (x >> 15)) >> 8
+        out[32 * i + np.arange(32)] = u24.astype(np.float32) * np.float32(2.0 ** -24)
+    return out
+
+
+def in_kernel_noise(seed, B, F):
+    """(B, F*512) uniforms the kernels draw for `seed` when no noise tensor is injected."""
+    return np.stack([np.concatenate([hop_noise(noise_key(seed, b), h) for h in range(F)]) for b in range(B)])

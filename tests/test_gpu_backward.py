@@ -90,6 +90,11 @@ def test_in_kernel_noise_gradient_matches_forward_stream():
     g = run_backward(d['ctrl'], d['f0_frames'], R, None, seed=seed)
     assert np.array_equal(g, run_backward(d['ctrl'], d['f0_frames'], R, None, seed=seed))     # deterministic
     assert not np.array_equal(g, run_backward(d['ctrl'], d['f0_frames'], R, None, seed=seed + 1))
+    # the same stream injected as a tensor gives the same gradient bit for bit, and that one is tied to autograd
+    from tests.gpu_util import in_kernel_noise
+    U = in_kernel_noise(seed, B, F)
+    assert np.array_equal(g, run_backward(d['ctrl'], d['f0_frames'], R, U))
+    assert_grad(g, port_grad(d['ctrl'], d['f0_frames'], U, R), 'in-kernel noise')
 
     def loss(ctrl):
         hm, hp, nm = ctrl_views(ctrl, 'combsubfast')

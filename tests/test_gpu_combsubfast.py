@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import ddsp_oracle as O
-from tests.gpu_util import HAS_CUDA, assert_waveform, ctrl_views, dev, snr_db, torch
+from tests.gpu_util import HAS_CUDA, assert_waveform, ctrl_views, dev, in_kernel_noise, snr_db, torch
 from ddsp_b200.synthetic import make_inputs
 
 pytestmark = pytest.mark.gpu
@@ -101,32 +101,10 @@ def test_in_kernel_noise_is_deterministic_and_uniform():
 
 def test_noise_generator_matches_host_restatement():
     """The counter-based generator is integer work: bit-exact against a numpy restatement."""
-    def key(seed, clip):
-        m = (1 << 64) - 1
-        z = (seed + 0x9E3779B97F4A7C15 * (clip + 1)) & m
-        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
-        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
-        z = z ^ (z >> 31)
-        return ((z >> 32) ^ z) & 0xffffffff
-
-    def hop_noise(k, hop):
-        """(512,) uniforms of one hop: lane l owns samples 32*i + l, an LCG stream seeded per (hop, lane)."""
-        lane = np.arange(32, dtype=np.uint64)
-        x = ((hop * 32 + lane) * 0x9E3779B1 + k) & 0xffffffff
-        x ^= x >> 16; x = (x * 0x7feb352d) & 0xffffffff
-        x ^= x >> 15; x = (x * 0x846ca68b) & 0xffffffff
-        x ^= x >> 16
-        out = np.zeros(512, np.float32)
-        for i in range(16):
-            x = (x * 747796405 + 2891336453) & 0xffffffff
-            u24 = (x ^ (x >> 15)) >> 8
-            out[32 * i + np.arange(32)] = u24.astype(np.float32) * np.float32(2.0 ** -24)
-        return out
-
     B, F = 2, 9
     d = make_inputs(B, F, 1539, seed=10, noise=False)
     seed = 4242
-    U = np.stack([np.concatenate([hop_noise(key(seed, b), h) for h in range(F)]) for b in range(B)])
+    U = in_kernel_noise(seed, B, F)
     a, _ = run_gpu(d['ctrl'], d['f0_frames'], None, seed=seed)
     b_, _ = run_gpu(d['ctrl'], d['f0_frames'], U)
     assert np.array_equal(a, b_)

@@ -160,6 +160,22 @@ def test_sins_nyquist_mask_in_the_oscillator():
         assert abs(peak / expect - 1.0) < 2e-2, (k, peak, expect)
 
 
+@pytest.mark.parametrize('model', ['combsub', 'sins'])
+def test_in_kernel_noise_matches_host_restatement(model):
+    """Without an injected U the noise filter draws the same (seed, clip, hop, lane) stream as CombSubFast:
+    injecting the host restatement of that stream reproduces all three outputs bit for bit."""
+    from tests.gpu_util import in_kernel_noise
+    B, F = 2, 11
+    d = make_inputs(B, F, sum(SPLITS[model]), seed=77, noise=False)
+    run = run_combsub if model == 'combsub' else run_sins
+    seed = 31337
+    a = run(d['ctrl'], d['f0_frames'], None, seed=seed)
+    b = run(d['ctrl'], d['f0_frames'], in_kernel_noise(seed, B, F))
+    for x, y in zip((a[0], a[2], a[3]), (b[0], b[2], b[3])):
+        assert np.array_equal(x, y)
+    assert np.abs(a[3]).max() > 0
+
+
 def test_models_batch_invariance():
     d = make_inputs(5, 120, 1024, seed=21, zero_f0_fraction=0.05)
     sig_all, *_ = run_combsub(d['ctrl'], d['f0_frames'], d['U'])
