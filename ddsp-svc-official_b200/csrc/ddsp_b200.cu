@@ -82,6 +82,10 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
     if (dev < 0 || dev >= 64) return DDSP_B200_ERR_UNSUPPORTED;
     std::lock_guard<std::mutex> lock(g_init_mutex);
     if (!g_device_ready[dev]) {
+        // the one-time setup synchronises the stream, which a capturing stream cannot do: ask for one warm-up call
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        CUDA_TRY(cudaStreamIsCapturing(st, &cap));
+        if (cap != cudaStreamCaptureStatusNone) return DDSP_B200_ERR_CAPTURE;
         CUDA_TRY(cudaFuncSetAttribute(ddsp::combsubfast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       ddsp::kCsfSmemBytes));
         CUDA_TRY(cudaFuncSetAttribute(ddsp::combsubfast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -146,6 +150,8 @@ const char* ddsp_b200_strerror(int status) {
         case DDSP_B200_ERR_WORKSPACE: return "workspace too small";
         case DDSP_B200_ERR_CUDA: return "CUDA runtime error (see ddsp_b200_last_cuda_error)";
         case DDSP_B200_ERR_BATCH_MISMATCH: return "batch size of audio and impulse response must be the same";
+        case DDSP_B200_ERR_CAPTURE:
+            return "the first call on a device sets up constant tables and cannot run under CUDA stream capture: issue one warm-up call first";
         default: return "unknown status";
     }
 }

@@ -35,7 +35,8 @@ typedef enum ddsp_b200_status {
     DDSP_B200_ERR_UNSUPPORTED = -2,       /* e.g. hop != 512 or n_mag not in {256,512} on a fused path */
     DDSP_B200_ERR_WORKSPACE = -3,         /* workspace too small                                  */
     DDSP_B200_ERR_CUDA = -4,              /* a CUDA runtime call failed (see ddsp_b200_last_cuda_error) */
-    DDSP_B200_ERR_BATCH_MISMATCH = -5     /* core.py:212-213 ValueError                            */
+    DDSP_B200_ERR_BATCH_MISMATCH = -5,    /* core.py:212-213 ValueError                            */
+    DDSP_B200_ERR_CAPTURE = -6            /* first call on a device (table setup) issued under stream capture */
 } ddsp_b200_status;
 
 /* filter window modes of ddsp/core.py:306-328 */

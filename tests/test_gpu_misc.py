@@ -139,3 +139,26 @@ def test_full_module_forward_with_builtin_control_network():
                                             f0, model.window, noise_u=U)
     assert (sig - ref).abs().max().item() < 3e-5
     assert (pf[..., 0] - pf_ref).abs().max().item() < 1e-6
+
+
+def test_first_call_under_graph_capture_is_refused_cleanly():
+    """The lazy per-device table setup synchronises; under capture the library must say so instead of
+    corrupting the capture (fresh process: the tables of this process are already initialised)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "from ddsp_b200 import core, _cabi\n"
+        "f0 = torch.full((1, 8, 1), 220.0, device='cuda'); ctrl = torch.zeros(1, 8, 1539, device='cuda')\n"
+        "hm, hp, nm = torch.split(ctrl, 513, dim=-1)\n"
+        "_, prefix, _ = core.phase_stage(f0, 512, 44100)\n"
+        "g = torch.cuda.CUDAGraph(); s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())\n"
+        "try:\n"
+        "    with torch.cuda.stream(s):\n"
+        "        with torch.cuda.graph(g, stream=s):\n"
+        "            core.combsubfast_stage(hm, hp, nm, f0, prefix, 512, 44100)\n"
+        "    print('NO ERROR')\n"
+        "except _cabi.DDSPB200Error as e:\n"
+        "    print('REFUSED', e)\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert 'REFUSED' in out.stdout and 'warm-up' in out.stdout, (out.stdout, out.stderr[-500:])
