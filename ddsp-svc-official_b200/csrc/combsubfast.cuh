@@ -69,15 +69,16 @@ __device__ __forceinline__ void csf_gen_hop(const CsfParams& P, int h, const Hop
         for (int i = 0; i < 16; ++i) dst[i] = 0.0f;
         return;
     }
-    float f[16], rot[16];
-    hop_rotation(in.x0, in.x1, in.base, P.inv_sr, lane, f, rot);
+    float2 f2[8], rot2[8];
+    hop_rotation2(in.x0, in.x1, in.base, P.inv_sr, lane, f2, rot2);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        // vocoder.py:459  sinc(sr * rot / (f0 + 1e-3))
-        const float x = __fmul_rn(P.sr, rot[i]) * rcp_approx(__fadd_rn(f[i], 1e-3f));
-        float c = sinc_f(x);
-        if (f[i] <= 0.0f) c = 0.0f;                        // vocoder.py:460
-        dst[i] = c;
+    for (int j = 0; j < 8; ++j) {
+        // vocoder.py:459  sinc(sr * rot / (f0 + 1e-3)), two samples per packed register pair
+        const float2 den = add2(f2[j], bc2(1e-3f));
+        const float2 xs = fma2(mul2(bc2(P.sr), rot2[j]), make_float2(rcp_approx(den.x), rcp_approx(den.y)), bc2(1e-30f));
+        const float2 c = sinc2_xs(xs);
+        dst[2 * j] = (f2[j].x <= 0.0f) ? 0.0f : c.x;       // vocoder.py:460
+        dst[2 * j + 1] = (f2[j].y <= 0.0f) ? 0.0f : c.y;
     }
 }
 
@@ -117,25 +118,33 @@ __device__ __forceinline__ void csf_load_frame(const CsfParams& P, Pts32& X, con
         stA = noise_seed(key, (uint32_t)(fm - 1), (uint32_t)lane);
         stB = noise_seed(key, (uint32_t)fm, (uint32_t)lane);
     }
+    // samples 32*n1 + lane for n1 = 2j, 2j+1 land in the two halves of one packed register
+    // (register index brev5(2j) and brev5(2j) + 16), so each window pair feeds packed multiplies
+    const float2* winA = reinterpret_cast<const float2*>(win);
 #pragma unroll
-    for (int n1 = 0; n1 < 32; ++n1) {
-        const int j = 32 * (n1 & 15);                                 // sample in hop = j + lane
-        const float w = win[32 * n1 + lane];
-        const float c = (n1 < 16 ? slotA : slotB)[j + (n1 & 15)];
-        const float wc = w * c;
-        float wz;
+    for (int j = 0; j < 16; ++j) {
+        const int n1 = 2 * j;                                         // both samples lie in the same hop (n1 < 16: hop fm-1)
+        const int m0 = n1 & 15, m1 = m0 + 1;                          // sample in hop = 32*m + lane, one pad word per 32
+        const float2 w = winA[j * 32 + lane];
+        const float* slot = (n1 < 16) ? slotA : slotB;
+        const float2 c = make_float2(slot[33 * m0], slot[33 * m1]);
+        float2 wz;
         if (HAS_U) {
-            const float u = __ldg(u_b + (n1 < 16 ? baseA : baseB) + j);
-            const float wn = w * (n1 < 16 ? okA : okB);
-            wz = fmaf(u, wn + wn, -wn);                                   // w * (2u - 1)   (vocoder.py:461)
+            const float* up = u_b + (n1 < 16 ? baseA : baseB);
+            const float2 u = make_float2(__ldg(up + 32 * m0), __ldg(up + 32 * m1));
+            const float2 wn = mul2(w, bc2(n1 < 16 ? okA : okB));
+            wz = fma2(u, add2(wn, wn), neg2(wn));                         // w * (2u - 1)   (vocoder.py:461)
         } else {
             uint32_t& st = (n1 < 16) ? stA : stB;
             st = noise_next(st);
+            const float v0 = (float)noise_s24(st);
+            st = noise_next(st);
+            const float v1 = (float)noise_s24(st);
             // 2u - 1 = v * 2^-23 with v the centred 24-bit draw; sclA/sclB carry the 2^-23 (or 0)
-            wz = (float)noise_s24(st) * (w * (n1 < 16 ? sclA : sclB));
+            wz = mul2(make_float2(v0, v1), mul2(w, bc2(n1 < 16 ? sclA : sclB)));
         }
-        DDSP_RE(X, brev5(n1)) = wc;
-        DDSP_IM(X, brev5(n1)) = wz;
+        X.R[brev5(n1)] = mul2(w, c);
+        X.I[brev5(n1)] = wz;
     }
 }
 
@@ -159,7 +168,11 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
         __syncthreads();
         cudaGridDependencySynchronize();      // launched with programmatic stream serialisation (see ddsp_b200.cu)
         if (P.window) {
-            for (int e = threadIdx.x; e < 1024; e += kCsfThreads) win[e] = __ldg(P.window + e);
+            for (int e = threadIdx.x; e < 1024; e += kCsfThreads) {
+                const float w = __ldg(P.window + e);
+                win[win_analysis_index(e)] = w;
+                win[win_synthesis_index(e)] = w;
+            }
             __syncthreads();
         }
     }
@@ -320,30 +333,38 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             float* oA = out_b + (int64_t)hopA * kHop;
             float* oB = out_b + (int64_t)hopB * kHop;
             float* oC = out_b + (int64_t)hopC * kHop;
+            // window both frames of the pair in place: I[q] -> (hop A part, hop B part of frame 2p),
+            // R[q] -> (hop B part, hop C part of frame 2p+1)
+            const float2* winB = reinterpret_cast<const float2*>(win + 1024);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float2 w = winB[q * 32 + lane];
+                X.I[q] = mul2(X.I[q], w);
+                X.R[q] = mul2(X.R[q], w);
+            }
             if (first) {
                 if (seam_head) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) atomicAdd(oA + 32 * q, __fmul_rn(DDSP_IM(X, q), win[lane + 32 * q]));
+                    for (int q = 0; q < 16; ++q) atomicAdd(oA + 32 * q, X.I[q].x);
                 }
             } else {
                 float prev[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) prev[q] = oA[32 * q];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) oA[32 * q] = __fadd_rn(prev[q], __fmul_rn(DDSP_IM(X, q), win[lane + 32 * q]));
+                for (int q = 0; q < 16; ++q) oA[32 * q] = __fadd_rn(prev[q], X.I[q].x);
             }
             if (hopB < F) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q)
-                    oB[32 * q] = __fadd_rn(__fmul_rn(DDSP_IM(X, q + 16), win[lane + 32 * q + kHop]), __fmul_rn(DDSP_RE(X, q), win[lane + 32 * q]));
+                for (int q = 0; q < 16; ++q) oB[32 * q] = __fadd_rn(X.I[q].y, X.R[q].x);
             }
             if (hopC < F) {
                 if (!last) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) oC[32 * q] = __fmul_rn(DDSP_RE(X, q + 16), win[lane + 32 * q + kHop]);
+                    for (int q = 0; q < 16; ++q) oC[32 * q] = X.R[q].y;
                 } else if (seam_tail) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) atomicAdd(oC + 32 * q, __fmul_rn(DDSP_RE(X, q + 16), win[lane + 32 * q + kHop]));
+                    for (int q = 0; q < 16; ++q) atomicAdd(oC + 32 * q, X.R[q].y);
                 }
             }
             if (++p >= p_end) break;

@@ -57,7 +57,11 @@ __global__ void __launch_bounds__(kCsbThreads, 1) combsubfast_backward_kernel(co
         for (int e = threadIdx.x; e < kTableBytes / 16; e += kCsbThreads) dst[e] = __ldg(src + e);
         __syncthreads();
         if (P.window) {
-            for (int e = threadIdx.x; e < 1024; e += kCsbThreads) win[e] = __ldg(P.window + e);
+            for (int e = threadIdx.x; e < 1024; e += kCsbThreads) {
+                const float w = __ldg(P.window + e);
+                win[win_analysis_index(e)] = w;
+                win[win_synthesis_index(e)] = w;
+            }
             __syncthreads();
         }
     }
@@ -109,7 +113,8 @@ __global__ void __launch_bounds__(kCsbThreads, 1) combsubfast_backward_kernel(co
             const float okA = vA ? 1.0f : 0.0f, okB = vB ? 1.0f : 0.0f, okC = vC ? 1.0f : 0.0f;
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) {
-                const float w0 = win[32 * n1 + lane], w1 = win[32 * n1 + lane + kHop];
+                const float2 wp = reinterpret_cast<const float2*>(win + 1024)[n1 * 32 + lane];   // synthesis-order pairs
+                const float w0 = wp.x, w1 = wp.y;
                 const float a = __ldg(gA + 32 * n1) * okA, bm = __ldg(gB_ + 32 * n1) * okB, c = __ldg(gC + 32 * n1) * okC;
                 DDSP_RE(X, brev5(n1)) = w0 * a;              // frame 2p,   first half
                 DDSP_RE(X, brev5(n1 + 16)) = w1 * bm;        // frame 2p,   second half

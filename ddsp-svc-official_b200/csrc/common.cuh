@@ -14,6 +14,14 @@ constexpr unsigned kFullMask = 0xffffffffu;
 #define DDSP_PI_F 3.14159265358979323846f
 #define DDSP_LOG2E_F 1.44269504088896340736f
 
+// Packed fp32x2 arithmetic (sm_100+: FADD2 / FMUL2 / FFMA2, one issue slot for two IEEE-rn results).
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }   // folds into an operand modifier
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }            // folds into a broadcast immediate
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return fma2(b, bc2(-1.0f), a); }
+
 // torch upsample_linear1d(align_corners=True) arithmetic for one sample (core.py:17):
 // fma(w0, x0, fl32(w1*x1)) with w1 = j/hop (exact for power-of-two hop), w0 = 1 - w1.
 __device__ __forceinline__ float lerp_torch(float x0, float x1, float w1) {
@@ -89,6 +97,22 @@ __device__ __forceinline__ float sinc_f(float x) {
     p = fmaf(p, u, 1.0f);
     const float v = p * (r * rcp_approx(xs));
     return __int_as_float(__float_as_int(v) ^ (__float_as_int(t) << 31));   // (-1)^n
+}
+
+// Two samples at once: the same arithmetic as sinc_f on both halves of packed registers (the
+// reciprocals, the sign flip and nothing else stay scalar).
+__device__ __forceinline__ float2 sinc2_xs(float2 xs) {          // xs = x + 1e-30 already formed
+    const float2 t = add2(xs, bc2(12582912.0f));
+    const float2 n = add2(t, bc2(-12582912.0f));
+    const float2 r = sub2(xs, n);
+    const float2 u = mul2(r, r);
+    float2 p = fma2(bc2(0.024718644097447395f), u, bc2(-0.19044175744056702f));
+    p = fma2(p, u, bc2(0.8117148280143738f));
+    p = fma2(p, u, bc2(-1.6449332237243652f));
+    p = fma2(p, u, bc2(1.0f));
+    const float2 v = mul2(p, mul2(r, make_float2(rcp_approx(xs.x), rcp_approx(xs.y))));
+    return make_float2(__int_as_float(__float_as_int(v.x) ^ (__float_as_int(t.x) << 31)),
+                       __int_as_float(__float_as_int(v.y) ^ (__float_as_int(t.y) << 31)));
 }
 
 // rot (fp32, wrapped to [-0.5,0.5], half-to-even) from an fp64 rotation count (core.py:46-49)

@@ -38,12 +38,7 @@ __device__ __forceinline__ constexpr float sin32(int j) {
          : 0.19509032201612826785f;
 }
 
-__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }   // folds into an operand modifier
-__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }            // folds into a broadcast immediate
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return fma2(b, bc2(-1.0f), a); }
+// (packed fp32x2 helpers add2 / mul2 / fma2 / neg2 / bc2 / sub2 live in common.cuh)
 
 // The 32 points of one lane: element with register-index r lives in R[r & 15] (.x for r < 16,
 // .y for r >= 16), real parts in R, imaginary parts in I.
@@ -189,8 +184,18 @@ __device__ __forceinline__ void warp_fft1024(Pts32& P, float* __restrict__ plane
 // Device-wide constant tables (filled once per device by fft_tables_kernel):
 //   [0, 512) float4 twiddles tw4[(e/2)*32 + lane] = (cos(e l), cos((e+1) l), -sin(e l), -sin((e+1) l)),
 //            angles 2 pi e l / 1024, e even
-//   then 1024 floats sin(pi i / 1024) = sqrt(hann_periodic(1024))[i]
-constexpr int kTableBytes = 512 * 16 + 1024 * 4;
+//   then the window w[i] = sin(pi i / 1024) = sqrt(hann_periodic(1024))[i] twice, as float2 pairs in the
+//   two orders the kernels consume it (one 64-bit shared load feeds one packed fp32x2 multiply):
+//     analysis order  A[j*32 + lane] = (w[64j + lane], w[64j + 32 + lane])        j < 16
+//     synthesis order B[q*32 + lane] = (w[32q + lane], w[512 + 32q + lane])       q < 16
+constexpr int kTableBytes = 512 * 16 + 2048 * 4;
+
+__host__ __device__ __forceinline__ int win_analysis_index(int i) {      // float index of w[i] in table A
+    return 2 * ((i >> 6) * 32 + (i & 31)) + ((i >> 5) & 1);
+}
+__host__ __device__ __forceinline__ int win_synthesis_index(int i) {     // float index of w[i] in table B (after A)
+    return 1024 + 2 * (((i & 511) >> 5) * 32 + (i & 31)) + (i >> 9);
+}
 
 __global__ void fft_tables_kernel(float4* __restrict__ tw4, float* __restrict__ win) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -204,7 +209,8 @@ __global__ void fft_tables_kernel(float4* __restrict__ tw4, float* __restrict__ 
         tw4[t] = make_float4((float)c, (float)c1, (float)(-s), (float)(-s1));
     }
     sincospi((double)t / 1024.0, &s, &c);
-    win[t] = (float)s;
+    win[win_analysis_index(t)] = (float)s;
+    win[win_synthesis_index(t)] = (float)s;
 }
 
 }  // namespace ddsp

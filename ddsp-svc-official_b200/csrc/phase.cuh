@@ -150,15 +150,23 @@ __global__ void __launch_bounds__(1024) phase_fused_kernel(const float* __restri
 // One hop of per-sample rotation, computed by a warp: lane owns 16 consecutive samples.
 // f[i] = upsampled f0, rot[i] = wrapped rotation (fp32) of sample 16*lane + i of hop h.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void hop_rotation(float x0, float x1, double base, double inv_sr, int lane,
-                                             float (&f)[16], float (&rot)[16]) {
+// Packed form: sample pairs (2j, 2j+1) share fp32x2 registers; the interpolation weights are exact
+// multiples of 1/512, so lambda_0 + i/512 equals (16 lane + i)/512 bit for bit.
+__device__ __forceinline__ void hop_rotation2(float x0, float x1, double base, double inv_sr, int lane,
+                                              float2 (&f2)[8], float2 (&rot2)[8]) {
     double sl[16];
     double s = 0.0;
+    const float lam0 = (float)(16 * lane) * (1.0f / kHop);
+    float2 lam = make_float2(lam0, lam0 + 1.0f / kHop);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        f[i] = lerp_torch(x0, x1, (float)(16 * lane + i) * (1.0f / kHop));
-        s += (double)f[i];
-        sl[i] = s;
+    for (int j = 0; j < 8; ++j) {
+        // lerp_torch on both halves: fma(1 - lambda, x0, fl(lambda * x1))
+        f2[j] = fma2(sub2(bc2(1.0f), lam), bc2(x0), mul2(lam, bc2(x1)));
+        lam = add2(lam, bc2(2.0f / kHop));
+        s += (double)f2[j].x;
+        sl[2 * j] = s;
+        s += (double)f2[j].y;
+        sl[2 * j + 1] = s;
     }
     double inc = s;
 #pragma unroll
@@ -168,7 +176,19 @@ __device__ __forceinline__ void hop_rotation(float x0, float x1, double base, do
     }
     const double off = (base + (inc - s)) * inv_sr;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) rot[i] = wrap_rot(fma(sl[i], inv_sr, off));
+    for (int j = 0; j < 8; ++j)
+        rot2[j] = make_float2(wrap_rot(fma(sl[2 * j], inv_sr, off)), wrap_rot(fma(sl[2 * j + 1], inv_sr, off)));
+}
+
+__device__ __forceinline__ void hop_rotation(float x0, float x1, double base, double inv_sr, int lane,
+                                             float (&f)[16], float (&rot)[16]) {
+    float2 f2[8], rot2[8];
+    hop_rotation2(x0, x1, base, inv_sr, lane, f2, rot2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        f[2 * j] = f2[j].x; f[2 * j + 1] = f2[j].y;
+        rot[2 * j] = rot2[j].x; rot[2 * j + 1] = rot2[j].y;
+    }
 }
 
 // A3 (Sins): full-rate phase = fl32(2*pi)*rot (vocoder.py:392), one warp per hop.
