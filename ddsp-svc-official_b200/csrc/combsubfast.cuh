@@ -216,16 +216,21 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
 
     // steps per pair: s=0 frame 2p, s=1 frame 2p+1, s=2 inverse FFT of the pair + overlap-add.
     // s=-1 (first iteration only) just generates the first hop of the run.
-    int p = CTX_PBEGIN, s = -1;
+    // (the step counter lives in the per-warp shared-memory context too: ptxas otherwise spills it to local memory)
+#define CTX_STEP ctx[4]
+    int p = CTX_PBEGIN;
+    if (lane == 0) CTX_STEP = -1;
+    __syncwarp();
 #pragma unroll 1
     for (;;) {
+        const int s = CTX_STEP;
         const int fm = 2 * p + s;                           // frame handled by steps 0 and 1
         if (s < 2) {
             // ---- excitation hop fm (second half of frame fm; fm = 2p-1 on the priming step) ----
             // (f0 / prefix of consecutive hops share cache lines: after the first hop of a run these are L2 hits)
             csf_gen_hop(P, fm, csf_load_hop(P, CTX_B, fm), ring + (fm & 1) * kRingSlot, lane);
             __syncwarp();
-            if (s < 0) { s = 0; continue; }
+            if (s < 0) { CTX_STEP = 0; __syncwarp(); continue; }
             {   // pull this frame's three control rows into L2 while the FFT runs (lanes 0..16: one line each)
                 const int64_t ro = (int64_t)CTX_B * P.cB + (int64_t)min(fm, F - 1) * P.cF + 32 * lane;
                 if (lane <= 16) { prefetch_l2(P.hm + ro); prefetch_l2(P.hp + ro); prefetch_l2(P.nm + ro); }
@@ -236,11 +241,11 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
 
         warp_fft1024(X, plane, tw4, lane);
 
-        if (s < 2) {
+        if (CTX_STEP < 2) {
             // ---- split the two real spectra, apply the filters (vocoder.py:472-481) ----------
             // last filter frame repeated (:473,476)
             const int64_t ro = (int64_t)CTX_B * P.cB + (int64_t)min(fm, F - 1) * P.cF + lane;
-            const int k16 = lane0 ? 512 : 0;                                  // bin 512 lives on lane 0 only; others read a dummy
+            const int k16 = 512 - lane;                                       // bin 512 (used by lane 0 only): every lane reads that one word
             const float* hm_r = P.hm + ro;
             const float* hp_r = P.hp + ro;
             const float* nm_r = P.nm + ro;
@@ -287,11 +292,11 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             // irfft ignores the imaginary part of the DC and Nyquist bins
             yi[0] = lane0 ? 0.0f : yi[0];
             yi[16] = 0.0f;
-            if (s == 0) {
+            if (CTX_STEP == 0) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) stash[q * 32 + lane] = make_float2(yr[q], yi[q]);
                 if (lane0) stash[16 * 32] = make_float2(yr[16], 0.0f);
-                s = 1;
+                CTX_STEP = 1;
             } else {
                 // ---- V = Y_m + j*Y_{m+1}; feed (Im V, Re V) to the forward FFT = inverse FFT ---
                 float xr[16], xi[16];
@@ -317,7 +322,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                     DDSP_RE(X, brev5(31 - q)) = ti;            // swapped
                     DDSP_IM(X, brev5(31 - q)) = tr;
                 }
-                s = 2;
+                CTX_STEP = 2;
             }
         } else {
             // ---- window (vocoder.py:486), overlap-add (:485-487), crop (:490) -----------------
@@ -368,8 +373,9 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                 }
             }
             if (++p >= p_end) break;
-            s = 0;
+            CTX_STEP = 0;
         }
+        __syncwarp();
     }
 }
 
