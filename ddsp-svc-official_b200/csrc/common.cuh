@@ -40,7 +40,7 @@ __host__ __device__ __forceinline__ uint32_t noise_key(uint64_t seed, uint32_t c
 }
 // Noise stream layout: the 16 samples {hop*512 + 32*i + lane, i = 0..15} that one lane feeds into
 // the FFT form one short LCG stream seeded by a strong hash of (clip key, hop, lane); one IMAD +
-// xorshift per sample instead of a full hash.
+// one shift per sample instead of a full hash.
 __host__ __device__ __forceinline__ uint32_t noise_seed(uint32_t key, uint32_t hop, uint32_t lane) {
     uint32_t x = (hop * 32u + lane) * 0x9E3779B1u + key;
     x ^= x >> 16; x *= 0x7feb352du;
@@ -49,12 +49,12 @@ __host__ __device__ __forceinline__ uint32_t noise_seed(uint32_t key, uint32_t h
     return x;
 }
 __host__ __device__ __forceinline__ uint32_t noise_next(uint32_t state) { return state * 747796405u + 2891336453u; }
-// uniform integer in [0, 2^24) from an LCG state (top bits, xorshift-mixed); U = value * 2^-24
-__host__ __device__ __forceinline__ uint32_t noise_u24(uint32_t state) { return (state ^ (state >> 15)) >> 8; }
+// uniform integer in [0, 2^24) from an LCG state: its top 24 bits (the streams are 16 draws long and
+// seeded by a strong hash, so no further output mixing is needed); U = value * 2^-24
+__host__ __device__ __forceinline__ uint32_t noise_u24(uint32_t state) { return (state >> 8) ^ 0x800000u; }
 // the same draw as a centred integer v = u24 - 2^23 in [-2^23, 2^23):  2U - 1 == v * 2^-23 exactly
-__host__ __device__ __forceinline__ int32_t noise_s24(uint32_t state) {
-    return (int32_t)(state ^ (state >> 15) ^ 0x80000000u) >> 8;
-}
+// (one arithmetic shift of the state read as a signed integer)
+__host__ __device__ __forceinline__ int32_t noise_s24(uint32_t state) { return (int32_t)state >> 8; }
 
 // Single-MUFU approximations (flush-to-zero forms: no denormal fix-up code around them).
 __device__ __forceinline__ float ex2_approx(float x) {

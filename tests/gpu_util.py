@@ -69,7 +69,7 @@ def hop_noise(k, hop):
     out = np.zeros(512, np.float32)
     for i in range(16):
         x = (x * 747796405 + 2891336453) & 0xffffffff
-        u24 = (x ^ (x >> 15)) >> 8
+        u24 = (x >> 8) ^ 0x800000
         out[32 * i + np.arange(32)] = u24.astype(np.float32) * np.float32(2.0 ** -24)
     return out
 
