@@ -90,6 +90,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 __global__ void __launch_bounds__(128) csf_zero_seams_kernel(float* __restrict__ signal, int F, int run_len,
                                                              int runs_per_clip, int n_seams) {
     const int seam = blockIdx.x;
+    cudaGridDependencySynchronize();          // launched with programmatic stream serialisation
     if (seam >= n_seams) return;
     const int b = seam / (runs_per_clip - 1), r = seam % (runs_per_clip - 1) + 1;
     const int hop = 2 * r * run_len - 1;

@@ -130,6 +130,19 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
     return 0;
 }
 
+// Launch with programmatic stream serialisation: the grid may be set up while its predecessor in the
+// stream drains; the kernel itself waits in cudaGridDependencySynchronize() before touching memory.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline int64_t grid_for(int64_t total, int per_block, int64_t cap) {
     int64_t g = (total + per_block - 1) / per_block;
     if (g < 1) g = 1;
@@ -238,7 +251,8 @@ int ddsp_b200_phase(const float* f0_frames, int64_t fB, int64_t fF, int B, int F
         ddsp::hop_totals_kernel<<<(unsigned)((hops + 8 * ddsp::kHopsPerWarp - 1) / (8 * ddsp::kHopsPerWarp)), 256, 0, st>>>(
             f0_frames, fB, fF, B, F, prefix);
         LAUNCH_CHECK();
-        ddsp::phase_scan_kernel<<<B, 1024, 0, st>>>(f0_frames, fB, fF, F, inv_sr, initial_phase, prefix, phase_frames);
+        CUDA_TRY(launch_pdl(ddsp::phase_scan_kernel, dim3(B), dim3(1024), 0, st, f0_frames, fB, fF, F, inv_sr, initial_phase,
+                            prefix, phase_frames));
         LAUNCH_CHECK();
     }
     if (phase_full) {
@@ -282,8 +296,8 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
     const unsigned grid = (unsigned)((runs + ddsp::kCsfWarps - 1) / ddsp::kCsfWarps);
     if (P.runs_per_clip > 1) {
         const int n_seams = B * (P.runs_per_clip - 1);
-        ddsp::csf_zero_seams_kernel<<<n_seams, 128, 0, (cudaStream_t)stream>>>(signal, F, P.run_len, P.runs_per_clip,
-                                                                                n_seams);
+        CUDA_TRY(launch_pdl(ddsp::csf_zero_seams_kernel, dim3(n_seams), dim3(128), 0, (cudaStream_t)stream, signal, F,
+                            P.run_len, P.runs_per_clip, n_seams));
         LAUNCH_CHECK();
     }
     // Programmatic dependent launch: the CTAs may be scheduled and stage their tables while the

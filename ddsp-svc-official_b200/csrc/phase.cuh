@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(1024) phase_scan_kernel(const float* __restric
     const float* row = f0_frames + (int64_t)b * fB;
     const int per = (F + blockDim.x - 1) / blockDim.x;
     const int h0 = min(F, (int)threadIdx.x * per), h1 = min(F, h0 + per);
+    cudaGridDependencySynchronize();          // launched with programmatic stream serialisation: totals come from A1
     double s = 0.0;
     for (int h = h0; h < h1; ++h) s += pf[h];
     double total;
