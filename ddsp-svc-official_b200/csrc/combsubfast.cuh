@@ -280,15 +280,18 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                 } else {        // bin 512: lane 0, register 16, its own partner (other lanes: harmless dummy)
                     a = DDSP_RE(X, 16); bb = DDSP_IM(X, 16); c = a; d = bb;
                 }
-                const float Cr = a + c, Ci = bb - d, Nr = bb + d, Ni = c - a;
+                // packed fp32x2 with single-register broadcast operands (same roundings as the scalar form):
+                //   (Cr, Ni) = (c + a, c - a),  (Nr, Ci) = (bb + d, bb - d)
+                const float2 CrNi = fma2(bc2(a), make_float2(1.0f, -1.0f), bc2(c));
+                const float2 NrCi = fma2(bc2(d), make_float2(1.0f, -1.0f), bc2(bb));
                 // H = exp(hm + j*pi*hp) (vocoder.py:472), N = exp(nm)/128 (:475); the 1/2 of the
                 // split and the 1/1024 of irfft are folded in as exact powers of two.
                 const float g = ex2_approx(fmaf(vhm, DDSP_LOG2E_F, -11.0f));
-                const float ang = DDSP_PI_F * vhp;
-                const float Hr = g * cos_approx(ang), Hi = g * sin_approx(ang);
                 const float nf = ex2_approx(fmaf(vnm, DDSP_LOG2E_F, -18.0f));
-                yr[q] = fmaf(Cr, Hr, fmaf(-Ci, Hi, Nr * nf));
-                yi[q] = fmaf(Cr, Hi, fmaf(Ci, Hr, Ni * nf));
+                const float ang = DDSP_PI_F * vhp;
+                const float2 H = mul2(bc2(g), make_float2(cos_approx(ang), sin_approx(ang)));
+                yr[q] = fmaf(CrNi.x, H.x, fmaf(-NrCi.y, H.y, NrCi.x * nf));
+                yi[q] = fmaf(CrNi.x, H.y, fmaf(NrCi.y, H.x, CrNi.y * nf));
             }
             // irfft ignores the imaginary part of the DC and Nyquist bins
             yi[0] = lane0 ? 0.0f : yi[0];

@@ -39,16 +39,17 @@ __host__ __device__ __forceinline__ uint32_t noise_key(uint64_t seed, uint32_t c
     return (uint32_t)(z >> 32) ^ (uint32_t)z;
 }
 // Noise stream layout: the 16 samples {hop*512 + 32*i + lane, i = 0..15} that one lane feeds into
-// the FFT form one short LCG stream seeded by a strong hash of (clip key, hop, lane); one IMAD +
-// one shift per sample instead of a full hash.
+// the FFT form one short multiplicative-congruential stream (x <- 747796405 x mod 2^32, odd seed)
+// seeded by a strong hash of (clip key, hop, lane); one IMAD + one shift per sample instead of a
+// full hash.  Only the top 24 bits of each state are used.
 __host__ __device__ __forceinline__ uint32_t noise_seed(uint32_t key, uint32_t hop, uint32_t lane) {
     uint32_t x = (hop * 32u + lane) * 0x9E3779B1u + key;
     x ^= x >> 16; x *= 0x7feb352du;
     x ^= x >> 15; x *= 0x846ca68bu;
     x ^= x >> 16;
-    return x;
+    return x | 1u;              // odd: the stream is a multiplicative congruential sequence mod 2^32
 }
-__host__ __device__ __forceinline__ uint32_t noise_next(uint32_t state) { return state * 747796405u + 2891336453u; }
+__host__ __device__ __forceinline__ uint32_t noise_next(uint32_t state) { return state * 747796405u; }
 // uniform integer in [0, 2^24) from an LCG state: its top 24 bits (the streams are 16 draws long and
 // seeded by a strong hash, so no further output mixing is needed); U = value * 2^-24
 __host__ __device__ __forceinline__ uint32_t noise_u24(uint32_t state) { return (state >> 8) ^ 0x800000u; }

@@ -66,9 +66,10 @@ def hop_noise(k, hop):
     x ^= x >> 16; x = (x * 0x7feb352d) & 0xffffffff
     x ^= x >> 15; x = (x * 0x846ca68b) & 0xffffffff
     x ^= x >> 16
+    x |= 1
     out = np.zeros(512, np.float32)
     for i in range(16):
-        x = (x * 747796405 + 2891336453) & 0xffffffff
+        x = (x * 747796405) & 0xffffffff
         u24 = (x >> 8) ^ 0x800000
         out[32 * i + np.arange(32)] = u24.astype(np.float32) * np.float32(2.0 ** -24)
     return out
