@@ -21,7 +21,10 @@
 
 namespace ddsp {
 
-constexpr int kCsfWarps = 16;                       // warps per CTA (one CTA per SM)
+#ifndef CSF_WARPS
+#define CSF_WARPS 16
+#endif
+constexpr int kCsfWarps = CSF_WARPS;                // warps per CTA (one CTA per SM)
 constexpr int kCsfThreads = kCsfWarps * 32;
 constexpr int kRingSlot = kHop + kHop / 32;         // 528 floats: one pad word per 32 samples
 constexpr int kStashFloat2 = 17 * 32;               // Y_m stash: 16 bins/lane (+ bin 512 on lane 0)
