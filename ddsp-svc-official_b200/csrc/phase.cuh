@@ -9,10 +9,10 @@
 namespace ddsp {
 
 // ---------------------------------------------------------------------------------------------
-// A1: per-hop totals.  One warp per hop: sum over the 512 upsampled fp32 f0 samples of the hop,
-// accumulated in fp64 (exact for any realistic f0: 24-bit mantissas, 512 terms).
+// A1: per-hop totals.  A warp sums the 512 upsampled fp32 f0 samples of a hop exactly (the total is
+// an fp64 number without rounding for any realistic f0: 24-bit mantissas, 512 terms).
 // ---------------------------------------------------------------------------------------------
-constexpr int kHopsPerWarp = 4;   // hops handled by one warp (amortises the interpolation weights)
+constexpr int kHopsPerWarp = 8;   // hops handled by one warp (amortises the interpolation weights)
 
 __global__ void __launch_bounds__(256) hop_totals_kernel(const float* __restrict__ f0_frames, int64_t fB,
                                                          int64_t fF, int B, int F,
@@ -21,11 +21,18 @@ __global__ void __launch_bounds__(256) hop_totals_kernel(const float* __restrict
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t first = warp * kHopsPerWarp, n_hops = (int64_t)B * F;
     if (first >= n_hops) return;
-    float w0[kHop / 32], w1[kHop / 32];
+    // lane owns the 16 consecutive samples 16*lane .. 16*lane+15 of a hop, as 8 packed fp32x2 pairs;
+    // the weights j/512 are exact, so lambda_0 + i/512 equals (16 lane + i)/512 bit for bit
+    float2 w0[8], w1[8];
+    {
+        const float lam0 = (float)(16 * lane) * (1.0f / kHop);
+        float2 lam = make_float2(lam0, lam0 + 1.0f / kHop);
 #pragma unroll
-    for (int i = 0; i < kHop / 32; ++i) {
-        w1[i] = (float)(lane + 32 * i) * (1.0f / kHop);
-        w0[i] = __fsub_rn(1.0f, w1[i]);
+        for (int j = 0; j < 8; ++j) {
+            w1[j] = lam;
+            w0[j] = sub2(bc2(1.0f), lam);
+            lam = add2(lam, bc2(2.0f / kHop));
+        }
     }
     // lane g (< kHopsPerWarp) fetches the two frame values of hop first+g
     float x0 = 0.0f, x1 = 0.0f;
@@ -35,12 +42,31 @@ __global__ void __launch_bounds__(256) hop_totals_kernel(const float* __restrict
         x0 = __ldg(row + (int64_t)h * fF);
         x1 = __ldg(row + (int64_t)min(h + 1, F - 1) * fF);
     }
-#pragma unroll
+#pragma unroll 2
     for (int g = 0; g < kHopsPerWarp; ++g) {
         const float a = __shfl_sync(kFullMask, x0, g), c = __shfl_sync(kFullMask, x1, g);
-        double s = 0.0;
+        double s;
+        if (fabsf(c - a) < 2.0f * fminf(a, c)) {
+            // Both frames voiced and within a factor 3 (every hop but onsets / offsets; warp-uniform test).
+            // The lane's 16 samples then differ by less than min(a,c)/16, so each difference f_i - f_0 is
+            // exact in fp32 (Sterbenz) and so is any sum of them: all are multiples of ulp(f_min) and stay
+            // below 2^24 ulps.  Two fp32->fp64 conversions per lane instead of 16, packed fp32x2 arithmetic,
+            // and the lane total is the same exact number.
+            const float2 f0p = fma2(w0[0], bc2(a), mul2(w1[0], bc2(c)));        // lerp_torch on both halves
+            float2 gs = make_float2(0.0f, __fsub_rn(f0p.y, f0p.x));
 #pragma unroll
-        for (int i = 0; i < kHop / 32; ++i) s += (double)__fmaf_rn(w0[i], a, __fmul_rn(w1[i], c));
+            for (int j = 1; j < 8; ++j)
+                gs = add2(gs, sub2(fma2(w0[j], bc2(a), mul2(w1[j], bc2(c))), bc2(f0p.x)));
+            s = fma(16.0, (double)f0p.x, (double)__fadd_rn(gs.x, gs.y));
+        } else {
+            s = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float2 f = fma2(w0[j], bc2(a), mul2(w1[j], bc2(c)));
+                s += (double)f.x;
+                s += (double)f.y;
+            }
+        }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(kFullMask, s, d);
         if (lane == 0 && first + g < n_hops) totals[first + g] = s;

@@ -10,11 +10,11 @@ from ddsp_b200.synthetic import make_inputs
 d = make_inputs(8, 301, 1539, seed=5, zero_f0_fraction=0.1)
 ctrl = torch.from_numpy(d['ctrl']).cuda(); hm, hp, nm = torch.split(ctrl, 513, dim=-1)
 f0 = torch.from_numpy(d['f0_frames']).cuda()[..., None]
-_, prefix, _ = core.phase_stage(f0, 512, 44100)
+pf, prefix, _ = core.phase_stage(f0, 512, 44100)
 a = core.combsubfast_stage(hm, hp, nm, f0, prefix, 512, 44100, seed=3)
 b = core.combsubfast_stage(hm, hp, nm, f0, prefix, 512, 44100, noise_u=torch.from_numpy(d['U']).cuda())
 torch.cuda.synchronize()
-print(hashlib.sha1(a.cpu().numpy().tobytes()).hexdigest(), hashlib.sha1(b.cpu().numpy().tobytes()).hexdigest())
+print(' '.join(hashlib.sha1(t.cpu().numpy().tobytes()).hexdigest()[:16] for t in (a, b, pf, prefix)))
 '''
 outs = []
 for lib in sys.argv[1:3]:
