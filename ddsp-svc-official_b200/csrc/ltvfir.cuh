@@ -552,12 +552,17 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                 }
             } else {
                 // y[2n] = Re z'[n] = X.im, y[2n+1] = Im z'[n] = X.re, n = lane + 32 q; overlap-add (core.py:233-235)
+                // (rs is a multiple of 512, so the ring index wraps only between 512-sample blocks)
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    float2* slot = reinterpret_cast<float2*>(ring + ((rs + 2 * lane + 64 * q) & (kLtvRing - 1)));
-                    float2 v = make_float2(DDSP_IM(X, q), DDSP_RE(X, q));
-                    if (q < 24) { const float2 o = *slot; v.x += o.x; v.y += o.y; }
-                    *slot = v;
+                for (int blk = 0; blk < 4; ++blk) {
+                    float2* base = reinterpret_cast<float2*>(ring + ((rs + blk * kHop) & (kLtvRing - 1)) + 2 * lane);
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq) {
+                        const int q = 8 * blk + qq;
+                        float2 v = make_float2(DDSP_IM(X, q), DDSP_RE(X, q));
+                        if (blk < 3) { const float2 o = base[32 * qq]; v.x += o.x; v.y += o.y; }
+                        base[32 * qq] = v;
+                    }
                 }
                 __syncwarp();
                 // retire the first 512 samples of the window: output index t = 512(m-1) - D + j  (core.py:238,177-182)
@@ -565,13 +570,20 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                 const bool complete = (m - 3 >= m_begin) || (m_begin == 0);
                 float* ob = P.out + (int64_t)CV_B * T;
                 const int64_t tb = t0 - D;
+                const float* blk0 = ring + rs + lane;
+                if (complete && tb >= 0 && tb + kHop <= T) {       // the common case: a whole finished hop inside the clip
+                    float* dst = ob + tb + lane;
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const int j = lane + 32 * r;
-                    const int64_t t = tb + j;
-                    if (t >= 0 && t < T) {
-                        const float v = ring[(rs + j) & (kLtvRing - 1)];
-                        if (complete) ob[t] = v; else atomicAdd(ob + t, v);
+                    for (int r = 0; r < 16; ++r) dst[32 * r] = blk0[32 * r];
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const int j = lane + 32 * r;
+                        const int64_t t = tb + j;
+                        if (t >= 0 && t < T) {
+                            const float v = blk0[32 * r];
+                            if (complete) ob[t] = v; else atomicAdd(ob + t, v);
+                        }
                     }
                 }
                 __syncwarp();
@@ -711,12 +723,15 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
             } else {
                 // after the swapped FFT: X.im = up*h, X.re = down*h, sample n = lane + 32 q.
                 // ring[rs + n] += up*h;  ring[rs + 512 + n] (+)= down*h -- its last 512 samples open a fresh hop
+                // (rs is a multiple of 512, so the ring index wraps only between 512-sample blocks)
+                float* blk0 = ring + rs + lane;
+                float* blk1 = ring + ((rs + kHop) & (kLtvRing - 1)) + lane;
+                float* blk2 = ring + ((rs + 2 * kHop) & (kLtvRing - 1)) + lane;
 #pragma unroll
-                for (int q = 0; q < 32; ++q) ring[(rs + lane + 32 * q) & (kLtvRing - 1)] += DDSP_IM(X, q);
-#pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    float* slot = ring + ((rs + kHop + lane + 32 * q) & (kLtvRing - 1));
-                    *slot = (q < 16) ? *slot + DDSP_RE(X, q) : DDSP_RE(X, q);
+                for (int q = 0; q < 16; ++q) {
+                    blk0[32 * q] += DDSP_IM(X, q);                                           // up*h, first 512
+                    blk1[32 * q] = (blk1[32 * q] + DDSP_IM(X, q + 16)) + DDSP_RE(X, q);      // up*h second, down*h first
+                    blk2[32 * q] = DDSP_RE(X, q + 16);                                       // down*h second: fresh hop
                 }
                 __syncwarp();
                 // retire the first 512 samples of the window: output index t = 512(m-1) - D + j  (core.py:238,177-182)
@@ -724,13 +739,19 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
                 const bool complete = (m - 2 >= m_begin) || (m_begin == 0);
                 float* ob = P.out + (int64_t)CV_B * T;
                 const int64_t tb = t0 - D;
+                if (complete && tb >= 0 && tb + kHop <= T) {       // the common case: a whole finished hop inside the clip
+                    float* dst = ob + tb + lane;
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const int j = lane + 32 * r;
-                    const int64_t t = tb + j;
-                    if (t >= 0 && t < T) {
-                        const float v = ring[(rs + j) & (kLtvRing - 1)];
-                        if (complete) ob[t] = v; else atomicAdd(ob + t, v);
+                    for (int r = 0; r < 16; ++r) dst[32 * r] = blk0[32 * r];
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const int j = lane + 32 * r;
+                        const int64_t t = tb + j;
+                        if (t >= 0 && t < T) {
+                            const float v = blk0[32 * r];
+                            if (complete) ob[t] = v; else atomicAdd(ob + t, v);
+                        }
                     }
                 }
                 __syncwarp();
