@@ -34,9 +34,10 @@ _PROTOS = {
                                                  c_f32p, c_f32p, c_f32p, i64, i64, C.c_void_p]),
     'ddsp_b200_performer_features': (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                                c_f32p, C.c_void_p]),
-    'ddsp_b200_performer_project_features': (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                                       C.c_float, c_f32p, C.c_void_p]),
-    'ddsp_b200_glu_dwconv_silu': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
+    'ddsp_b200_performer_project_features': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                       C.c_int, C.c_float, c_f32p, C.c_void_p]),
+    'ddsp_b200_glu_dwconv_silu': (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p,
+                                            C.c_void_p]),
     'ddsp_b200_apply_frame_mask': (C.c_int, [c_f32p, c_f32p, i64, i64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ddsp_b200_frequency_filter_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'ddsp_b200_frequency_filter': (C.c_int, [c_f32p, c_f32p, i64, i64, C.c_int, C.c_int, C.c_float, C.c_int, c_f32p,

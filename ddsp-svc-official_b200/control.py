@@ -104,24 +104,33 @@ class _SelfAttention(nn.Module):
         self.to_v = nn.Linear(dim, inner)
         self.to_out = nn.Linear(inner, dim)
 
-    def forward(self, x):
+    def forward(self, x, residual=None):
+        """`residual` (fused path only): returns residual + attention(x), with the output bias and the
+        residual folded into the output GEMM (addmm, beta = 1) instead of two more elementwise passes."""
         b, n, _ = x.shape
         split = lambda t: t.view(b, n, self.heads, _DIM_HEAD).transpose(1, 2)      # noqa: E731
         if _fused_ok(x):
             from . import core
             proj = self.fast_attention.projection_matrix
-            q, k = self.to_q(x), self.to_k(x)
             if b * n * self.heads >= _FUSED_PROJECTION_MIN_ROWS:
-                # large batches: projection fused into the feature kernel, the (B,N,H,266) products stay on chip
-                q = core.performer_project_features(q, proj, self.heads, True)
-                k = core.performer_project_features(k, proj, self.heads, False)
+                # large batches: projection fused into the feature kernel, the (B,N,H,266) products stay on
+                # chip; the q/k Linear biases are added there too (bias-free GEMMs skip cuBLASLt's separate
+                # epilogue kernel)
+                q = core.performer_project_features(F.linear(x, self.to_q.weight), proj, self.heads, True,
+                                                    x_bias=self.to_q.bias)
+                k = core.performer_project_features(F.linear(x, self.to_k.weight), proj, self.heads, False,
+                                                    x_bias=self.to_k.bias)
             else:
                 # streaming blocks: a library GEMM + the one-pass feature kernel has the lower latency
+                q, k = self.to_q(x), self.to_k(x)
                 scale = _DIM_HEAD ** -0.25
                 q, k = [core.performer_features(torch.matmul((scale * t).view(-1, _DIM_HEAD), proj.t()), t, self.heads, is_q)
                         for t, is_q in ((q, True), (k, False))]
             out = self.fast_attention.attend(q, k, split(self.to_v(x)))
-            return self.to_out(out.transpose(1, 2).reshape(b, n, self.heads * _DIM_HEAD))
+            out = out.transpose(1, 2).reshape(b * n, self.heads * _DIM_HEAD)
+            if residual is None:
+                return self.to_out(out).view(b, n, -1)
+            return torch.addmm((residual + self.to_out.bias).reshape(b * n, -1), out, self.to_out.weight.t()).view(b, n, -1)
         out = self.fast_attention(split(self.to_q(x)), split(self.to_k(x)), split(self.to_v(x)))
         return self.to_out(out.transpose(1, 2).reshape(b, n, self.heads * _DIM_HEAD))
 
@@ -142,12 +151,19 @@ class _ConvModule(nn.Module):
             nn.Dropout(0.0),
         )
 
-    def forward(self, x):
+    def forward(self, x, residual=None):
+        """`residual` (fused path only): returns residual + module(x) with bias and residual folded into the
+        last GEMM."""
         if _fused_ok(x):
             from . import core
             ln, _, pw1, _, dw, _, pw2, _, _ = self.net
-            u = F.linear(ln(x), pw1.weight.squeeze(-1), pw1.bias)                  # channels last: no transposes
-            return F.linear(core.glu_dwconv_silu(u, dw.weight, dw.bias), pw2.weight.squeeze(-1), pw2.bias)
+            u = F.linear(ln(x), pw1.weight.squeeze(-1))                            # channels last: no transposes
+            s = core.glu_dwconv_silu(u, dw.weight, dw.bias, u_bias=pw1.bias)
+            if residual is None:
+                return F.linear(s, pw2.weight.squeeze(-1), pw2.bias)
+            b, n, _ = x.shape
+            return torch.addmm((residual + pw2.bias).reshape(b * n, -1), s.view(b * n, -1),
+                               pw2.weight.squeeze(-1).t()).view(b, n, -1)
         return self.net(x)
 
 
@@ -159,6 +175,9 @@ class _EncoderLayer(nn.Module):
         self.local_mixer = _ConvModule(dim)
 
     def forward(self, x):
+        if _fused_ok(x):
+            x = self.attn(self.norm(x), residual=x)
+            return self.local_mixer(x, residual=x)
         x = x + self.attn(self.norm(x))
         return x + self.local_mixer(x)
 

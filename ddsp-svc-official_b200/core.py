@@ -377,10 +377,15 @@ def performer_features(dash, x, heads, is_query, eps=1e-4):
     return out
 
 
-def performer_project_features(x, projection, heads, is_query, eps=1e-4):
+def performer_project_features(x, projection, heads, is_query, eps=1e-4, x_bias=None):
     """`performer_features` with the random-feature projection fused: x (B,N,H*64), projection (M,64)
-    -> (B,H,N,M); the (B,N,H,M) projections never touch HBM."""
+    -> (B,H,N,M); the (B,N,H,M) projections never touch HBM.  `x_bias` (H*64): bias of the Linear that
+    produced x, added on load (lets the GEMM run without its separate bias epilogue)."""
     x = _need_cuda_f32(x, 'x').contiguous()
+    if x_bias is not None:
+        x_bias = _need_cuda_f32(x_bias, 'x_bias').contiguous()
+        if x_bias.numel() != int(heads) * 64:
+            raise ValueError('x_bias must have heads*64 entries')
     projection = _need_cuda_f32(projection, 'projection').contiguous()
     B, N = x.shape[0], x.shape[1]
     H = int(heads)
@@ -389,23 +394,28 @@ def performer_project_features(x, projection, heads, is_query, eps=1e-4):
     M = projection.shape[0]
     out = torch.empty((B, H, N, M), dtype=torch.float32, device=x.device)
     with _OnDevice(x.device) as _st:
-        _cabi.check(_cabi.lib().ddsp_b200_performer_project_features(x.data_ptr(), projection.data_ptr(), B, N, H, M,
+        _cabi.check(_cabi.lib().ddsp_b200_performer_project_features(x.data_ptr(), _ptr(x_bias), projection.data_ptr(), B, N, H, M,
                                                                      int(bool(is_query)), float(eps), out.data_ptr(), _st))
     return out
 
 
-def glu_dwconv_silu(u, weight, bias):
+def glu_dwconv_silu(u, weight, bias, u_bias=None):
     """GLU -> depthwise Conv1d(k=31, 'same') -> SiLU in channels-last layout (pcmer.py:53-55).
-    u (B,T,2C), weight (C,1,31) or (C,31), bias (C) -> (B,T,C)."""
+    u (B,T,2C), weight (C,1,31) or (C,31), bias (C) -> (B,T,C).  `u_bias` (2C): bias of the pointwise
+    conv that produced u, added on load."""
     u = _need_cuda_f32(u, 'u').contiguous()
     B, T, C2 = u.shape
     C = C2 // 2
+    if u_bias is not None:
+        u_bias = _need_cuda_f32(u_bias, 'u_bias').contiguous()
+        if u_bias.numel() != C2:
+            raise ValueError('u_bias must have 2C entries')
     weight = _need_cuda_f32(weight, 'weight').reshape(C, -1).contiguous()
     if weight.shape[1] != 31:
         raise ValueError('depthwise kernel size must be 31')
     bias = _need_cuda_f32(bias, 'bias').contiguous()
     out = torch.empty((B, T, C), dtype=torch.float32, device=u.device)
     with _OnDevice(u.device) as _st:
-        _cabi.check(_cabi.lib().ddsp_b200_glu_dwconv_silu(u.data_ptr(), weight.data_ptr(), bias.data_ptr(), B, T, C,
+        _cabi.check(_cabi.lib().ddsp_b200_glu_dwconv_silu(u.data_ptr(), _ptr(u_bias), weight.data_ptr(), bias.data_ptr(), B, T, C,
                                                           out.data_ptr(), _st))
     return out

@@ -78,8 +78,9 @@ constexpr int kPpfSmemBytes = (kPerfDim * kPpfCols + kPpfWarps * kPpfRows * kPer
 
 template <bool IS_QUERY>
 __global__ void __launch_bounds__(kPpfWarps * 32, 2) performer_project_features_kernel(
-    const float* __restrict__ x, const float* __restrict__ proj, float* __restrict__ out, int B, int N, int H, int M,
-    float normalizer, float normalizer2_half, float ratio, float eps) {
+    const float* __restrict__ x, const float* __restrict__ xbias, const float* __restrict__ proj,
+    float* __restrict__ out, int B, int N, int H, int M, float normalizer, float normalizer2_half, float ratio,
+    float eps) {
     extern __shared__ __align__(16) float ppf_smem[];
     float* PT = ppf_smem;                                       // [64][288]: PT[d][j] = proj[j][d]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -98,11 +99,20 @@ __global__ void __launch_bounds__(kPpfWarps * 32, 2) performer_project_features_
         {
             const int64_t row = r0 + (lane >> 2);
             const float4* src = reinterpret_cast<const float4*>(x + row * kPerfDim) + (lane & 3) * 4;
+            // optional bias of the producing Linear (H*64 entries, head h = row % H), added here so that the
+            // GEMM runs without a separate bias epilogue
+            const float4* bsrc = xbias ? reinterpret_cast<const float4*>(xbias + (row % H) * kPerfDim) + (lane & 3) * 4 : nullptr;
             float4* dst = reinterpret_cast<float4*>(xs + (lane >> 2) * kPerfDim) + (lane & 3) * 4;
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < rows) t = __ldg(src + v);
+                if (row < rows) {
+                    t = __ldg(src + v);
+                    if (bsrc) {
+                        const float4 bb = __ldg(bsrc + v);
+                        t.x += bb.x; t.y += bb.y; t.z += bb.z; t.w += bb.w;
+                    }
+                }
                 ss = fmaf(t.x, t.x, fmaf(t.y, t.y, fmaf(t.z, t.z, fmaf(t.w, t.w, ss))));
                 dst[v] = make_float4(normalizer * t.x, normalizer * t.y, normalizer * t.z, normalizer * t.w);
             }
@@ -172,9 +182,9 @@ __global__ void __launch_bounds__(kPpfWarps * 32, 2) performer_project_features_
 constexpr int kDwTaps = 31, kDwPad = 15;
 constexpr int kDwTileT = 64, kDwTileC = 64, kDwPerThread = 16;      // 256 threads: 64 channels x 4 time groups
 
-__global__ void __launch_bounds__(256) glu_dwconv_silu_kernel(const float* __restrict__ u, const float* __restrict__ w,
-                                                              const float* __restrict__ bias, float* __restrict__ out,
-                                                              int B, int T, int C) {
+__global__ void __launch_bounds__(256) glu_dwconv_silu_kernel(const float* __restrict__ u, const float* __restrict__ ubias,
+                                                              const float* __restrict__ w, const float* __restrict__ bias,
+                                                              float* __restrict__ out, int B, int T, int C) {
     __shared__ float g[(kDwTileT + kDwTaps - 1) * kDwTileC];
     const int c0 = blockIdx.x * kDwTileC, t0 = blockIdx.y * kDwTileT, b = blockIdx.z;
     const int cl = threadIdx.x & (kDwTileC - 1), tg = threadIdx.x / kDwTileC;
@@ -185,8 +195,9 @@ __global__ void __launch_bounds__(256) glu_dwconv_silu_kernel(const float* __res
         const int t = t0 + tt - kDwPad;
         float val = 0.0f;
         if (t >= 0 && t < T && c0 + cc < C) {
-            const float a = __ldg(ub + (int64_t)t * 2 * C + c0 + cc);
-            const float gate = __ldg(ub + (int64_t)t * 2 * C + C + c0 + cc);
+            float a = __ldg(ub + (int64_t)t * 2 * C + c0 + cc);
+            float gate = __ldg(ub + (int64_t)t * 2 * C + C + c0 + cc);
+            if (ubias) { a += __ldg(ubias + c0 + cc); gate += __ldg(ubias + C + c0 + cc); }   // bias of the producing Linear
             val = a / (1.0f + expf(-gate));
         }
         g[e] = val;

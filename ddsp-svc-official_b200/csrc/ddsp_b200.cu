@@ -511,11 +511,11 @@ int ddsp_b200_performer_features(const float* dash, const float* x, int B, int N
     return DDSP_B200_OK;
 }
 
-int ddsp_b200_performer_project_features(const float* x, const float* projection, int B, int N, int H, int M,
-                                         int is_query, float eps, float* out, void* stream) {
+int ddsp_b200_performer_project_features(const float* x, const float* x_bias, const float* projection, int B, int N,
+                                         int H, int M, int is_query, float eps, float* out, void* stream) {
     g_launches = 0;
     if (!x || !projection || !out || B <= 0 || N <= 0 || H <= 0 || M <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
-    if (M > ddsp::kPpfCols || ((uintptr_t)x & 15)) return DDSP_B200_ERR_UNSUPPORTED;
+    if (M > ddsp::kPpfCols || ((uintptr_t)x & 15) || ((uintptr_t)x_bias & 15)) return DDSP_B200_ERR_UNSUPPORTED;
     const float* tables = nullptr;
     if (int rc = ensure_device_ready((cudaStream_t)stream, &tables)) return rc;     // shared-memory opt-in
     const int64_t groups = ((int64_t)B * N * H + ddsp::kPpfRows - 1) / ddsp::kPpfRows;
@@ -524,21 +524,21 @@ int ddsp_b200_performer_project_features(const float* x, const float* projection
     const float ratio = 1.0f / sqrtf((float)M);
     if (is_query)
         ddsp::performer_project_features_kernel<true><<<grid, ddsp::kPpfWarps * 32, ddsp::kPpfSmemBytes, (cudaStream_t)stream>>>(
-            x, projection, out, B, N, H, M, normalizer, 0.0625f, ratio, eps);
+            x, x_bias, projection, out, B, N, H, M, normalizer, 0.0625f, ratio, eps);
     else
         ddsp::performer_project_features_kernel<false><<<grid, ddsp::kPpfWarps * 32, ddsp::kPpfSmemBytes, (cudaStream_t)stream>>>(
-            x, projection, out, B, N, H, M, normalizer, 0.0625f, ratio, eps);
+            x, x_bias, projection, out, B, N, H, M, normalizer, 0.0625f, ratio, eps);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }
 
-int ddsp_b200_glu_dwconv_silu(const float* u, const float* weight, const float* bias, int B, int T, int C, float* out,
-                              void* stream) {
+int ddsp_b200_glu_dwconv_silu(const float* u, const float* u_bias, const float* weight, const float* bias, int B, int T,
+                              int C, float* out, void* stream) {
     g_launches = 0;
     if (!u || !weight || !bias || !out || B <= 0 || T <= 0 || C <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
     if (B > 65535) return DDSP_B200_ERR_UNSUPPORTED;
     const dim3 grid((C + ddsp::kDwTileC - 1) / ddsp::kDwTileC, (T + ddsp::kDwTileT - 1) / ddsp::kDwTileT, B);
-    ddsp::glu_dwconv_silu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(u, weight, bias, out, B, T, C);
+    ddsp::glu_dwconv_silu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(u, u_bias, weight, bias, out, B, T, C);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }

@@ -194,12 +194,13 @@ int ddsp_b200_apply_frame_mask(float *signal, const float *mask_frames, int64_t 
 int ddsp_b200_performer_features(const float *dash, const float *x, int B, int N, int H, int M,
                                  int is_query, float eps, float *out, void *stream);
 /* Same feature map with the projection fused (dash never stored): x (B,N,H,64) contiguous,
- * projection (M,64) contiguous, M <= 288, out (B,H,N,M). */
-int ddsp_b200_performer_project_features(const float *x, const float *projection, int B, int N,
-                                         int H, int M, int is_query, float eps, float *out,
-                                         void *stream);
-int ddsp_b200_glu_dwconv_silu(const float *u, const float *weight, const float *bias, int B, int T,
-                              int C, float *out, void *stream);
+ * projection (M,64) contiguous, M <= 288, out (B,H,N,M).  x_bias (H*64) / u_bias (2C): optional (NULL)
+ * bias of the Linear that produced x / u, added on load so that GEMM can run without a bias epilogue. */
+int ddsp_b200_performer_project_features(const float *x, const float *x_bias, const float *projection,
+                                         int B, int N, int H, int M, int is_query, float eps,
+                                         float *out, void *stream);
+int ddsp_b200_glu_dwconv_silu(const float *u, const float *u_bias, const float *weight,
+                              const float *bias, int B, int T, int C, float *out, void *stream);
 
 /* Number of kernel launches the last call of each entry point enqueued on this thread
  * (bench.py reports it as gpu_launches). */

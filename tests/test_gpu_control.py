@@ -39,6 +39,23 @@ def test_performer_project_features(B, N, H, is_query):
     assert ((out.double() - ref).abs() <= 1e-4 * ref.abs() + 1e-9).all(), (out.double() - ref).abs().max().item()
 
 
+def test_bias_folded_into_the_fused_stages():
+    """x_bias / u_bias: the bias of the producing Linear added on load equals adding it beforehand."""
+    torch.manual_seed(3)
+    x = torch.randn(2, 50, 8 * 64, device='cuda')
+    bias = torch.randn(8 * 64, device='cuda') * 0.3
+    proj = torch.randn(266, 64, device='cuda')
+    for is_query in (True, False):
+        a = core.performer_project_features(x, proj, 8, is_query, x_bias=bias)
+        b = core.performer_project_features(x + bias, proj, 8, is_query)
+        assert ((a - b).abs() <= 1e-5 * b.abs() + 1e-9).all()
+    u = torch.randn(2, 70, 1024, device='cuda')
+    ub = torch.randn(1024, device='cuda') * 0.3
+    w = torch.randn(512, 1, 31, device='cuda') * 0.2
+    db = torch.randn(512, device='cuda')
+    assert torch.equal(core.glu_dwconv_silu(u, w, db, u_bias=ub), core.glu_dwconv_silu(u + ub, w, db))
+
+
 @pytest.mark.parametrize('B,T,C', [(1, 5, 512), (2, 64, 512), (2, 131, 512), (1, 300, 96)])
 def test_glu_dwconv_silu(B, T, C):
     torch.manual_seed(T)
