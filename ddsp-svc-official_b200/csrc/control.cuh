@@ -6,11 +6,14 @@
 //     projections: one read of `dash`, one write of the features (was ~10 passes);
 //   * glu_dwconv_silu_kernel: GLU -> depthwise Conv1d(k=31, 'same') -> SiLU of the conformer
 //     convolution module (pcmer.py:41-63) in channels-last layout, no transposes.
-// Both are HBM-bound streaming kernels in fp32 with full-precision expf (they feed exp() of the
-// synthesizer, so no approximate transcendentals here).
+// They are streaming kernels in fp32; the one-pass feature kernel and the conv stage use full-precision
+// expf, the projection-fused kernel (whose exp argument already carries the fp32 rounding of a 64-term
+// dot product) uses __expf.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "common.cuh"
 
 namespace ddsp {
 
@@ -72,7 +75,8 @@ __global__ void __launch_bounds__(256) performer_features_kernel(const float* __
 // dash[r][j] = sum_d fl(normalizer * x[r][d]) * proj[j][d]  (fp32 FMA chain over d), then the feature
 // map above.  A CTA keeps proj^T (64 x 288, zero padded) in shared memory; a warp owns kPpfRows rows
 // at a time (72 accumulators per lane: 8 rows x 9 column groups), x is staged per warp in shared
-// memory and read back as broadcast float4s: 9 + 2 shared loads per 72 FMAs.
+// memory, transposed and row-pair interleaved, and read back as broadcast float4s: 9 + 2 shared loads
+// per 36 packed FFMA2 (= 72 FMAs; the projection value is the broadcast operand).
 constexpr int kPpfRows = 8, kPpfCols = 288, kPpfWarps = 8;
 constexpr int kPpfSmemBytes = (kPerfDim * kPpfCols + kPpfWarps * kPpfRows * kPerfDim) * 4;
 
@@ -102,7 +106,9 @@ __global__ void __launch_bounds__(kPpfWarps * 32, 2) performer_project_features_
             // optional bias of the producing Linear (H*64 entries, head h = row % H), added here so that the
             // GEMM runs without a separate bias epilogue
             const float4* bsrc = xbias ? reinterpret_cast<const float4*>(xbias + (row % H) * kPerfDim) + (lane & 3) * 4 : nullptr;
-            float4* dst = reinterpret_cast<float4*>(xs + (lane >> 2) * kPerfDim) + (lane & 3) * 4;
+            // staged transposed and row-pair interleaved: xs[(d*4 + rp)*2 + e] = x[2 rp + e][d], so that the main
+            // loop reads the same d of two rows as one packed fp32x2 operand
+            float* dst = xs + ((lane & 3) * 16 * 4 + (lane >> 3)) * 2 + ((lane >> 2) & 1);
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -114,64 +120,67 @@ __global__ void __launch_bounds__(kPpfWarps * 32, 2) performer_project_features_
                     }
                 }
                 ss = fmaf(t.x, t.x, fmaf(t.y, t.y, fmaf(t.z, t.z, fmaf(t.w, t.w, ss))));
-                dst[v] = make_float4(normalizer * t.x, normalizer * t.y, normalizer * t.z, normalizer * t.w);
+                dst[(4 * v + 0) * 8] = normalizer * t.x;
+                dst[(4 * v + 1) * 8] = normalizer * t.y;
+                dst[(4 * v + 2) * 8] = normalizer * t.z;
+                dst[(4 * v + 3) * 8] = normalizer * t.w;
             }
             ss += __shfl_xor_sync(0xffffffffu, ss, 1);
             ss += __shfl_xor_sync(0xffffffffu, ss, 2);           // lanes 4r..4r+3 hold |x_r|^2
         }
         __syncwarp();
-        float acc[kPpfRows][9];
+        float2 acc[kPpfRows / 2][9];                             // .x: row 2 rp, .y: row 2 rp + 1
 #pragma unroll
-        for (int r = 0; r < kPpfRows; ++r)
+        for (int rp = 0; rp < kPpfRows / 2; ++rp)
 #pragma unroll
-            for (int i = 0; i < 9; ++i) acc[r][i] = 0.0f;
-#pragma unroll 1
-        for (int d4 = 0; d4 < kPerfDim; d4 += 4) {
-            float4 xv[kPpfRows];
+            for (int i = 0; i < 9; ++i) acc[rp][i] = make_float2(0.0f, 0.0f);
+        const float4* xs4 = reinterpret_cast<const float4*>(xs);
+#pragma unroll 4
+        for (int d = 0; d < kPerfDim; ++d) {
+            const float4 xa = xs4[2 * d], xb = xs4[2 * d + 1];   // rows (0,1),(2,3) and (4,5),(6,7) at this d
+            float pv[9];
 #pragma unroll
-            for (int r = 0; r < kPpfRows; ++r) xv[r] = *reinterpret_cast<const float4*>(xs + r * kPerfDim + d4);
+            for (int i = 0; i < 9; ++i) pv[i] = PT[d * kPpfCols + lane + 32 * i];
 #pragma unroll
-            for (int dd = 0; dd < 4; ++dd) {
-                float pv[9];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) pv[i] = PT[(d4 + dd) * kPpfCols + lane + 32 * i];
-#pragma unroll
-                for (int r = 0; r < kPpfRows; ++r) {
-                    const float xr = dd == 0 ? xv[r].x : dd == 1 ? xv[r].y : dd == 2 ? xv[r].z : xv[r].w;
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) acc[r][i] = fmaf(xr, pv[i], acc[r][i]);
-                }
+            for (int i = 0; i < 9; ++i) {
+                acc[0][i] = fma2(make_float2(xa.x, xa.y), bc2(pv[i]), acc[0][i]);
+                acc[1][i] = fma2(make_float2(xa.z, xa.w), bc2(pv[i]), acc[1][i]);
+                acc[2][i] = fma2(make_float2(xb.x, xb.y), bc2(pv[i]), acc[2][i]);
+                acc[3][i] = fma2(make_float2(xb.z, xb.w), bc2(pv[i]), acc[3][i]);
             }
         }
         __syncwarp();                                            // xs is rewritten by the next group
+#define ACC(r, i) ((r) & 1 ? acc[(r) >> 1][i].y : acc[(r) >> 1][i].x)
+        // feature map as one FFMA + ex2 per element:  ratio*exp(a - c) = 2^(a*log2e + k),
+        // k = log2(ratio) - c*log2e per row (ex2.approx of a 64-term fp32 dot product: same error order)
+        const float log2_ratio = log2f(ratio);
+        const bool tail_ok = lane + 256 < M;                 // column group i = 8 is the only partial one (M > 256)
 #pragma unroll
         for (int r = 0; r < kPpfRows; ++r) {
             const int64_t row = r0 + r;
             const float diag = __shfl_sync(0xffffffffu, ss, 4 * r) * normalizer2_half;
-            float mx = -INFINITY;
+            float mx = 0.0f;
             if (IS_QUERY) {
+                mx = tail_ok ? ACC(r, 8) : -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) mx = fmaxf(mx, (lane + 32 * i < M) ? acc[r][i] : -INFINITY);
+                for (int i = 0; i < 8; ++i) mx = fmaxf(mx, ACC(r, i));
 #pragma unroll
                 for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             }
+            const float k = IS_QUERY ? fmaf(-(diag + mx), 1.4426950408889634f, log2_ratio)
+                                     : fmaf(eps - diag, 1.4426950408889634f, log2_ratio);
+            const float add = IS_QUERY ? ratio * eps : 0.0f;
             if (row < rows) {
                 const int h = (int)(row % H);
                 const int64_t bn = row / H;
                 const int n = (int)(bn % N), b = (int)(bn / N);
-                float* orow = out + (((int64_t)b * H + h) * N + n) * M;
+                float* orow = out + (((int64_t)b * H + h) * N + n) * M + lane;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) {
-                    const int j = lane + 32 * i;
-                    if (j < M) {
-                        float y;
-                        if (IS_QUERY) y = ratio * (expf(acc[r][i] - diag - mx) + eps);
-                        else y = ratio * expf(acc[r][i] - diag + eps);
-                        orow[j] = y;
-                    }
-                }
+                for (int i = 0; i < 8; ++i) orow[32 * i] = ex2_approx(fmaf(ACC(r, i), 1.4426950408889634f, k)) + add;
+                if (tail_ok) orow[256] = ex2_approx(fmaf(ACC(r, 8), 1.4426950408889634f, k)) + add;
             }
         }
+#undef ACC
     }
 }
 

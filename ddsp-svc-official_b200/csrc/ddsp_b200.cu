@@ -515,7 +515,7 @@ int ddsp_b200_performer_project_features(const float* x, const float* x_bias, co
                                          int H, int M, int is_query, float eps, float* out, void* stream) {
     g_launches = 0;
     if (!x || !projection || !out || B <= 0 || N <= 0 || H <= 0 || M <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
-    if (M > ddsp::kPpfCols || ((uintptr_t)x & 15) || ((uintptr_t)x_bias & 15)) return DDSP_B200_ERR_UNSUPPORTED;
+    if (M < 256 || M > ddsp::kPpfCols || ((uintptr_t)x & 15) || ((uintptr_t)x_bias & 15)) return DDSP_B200_ERR_UNSUPPORTED;
     const float* tables = nullptr;
     if (int rc = ensure_device_ready((cudaStream_t)stream, &tables)) return rc;     // shared-memory opt-in
     const int64_t groups = ((int64_t)B * N * H + ddsp::kPpfRows - 1) / ddsp::kPpfRows;

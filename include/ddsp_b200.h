@@ -194,7 +194,7 @@ int ddsp_b200_apply_frame_mask(float *signal, const float *mask_frames, int64_t 
 int ddsp_b200_performer_features(const float *dash, const float *x, int B, int N, int H, int M,
                                  int is_query, float eps, float *out, void *stream);
 /* Same feature map with the projection fused (dash never stored): x (B,N,H,64) contiguous,
- * projection (M,64) contiguous, M <= 288, out (B,H,N,M).  x_bias (H*64) / u_bias (2C): optional (NULL)
+ * projection (M,64) contiguous, 256 <= M <= 288 (the network's M = int(64 ln 64) = 266), out (B,H,N,M).  x_bias (H*64) / u_bias (2C): optional (NULL)
  * bias of the Linear that produced x / u, added on load so that GEMM can run without a bias epilogue. */
 int ddsp_b200_performer_project_features(const float *x, const float *x_bias, const float *projection,
                                          int B, int N, int H, int M, int is_query, float eps,
