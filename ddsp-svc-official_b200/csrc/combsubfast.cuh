@@ -210,11 +210,11 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
     const bool lane0 = lane == 0;
 
     Pts32 X;
-    // De-phase the four warps that share a scheduler (wid, wid+4, wid+8, wid+12) by 2 us each so that
-    // their FMA-heavy FFT phases do not start in lockstep (measured: -2 % on the 12-pairs-per-warp
-    // headline launch); skipped for short runs where it would only add latency.
+    // De-phase the four warps that share a scheduler (wid, wid+4, wid+8, wid+12) by 1 us each so that
+    // their FMA-heavy FFT phases do not start in lockstep (measured on the 12-pairs-per-warp headline launch:
+    // 0 us 206.0, 0.5 us 203.3, 1 us 201.9, 2 us 206.2 us); skipped for short runs where it would only add latency.
 #ifndef CSF_STAGGER_NS
-#define CSF_STAGGER_NS 2000u
+#define CSF_STAGGER_NS 1000u
 #endif
     if (P.run_len >= 4) __nanosleep((unsigned)(wid >> 2) * CSF_STAGGER_NS);
 
