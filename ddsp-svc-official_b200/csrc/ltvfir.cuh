@@ -30,6 +30,9 @@
 
 namespace ddsp {
 
+#ifndef LTV_STAGGER_NS
+#define LTV_STAGGER_NS 2000u
+#endif
 constexpr int kLtvWarps = 16;                      // warps per CTA, both kernels
 constexpr int kLtvThreads = kLtvWarps * 32;
 constexpr int kLtvRing = 2048;                     // floats: overlap-add ring of the convolution kernel
@@ -96,6 +99,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
 #define IR_D (P.n_mag - 1)
     const int64_t n_frames = (int64_t)P.B * P.F;
 
+    __nanosleep((unsigned)(wid >> 2) * LTV_STAGGER_NS);
     Pts32 X;
     for (int64_t fr0 = (int64_t)blockIdx.x * kLtvWarps + wid; fr0 < n_frames; fr0 += (int64_t)gridDim.x * kLtvWarps) {
         if (lane == 0) { ctx[0] = (int)(fr0 / P.F); ctx[1] = (int)(fr0 % P.F); }
@@ -292,6 +296,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_dual_kernel(const LtvDu
     const float2* chirp_d = reinterpret_cast<const float2*>(P.chirp_d_dual);
     const int64_t n_frames = (int64_t)P.B * P.F;
 
+    __nanosleep((unsigned)(wid >> 2) * LTV_STAGGER_NS);
     Pts32 X;
     for (int64_t fr0 = (int64_t)blockIdx.x * kLtvWarps + wid; fr0 < n_frames; fr0 += (int64_t)gridDim.x * kLtvWarps) {
         if (lane == 0) { ctx[0] = (int)(fr0 / P.F); ctx[1] = (int)(fr0 % P.F); }
@@ -458,6 +463,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
 
     for (int i = lane; i < kLtvRing; i += 32) ring[i] = 0.0f;
     __syncwarp();
+    if (P.run_len >= 4) __nanosleep((unsigned)(wid >> 2) * LTV_STAGGER_NS);   // de-phase the warps of a scheduler (see combsubfast.cuh)
     int rs = 0;                                          // ring start (logical sample 0 of the current frame)
 
     Pts32 X;
@@ -653,6 +659,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
 
     for (int i = lane; i < kLtvRing; i += 32) ring[i] = 0.0f;
     __syncwarp();
+    if (P.run_len >= 4) __nanosleep((unsigned)(wid >> 2) * LTV_STAGGER_NS);   // de-phase the warps of a scheduler (see combsubfast.cuh)
     int rs = 0;
 
     Pts32 X;
