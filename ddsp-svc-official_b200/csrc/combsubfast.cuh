@@ -43,7 +43,9 @@ struct CsfParams {
     float* signal;                                        // (B,T)
     uint64_t seed;
     int B, F;
-    int pairs_per_clip, run_len, runs_per_clip;
+    // run partition: run r of a clip owns pairs [r*run_len + min(r,run_rem), ... + run_len + (r < run_rem));
+    // all runs differ by at most one pair and together fill the chip's warp slots (see csf_partition)
+    int pairs_per_clip, run_len, run_rem, runs_per_clip;
     double inv_sr; float sr;
 };
 
@@ -90,13 +92,15 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 }
 
 // Zero the seam hops (first output hop of every run that does not start a clip).
-__global__ void __launch_bounds__(128) csf_zero_seams_kernel(float* __restrict__ signal, int F, int run_len,
+__device__ __forceinline__ int csf_run_begin(int r, int run_len, int run_rem) { return r * run_len + min(r, run_rem); }
+
+__global__ void __launch_bounds__(128) csf_zero_seams_kernel(float* __restrict__ signal, int F, int run_len, int run_rem,
                                                              int runs_per_clip, int n_seams) {
     const int seam = blockIdx.x;
     cudaGridDependencySynchronize();          // launched with programmatic stream serialisation
     if (seam >= n_seams) return;
     const int b = seam / (runs_per_clip - 1), r = seam % (runs_per_clip - 1) + 1;
-    const int hop = 2 * r * run_len - 1;
+    const int hop = 2 * csf_run_begin(r, run_len, run_rem) - 1;
     if (hop >= F) return;
     float4* dst = reinterpret_cast<float4*>(signal + ((int64_t)b * F + hop) * kHop);
     dst[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -186,14 +190,16 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
     // across it would be spilled to local memory, whose reloads miss the (tiny) L1 here.
     volatile int* ctx = reinterpret_cast<volatile int*>(stash + kStashFloat2);
     {
-        const int64_t run = (int64_t)blockIdx.x * kCsfWarps + wid;
+        // runs are dealt round-robin over the CTAs so that every SM gets the same mix of long and short runs
+        const int64_t run = (int64_t)wid * gridDim.x + blockIdx.x;
         if (run >= (int64_t)P.B * P.runs_per_clip) return;
         const int b0 = (int)(run / P.runs_per_clip);
-        const int pb = (int)(run % P.runs_per_clip) * P.run_len;
+        const int r = (int)(run % P.runs_per_clip);
+        const int pb = csf_run_begin(r, P.run_len, P.run_rem);
         if (lane == 0) {
             ctx[0] = b0;
             ctx[1] = pb;                                        // p_begin
-            ctx[2] = min(P.pairs_per_clip, pb + P.run_len);     // p_end
+            ctx[2] = pb + P.run_len + (r < P.run_rem ? 1 : 0);  // p_end
             ctx[3] = (int)noise_key(P.seed, (uint32_t)b0);
         }
         __syncwarp();

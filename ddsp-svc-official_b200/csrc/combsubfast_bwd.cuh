@@ -68,14 +68,15 @@ __global__ void __launch_bounds__(kCsbThreads, 1) combsubfast_backward_kernel(co
 
     volatile int* ctx = reinterpret_cast<volatile int*>(stash + 2 * kStashFloat2);
     {
-        const int64_t run = (int64_t)blockIdx.x * kCsbWarps + wid;
+        const int64_t run = (int64_t)wid * gridDim.x + blockIdx.x;          // round-robin over the CTAs
         if (run >= (int64_t)P.B * P.runs_per_clip) return;
         const int b0 = (int)(run / P.runs_per_clip);
-        const int pb = (int)(run % P.runs_per_clip) * P.run_len;
+        const int r = (int)(run % P.runs_per_clip);
+        const int pb = csf_run_begin(r, P.run_len, P.run_rem);
         if (lane == 0) {
             ctx[0] = b0;
             ctx[1] = pb;
-            ctx[2] = min(P.pairs_per_clip, pb + P.run_len);
+            ctx[2] = pb + P.run_len + (r < P.run_rem ? 1 : 0);
             ctx[3] = (int)noise_key(P.seed, (uint32_t)b0);
         }
         __syncwarp();

@@ -143,6 +143,18 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// Split the frame pairs of every clip into runs (one warp each) so that all runs of the launch fit
+// one resident wave of `slots` warps and differ by at most one pair: as many runs per clip as the
+// slots allow, the first `run_rem` of them one pair longer.
+void csf_partition(ddsp::CsfParams& P, int B, int64_t slots) {
+    int64_t R = slots / B;
+    if (R < 1) R = 1;
+    if (R > P.pairs_per_clip) R = P.pairs_per_clip;
+    P.runs_per_clip = (int)R;
+    P.run_len = P.pairs_per_clip / (int)R;
+    P.run_rem = P.pairs_per_clip % (int)R;
+}
+
 inline int64_t grid_for(int64_t total, int per_block, int64_t cap) {
     int64_t g = (total + per_block - 1) / per_block;
     if (g < 1) g = 1;
@@ -281,23 +293,14 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
     P.prefix = prefix; (void)initial_phase; P.noise_u = noise_u; P.window = window;
     P.signal = signal; P.seed = seed; P.B = B; P.F = F;
     P.pairs_per_clip = (F + 2) / 2;                 // frames 0..F in pairs
-    const int64_t slots = (int64_t)sm_count() * ddsp::kCsfWarps;
-    const int64_t total_pairs = (int64_t)B * P.pairs_per_clip;
-    int run_len = (int)((total_pairs + slots - 1) / slots);
-    if (run_len < 1) run_len = 1;
-    if (run_len > P.pairs_per_clip) run_len = P.pairs_per_clip;
-    // one resident wave: grow the run until all runs fit the warp slots of the chip (the per-clip
-    // remainder run can otherwise push the count over and cost a second, nearly empty wave)
-    while (run_len < P.pairs_per_clip && (int64_t)B * ((P.pairs_per_clip + run_len - 1) / run_len) > slots) ++run_len;
-    P.run_len = run_len;
-    P.runs_per_clip = (P.pairs_per_clip + run_len - 1) / run_len;
+    csf_partition(P, B, (int64_t)sm_count() * ddsp::kCsfWarps);
     P.inv_sr = 1.0 / sr; P.sr = (float)sr;
     const int64_t runs = (int64_t)B * P.runs_per_clip;
     const unsigned grid = (unsigned)((runs + ddsp::kCsfWarps - 1) / ddsp::kCsfWarps);
     if (P.runs_per_clip > 1) {
         const int n_seams = B * (P.runs_per_clip - 1);
         CUDA_TRY(launch_pdl(ddsp::csf_zero_seams_kernel, dim3(n_seams), dim3(128), 0, (cudaStream_t)stream, signal, F,
-                            P.run_len, P.runs_per_clip, n_seams));
+                            P.run_len, P.run_rem, P.runs_per_clip, n_seams));
         LAUNCH_CHECK();
     }
     // Programmatic dependent launch: the CTAs may be scheduled and stage their tables while the
@@ -338,14 +341,7 @@ int ddsp_b200_combsubfast_backward(const float* harmonic_magnitude, const float*
     P.prefix = prefix; P.noise_u = noise_u; P.window = window;
     P.signal = nullptr; P.seed = seed; P.B = B; P.F = F;
     P.pairs_per_clip = (F + 2) / 2;
-    const int64_t slots = (int64_t)sm_count() * ddsp::kCsbWarps;
-    const int64_t total_pairs = (int64_t)B * P.pairs_per_clip;
-    int run_len = (int)((total_pairs + slots - 1) / slots);
-    if (run_len < 1) run_len = 1;
-    if (run_len > P.pairs_per_clip) run_len = P.pairs_per_clip;
-    while (run_len < P.pairs_per_clip && (int64_t)B * ((P.pairs_per_clip + run_len - 1) / run_len) > slots) ++run_len;
-    P.run_len = run_len;
-    P.runs_per_clip = (P.pairs_per_clip + run_len - 1) / run_len;
+    csf_partition(P, B, (int64_t)sm_count() * ddsp::kCsbWarps);
     P.inv_sr = 1.0 / sr; P.sr = (float)sr;
     PB.grad_signal = grad_signal;
     PB.ghm = grad_harmonic_magnitude; PB.ghp = grad_harmonic_phase; PB.gnm = grad_noise_magnitude;
