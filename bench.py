@@ -52,9 +52,9 @@ def recorded_traffic(model):
 
 
 # FP32 work of the CombSubFast kernel: FMA-pipe operations per frame pair counted from the ncu source
-# page (profiles/r01_ncu_combsubfast_v10.txt): scalar FFMA+FMUL+FADD 1191 + IMAD 137 + packed fp32x2
-# 1440 (each occupies the pipe like two scalar ops) = 4208 warp-level FMA-pipe slots per pair.
-CSF_FMA_SLOTS_PER_PAIR = 4208
+# page (profiles/r01_ncu_combsubfast_v11.txt): scalar FFMA+FMUL+FADD 991 + IMAD 137 + packed fp32x2
+# 1542 (each occupies the pipe like two scalar ops) = 4213 warp-level FMA-pipe slots per pair.
+CSF_FMA_SLOTS_PER_PAIR = 4213
 
 
 def fp32_roofline(model, B, F, kern_ms, clocks):
