@@ -232,6 +232,16 @@ class Unit2Control(nn.Module):
 
     def _forward(self, units, f0, phase, volume, spk_id, spk_mix_dict=None):
         x = self.unit_prenet(units)
+        if _fused_ok(x) and f0.dtype == torch.float32 and phase.dtype == torch.float32 and volume.dtype == torch.float32:
+            from . import core
+            if spk_mix_dict is not None:                 # weighted mix of speaker embeddings (unit2control.py:89-93)
+                spk = sum(v * self.spk_embed.weight[int(k) - 1] for k, v in spk_mix_dict.items()).reshape(1, -1)
+            else:
+                spk = self.spk_embed(spk_id - 1)
+            x = core.embed_sum(x, f0, phase, volume, self.f0_embed, self.phase_embed, self.volume_embed, spk)
+            e = self.dec_post(x)
+            names, sizes = list(self.output_splits), list(self.output_splits.values())
+            return dict(zip(names, torch.split(e, sizes, dim=-1)))
         x = x + self.f0_embed((1 + f0 / 700).log()) + self.phase_embed(phase.unsqueeze(-1) / math.pi) \
             + self.volume_embed(volume.unsqueeze(-1))
         if spk_mix_dict is not None:                     # weighted mix of speaker embeddings (unit2control.py:89-93)

@@ -419,3 +419,28 @@ def glu_dwconv_silu(u, weight, bias, u_bias=None):
         _cabi.check(_cabi.lib().ddsp_b200_glu_dwconv_silu(u.data_ptr(), _ptr(u_bias), weight.data_ptr(), bias.data_ptr(), B, T, C,
                                                           out.data_ptr(), _st))
     return out
+
+
+def embed_sum(x, f0, phase, volume, f0_embed, phase_embed, volume_embed, spk_rows):
+    """Input embedding sum of Unit2Control.forward (unit2control.py:80-95) in one kernel.
+    x (B,N,C) any strides; f0 (B,N,1) or (B,N); phase, volume (B,N); *_embed: nn.Linear(1,C);
+    spk_rows (1,C), (B,C) or (B,1,C).  Returns a contiguous (B,N,C) tensor."""
+    x = _need_cuda_f32(x, 'x')
+    B, N, Cc = x.shape
+    f0 = _f0_2d(f0)
+    phase = _need_cuda_f32(phase, 'phase').reshape(B, N)
+    volume = _need_cuda_f32(volume, 'volume').reshape(B, N)
+    spk = _need_cuda_f32(spk_rows, 'spk_rows').reshape(-1, Cc).contiguous()
+    if spk.shape[0] not in (1, B):
+        raise ValueError('spk_rows must have 1 or B rows')
+    ws = []
+    for lin in (f0_embed, phase_embed, volume_embed):
+        ws += [lin.weight.detach().reshape(-1).contiguous(), lin.bias.detach().contiguous()]
+    out = torch.empty((B, N, Cc), dtype=torch.float32, device=x.device)
+    with _OnDevice(x.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_embed_sum(
+            x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), f0.data_ptr(), f0.stride(0), f0.stride(1),
+            phase.data_ptr(), phase.stride(0), phase.stride(1), volume.data_ptr(), volume.stride(0), volume.stride(1),
+            ws[0].data_ptr(), ws[1].data_ptr(), ws[2].data_ptr(), ws[3].data_ptr(), ws[4].data_ptr(), ws[5].data_ptr(),
+            spk.data_ptr(), 0 if spk.shape[0] == 1 else Cc, B, N, Cc, out.data_ptr(), _st))
+    return out

@@ -184,6 +184,36 @@ __global__ void __launch_bounds__(kPpfWarps * 32, 2) performer_project_features_
     }
 }
 
+// Input embedding sum of Unit2Control.forward (unit2control.py:80-95) in one pass:
+//   out[b,n,c] = x[b,n,c] + (wf[c]*log(1 + f0/700) + bf[c]) + (wp[c]*(phase/pi) + bp[c]) + (wv[c]*vol + bv[c]) + spk[b?,c]
+// x may be any strided (B,N,C) view (the pre-net output is a transposed view); out is contiguous.
+// spk is (1,C) or (B,C): the (possibly mixed) speaker embedding row.  Replaces ~12 tiny kernels.
+__global__ void __launch_bounds__(256) embed_sum_kernel(const float* __restrict__ x, int64_t xB, int64_t xN, int64_t xC,
+                                                        const float* __restrict__ f0, int64_t fB, int64_t fN,
+                                                        const float* __restrict__ phase, int64_t pB, int64_t pN,
+                                                        const float* __restrict__ vol, int64_t vB, int64_t vN,
+                                                        const float* __restrict__ wf, const float* __restrict__ bf,
+                                                        const float* __restrict__ wp, const float* __restrict__ bp,
+                                                        const float* __restrict__ wv, const float* __restrict__ bv,
+                                                        const float* __restrict__ spk, int64_t sB, int B, int N, int C,
+                                                        float* __restrict__ out) {
+    const int64_t total = (int64_t)B * N * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t bn = i / C;
+        const int n = (int)(bn % N), b = (int)(bn / N);
+        const float lf0 = logf(__fadd_rn(1.0f, __fdiv_rn(__ldg(f0 + b * fB + n * fN), 700.0f)));
+        const float ph = __fdiv_rn(__ldg(phase + b * pB + n * pN), 3.14159265358979323846f);
+        const float vv = __ldg(vol + b * vB + n * vN);
+        float v = __ldg(x + b * xB + n * xN + c * xC);
+        v = __fadd_rn(v, fmaf(lf0, __ldg(wf + c), __ldg(bf + c)));
+        v = __fadd_rn(v, fmaf(ph, __ldg(wp + c), __ldg(bp + c)));
+        v = __fadd_rn(v, fmaf(vv, __ldg(wv + c), __ldg(bv + c)));
+        v = __fadd_rn(v, __ldg(spk + b * sB + c));
+        out[i] = v;
+    }
+}
+
 // GLU + depthwise conv (k=31, zero 'same' padding) + SiLU, channels last.
 //   u   : (B, T, 2C) contiguous (output of the first pointwise conv, bias included)
 //   w   : (C, 31) depthwise taps (Conv1d weight (C,1,31)), bias (C)

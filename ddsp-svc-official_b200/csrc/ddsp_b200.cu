@@ -528,6 +528,23 @@ int ddsp_b200_performer_project_features(const float* x, const float* x_bias, co
     return DDSP_B200_OK;
 }
 
+int ddsp_b200_embed_sum(const float* x, int64_t xB, int64_t xN, int64_t xC, const float* f0, int64_t fB, int64_t fN,
+                        const float* phase, int64_t pB, int64_t pN, const float* volume, int64_t vB, int64_t vN,
+                        const float* w_f0, const float* b_f0, const float* w_phase, const float* b_phase,
+                        const float* w_volume, const float* b_volume, const float* spk, int64_t sB, int B, int N, int C,
+                        float* out, void* stream) {
+    g_launches = 0;
+    if (!x || !f0 || !phase || !volume || !w_f0 || !b_f0 || !w_phase || !b_phase || !w_volume || !b_volume || !spk ||
+        !out || B <= 0 || N <= 0 || C <= 0)
+        return DDSP_B200_ERR_INVALID_ARGUMENT;
+    const int64_t total = (int64_t)B * N * C;
+    ddsp::embed_sum_kernel<<<(unsigned)grid_for(total, 256, (int64_t)sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(
+        x, xB, xN, xC, f0, fB, fN, phase, pB, pN, volume, vB, vN, w_f0, b_f0, w_phase, b_phase, w_volume, b_volume, spk,
+        sB, B, N, C, out);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
 int ddsp_b200_glu_dwconv_silu(const float* u, const float* u_bias, const float* weight, const float* bias, int B, int T,
                               int C, float* out, void* stream) {
     g_launches = 0;

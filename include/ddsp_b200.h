@@ -202,6 +202,18 @@ int ddsp_b200_performer_project_features(const float *x, const float *x_bias, co
 int ddsp_b200_glu_dwconv_silu(const float *u, const float *u_bias, const float *weight,
                               const float *bias, int B, int T, int C, float *out, void *stream);
 
+/* Input embedding sum of Unit2Control.forward                     unit2control.py:80-95
+ *   out[b,n,c] = x[b,n,c] + f0_embed(log(1 + f0/700)) + phase_embed(phase/pi) + volume_embed(volume) + spk[b,c]
+ * x: (B,N,C) view with element strides (xB,xN,xC); f0 / phase / volume: (B,N) views with strides;
+ * w* / b*: weight (C) and bias (C) of the three Linear(1,C); spk: speaker row(s) (1,C) [sB = 0] or
+ * (B,C) [sB = C]; out (B,N,C) contiguous. */
+int ddsp_b200_embed_sum(const float *x, int64_t xB, int64_t xN, int64_t xC, const float *f0, int64_t fB,
+                        int64_t fN, const float *phase, int64_t pB, int64_t pN, const float *volume,
+                        int64_t vB, int64_t vN, const float *w_f0, const float *b_f0,
+                        const float *w_phase, const float *b_phase, const float *w_volume,
+                        const float *b_volume, const float *spk, int64_t sB, int B, int N, int C,
+                        float *out, void *stream);
+
 /* Number of kernel launches the last call of each entry point enqueued on this thread
  * (bench.py reports it as gpu_launches). */
 int ddsp_b200_last_launch_count(void);

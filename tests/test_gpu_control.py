@@ -95,6 +95,25 @@ def test_unit2control_fused_matches_plain_ops(B, F_):
     assert out['harmonic_phase'].data_ptr() == out['harmonic_magnitude'].data_ptr() + 513 * 4
 
 
+def test_embed_sum_and_speaker_mix():
+    torch.manual_seed(9)
+    net = Unit2Control(16, 3, {'a': 513, 'b': 513, 'c': 513}).cuda().eval()
+    B, N = 2, 33
+    units = torch.randn(B, N, 16, device='cuda')
+    f0 = torch.rand(B, N, 1, device='cuda') * 500 + 80
+    f0[0, 3:6] = 0.0                                             # unvoiced frames: log(1 + 0)
+    ph = (torch.rand(B, N, device='cuda') - 0.5) * 6
+    vol = torch.rand(B, N, device='cuda')
+    spk = torch.tensor([[1], [3]], device='cuda')
+    for mix in (None, {1: 0.25, 3: 0.75}):
+        with torch.enable_grad():
+            ref = net(units, f0, ph, vol, spk, spk_mix_dict=mix)
+        with torch.no_grad():
+            out = net(units, f0, ph, vol, spk, spk_mix_dict=mix)
+        for k in ref:
+            assert (out[k] - ref[k].detach()).abs().max().item() < 1e-4, (k, mix)
+
+
 def test_fused_forward_is_graph_capturable():
     torch.manual_seed(8)
     net = Unit2Control(16, 1, {'a': 513, 'b': 513, 'c': 513}).cuda().eval()
