@@ -29,6 +29,7 @@ _DIM = 256
 _HEADS = 8
 _DIM_HEAD = 64
 _FUSED_PROJECTION_MIN_ROWS = 1 << 16      # (batch x frames x heads) above which the fused projection kernel wins
+_ATTENTION_KERNEL_MAX_FRAMES = 32         # frames per call up to which the one-kernel attention (one CTA per head) is used
 
 
 class _Swap(nn.Module):
@@ -120,14 +121,22 @@ class _SelfAttention(nn.Module):
                                                     x_bias=self.to_q.bias)
                 k = core.performer_project_features(F.linear(x, self.to_k.weight), proj, self.heads, False,
                                                     x_bias=self.to_k.bias)
-            else:
-                # streaming blocks: a library GEMM + the one-pass feature kernel has the lower latency
+                out = self.fast_attention.attend(q, k, split(self.to_v(x)))
+                out = out.transpose(1, 2).reshape(b * n, self.heads * _DIM_HEAD)
+            elif n > _ATTENTION_KERNEL_MAX_FRAMES:
+                # mid-sized calls: a library GEMM + the one-pass feature kernel
                 q, k = self.to_q(x), self.to_k(x)
                 scale = _DIM_HEAD ** -0.25
                 q, k = [core.performer_features(torch.matmul((scale * t).view(-1, _DIM_HEAD), proj.t()), t, self.heads, is_q)
                         for t, is_q in ((q, True), (k, False))]
-            out = self.fast_attention.attend(q, k, split(self.to_v(x)))
-            out = out.transpose(1, 2).reshape(b * n, self.heads * _DIM_HEAD)
+                out = self.fast_attention.attend(q, k, split(self.to_v(x)))
+                out = out.transpose(1, 2).reshape(b * n, self.heads * _DIM_HEAD)
+            else:
+                # streaming blocks: the whole attention after the three (bias-free) projection GEMMs is one
+                # kernel -- launch latencies, not bytes, bound a GUI block
+                out = core.performer_attention(F.linear(x, self.to_q.weight), F.linear(x, self.to_k.weight),
+                                               F.linear(x, self.to_v.weight), proj, self.heads, self.to_q.bias,
+                                               self.to_k.bias, self.to_v.bias).view(b * n, -1)
             if residual is None:
                 return self.to_out(out).view(b, n, -1)
             return torch.addmm((residual + self.to_out.bias).reshape(b * n, -1), out, self.to_out.weight.t()).view(b, n, -1)

@@ -444,3 +444,30 @@ def embed_sum(x, f0, phase, volume, f0_embed, phase_embed, volume_embed, spk_row
             ws[0].data_ptr(), ws[1].data_ptr(), ws[2].data_ptr(), ws[3].data_ptr(), ws[4].data_ptr(), ws[5].data_ptr(),
             spk.data_ptr(), 0 if spk.shape[0] == 1 else Cc, B, N, Cc, out.data_ptr(), _st))
     return out
+
+
+def performer_attention(q, k, v, projection, heads, q_bias=None, k_bias=None, v_bias=None, eps=1e-4):
+    """Non-causal Performer attention of streaming-sized blocks in one kernel (pcmer.py:69-78,124-160):
+    q, k, v (B,N,H*64) -- optionally without the biases of their Linears, passed separately --,
+    projection (M,64) -> (B,N,H*64) head-merged attention output (before `to_out`)."""
+    q = _need_cuda_f32(q, 'q').contiguous()
+    k = _need_cuda_f32(k, 'k').contiguous()
+    v = _need_cuda_f32(v, 'v').contiguous()
+    projection = _need_cuda_f32(projection, 'projection').contiguous()
+    B, N, HD = q.shape
+    H = int(heads)
+    if HD != H * 64 or k.shape != q.shape or v.shape != q.shape or projection.shape[1] != 64:
+        raise ValueError('q, k, v must be (B, N, heads*64) and projection (M, 64)')
+    biases = []
+    for bvec in (q_bias, k_bias, v_bias):
+        if bvec is not None:
+            bvec = _need_cuda_f32(bvec.detach(), 'bias').contiguous()
+            if bvec.numel() != HD:
+                raise ValueError('bias must have heads*64 entries')
+        biases.append(bvec)
+    out = torch.empty((B, N, HD), dtype=torch.float32, device=q.device)
+    with _OnDevice(q.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_performer_attention(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), _ptr(biases[0]), _ptr(biases[1]), _ptr(biases[2]),
+            projection.data_ptr(), B, N, H, projection.shape[0], float(eps), out.data_ptr(), _st))
+    return out

@@ -184,6 +184,198 @@ __global__ void __launch_bounds__(kPpfWarps * 32, 2) performer_project_features_
     }
 }
 
+// Whole non-causal Performer attention of one (clip, head) for streaming-sized blocks
+// (pcmer.py:69-78,124-160,191-251 after the q/k/v projections): feature maps of q and k, k_sum,
+// context = k'^T v, out = (q' context) / (q' k_sum + 1e-8), written head-merged as (B, N, H*64).
+// Replaces ~16 small kernels per layer (scales, two projection GEMMs, two feature maps, sum, gemv,
+// reciprocal, two batched GEMMs, scaling, two layout copies) whose launch latencies dominate the
+// graph-replay time of a GUI block.  One CTA of 288 threads per (head, clip); thread j owns feature
+// column j (< M <= 288) in the projection and context phases.  Everything is laid out for latency:
+// the CTA is alone on its SM, so loads are batched and dependent chains are split.
+//   q, k, v : (B, N, H*64) contiguous, optional biases (H*64) of the producing Linears added on load
+//   proj    : (M, 64);  out : (B, N, H*64)
+constexpr int kPasThreads = 288, kPasRows = 8, kPasWarps = kPasThreads / 32;
+constexpr int kPasPStride = kPerfDim + 1;                      // proj rows padded: thread j reads P[j*65 + d] conflict-free
+constexpr int kPasSmemFloats = kPpfCols * kPasPStride          // P[j][d]
+                               + kPpfCols * kPasPStride        // ctx[j][0..63], ctx[j][64] = k_sum[j]
+                               + kPasRows * kPpfCols           // feature tile
+                               + 2 * kPasRows * kPerfDim       // x tile (scaled), v tile
+                               + 3 * kPasRows + kPasWarps * kPasRows;   // per-row diag / max / denominators, warp maxima
+constexpr int kPasSmemBytes = kPasSmemFloats * 4;
+
+// Feature tile of rows n0 .. n0+rows-1 of `src` (q or k of this head) into ft[r][j].
+__device__ __forceinline__ void pas_features(const float* __restrict__ src, const float* __restrict__ bias, int h,
+                                             int H, int n0, int rows, const float* P, float* xt, float* ft,
+                                             float* rowstat, float* wmax, int M, bool is_query, float ratio, float eps) {
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    // stage the tile's rows scaled by normalizer = 64^-0.25 (pcmer.py:137,146): 512 floats, 2 per thread (first 256)
+    if (t < kPasRows * kPerfDim / 2) {
+        const int r = t / (kPerfDim / 2), d = 2 * (t % (kPerfDim / 2));
+        float2 v = make_float2(0.0f, 0.0f);
+        if (r < rows) {
+            v = __ldg(reinterpret_cast<const float2*>(src + ((int64_t)(n0 + r) * H + h) * kPerfDim + d));
+            if (bias) { v.x += __ldg(bias + h * kPerfDim + d); v.y += __ldg(bias + h * kPerfDim + d + 1); }
+        }
+        *reinterpret_cast<float2*>(xt + r * kPerfDim + d) = make_float2(0.35355339059327373f * v.x, 0.35355339059327373f * v.y);
+    }
+    __syncthreads();
+    if (wid < kPasRows) {                                   // warp r: |x_r|^2 / 16 = |normalizer x_r|^2 / 2  (pcmer.py:149-152)
+        const float a = xt[wid * kPerfDim + lane], b = xt[wid * kPerfDim + 32 + lane];
+        float ss = fmaf(a, a, b * b);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) rowstat[wid] = ss * 0.5f;
+    }
+    // dash[r][j] = sum_d (normalizer * x[r][d]) * proj[j][d], thread j = t; 4 values of d per step
+    float acc[kPasRows];
+#pragma unroll
+    for (int r = 0; r < kPasRows; ++r) acc[r] = 0.0f;
+    const float* prow = P + t * kPasPStride;
+#pragma unroll 4
+    for (int d = 0; d < kPerfDim; d += 4) {
+        const float p0 = prow[d], p1 = prow[d + 1], p2 = prow[d + 2], p3 = prow[d + 3];
+#pragma unroll
+        for (int r = 0; r < kPasRows; ++r) {
+            const float4 xv = *reinterpret_cast<const float4*>(xt + r * kPerfDim + d);     // broadcast
+            acc[r] = fmaf(xv.w, p3, fmaf(xv.z, p2, fmaf(xv.y, p1, fmaf(xv.x, p0, acc[r]))));
+        }
+    }
+    if (is_query) {                                         // row maxima over the M valid columns: warp, then CTA
+#pragma unroll
+        for (int r = 0; r < kPasRows; ++r) {
+            float m = (t < M) ? acc[r] : -INFINITY;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) wmax[wid * kPasRows + r] = m;
+        }
+    }
+    __syncthreads();                                        // rowstat / wmax visible
+#pragma unroll
+    for (int r = 0; r < kPasRows; ++r) {
+        float y = 0.0f;
+        if (t < M && r < rows) {
+            if (is_query) {
+                float mm = wmax[r];
+#pragma unroll
+                for (int w = 1; w < kPasWarps; ++w) mm = fmaxf(mm, wmax[w * kPasRows + r]);
+                y = ratio * (expf(acc[r] - rowstat[r] - mm) + eps);
+            } else {
+                y = ratio * expf(acc[r] - rowstat[r] + eps);
+            }
+        }
+        ft[r * kPpfCols + t] = y;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kPasThreads) performer_attention_small_kernel(
+    const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+    const float* __restrict__ qb, const float* __restrict__ kb, const float* __restrict__ vb,
+    const float* __restrict__ proj, float* __restrict__ out, int N, int H, int M, float ratio, float eps) {
+    extern __shared__ __align__(16) float pas_smem[];
+    float* P = pas_smem;
+    float* ctx = P + kPpfCols * kPasPStride;
+    float* ft = ctx + kPpfCols * kPasPStride;
+    float* xt = ft + kPasRows * kPpfCols;
+    float* vt = xt + kPasRows * kPerfDim;
+    float* rowstat = vt + kPasRows * kPerfDim;
+    float* wmax = rowstat + 3 * kPasRows;
+    const int t = threadIdx.x, h = blockIdx.x, b = blockIdx.y;
+    const int64_t clip = (int64_t)b * N * H * kPerfDim;
+    {   // proj (M x 64, contiguous) -> P[j*65 + d]; all loads of a thread in flight before the first store
+        const int n4 = M * kPerfDim / 4;
+        constexpr int kPer = (kPpfCols * kPerfDim / 4 + kPasThreads - 1) / kPasThreads;      // 16
+        float4 buf[kPer];
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            const int f = t + i * kPasThreads;
+            buf[i] = (f < n4) ? __ldg(reinterpret_cast<const float4*>(proj) + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            const int f = t + i * kPasThreads;
+            if (f < kPpfCols * kPerfDim / 4) {
+                float* dst = P + (f / (kPerfDim / 4)) * kPasPStride + 4 * (f % (kPerfDim / 4));
+                dst[0] = buf[i].x; dst[1] = buf[i].y; dst[2] = buf[i].z; dst[3] = buf[i].w;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- keys: context[j][e] = sum_n k'[n][j] v[n][e],  k_sum[j] = sum_n k'[n][j] ----------------
+    float c[kPerfDim + 1];
+#pragma unroll
+    for (int e = 0; e <= kPerfDim; ++e) c[e] = 0.0f;
+    for (int n0 = 0; n0 < N; n0 += kPasRows) {
+        const int rows = min(kPasRows, N - n0);
+        if (t >= kPasThreads - kPasRows * kPerfDim / 16) {   // the last 32 threads stage the v tile (512 floats, float4 each x4)
+            const int u = t - (kPasThreads - kPasRows * kPerfDim / 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int f = u + 32 * i, r = f / (kPerfDim / 4), d = 4 * (f % (kPerfDim / 4));
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < rows) {
+                    x = __ldg(reinterpret_cast<const float4*>(v + clip + ((int64_t)(n0 + r) * H + h) * kPerfDim + d));
+                    if (vb) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(vb + h * kPerfDim + d));
+                        x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+                    }
+                }
+                *reinterpret_cast<float4*>(vt + r * kPerfDim + d) = x;
+            }
+        }
+        pas_features(k + clip, kb, h, H, n0, rows, P, xt, ft, rowstat, wmax, M, false, ratio, eps);
+#pragma unroll 2
+        for (int r = 0; r < kPasRows; ++r) {                // rows beyond the tile hold zero features
+            const float kf = ft[r * kPpfCols + t];
+            const float4* vr = reinterpret_cast<const float4*>(vt + r * kPerfDim);
+#pragma unroll
+            for (int e4 = 0; e4 < kPerfDim / 4; ++e4) {
+                const float4 vv = vr[e4];
+                c[4 * e4 + 0] = fmaf(kf, vv.x, c[4 * e4 + 0]);
+                c[4 * e4 + 1] = fmaf(kf, vv.y, c[4 * e4 + 1]);
+                c[4 * e4 + 2] = fmaf(kf, vv.z, c[4 * e4 + 2]);
+                c[4 * e4 + 3] = fmaf(kf, vv.w, c[4 * e4 + 3]);
+            }
+            c[kPerfDim] += kf;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int e = 0; e <= kPerfDim; ++e) ctx[t * kPasPStride + e] = c[e];
+    __syncthreads();
+    // ---- queries: out[n][e] = sum_j q'[n][j] context[j][e] / (sum_j q'[n][j] k_sum[j] + 1e-8) ----
+    for (int n0 = 0; n0 < N; n0 += kPasRows) {
+        const int rows = min(kPasRows, N - n0);
+        pas_features(q + clip, qb, h, H, n0, rows, P, xt, ft, rowstat, wmax, M, true, ratio, eps);
+        // 8 rows x 65 columns (64 outputs + the denominator): thread -> (row, column), four partial sums
+        for (int o = t; o < kPasRows * kPasPStride; o += kPasThreads) {
+            const int r = o / kPasPStride, e = o % kPasPStride;
+            const float* fr = ft + r * kPpfCols;
+            const float* cc = ctx + e;
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            int j = 0;
+#pragma unroll 4
+            for (; j + 4 <= M; j += 4) {                    // (unrolled x4: 16 loads in flight per step)
+                const float4 f4 = *reinterpret_cast<const float4*>(fr + j);
+                a0 = fmaf(f4.x, cc[j * kPasPStride], a0);
+                a1 = fmaf(f4.y, cc[(j + 1) * kPasPStride], a1);
+                a2 = fmaf(f4.z, cc[(j + 2) * kPasPStride], a2);
+                a3 = fmaf(f4.w, cc[(j + 3) * kPasPStride], a3);
+            }
+            for (; j < M; ++j) a0 = fmaf(fr[j], cc[j * kPasPStride], a0);
+            const float a = (a0 + a1) + (a2 + a3);
+            if (e == kPerfDim) rowstat[2 * kPasRows + r] = a;
+            else xt[r * kPerfDim + e] = a;                  // xt is free again: numerators
+        }
+        __syncthreads();
+        for (int o = t; o < rows * kPerfDim; o += kPasThreads) {
+            const int r = o / kPerfDim;
+            out[clip + ((int64_t)(n0 + r) * H + h) * kPerfDim + (o % kPerfDim)] = xt[o] * (1.0f / (rowstat[2 * kPasRows + r] + 1e-8f));
+        }
+        __syncthreads();
+    }
+}
+
 // Input embedding sum of Unit2Control.forward (unit2control.py:80-95) in one pass:
 //   out[b,n,c] = x[b,n,c] + (wf[c]*log(1 + f0/700) + bf[c]) + (wp[c]*(phase/pi) + bp[c]) + (wv[c]*vol + bv[c]) + spk[b?,c]
 // x may be any strided (B,N,C) view (the pre-net output is a transposed view); out is contiguous.

@@ -98,6 +98,8 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kPpfSmemBytes));
         CUDA_TRY(cudaFuncSetAttribute(ddsp::performer_project_features_kernel<true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kPpfSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(ddsp::performer_attention_small_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kPasSmemBytes));
         float* ptr = nullptr;
         CUDA_TRY(cudaGetSymbolAddress((void**)&ptr, g_tables));
         ddsp::fft_tables_kernel<<<4, 256, 0, st>>>(reinterpret_cast<float4*>(ptr), ptr + 2048);
@@ -524,6 +526,20 @@ int ddsp_b200_performer_project_features(const float* x, const float* x_bias, co
     else
         ddsp::performer_project_features_kernel<false><<<grid, ddsp::kPpfWarps * 32, ddsp::kPpfSmemBytes, (cudaStream_t)stream>>>(
             x, x_bias, projection, out, B, N, H, M, normalizer, 0.0625f, ratio, eps);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int ddsp_b200_performer_attention(const float* q, const float* k, const float* v, const float* q_bias,
+                                  const float* k_bias, const float* v_bias, const float* projection, int B, int N, int H,
+                                  int M, float eps, float* out, void* stream) {
+    g_launches = 0;
+    if (!q || !k || !v || !projection || !out || B <= 0 || N <= 0 || H <= 0 || M <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (M > ddsp::kPpfCols || B > 65535) return DDSP_B200_ERR_UNSUPPORTED;
+    const float* tables = nullptr;
+    if (int rc = ensure_device_ready((cudaStream_t)stream, &tables)) return rc;     // shared-memory opt-in
+    ddsp::performer_attention_small_kernel<<<dim3(H, B), ddsp::kPasThreads, ddsp::kPasSmemBytes, (cudaStream_t)stream>>>(
+        q, k, v, q_bias, k_bias, v_bias, projection, out, N, H, M, 1.0f / sqrtf((float)M), eps);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }

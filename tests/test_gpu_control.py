@@ -95,6 +95,25 @@ def test_unit2control_fused_matches_plain_ops(B, F_):
     assert out['harmonic_phase'].data_ptr() == out['harmonic_magnitude'].data_ptr() + 513 * 4
 
 
+@pytest.mark.parametrize('B,N,H', [(1, 1, 8), (1, 9, 8), (2, 26, 8), (1, 130, 8), (3, 37, 4)])
+def test_performer_attention_single_kernel(B, N, H):
+    """One-kernel attention (streaming sizes) against the plain PyTorch formulation (pcmer.py:69-78,124-160)."""
+    from ddsp_b200.control import _FastAttention
+    torch.manual_seed(N)
+    q, k, v = (torch.randn(B, N, H * 64, device='cuda') for _ in range(3))
+    qb, kb, vb = (torch.randn(H * 64, device='cuda') * 0.2 for _ in range(3))
+    fa = _FastAttention(64).cuda()
+    split = lambda t: t.view(B, N, H, 64).transpose(1, 2).double()      # noqa: E731
+    fa64 = _FastAttention(64).cuda().double()
+    fa64.projection_matrix.copy_(fa.projection_matrix.double())
+    ref = fa64(split(q + qb), split(k + kb), split(v + vb)).transpose(1, 2).reshape(B, N, H * 64)
+    out = core.performer_attention(q, k, v, fa.projection_matrix, H, qb, kb, vb)
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert (out.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-6
+    out_nb = core.performer_attention(q + qb, k + kb, v + vb, fa.projection_matrix, H)
+    assert (out_nb - out).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-6
+
+
 def test_embed_sum_and_speaker_mix():
     torch.manual_seed(9)
     net = Unit2Control(16, 3, {'a': 513, 'b': 513, 'c': 513}).cuda().eval()
