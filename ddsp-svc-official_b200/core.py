@@ -447,7 +447,8 @@ def embed_sum(x, f0, phase, volume, f0_embed, phase_embed, volume_embed, spk_row
 
 
 def performer_attention(q, k, v, projection, heads, q_bias=None, k_bias=None, v_bias=None, eps=1e-4):
-    """Non-causal Performer attention of streaming-sized blocks in one kernel (pcmer.py:69-78,124-160):
+    """Non-causal Performer attention after the q/k/v projections as one kernel (blocks of up to 16 frames)
+    or three kernels over 8-frame tiles (pcmer.py:69-78,124-160):
     q, k, v (B,N,H*64) -- optionally without the biases of their Linears, passed separately --,
     projection (M,64) -> (B,N,H*64) head-merged attention output (before `to_out`)."""
     q = _need_cuda_f32(q, 'q').contiguous()
@@ -466,8 +467,10 @@ def performer_attention(q, k, v, projection, heads, q_bias=None, k_bias=None, v_
                 raise ValueError('bias must have heads*64 entries')
         biases.append(bvec)
     out = torch.empty((B, N, HD), dtype=torch.float32, device=q.device)
+    nbytes = _cabi.lib().ddsp_b200_performer_attention_workspace_bytes(B, N, H)
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=q.device)
     with _OnDevice(q.device) as _st:
         _cabi.check(_cabi.lib().ddsp_b200_performer_attention(
             q.data_ptr(), k.data_ptr(), v.data_ptr(), _ptr(biases[0]), _ptr(biases[1]), _ptr(biases[2]),
-            projection.data_ptr(), B, N, H, projection.shape[0], float(eps), out.data_ptr(), _st))
+            projection.data_ptr(), B, N, H, projection.shape[0], float(eps), out.data_ptr(), ws.data_ptr(), nbytes, _st))
     return out

@@ -376,6 +376,146 @@ __global__ void __launch_bounds__(kPasThreads) performer_attention_small_kernel(
     }
 }
 
+// The same attention for longer blocks, spread over the chip: one CTA per (head, clip, 8-frame tile).
+//   1. performer_context_partial_kernel: key features of the tile and its 288 x 65 partial context
+//      (last column: partial k_sum) -> workspace[(clip*H + head)*tiles + tile]
+//   2. performer_context_reduce_kernel: sums the tiles in a fixed order (deterministic) -> context
+//   3. performer_output_kernel: query features of the tile, (q' context) / (q' k_sum + 1e-8), head merge
+__device__ __forceinline__ void pas_stage_projection(const float* __restrict__ proj, int M, float* P) {
+    const int t = threadIdx.x;
+    const int n4 = M * kPerfDim / 4;
+    constexpr int kPer = (kPpfCols * kPerfDim / 4 + kPasThreads - 1) / kPasThreads;      // 16
+    float4 buf[kPer];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+        const int f = t + i * kPasThreads;
+        buf[i] = (f < n4) ? __ldg(reinterpret_cast<const float4*>(proj) + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+        const int f = t + i * kPasThreads;
+        if (f < kPpfCols * kPerfDim / 4) {
+            float* dst = P + (f / (kPerfDim / 4)) * kPasPStride + 4 * (f % (kPerfDim / 4));
+            dst[0] = buf[i].x; dst[1] = buf[i].y; dst[2] = buf[i].z; dst[3] = buf[i].w;
+        }
+    }
+}
+
+constexpr int kPctxFloats = kPpfCols * kPasPStride;            // one (partial) context incl. the k_sum column
+
+__global__ void __launch_bounds__(kPasThreads) performer_context_partial_kernel(
+    const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ kb, const float* __restrict__ vb,
+    const float* __restrict__ proj, float* __restrict__ partial, int N, int H, int M, float ratio, float eps) {
+    extern __shared__ __align__(16) float pas_smem[];
+    float* P = pas_smem;
+    float* ft = P + kPpfCols * kPasPStride;
+    float* xt = ft + kPasRows * kPpfCols;
+    float* vt = xt + kPasRows * kPerfDim;
+    float* rowstat = vt + kPasRows * kPerfDim;
+    float* wmax = rowstat + 3 * kPasRows;
+    const int t = threadIdx.x, h = blockIdx.x, b = blockIdx.y, tile = blockIdx.z;
+    const int64_t clip = (int64_t)b * N * H * kPerfDim;
+    const int n0 = tile * kPasRows, rows = min(kPasRows, N - n0);
+    pas_stage_projection(proj, M, P);
+    if (t >= kPasThreads - 32) {                             // the last warp stages the v tile
+        const int u = t - (kPasThreads - 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int f = u + 32 * i, r = f / (kPerfDim / 4), d = 4 * (f % (kPerfDim / 4));
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < rows) {
+                x = __ldg(reinterpret_cast<const float4*>(v + clip + ((int64_t)(n0 + r) * H + h) * kPerfDim + d));
+                if (vb) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(vb + h * kPerfDim + d));
+                    x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+                }
+            }
+            *reinterpret_cast<float4*>(vt + r * kPerfDim + d) = x;
+        }
+    }
+    __syncthreads();
+    pas_features(k + clip, kb, h, H, n0, rows, P, xt, ft, rowstat, wmax, M, false, ratio, eps);
+    float c[kPerfDim + 1];
+#pragma unroll
+    for (int e = 0; e <= kPerfDim; ++e) c[e] = 0.0f;
+#pragma unroll 2
+    for (int r = 0; r < kPasRows; ++r) {
+        const float kf = ft[r * kPpfCols + t];
+        const float4* vr = reinterpret_cast<const float4*>(vt + r * kPerfDim);
+#pragma unroll
+        for (int e4 = 0; e4 < kPerfDim / 4; ++e4) {
+            const float4 vv = vr[e4];
+            c[4 * e4 + 0] = fmaf(kf, vv.x, c[4 * e4 + 0]);
+            c[4 * e4 + 1] = fmaf(kf, vv.y, c[4 * e4 + 1]);
+            c[4 * e4 + 2] = fmaf(kf, vv.z, c[4 * e4 + 2]);
+            c[4 * e4 + 3] = fmaf(kf, vv.w, c[4 * e4 + 3]);
+        }
+        c[kPerfDim] += kf;
+    }
+    float* dst = partial + (((int64_t)b * H + h) * gridDim.z + tile) * kPctxFloats + t * kPasPStride;
+#pragma unroll
+    for (int e = 0; e <= kPerfDim; ++e) dst[e] = c[e];
+}
+
+__global__ void __launch_bounds__(256) performer_context_reduce_kernel(const float* __restrict__ partial,
+                                                                       float* __restrict__ context, int tiles) {
+    const int64_t bh = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kPctxFloats) return;
+    const float* src = partial + bh * tiles * kPctxFloats + i;
+    float a = 0.0f;
+    for (int tl = 0; tl < tiles; ++tl) a += __ldg(src + (int64_t)tl * kPctxFloats);      // fixed order
+    context[bh * kPctxFloats + i] = a;
+}
+
+__global__ void __launch_bounds__(kPasThreads) performer_output_kernel(
+    const float* __restrict__ q, const float* __restrict__ qb, const float* __restrict__ proj,
+    const float* __restrict__ context, float* __restrict__ out, int N, int H, int M, float ratio, float eps) {
+    extern __shared__ __align__(16) float pas_smem[];
+    float* P = pas_smem;
+    float* ctx = P + kPpfCols * kPasPStride;
+    float* ft = ctx + kPpfCols * kPasPStride;
+    float* xt = ft + kPasRows * kPpfCols;
+    float* vt = xt + kPasRows * kPerfDim;
+    float* rowstat = vt + kPasRows * kPerfDim;
+    float* wmax = rowstat + 3 * kPasRows;
+    const int t = threadIdx.x, h = blockIdx.x, b = blockIdx.y, tile = blockIdx.z;
+    const int64_t clip = (int64_t)b * N * H * kPerfDim;
+    const int n0 = tile * kPasRows, rows = min(kPasRows, N - n0);
+    pas_stage_projection(proj, M, P);
+    {
+        const float4* src = reinterpret_cast<const float4*>(context + ((int64_t)b * H + h) * kPctxFloats);
+        float4* dst = reinterpret_cast<float4*>(ctx);
+        for (int e = t; e < kPctxFloats / 4; e += kPasThreads) dst[e] = __ldg(src + e);
+    }
+    __syncthreads();
+    pas_features(q + clip, qb, h, H, n0, rows, P, xt, ft, rowstat, wmax, M, true, ratio, eps);
+    for (int o = t; o < kPasRows * kPasPStride; o += kPasThreads) {
+        const int r = o / kPasPStride, e = o % kPasPStride;
+        const float* fr = ft + r * kPpfCols;
+        const float* cc = ctx + e;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        int j = 0;
+#pragma unroll 4
+        for (; j + 4 <= M; j += 4) {
+            const float4 f4 = *reinterpret_cast<const float4*>(fr + j);
+            a0 = fmaf(f4.x, cc[j * kPasPStride], a0);
+            a1 = fmaf(f4.y, cc[(j + 1) * kPasPStride], a1);
+            a2 = fmaf(f4.z, cc[(j + 2) * kPasPStride], a2);
+            a3 = fmaf(f4.w, cc[(j + 3) * kPasPStride], a3);
+        }
+        for (; j < M; ++j) a0 = fmaf(fr[j], cc[j * kPasPStride], a0);
+        const float a = (a0 + a1) + (a2 + a3);
+        if (e == kPerfDim) rowstat[2 * kPasRows + r] = a;
+        else xt[r * kPerfDim + e] = a;
+    }
+    __syncthreads();
+    for (int o = t; o < rows * kPerfDim; o += kPasThreads) {
+        const int r = o / kPerfDim;
+        out[clip + ((int64_t)(n0 + r) * H + h) * kPerfDim + (o % kPerfDim)] = xt[o] * (1.0f / (rowstat[2 * kPasRows + r] + 1e-8f));
+    }
+}
+
 // Input embedding sum of Unit2Control.forward (unit2control.py:80-95) in one pass:
 //   out[b,n,c] = x[b,n,c] + (wf[c]*log(1 + f0/700) + bf[c]) + (wp[c]*(phase/pi) + bp[c]) + (wv[c]*vol + bv[c]) + spk[b?,c]
 // x may be any strided (B,N,C) view (the pre-net output is a transposed view); out is contiguous.

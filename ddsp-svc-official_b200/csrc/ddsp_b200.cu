@@ -100,6 +100,10 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kPpfSmemBytes));
         CUDA_TRY(cudaFuncSetAttribute(ddsp::performer_attention_small_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kPasSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(ddsp::performer_context_partial_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kPasSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(ddsp::performer_output_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kPasSmemBytes));
         float* ptr = nullptr;
         CUDA_TRY(cudaGetSymbolAddress((void**)&ptr, g_tables));
         ddsp::fft_tables_kernel<<<4, 256, 0, st>>>(reinterpret_cast<float4*>(ptr), ptr + 2048);
@@ -530,16 +534,41 @@ int ddsp_b200_performer_project_features(const float* x, const float* x_bias, co
     return DDSP_B200_OK;
 }
 
+size_t ddsp_b200_performer_attention_workspace_bytes(int B, int N, int H) {
+    if (B <= 0 || N <= 0 || H <= 0) return 0;
+    const size_t tiles = (size_t)(N + ddsp::kPasRows - 1) / ddsp::kPasRows;
+    return (size_t)B * H * (tiles + 1) * ddsp::kPctxFloats * sizeof(float);
+}
+
 int ddsp_b200_performer_attention(const float* q, const float* k, const float* v, const float* q_bias,
                                   const float* k_bias, const float* v_bias, const float* projection, int B, int N, int H,
-                                  int M, float eps, float* out, void* stream) {
+                                  int M, float eps, float* out, void* workspace, size_t workspace_bytes, void* stream) {
     g_launches = 0;
     if (!q || !k || !v || !projection || !out || B <= 0 || N <= 0 || H <= 0 || M <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
     if (M > ddsp::kPpfCols || B > 65535) return DDSP_B200_ERR_UNSUPPORTED;
     const float* tables = nullptr;
-    if (int rc = ensure_device_ready((cudaStream_t)stream, &tables)) return rc;     // shared-memory opt-in
-    ddsp::performer_attention_small_kernel<<<dim3(H, B), ddsp::kPasThreads, ddsp::kPasSmemBytes, (cudaStream_t)stream>>>(
-        q, k, v, q_bias, k_bias, v_bias, projection, out, N, H, M, 1.0f / sqrtf((float)M), eps);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = ensure_device_ready(st, &tables)) return rc;     // shared-memory opt-in
+    const float ratio = 1.0f / sqrtf((float)M);
+    if (N <= 2 * ddsp::kPasRows) {
+        ddsp::performer_attention_small_kernel<<<dim3(H, B), ddsp::kPasThreads, ddsp::kPasSmemBytes, st>>>(
+            q, k, v, q_bias, k_bias, v_bias, projection, out, N, H, M, ratio, eps);
+        LAUNCH_CHECK();
+        return DDSP_B200_OK;
+    }
+    const int tiles = (N + ddsp::kPasRows - 1) / ddsp::kPasRows;
+    if (tiles > 65535) return DDSP_B200_ERR_UNSUPPORTED;
+    if (!workspace || ((uintptr_t)workspace & 15) || workspace_bytes < ddsp_b200_performer_attention_workspace_bytes(B, N, H))
+        return DDSP_B200_ERR_WORKSPACE;
+    float* partial = (float*)workspace;
+    float* context = partial + (size_t)B * H * tiles * ddsp::kPctxFloats;
+    ddsp::performer_context_partial_kernel<<<dim3(H, B, tiles), ddsp::kPasThreads, ddsp::kPasSmemBytes, st>>>(
+        k, v, k_bias, v_bias, projection, partial, N, H, M, ratio, eps);
+    LAUNCH_CHECK();
+    ddsp::performer_context_reduce_kernel<<<dim3((ddsp::kPctxFloats + 255) / 256, B * H), 256, 0, st>>>(partial, context, tiles);
+    LAUNCH_CHECK();
+    ddsp::performer_output_kernel<<<dim3(H, B, tiles), ddsp::kPasThreads, ddsp::kPasSmemBytes, st>>>(
+        q, q_bias, projection, context, out, N, H, M, ratio, eps);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }

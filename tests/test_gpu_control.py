@@ -95,9 +95,10 @@ def test_unit2control_fused_matches_plain_ops(B, F_):
     assert out['harmonic_phase'].data_ptr() == out['harmonic_magnitude'].data_ptr() + 513 * 4
 
 
-@pytest.mark.parametrize('B,N,H', [(1, 1, 8), (1, 9, 8), (2, 26, 8), (1, 130, 8), (3, 37, 4)])
-def test_performer_attention_single_kernel(B, N, H):
-    """One-kernel attention (streaming sizes) against the plain PyTorch formulation (pcmer.py:69-78,124-160)."""
+@pytest.mark.parametrize('B,N,H', [(1, 1, 8), (1, 9, 8), (1, 16, 8), (1, 17, 8), (2, 26, 8), (1, 130, 8), (3, 37, 4), (2, 862, 8)])
+def test_performer_attention_fused(B, N, H):
+    """Fused attention (one kernel up to 16 frames, three tiled kernels beyond) against the plain PyTorch
+    formulation (pcmer.py:69-78,124-160); the tiled path sums its partial contexts in a fixed order."""
     from ddsp_b200.control import _FastAttention
     torch.manual_seed(N)
     q, k, v = (torch.randn(B, N, H * 64, device='cuda') for _ in range(3))
@@ -112,6 +113,7 @@ def test_performer_attention_single_kernel(B, N, H):
     assert (out.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-6
     out_nb = core.performer_attention(q + qb, k + kb, v + vb, fa.projection_matrix, H)
     assert (out_nb - out).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-6
+    assert torch.equal(out, core.performer_attention(q, k, v, fa.projection_matrix, H, qb, kb, vb))      # deterministic
 
 
 def test_embed_sum_and_speaker_mix():
