@@ -139,7 +139,8 @@ class _SelfAttention(nn.Module):
                                                self.to_k.bias, self.to_v.bias).view(b * n, -1)
             if residual is None:
                 return self.to_out(out).view(b, n, -1)
-            return torch.addmm((residual + self.to_out.bias).reshape(b * n, -1), out, self.to_out.weight.t()).view(b, n, -1)
+            # residual + bias lands in a fresh buffer that the GEMM then accumulates into in place (no copy of C)
+            return (residual + self.to_out.bias).reshape(b * n, -1).addmm_(out, self.to_out.weight.t()).view(b, n, -1)
         out = self.fast_attention(split(self.to_q(x)), split(self.to_k(x)), split(self.to_v(x)))
         return self.to_out(out.transpose(1, 2).reshape(b, n, self.heads * _DIM_HEAD))
 
@@ -171,8 +172,7 @@ class _ConvModule(nn.Module):
             if residual is None:
                 return F.linear(s, pw2.weight.squeeze(-1), pw2.bias)
             b, n, _ = x.shape
-            return torch.addmm((residual + pw2.bias).reshape(b * n, -1), s.view(b * n, -1),
-                               pw2.weight.squeeze(-1).t()).view(b, n, -1)
+            return (residual + pw2.bias).reshape(b * n, -1).addmm_(s.view(b * n, -1), pw2.weight.squeeze(-1).t()).view(b, n, -1)
         return self.net(x)
 
 
