@@ -37,8 +37,8 @@ _PROTOS = {
     'ddsp_b200_performer_project_features': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                        C.c_int, C.c_float, c_f32p, C.c_void_p]),
     'ddsp_b200_performer_attention_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
-    'ddsp_b200_performer_attention': (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int,
-                                                C.c_int, C.c_int, C.c_float, c_f32p, C.c_void_p, C.c_size_t,
+    'ddsp_b200_performer_attention': (C.c_int, [c_f32p, c_f32p, c_f32p, i64, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int,
+                                                C.c_int, C.c_int, C.c_int, C.c_float, c_f32p, C.c_void_p, C.c_size_t,
                                                 C.c_void_p]),
     'ddsp_b200_embed_sum': (C.c_int, [c_f32p, i64, i64, i64, c_f32p, i64, i64, c_f32p, i64, i64, c_f32p, i64, i64,
                                       c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, i64, C.c_int, C.c_int,

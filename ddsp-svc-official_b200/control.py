@@ -105,6 +105,16 @@ class _SelfAttention(nn.Module):
         self.to_v = nn.Linear(dim, inner)
         self.to_out = nn.Linear(inner, dim)
 
+    def _merged_qkv_weight(self):
+        """[W_q; W_k; W_v] for the one-GEMM projection of the streaming path, rebuilt when a weight changes
+        (in-place update, load_state_dict, .to())."""
+        ws = (self.to_q.weight, self.to_k.weight, self.to_v.weight)
+        key = tuple((w._version, w.data_ptr()) for w in ws)
+        if getattr(self, '_qkv_key', None) != key:
+            self._qkv_cache = torch.cat([w.detach() for w in ws])
+            self._qkv_key = key
+        return self._qkv_cache
+
     def forward(self, x, residual=None):
         """`residual` (fused path only): returns residual + attention(x), with the output bias and the
         residual folded into the output GEMM (addmm, beta = 1) instead of two more elementwise passes."""
@@ -134,9 +144,9 @@ class _SelfAttention(nn.Module):
             else:
                 # streaming blocks: the whole attention after the three (bias-free) projection GEMMs is one
                 # kernel (<= 16 frames) or three tiled ones -- launch latencies, not bytes, bound a GUI block
-                out = core.performer_attention(F.linear(x, self.to_q.weight), F.linear(x, self.to_k.weight),
-                                               F.linear(x, self.to_v.weight), proj, self.heads, self.to_q.bias,
-                                               self.to_k.bias, self.to_v.bias).view(b * n, -1)
+                q, k, v = F.linear(x, self._merged_qkv_weight()).chunk(3, dim=-1)      # one GEMM, three strided slices
+                out = core.performer_attention(q, k, v, proj, self.heads, self.to_q.bias, self.to_k.bias,
+                                               self.to_v.bias).view(b * n, -1)
             if residual is None:
                 return self.to_out(out).view(b, n, -1)
             # residual + bias lands in a fresh buffer that the GEMM then accumulates into in place (no copy of C)

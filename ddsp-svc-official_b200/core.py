@@ -451,14 +451,19 @@ def performer_attention(q, k, v, projection, heads, q_bias=None, k_bias=None, v_
     or three kernels over 8-frame tiles (pcmer.py:69-78,124-160):
     q, k, v (B,N,H*64) -- optionally without the biases of their Linears, passed separately --,
     projection (M,64) -> (B,N,H*64) head-merged attention output (before `to_out`)."""
-    q = _need_cuda_f32(q, 'q').contiguous()
-    k = _need_cuda_f32(k, 'k').contiguous()
-    v = _need_cuda_f32(v, 'v').contiguous()
+    q, k, v = (_need_cuda_f32(t, n) for t, n in ((q, 'q'), (k, 'k'), (v, 'v')))
     projection = _need_cuda_f32(projection, 'projection').contiguous()
     B, N, HD = q.shape
     H = int(heads)
     if HD != H * 64 or k.shape != q.shape or v.shape != q.shape or projection.shape[1] != 64:
         raise ValueError('q, k, v must be (B, N, heads*64) and projection (M, 64)')
+    # accepted as they are: slices of one merged (B, N, 3*heads*64) projection (common frame stride, clips
+    # back to back); anything else is made contiguous
+    rs = q.stride(1)
+    ok = all(t.stride(2) == 1 and t.stride(1) == rs and t.stride(0) == N * rs and t.data_ptr() % 16 == 0 for t in (q, k, v))
+    if not ok or rs % 4 or rs < HD:
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        rs = HD
     biases = []
     for bvec in (q_bias, k_bias, v_bias):
         if bvec is not None:
@@ -471,6 +476,6 @@ def performer_attention(q, k, v, projection, heads, q_bias=None, k_bias=None, v_
     ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=q.device)
     with _OnDevice(q.device) as _st:
         _cabi.check(_cabi.lib().ddsp_b200_performer_attention(
-            q.data_ptr(), k.data_ptr(), v.data_ptr(), _ptr(biases[0]), _ptr(biases[1]), _ptr(biases[2]),
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), rs, _ptr(biases[0]), _ptr(biases[1]), _ptr(biases[2]),
             projection.data_ptr(), B, N, H, projection.shape[0], float(eps), out.data_ptr(), ws.data_ptr(), nbytes, _st))
     return out

@@ -205,7 +205,7 @@ constexpr int kPasSmemBytes = kPasSmemFloats * 4;
 
 // Feature tile of rows n0 .. n0+rows-1 of `src` (q or k of this head) into ft[r][j].
 __device__ __forceinline__ void pas_features(const float* __restrict__ src, const float* __restrict__ bias, int h,
-                                             int H, int n0, int rows, const float* P, float* xt, float* ft,
+                                             int64_t rs, int n0, int rows, const float* P, float* xt, float* ft,
                                              float* rowstat, float* wmax, int M, bool is_query, float ratio, float eps) {
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     // stage the tile's rows scaled by normalizer = 64^-0.25 (pcmer.py:137,146): 512 floats, 2 per thread (first 256)
@@ -213,7 +213,7 @@ __device__ __forceinline__ void pas_features(const float* __restrict__ src, cons
         const int r = t / (kPerfDim / 2), d = 2 * (t % (kPerfDim / 2));
         float2 v = make_float2(0.0f, 0.0f);
         if (r < rows) {
-            v = __ldg(reinterpret_cast<const float2*>(src + ((int64_t)(n0 + r) * H + h) * kPerfDim + d));
+            v = __ldg(reinterpret_cast<const float2*>(src + (int64_t)(n0 + r) * rs + h * kPerfDim + d));
             if (bias) { v.x += __ldg(bias + h * kPerfDim + d); v.y += __ldg(bias + h * kPerfDim + d + 1); }
         }
         *reinterpret_cast<float2*>(xt + r * kPerfDim + d) = make_float2(0.35355339059327373f * v.x, 0.35355339059327373f * v.y);
@@ -271,7 +271,7 @@ __device__ __forceinline__ void pas_features(const float* __restrict__ src, cons
 __global__ void __launch_bounds__(kPasThreads) performer_attention_small_kernel(
     const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
     const float* __restrict__ qb, const float* __restrict__ kb, const float* __restrict__ vb,
-    const float* __restrict__ proj, float* __restrict__ out, int N, int H, int M, float ratio, float eps) {
+    const float* __restrict__ proj, float* __restrict__ out, int N, int H, int M, int64_t rs, float ratio, float eps) {
     extern __shared__ __align__(16) float pas_smem[];
     float* P = pas_smem;
     float* ctx = P + kPpfCols * kPasPStride;
@@ -281,7 +281,8 @@ __global__ void __launch_bounds__(kPasThreads) performer_attention_small_kernel(
     float* rowstat = vt + kPasRows * kPerfDim;
     float* wmax = rowstat + 3 * kPasRows;
     const int t = threadIdx.x, h = blockIdx.x, b = blockIdx.y;
-    const int64_t clip = (int64_t)b * N * H * kPerfDim;
+    const int64_t clip = (int64_t)b * N * rs;                 // q / k / v: rs elements between consecutive frames
+    const int64_t oclip = (int64_t)b * N * H * kPerfDim;      // out: head-merged, contiguous
     {   // proj (M x 64, contiguous) -> P[j*65 + d]; all loads of a thread in flight before the first store
         const int n4 = M * kPerfDim / 4;
         constexpr int kPer = (kPpfCols * kPerfDim / 4 + kPasThreads - 1) / kPasThreads;      // 16
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(kPasThreads) performer_attention_small_kernel(
                 const int f = u + 32 * i, r = f / (kPerfDim / 4), d = 4 * (f % (kPerfDim / 4));
                 float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (r < rows) {
-                    x = __ldg(reinterpret_cast<const float4*>(v + clip + ((int64_t)(n0 + r) * H + h) * kPerfDim + d));
+                    x = __ldg(reinterpret_cast<const float4*>(v + clip + (int64_t)(n0 + r) * rs + h * kPerfDim + d));
                     if (vb) {
                         const float4 bb = __ldg(reinterpret_cast<const float4*>(vb + h * kPerfDim + d));
                         x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(kPasThreads) performer_attention_small_kernel(
                 *reinterpret_cast<float4*>(vt + r * kPerfDim + d) = x;
             }
         }
-        pas_features(k + clip, kb, h, H, n0, rows, P, xt, ft, rowstat, wmax, M, false, ratio, eps);
+        pas_features(k + clip, kb, h, rs, n0, rows, P, xt, ft, rowstat, wmax, M, false, ratio, eps);
 #pragma unroll 2
         for (int r = 0; r < kPasRows; ++r) {                // rows beyond the tile hold zero features
             const float kf = ft[r * kPpfCols + t];
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(kPasThreads) performer_attention_small_kernel(
     // ---- queries: out[n][e] = sum_j q'[n][j] context[j][e] / (sum_j q'[n][j] k_sum[j] + 1e-8) ----
     for (int n0 = 0; n0 < N; n0 += kPasRows) {
         const int rows = min(kPasRows, N - n0);
-        pas_features(q + clip, qb, h, H, n0, rows, P, xt, ft, rowstat, wmax, M, true, ratio, eps);
+        pas_features(q + clip, qb, h, rs, n0, rows, P, xt, ft, rowstat, wmax, M, true, ratio, eps);
         // 8 rows x 65 columns (64 outputs + the denominator): thread -> (row, column), four partial sums
         for (int o = t; o < kPasRows * kPasPStride; o += kPasThreads) {
             const int r = o / kPasPStride, e = o % kPasPStride;
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(kPasThreads) performer_attention_small_kernel(
         __syncthreads();
         for (int o = t; o < rows * kPerfDim; o += kPasThreads) {
             const int r = o / kPerfDim;
-            out[clip + ((int64_t)(n0 + r) * H + h) * kPerfDim + (o % kPerfDim)] = xt[o] * (1.0f / (rowstat[2 * kPasRows + r] + 1e-8f));
+            out[oclip + ((int64_t)(n0 + r) * H + h) * kPerfDim + (o % kPerfDim)] = xt[o] * (1.0f / (rowstat[2 * kPasRows + r] + 1e-8f));
         }
         __syncthreads();
     }
@@ -405,7 +406,7 @@ constexpr int kPctxFloats = kPpfCols * kPasPStride;            // one (partial) 
 
 __global__ void __launch_bounds__(kPasThreads) performer_context_partial_kernel(
     const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ kb, const float* __restrict__ vb,
-    const float* __restrict__ proj, float* __restrict__ partial, int N, int H, int M, float ratio, float eps) {
+    const float* __restrict__ proj, float* __restrict__ partial, int N, int H, int M, int64_t rs, float ratio, float eps) {
     extern __shared__ __align__(16) float pas_smem[];
     float* P = pas_smem;
     float* ft = P + kPpfCols * kPasPStride;
@@ -414,7 +415,9 @@ __global__ void __launch_bounds__(kPasThreads) performer_context_partial_kernel(
     float* rowstat = vt + kPasRows * kPerfDim;
     float* wmax = rowstat + 3 * kPasRows;
     const int t = threadIdx.x, h = blockIdx.x, b = blockIdx.y, tile = blockIdx.z;
-    const int64_t clip = (int64_t)b * N * H * kPerfDim;
+    const int64_t clip = (int64_t)b * N * rs;
+    const int64_t oclip = (int64_t)b * N * H * kPerfDim;
+    (void)oclip;
     const int n0 = tile * kPasRows, rows = min(kPasRows, N - n0);
     pas_stage_projection(proj, M, P);
     if (t >= kPasThreads - 32) {                             // the last warp stages the v tile
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(kPasThreads) performer_context_partial_kernel(
             const int f = u + 32 * i, r = f / (kPerfDim / 4), d = 4 * (f % (kPerfDim / 4));
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < rows) {
-                x = __ldg(reinterpret_cast<const float4*>(v + clip + ((int64_t)(n0 + r) * H + h) * kPerfDim + d));
+                x = __ldg(reinterpret_cast<const float4*>(v + clip + (int64_t)(n0 + r) * rs + h * kPerfDim + d));
                 if (vb) {
                     const float4 bb = __ldg(reinterpret_cast<const float4*>(vb + h * kPerfDim + d));
                     x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
@@ -434,7 +437,7 @@ __global__ void __launch_bounds__(kPasThreads) performer_context_partial_kernel(
         }
     }
     __syncthreads();
-    pas_features(k + clip, kb, h, H, n0, rows, P, xt, ft, rowstat, wmax, M, false, ratio, eps);
+    pas_features(k + clip, kb, h, rs, n0, rows, P, xt, ft, rowstat, wmax, M, false, ratio, eps);
     float c[kPerfDim + 1];
 #pragma unroll
     for (int e = 0; e <= kPerfDim; ++e) c[e] = 0.0f;
@@ -470,7 +473,7 @@ __global__ void __launch_bounds__(256) performer_context_reduce_kernel(const flo
 
 __global__ void __launch_bounds__(kPasThreads) performer_output_kernel(
     const float* __restrict__ q, const float* __restrict__ qb, const float* __restrict__ proj,
-    const float* __restrict__ context, float* __restrict__ out, int N, int H, int M, float ratio, float eps) {
+    const float* __restrict__ context, float* __restrict__ out, int N, int H, int M, int64_t rs, float ratio, float eps) {
     extern __shared__ __align__(16) float pas_smem[];
     float* P = pas_smem;
     float* ctx = P + kPpfCols * kPasPStride;
@@ -480,7 +483,9 @@ __global__ void __launch_bounds__(kPasThreads) performer_output_kernel(
     float* rowstat = vt + kPasRows * kPerfDim;
     float* wmax = rowstat + 3 * kPasRows;
     const int t = threadIdx.x, h = blockIdx.x, b = blockIdx.y, tile = blockIdx.z;
-    const int64_t clip = (int64_t)b * N * H * kPerfDim;
+    const int64_t clip = (int64_t)b * N * rs;
+    const int64_t oclip = (int64_t)b * N * H * kPerfDim;
+    (void)oclip;
     const int n0 = tile * kPasRows, rows = min(kPasRows, N - n0);
     pas_stage_projection(proj, M, P);
     {
@@ -489,7 +494,7 @@ __global__ void __launch_bounds__(kPasThreads) performer_output_kernel(
         for (int e = t; e < kPctxFloats / 4; e += kPasThreads) dst[e] = __ldg(src + e);
     }
     __syncthreads();
-    pas_features(q + clip, qb, h, H, n0, rows, P, xt, ft, rowstat, wmax, M, true, ratio, eps);
+    pas_features(q + clip, qb, h, rs, n0, rows, P, xt, ft, rowstat, wmax, M, true, ratio, eps);
     for (int o = t; o < kPasRows * kPasPStride; o += kPasThreads) {
         const int r = o / kPasPStride, e = o % kPasPStride;
         const float* fr = ft + r * kPpfCols;
@@ -512,7 +517,7 @@ __global__ void __launch_bounds__(kPasThreads) performer_output_kernel(
     __syncthreads();
     for (int o = t; o < rows * kPerfDim; o += kPasThreads) {
         const int r = o / kPerfDim;
-        out[clip + ((int64_t)(n0 + r) * H + h) * kPerfDim + (o % kPerfDim)] = xt[o] * (1.0f / (rowstat[2 * kPasRows + r] + 1e-8f));
+        out[oclip + ((int64_t)(n0 + r) * H + h) * kPerfDim + (o % kPerfDim)] = xt[o] * (1.0f / (rowstat[2 * kPasRows + r] + 1e-8f));
     }
 }
 

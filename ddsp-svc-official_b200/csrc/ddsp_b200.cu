@@ -540,11 +540,15 @@ size_t ddsp_b200_performer_attention_workspace_bytes(int B, int N, int H) {
     return (size_t)B * H * (tiles + 1) * ddsp::kPctxFloats * sizeof(float);
 }
 
-int ddsp_b200_performer_attention(const float* q, const float* k, const float* v, const float* q_bias,
-                                  const float* k_bias, const float* v_bias, const float* projection, int B, int N, int H,
-                                  int M, float eps, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+int ddsp_b200_performer_attention(const float* q, const float* k, const float* v, int64_t row_stride,
+                                  const float* q_bias, const float* k_bias, const float* v_bias, const float* projection,
+                                  int B, int N, int H, int M, float eps, float* out, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
     g_launches = 0;
-    if (!q || !k || !v || !projection || !out || B <= 0 || N <= 0 || H <= 0 || M <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (!q || !k || !v || !projection || !out || B <= 0 || N <= 0 || H <= 0 || M <= 0 || row_stride < (int64_t)H * 64 ||
+        (row_stride & 3) || ((uintptr_t)q & 15) || ((uintptr_t)k & 15) || ((uintptr_t)v & 15))
+        return DDSP_B200_ERR_INVALID_ARGUMENT;
+    const int64_t rs = row_stride;
     if (M > ddsp::kPpfCols || B > 65535) return DDSP_B200_ERR_UNSUPPORTED;
     const float* tables = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
@@ -552,7 +556,7 @@ int ddsp_b200_performer_attention(const float* q, const float* k, const float* v
     const float ratio = 1.0f / sqrtf((float)M);
     if (N <= 2 * ddsp::kPasRows) {
         ddsp::performer_attention_small_kernel<<<dim3(H, B), ddsp::kPasThreads, ddsp::kPasSmemBytes, st>>>(
-            q, k, v, q_bias, k_bias, v_bias, projection, out, N, H, M, ratio, eps);
+            q, k, v, q_bias, k_bias, v_bias, projection, out, N, H, M, rs, ratio, eps);
         LAUNCH_CHECK();
         return DDSP_B200_OK;
     }
@@ -563,12 +567,12 @@ int ddsp_b200_performer_attention(const float* q, const float* k, const float* v
     float* partial = (float*)workspace;
     float* context = partial + (size_t)B * H * tiles * ddsp::kPctxFloats;
     ddsp::performer_context_partial_kernel<<<dim3(H, B, tiles), ddsp::kPasThreads, ddsp::kPasSmemBytes, st>>>(
-        k, v, k_bias, v_bias, projection, partial, N, H, M, ratio, eps);
+        k, v, k_bias, v_bias, projection, partial, N, H, M, rs, ratio, eps);
     LAUNCH_CHECK();
     ddsp::performer_context_reduce_kernel<<<dim3((ddsp::kPctxFloats + 255) / 256, B * H), 256, 0, st>>>(partial, context, tiles);
     LAUNCH_CHECK();
     ddsp::performer_output_kernel<<<dim3(H, B, tiles), ddsp::kPasThreads, ddsp::kPasSmemBytes, st>>>(
-        q, q_bias, projection, context, out, N, H, M, ratio, eps);
+        q, q_bias, projection, context, out, N, H, M, rs, ratio, eps);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }

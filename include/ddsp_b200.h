@@ -204,16 +204,18 @@ int ddsp_b200_glu_dwconv_silu(const float *u, const float *u_bias, const float *
 
 /* Whole non-causal Performer attention for streaming-sized blocks (after the q/k/v projections):
  * feature maps, k_sum, context, normalised output, head-merged.  pcmer.py:69-78,124-160,191-251
- * q, k, v (B,N,H*64) contiguous; q_bias / k_bias / v_bias (H*64) optional (NULL): biases of the
+ * q, k, v: (B,N,H*64) views with `row_stride` elements between consecutive frames (H*64 when
+ * contiguous; 3*H*64 for the three slices of one merged q|k|v projection) and B*N*row_stride per
+ * clip; q_bias / k_bias / v_bias (H*64) optional (NULL): biases of the
  * producing Linears, added on load; projection (M,64), M <= 288; out (B,N,H*64) contiguous.
  * Blocks of up to 16 frames run as one kernel (one CTA per clip and head); longer ones as three
  * kernels over 8-frame tiles (partial contexts -> fixed-order sum -> outputs), which need the
  * workspace. */
 size_t ddsp_b200_performer_attention_workspace_bytes(int B, int N, int H);
-int ddsp_b200_performer_attention(const float *q, const float *k, const float *v, const float *q_bias,
-                                  const float *k_bias, const float *v_bias, const float *projection,
-                                  int B, int N, int H, int M, float eps, float *out, void *workspace,
-                                  size_t workspace_bytes, void *stream);
+int ddsp_b200_performer_attention(const float *q, const float *k, const float *v, int64_t row_stride,
+                                  const float *q_bias, const float *k_bias, const float *v_bias,
+                                  const float *projection, int B, int N, int H, int M, float eps,
+                                  float *out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Input embedding sum of Unit2Control.forward                     unit2control.py:80-95
  *   out[b,n,c] = x[b,n,c] + f0_embed(log(1 + f0/700)) + phase_embed(phase/pi) + volume_embed(volume) + spk[b,c]

@@ -116,6 +116,30 @@ def test_performer_attention_fused(B, N, H):
     assert torch.equal(out, core.performer_attention(q, k, v, fa.projection_matrix, H, qb, kb, vb))      # deterministic
 
 
+@pytest.mark.parametrize('N', [9, 40])
+def test_performer_attention_takes_slices_of_a_merged_projection(N):
+    torch.manual_seed(N)
+    B, H = 2, 8
+    proj = torch.randn(266, 64, device='cuda')
+    qkv = torch.randn(B, N, 3 * H * 64, device='cuda')
+    q, k, v = qkv.chunk(3, dim=-1)                               # frame stride 1536, no copies
+    a = core.performer_attention(q, k, v, proj, H)
+    b = core.performer_attention(q.contiguous(), k.contiguous(), v.contiguous(), proj, H)
+    assert torch.equal(a, b)
+
+
+def test_merged_qkv_weight_follows_weight_updates():
+    from ddsp_b200.control import _SelfAttention
+    att = _SelfAttention(256, 8).cuda()
+    w0 = att._merged_qkv_weight()
+    assert w0.shape == (1536, 256) and att._merged_qkv_weight() is w0
+    with torch.no_grad():
+        att.to_k.weight.add_(1.0)
+    w1 = att._merged_qkv_weight()
+    assert w1 is not w0 and torch.equal(w1[512:1024], att.to_k.weight)
+    assert '_qkv_cache' not in att.state_dict()
+
+
 def test_embed_sum_and_speaker_mix():
     torch.manual_seed(9)
     net = Unit2Control(16, 3, {'a': 513, 'b': 513, 'c': 513}).cuda().eval()
