@@ -459,8 +459,32 @@ def run_latency(args):
         rows.append({'frames': F, 'audio_ms': F * HOP / SR * 1e3,
                      'graph_device_ms_p50': float(np.percentile(devt, 50)), 'graph_device_ms_p99': float(np.percentile(devt, 99)),
                      'eager_wall_ms_p50': float(np.percentile(wall, 50)), 'eager_wall_ms_p99': float(np.percentile(wall, 99))})
+    stream_rows = []
+    if model == 'combsubfast':
+        # carried-state stream (ddsp_b200.streaming): every push synthesises only its k new frames plus 3 frames of
+        # context instead of the GUI's whole window (gui.py:373-388: block + crossfade + extra_time, 26 frames
+        # for a 9-frame block at the default settings); eager host wall clock per push including the sync
+        from ddsp_b200.streaming import CombSubFastStream
+        for k in (9, 26):
+            n_blocks = 64
+            d = make_inputs(1, k * n_blocks, a + b_ + c, seed=7 + k, noise=False)
+            ctrl = torch.from_numpy(d['ctrl']).to(dev)
+            f0 = torch.from_numpy(d['f0_frames']).to(dev)
+            c0, c1, c2 = torch.split(ctrl, [a, b_, c], dim=-1)
+            st = CombSubFastStream(HOP, SR, window=window, seed=1)
+            wall = []
+            for it in range(args.latency_iters + 10):
+                j = (it % n_blocks) * k
+                t0 = time.perf_counter()
+                st.push(c0[:, j:j + k], c1[:, j:j + k], c2[:, j:j + k], f0[:, j:j + k])
+                torch.cuda.synchronize()
+                if it >= 10:
+                    wall.append((time.perf_counter() - t0) * 1e3)
+            stream_rows.append({'new_frames': k, 'synthesised_frames': k + 3, 'audio_ms': k * HOP / SR * 1e3,
+                                'eager_wall_ms_p50': float(np.percentile(wall, 50)),
+                                'eager_wall_ms_p99': float(np.percentile(wall, 99))})
     print(json.dumps({'metric': 'streaming synth latency per block', 'unit': 'ms', 'model': model, 'higher_is_better': False,
-                      'iters': args.latency_iters, 'rows': rows}), flush=True)
+                      'iters': args.latency_iters, 'rows': rows, 'carried_state_stream': stream_rows}), flush=True)
 
 
 def run_forward(args):

@@ -146,6 +146,30 @@ def phase_stage(f0_frames, block_size, sampling_rate, initial_phase=None, infer=
     return phase_frames, prefix, phase_full
 
 
+def phase_stage_stream(f0_frames, block_size, sampling_rate, carry=None, initial_phase=None):
+    """Stage A for a block that continues a stream (gui.py:373-388).
+
+    `carry` (B,) float64 view (any stride): the prefix the stream reached at this block's first frame --
+    a column of the previous block's `prefix`; None at stream start (then `initial_phase` applies).
+    Returns (phase_frames (B,F) fp32, prefix (B,F) fp64)."""
+    f0 = _f0_2d(f0_frames)
+    B, F = f0.shape
+    dev = f0.device
+    phase_frames = torch.empty((B, F), dtype=torch.float32, device=dev)
+    prefix = torch.empty((B, F), dtype=torch.float64, device=dev)
+    ip = _init_phase(initial_phase, B, dev)
+    cptr, cstride = 0, 0
+    if carry is not None:
+        if not carry.is_cuda or carry.dtype != torch.float64 or carry.dim() != 1 or carry.numel() != B:
+            raise ValueError('carry must be a CUDA float64 tensor with one entry per clip')
+        cptr, cstride = carry.data_ptr(), carry.stride(0)
+    with _OnDevice(dev) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_phase_stream(f0.data_ptr(), f0.stride(0), f0.stride(1), B, F, int(block_size),
+                                                       float(sampling_rate), _ptr(ip), cptr, cstride,
+                                                       phase_frames.data_ptr(), prefix.data_ptr(), _st))
+    return phase_frames, prefix
+
+
 def _common_views(tensors, names):
     """Control tensors arrive as non-contiguous `torch.split` views of one (B,F,sumK) tensor
     (unit2control.py:10-20).  Pass them through untouched when they share (batch,row) strides and
@@ -159,8 +183,9 @@ def _common_views(tensors, names):
 
 
 def combsubfast_stage(harmonic_magnitude, harmonic_phase, noise_magnitude, f0_frames, prefix, block_size,
-                      sampling_rate, initial_phase=None, noise_u=None, seed=0, window=None, out=None):
-    """Stage B of CombSubFast.forward (vocoder.py:455-492) -> signal (B,T)."""
+                      sampling_rate, initial_phase=None, noise_u=None, seed=0, window=None, out=None, hop_offset=None):
+    """Stage B of CombSubFast.forward (vocoder.py:455-492) -> signal (B,T).
+    `hop_offset` (streaming only): stream index of this block's first hop, see `phase_stage_stream`."""
     hm, hp, nm = _common_views((harmonic_magnitude, harmonic_phase, noise_magnitude),
                                ('harmonic_magnitude', 'harmonic_phase', 'noise_magnitude'))
     f0 = _f0_2d(f0_frames)
@@ -182,10 +207,16 @@ def combsubfast_stage(harmonic_magnitude, harmonic_phase, noise_magnitude, f0_fr
     ip = _init_phase(initial_phase, B, dev)
     signal = out if out is not None else torch.empty((B, T), dtype=torch.float32, device=dev)
     with _OnDevice(dev) as _st:
-        _cabi.check(_cabi.lib().ddsp_b200_combsubfast(
-            hm.data_ptr(), hp.data_ptr(), nm.data_ptr(), hm.stride(0), hm.stride(1), f0.data_ptr(), f0.stride(0),
-            f0.stride(1), prefix.data_ptr(), _ptr(ip), _ptr(noise_u), int(seed) % _TWO62, _ptr(window), B, F, hop,
-            float(sampling_rate), signal.data_ptr(), _st))
+        if hop_offset is None:
+            _cabi.check(_cabi.lib().ddsp_b200_combsubfast(
+                hm.data_ptr(), hp.data_ptr(), nm.data_ptr(), hm.stride(0), hm.stride(1), f0.data_ptr(), f0.stride(0),
+                f0.stride(1), prefix.data_ptr(), _ptr(ip), _ptr(noise_u), int(seed) % _TWO62, _ptr(window), B, F, hop,
+                float(sampling_rate), signal.data_ptr(), _st))
+        else:
+            _cabi.check(_cabi.lib().ddsp_b200_combsubfast_stream(
+                hm.data_ptr(), hp.data_ptr(), nm.data_ptr(), hm.stride(0), hm.stride(1), f0.data_ptr(), f0.stride(0),
+                f0.stride(1), prefix.data_ptr(), _ptr(noise_u), int(seed) % _TWO62, int(hop_offset), _ptr(window), B, F,
+                hop, float(sampling_rate), signal.data_ptr(), _st))
     return signal
 
 

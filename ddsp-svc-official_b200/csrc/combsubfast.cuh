@@ -42,6 +42,7 @@ struct CsfParams {
     const float* tables;                                  // device tables (twiddles + exact window)
     float* signal;                                        // (B,T)
     uint64_t seed;
+    uint32_t key_offset;                                  // streaming: noise key shift of hop_offset hops (0 otherwise)
     int B, F;
     // run partition: run r of a clip owns pairs [r*run_len + min(r,run_rem), ... + run_len + (r < run_rem));
     // all runs differ by at most one pair and together fill the chip's warp slots (see csf_partition)
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             ctx[0] = b0;
             ctx[1] = pb;                                        // p_begin
             ctx[2] = pb + P.run_len + (r < P.run_rem ? 1 : 0);  // p_end
-            ctx[3] = (int)noise_key(P.seed, (uint32_t)b0);
+            ctx[3] = (int)(noise_key(P.seed, (uint32_t)b0) + P.key_offset);
         }
         __syncwarp();
     }

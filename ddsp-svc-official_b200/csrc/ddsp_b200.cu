@@ -250,11 +250,10 @@ int ddsp_b200_remove_above_fmax(const float* amplitudes, int64_t aB, int64_t aF,
     return DDSP_B200_OK;
 }
 
-int ddsp_b200_phase(const float* f0_frames, int64_t fB, int64_t fF, int B, int F, int hop, double sr,
-                    const float* initial_phase, int precise, float* phase_frames, double* prefix,
-                    float* phase_full, void* stream) {
+static int phase_impl(const float* f0_frames, int64_t fB, int64_t fF, int B, int F, int hop, double sr,
+                      const float* initial_phase, const double* carry, int64_t carry_stride, float* phase_frames,
+                      double* prefix, float* phase_full, void* stream) {
     g_launches = 0;
-    (void)precise;   // the fused path always accumulates in fp64 (inference path, core.py:40)
     if (!f0_frames || !phase_frames || !prefix || B <= 0 || F <= 0 || !(sr > 0)) return DDSP_B200_ERR_INVALID_ARGUMENT;
     if (hop != ddsp::kHop) return DDSP_B200_ERR_UNSUPPORTED;
     if ((int64_t)F * hop >= (1ll << 24)) return DDSP_B200_ERR_UNSUPPORTED;   // fp32-exact sample index (torch's own limit)
@@ -263,14 +262,15 @@ int ddsp_b200_phase(const float* f0_frames, int64_t fB, int64_t fF, int B, int F
     const int64_t hops = (int64_t)B * F;
     // Small clips: one launch does totals + scan per clip.  Otherwise spread the totals over the chip.
     if (F <= 64 || (int64_t)B * 32 >= (int64_t)sm_count() * 64) {
-        ddsp::phase_fused_kernel<<<B, 1024, 0, st>>>(f0_frames, fB, fF, F, inv_sr, initial_phase, prefix, phase_frames);
+        ddsp::phase_fused_kernel<<<B, 1024, 0, st>>>(f0_frames, fB, fF, F, inv_sr, initial_phase, carry, carry_stride, prefix,
+                                                     phase_frames);
         LAUNCH_CHECK();
     } else {
         ddsp::hop_totals_kernel<<<(unsigned)((hops + 8 * ddsp::kHopsPerWarp - 1) / (8 * ddsp::kHopsPerWarp)), 256, 0, st>>>(
             f0_frames, fB, fF, B, F, prefix);
         LAUNCH_CHECK();
         CUDA_TRY(launch_pdl(ddsp::phase_scan_kernel, dim3(B), dim3(1024), 0, st, f0_frames, fB, fF, F, inv_sr, initial_phase,
-                            prefix, phase_frames));
+                            carry, carry_stride, prefix, phase_frames));
         LAUNCH_CHECK();
     }
     if (phase_full) {
@@ -281,10 +281,26 @@ int ddsp_b200_phase(const float* f0_frames, int64_t fB, int64_t fF, int B, int F
     return DDSP_B200_OK;
 }
 
-int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic_phase, const float* noise_magnitude,
-                          int64_t cB, int64_t cF, const float* f0_frames, int64_t fB, int64_t fF,
-                          const double* prefix, const float* initial_phase, const float* noise_u, uint64_t seed,
-                          const float* window, int B, int F, int hop, double sr, float* signal, void* stream) {
+int ddsp_b200_phase(const float* f0_frames, int64_t fB, int64_t fF, int B, int F, int hop, double sr,
+                    const float* initial_phase, int precise, float* phase_frames, double* prefix,
+                    float* phase_full, void* stream) {
+    (void)precise;   // the fused path always accumulates in fp64 (inference path, core.py:40)
+    return phase_impl(f0_frames, fB, fF, B, F, hop, sr, initial_phase, nullptr, 0, phase_frames, prefix, phase_full,
+                      stream);
+}
+
+int ddsp_b200_phase_stream(const float* f0_frames, int64_t fB, int64_t fF, int B, int F, int hop, double sr,
+                           const float* initial_phase, const double* carry, int64_t carry_stride,
+                           float* phase_frames, double* prefix, void* stream) {
+    if (carry && (carry == prefix || carry_stride < 0)) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    return phase_impl(f0_frames, fB, fF, B, F, hop, sr, initial_phase, carry, carry_stride, phase_frames, prefix,
+                      nullptr, stream);
+}
+
+static int combsubfast_impl(const float* harmonic_magnitude, const float* harmonic_phase, const float* noise_magnitude,
+                            int64_t cB, int64_t cF, const float* f0_frames, int64_t fB, int64_t fF,
+                            const double* prefix, const float* noise_u, uint64_t seed, int64_t hop_offset,
+                            const float* window, int B, int F, int hop, double sr, float* signal, void* stream) {
     g_launches = 0;
     if (!harmonic_magnitude || !harmonic_phase || !noise_magnitude || !f0_frames || !prefix || !signal || B <= 0 ||
         F <= 0 || !(sr > 0))
@@ -296,8 +312,11 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
     P.hm = harmonic_magnitude; P.hp = harmonic_phase; P.nm = noise_magnitude;
     P.cB = cB; P.cF = cF;
     P.f0_frames = f0_frames; P.fB = fB; P.fF = fF;
-    P.prefix = prefix; (void)initial_phase; P.noise_u = noise_u; P.window = window;
+    P.prefix = prefix; P.noise_u = noise_u; P.window = window;
     P.signal = signal; P.seed = seed; P.B = B; P.F = F;
+    // hop h of this call is hop hop_offset + h of the stream: the in-kernel noise is keyed by
+    // (hop*32 + lane)*c + key (common.cuh noise_seed), so the offset folds into the per-clip key
+    P.key_offset = (uint32_t)((uint64_t)hop_offset * 32ull) * 0x9E3779B1u;
     P.pairs_per_clip = (F + 2) / 2;                 // frames 0..F in pairs
     csf_partition(P, B, (int64_t)sm_count() * ddsp::kCsfWarps);
     P.inv_sr = 1.0 / sr; P.sr = (float)sr;
@@ -323,6 +342,25 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
     else CUDA_TRY(cudaLaunchKernelEx(&cfg, ddsp::combsubfast_kernel<false>, P));
     LAUNCH_CHECK();
     return DDSP_B200_OK;
+}
+
+int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic_phase, const float* noise_magnitude,
+                          int64_t cB, int64_t cF, const float* f0_frames, int64_t fB, int64_t fF,
+                          const double* prefix, const float* initial_phase, const float* noise_u, uint64_t seed,
+                          const float* window, int B, int F, int hop, double sr, float* signal, void* stream) {
+    (void)initial_phase;   // carried by `prefix`
+    return combsubfast_impl(harmonic_magnitude, harmonic_phase, noise_magnitude, cB, cF, f0_frames, fB, fF, prefix,
+                            noise_u, seed, 0, window, B, F, hop, sr, signal, stream);
+}
+
+int ddsp_b200_combsubfast_stream(const float* harmonic_magnitude, const float* harmonic_phase,
+                                 const float* noise_magnitude, int64_t cB, int64_t cF, const float* f0_frames,
+                                 int64_t fB, int64_t fF, const double* prefix, const float* noise_u, uint64_t seed,
+                                 int64_t hop_offset, const float* window, int B, int F, int hop, double sr,
+                                 float* signal, void* stream) {
+    if (hop_offset < 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    return combsubfast_impl(harmonic_magnitude, harmonic_phase, noise_magnitude, cB, cF, f0_frames, fB, fF, prefix,
+                            noise_u, seed, hop_offset, window, B, F, hop, sr, signal, stream);
 }
 
 int ddsp_b200_combsubfast_backward(const float* harmonic_magnitude, const float* harmonic_phase,

@@ -107,9 +107,26 @@ __device__ __forceinline__ Acc block_exclusive_scan(Acc v, Acc* smem /* >= 32 */
     return off + (inc - v);
 }
 
+// Streaming: the prefix (sum of upsampled f0 in Hz*samples) a previous block ended with; must not
+// alias this call's `prefix` output.  Only its value modulo sr matters for the phase; it is folded
+// once it exceeds 2^40 (hours of audio) so that an endless stream never runs out of fp64 mantissa,
+// and left untouched below that so that a stream of blocks stays bit-identical to one call over
+// the concatenated frames.
+__device__ __forceinline__ double stream_carry(const double* __restrict__ carry, int64_t carry_stride, int b,
+                                               double inv_sr) {
+    if (!carry) return 0.0;
+    double c = carry[(int64_t)b * carry_stride];
+    if (fabs(c) >= 0x1p40) {
+        const double sr = 1.0 / inv_sr, sri = rint(sr);
+        c = fmod(c, fabs(sr - sri) < 1e-9 * sr ? sri : sr);
+    }
+    return c;
+}
+
 __global__ void __launch_bounds__(1024) phase_scan_kernel(const float* __restrict__ f0_frames, int64_t fB,
                                                           int64_t fF, int F, double inv_sr,
                                                           const float* __restrict__ initial_phase,
+                                                          const double* __restrict__ carry, int64_t carry_stride,
                                                           double* __restrict__ prefix /* in: totals */,
                                                           float* __restrict__ phase_frames) {
     __shared__ double sm[33];
@@ -125,6 +142,7 @@ __global__ void __launch_bounds__(1024) phase_scan_kernel(const float* __restric
     double run = block_exclusive_scan<double>(s, sm, total);
     // initial_phase/2/pi rotations (core.py:45), carried inside the prefix in Hz*samples
     run += initial_phase ? (((double)initial_phase[b] / 2.0) / 3.14159265358979323846) / inv_sr : 0.0;
+    run += stream_carry(carry, carry_stride, b, inv_sr);
     for (int h = h0; h < h1; ++h) {
         const double t = pf[h];
         pf[h] = run;
@@ -138,6 +156,7 @@ __global__ void __launch_bounds__(1024) phase_scan_kernel(const float* __restric
 __global__ void __launch_bounds__(1024) phase_fused_kernel(const float* __restrict__ f0_frames, int64_t fB,
                                                            int64_t fF, int F, double inv_sr,
                                                            const float* __restrict__ initial_phase,
+                                                           const double* __restrict__ carry, int64_t carry_stride,
                                                            double* __restrict__ prefix,
                                                            float* __restrict__ phase_frames) {
     __shared__ double sm[33];
@@ -164,6 +183,7 @@ __global__ void __launch_bounds__(1024) phase_fused_kernel(const float* __restri
     double run = block_exclusive_scan<double>(s, sm, total);
     // initial_phase/2/pi rotations (core.py:45), carried inside the prefix in Hz*samples
     run += initial_phase ? (((double)initial_phase[b] / 2.0) / 3.14159265358979323846) / inv_sr : 0.0;
+    run += stream_carry(carry, carry_stride, b, inv_sr);
     for (int h = h0; h < h1; ++h) {
         const double t = pf[h];
         pf[h] = run;

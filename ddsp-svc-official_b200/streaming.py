@@ -1,0 +1,178 @@
+"""Streaming CombSubFast: blocks of frames that continue one another.
+
+The reference GUI (gui.py:373-388) re-synthesises its whole window -- the new block plus crossfade and
+`extra_time` context -- from phase 0 on every block and hides the phase jump with a SOLA splice
+(gui.py:408-426).  Here the synthesizer carries its state instead:
+
+* the fp64 phase prefix of stage A (`ddsp_b200_phase_stream`), so the comb never jumps;
+* the last `CONTEXT` = 3 frames of f0 and control rows, which are synthesised again at the head of the
+  next block, because output hop h is final only once frames h .. h+2 are known (hop h overlap-adds
+  STFT frames h and h+1, frame h+1 spans excitation hops h and h+1, and hop h+1 interpolates f0 towards
+  frame h+2): every push of k frames returns k finished hops, `LATENCY` = 2 hops (23 ms) behind its input;
+* the hop index of the in-kernel noise (`ddsp_b200_combsubfast_stream`), so re-synthesised hops get the
+  same noise.
+
+What comes out is the signal ONE call over all frames pushed so far would have produced -- same phase,
+same excitation, same noise; equal to the last fp32 ulp or two (measured 7e-8) rather than bitwise, because
+the inverse FFT handles STFT frames in pairs and which frames share a pair depends on the parity of a
+block's first frame (tests/test_gpu_stream.py); `flush()` hands out the last two hops with the
+reference's hold-last ending.
+Only CombSubFast streams: the `frequency_filter` models need an (L-1)-sample tail per filter as well.
+"""
+import torch
+
+from . import core
+
+CONTEXT = 3        # frames re-synthesised at the head of every block
+LATENCY = 2        # hops between the newest frame pushed and the newest hop returned
+
+
+class CombSubFastStream:
+    """Stage-level stream (control rows in, samples out) for `B` parallel clips.
+
+        ph = stream.begin(f0_new)                      # (B,k) phase of the new frames, input of the control network
+        audio = stream.finish(hm, hp, nm)              # (B, 512*n) finished samples, n = k (k-2 on the first push)
+        audio = stream.push(hm, hp, nm, f0_new)        # both steps, when the rows do not depend on the phase
+        tail = stream.flush()                          # the last 2 hops; the stream is reset afterwards
+    """
+
+    def __init__(self, block_size=512, sampling_rate=44100, window=None, seed=0, initial_phase=None):
+        self.hop = int(block_size)
+        self.sr = float(sampling_rate)
+        self.window = window
+        self.seed = int(seed)
+        self.initial_phase = initial_phase
+        self.reset()
+
+    def reset(self):
+        self.frames_pushed = 0          # frames handed to finish() so far
+        self.hops_emitted = 0
+        self._f0_tail = None            # (B,t) f0 of the last t <= CONTEXT frames
+        self._rows_tail = None          # (B,t,3*(hop+1)) their control rows
+        self._noise_tail = None         # (B,t*hop) their injected noise, parity mode only
+        self._carry = None              # (B,) fp64 view: prefix at the first tail frame
+        self._pending = None            # state of a begin() waiting for its finish()
+        self._last_tail = None          # (B,2*hop) hold-last ending of the newest block, for flush()
+
+    # ---------------------------------------------------------------------------------------------
+    def begin(self, f0_new):
+        """Stage A for the k new frames `f0_new` (B,k) or (B,k,1).  Returns their frame-rate phase (B,k) --
+        the `phase_frames` input of Unit2Control (vocoder.py:451,454)."""
+        f0_new = core._f0_2d(core.as_f32(f0_new))
+        if f0_new.shape[1] < 1:
+            raise ValueError('begin() needs at least one new frame')
+        t = 0 if self._f0_tail is None else self._f0_tail.shape[1]
+        if t and self._f0_tail.shape[0] != f0_new.shape[0]:
+            raise ValueError('the number of clips must not change inside a stream (reset() first)')
+        f0_win = f0_new.contiguous() if t == 0 else torch.cat((self._f0_tail, f0_new), dim=1)
+        phase_win, prefix = core.phase_stage_stream(f0_win, self.hop, self.sr, carry=self._carry,
+                                                    initial_phase=self.initial_phase if self._carry is None else None)
+        self._pending = (f0_win, prefix, t)
+        return phase_win[:, t:]
+
+    def finish(self, harmonic_magnitude, harmonic_phase, noise_magnitude, noise_u=None):
+        """Stage B for the frames given to `begin`: control rows (B,k,513) each (any strides) and, in parity
+        mode, their noise (B,k*512).  Returns the finished samples (B, 512*n)."""
+        if self._pending is None:
+            raise RuntimeError('finish() without begin()')
+        f0_win, prefix, t = self._pending
+        B, W = f0_win.shape
+        k = W - t
+        K = self.hop + 1
+        rows = (harmonic_magnitude, harmonic_phase, noise_magnitude)
+        for r in rows:
+            if tuple(r.shape) != (B, k, K):
+                raise ValueError(f'control rows must be (B, {k}, {K}); got {tuple(r.shape)}')
+        rows_win = torch.empty((B, W, 3 * K), dtype=torch.float32, device=f0_win.device)
+        if t:
+            rows_win[:, :t] = self._rows_tail
+        for i, r in enumerate(rows):
+            rows_win[:, t:, i * K:(i + 1) * K] = core.as_f32(r)
+        if (noise_u is None) != (self._noise_tail is None) and t:
+            raise ValueError('either every block of a stream injects noise_u or none does')
+        noise_win = None
+        if noise_u is not None:
+            noise_u = core._need_cuda_f32(noise_u, 'noise_u')
+            if tuple(noise_u.shape) != (B, k * self.hop):
+                raise ValueError('noise_u must be (B, k*block_size)')
+            noise_win = noise_u.contiguous() if t == 0 else torch.cat((self._noise_tail, noise_u), dim=1)
+        hm, hp, nm = torch.split(rows_win, K, dim=-1)
+        first_hop = self.frames_pushed - t                 # stream index of the window's first hop
+        signal = core.combsubfast_stage(hm, hp, nm, f0_win, prefix, self.hop, self.sr, noise_u=noise_win,
+                                        seed=self.seed, window=self.window, hop_offset=first_hop)
+        # hop j of the window is final for j <= W-3 (and for j >= 1 unless the window starts the stream: lo is
+        # 1 in the steady state, 0 while the window still begins at frame 0)
+        lo = self.hops_emitted - first_hop
+        hi = max(lo, W - LATENCY)
+        out = signal[:, lo * self.hop:hi * self.hop]
+        self._last_tail = signal[:, hi * self.hop:]
+        # state for the next block: its window starts at frame W - CONTEXT of this one
+        keep = min(CONTEXT, W)
+        self._f0_tail = f0_win[:, W - keep:]
+        self._rows_tail = rows_win[:, W - keep:]
+        self._noise_tail = None if noise_win is None else noise_win[:, (W - keep) * self.hop:]
+        self._carry = prefix[:, W - keep]
+        self.frames_pushed += k
+        self.hops_emitted += hi - lo
+        self._pending = None
+        return out
+
+    def push(self, harmonic_magnitude, harmonic_phase, noise_magnitude, f0_new, noise_u=None):
+        self.begin(f0_new)
+        return self.finish(harmonic_magnitude, harmonic_phase, noise_magnitude, noise_u=noise_u)
+
+    def flush(self):
+        """The hops still held back (at most LATENCY), ending the way one call over all pushed frames ends
+        (f0 and control rows held after the last frame, core.py:17 / vocoder.py:470-474).  Resets the stream."""
+        if self._last_tail is None:
+            raise RuntimeError('flush() on an empty stream')
+        out = self._last_tail
+        self.reset()
+        return out
+
+
+class StreamingCombSubFast:
+    """Module-level stream around a `ddsp_b200.vocoder.CombSubFast` (or any module with its `unit2ctrl`,
+    `window`, `_hop`, `_sr`):
+
+        audio, phase = s.push(units, f0, volume, spk_id, n_context=c)
+
+    `units` (B,c+k,n_unit), `f0`, `volume` (B,c+k,1): the k new frames preceded by c frames that were
+    pushed before and are repeated only as left context for the (non-causal) control network -- what
+    `extra_time` is for in gui.py:373-388.  The network runs over all c+k frames, the synthesizer only
+    continues with the rows of the k new ones.  c may be 0 and must not exceed `history` (frames of
+    phase kept) or the frames pushed so far."""
+
+    def __init__(self, model, history=256, seed=None, initial_phase=None):
+        self.model = model
+        self.history = int(history)
+        self.stream = CombSubFastStream(model._hop, model._sr, window=model.window,
+                                        seed=model._next_seed() if seed is None else seed,
+                                        initial_phase=initial_phase)
+        self._phase_hist = None
+
+    def reset(self):
+        self.stream.reset()
+        self._phase_hist = None
+
+    @torch.no_grad()
+    def push(self, units_frames, f0_frames, volume_frames, spk_id=None, spk_mix_dict=None, n_context=0, noise_u=None):
+        c = int(n_context)
+        f0_frames = core.as_f32(f0_frames)
+        have = 0 if self._phase_hist is None else self._phase_hist.shape[1]
+        if c < 0 or c > have or c >= f0_frames.shape[1]:
+            raise ValueError(f'n_context={c}: only {have} frames of history are kept and at least one frame must be new')
+        f0_2d = core._f0_2d(f0_frames)
+        phase_new = self.stream.begin(f0_2d[:, c:])
+        phase_win = phase_new if c == 0 else torch.cat((self._phase_hist[:, have - c:], phase_new), dim=1)
+        ctrls = self.model.unit2ctrl(units_frames, f0_frames, phase_win, volume_frames, spk_id, spk_mix_dict=spk_mix_dict)
+        audio = self.stream.finish(ctrls['harmonic_magnitude'][:, c:], ctrls['harmonic_phase'][:, c:],
+                                   ctrls['noise_magnitude'][:, c:], noise_u=noise_u)
+        hist = phase_new if self._phase_hist is None else torch.cat((self._phase_hist, phase_new), dim=1)
+        self._phase_hist = hist[:, -self.history:]
+        return audio, phase_new.unsqueeze(-1)
+
+    def flush(self):
+        out = self.stream.flush()
+        self._phase_hist = None
+        return out

@@ -126,6 +126,33 @@ int ddsp_b200_combsubfast(const float *harmonic_magnitude, const float *harmonic
                           void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Streaming forms of the two calls above: a block of frames that CONTINUES a
+ * stream instead of starting at phase 0 -- what gui.py:373-388 emulates by re-synthesising its
+ * whole window every block and splicing with SOLA (gui.py:408-426).
+ *   ddsp_b200_phase_stream: `carry` points at the fp64 prefix the stream reached at this block's
+ *     first frame (element b at carry[b*carry_stride]; typically a column of the previous block's
+ *     `prefix` output, which must not be the same buffer as this call's) or NULL at stream start
+ *     (then initial_phase applies as in core.py:44-45).
+ *   ddsp_b200_combsubfast_stream: `hop_offset` = stream index of this block's first hop; it only
+ *     shifts the in-kernel noise stream (ignored with an injected noise_u) so that a hop that is
+ *     synthesised again as context of the next block gets the same noise.
+ * A stream of blocks, each overlapping its predecessor by 3 frames and keeping hops 1..F-3 of
+ * every block, equals one call over the concatenated frames to the last fp32 ulp or two (same
+ * phase, excitation and noise; the pair-packed inverse FFT rounds differently when a block starts
+ * on an odd frame) -- tests/test_gpu_stream.py; the host side of that bookkeeping is
+ * ddsp_b200.streaming.
+ * ---------------------------------------------------------------------------------------- */
+int ddsp_b200_phase_stream(const float *f0_frames, int64_t fB, int64_t fF, int B, int F, int hop,
+                           double sr, const float *initial_phase, const double *carry,
+                           int64_t carry_stride, float *phase_frames, double *prefix, void *stream);
+int ddsp_b200_combsubfast_stream(const float *harmonic_magnitude, const float *harmonic_phase,
+                                 const float *noise_magnitude, int64_t cB, int64_t cF,
+                                 const float *f0_frames, int64_t fB, int64_t fF, const double *prefix,
+                                 const float *noise_u, uint64_t seed, int64_t hop_offset,
+                                 const float *window, int B, int F, int hop, double sr, float *signal,
+                                 void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Gradient of stage B of CombSubFast.forward with respect to the three control tensors -- what
  * autograd derives for vocoder.py:455-492 when the module is trained (solver.py:111,113).
  * Inputs are those of the forward call (same noise_u or seed, same window, same prefix) plus
