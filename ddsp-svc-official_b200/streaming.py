@@ -47,24 +47,49 @@ class CombSubFastStream:
     def reset(self):
         self.frames_pushed = 0          # frames handed to finish() so far
         self.hops_emitted = 0
-        self._f0_tail = None            # (B,t) f0 of the last t <= CONTEXT frames
-        self._rows_tail = None          # (B,t,3*(hop+1)) their control rows
-        self._noise_tail = None         # (B,t*hop) their injected noise, parity mode only
+        # f0 and control rows of the stream live in one linear device buffer each; the window of a block is
+        # the slice [end - t, end + k): its t <= CONTEXT tail frames are already in place, so a push costs one
+        # copy of the new f0 and one of the new rows (no concatenation).  When the buffer is full the tail
+        # moves back to the front.
+        self._f0_buf = None             # (B,cap)
+        self._rows_buf = None           # (B,cap,3*(hop+1))
+        self._end = 0                   # frames of the buffer in use
+        self._t = 0                     # tail frames (<= CONTEXT) ending at _end
+        self._noise_tail = None         # (B,t*hop) injected noise of the tail, parity mode only
         self._carry = None              # (B,) fp64 view: prefix at the first tail frame
         self._pending = None            # state of a begin() waiting for its finish()
         self._last_tail = None          # (B,2*hop) hold-last ending of the newest block, for flush()
+
+    def _room(self, B, k, device):
+        """Make sure k more frames fit behind the tail."""
+        t, K3 = self._t, 3 * (self.hop + 1)
+        if self._f0_buf is not None and self._f0_buf.shape[0] != B:
+            raise ValueError('the number of clips must not change inside a stream (reset() first)')
+        if self._f0_buf is not None and self._end + k <= self._f0_buf.shape[1]:
+            return
+        cap = max(64, 4 * (k + CONTEXT))
+        if self._f0_buf is not None and t + k <= self._f0_buf.shape[1] and self._end - t >= t:
+            f0_buf, rows_buf = self._f0_buf, self._rows_buf            # same buffers, tail back to the front
+        else:
+            f0_buf = torch.empty((B, cap), dtype=torch.float32, device=device)
+            rows_buf = torch.empty((B, cap, K3), dtype=torch.float32, device=device)
+        if t:
+            f0_buf[:, :t] = self._f0_buf[:, self._end - t:self._end]
+            rows_buf[:, :t] = self._rows_buf[:, self._end - t:self._end]
+        self._f0_buf, self._rows_buf, self._end = f0_buf, rows_buf, t
 
     # ---------------------------------------------------------------------------------------------
     def begin(self, f0_new):
         """Stage A for the k new frames `f0_new` (B,k) or (B,k,1).  Returns their frame-rate phase (B,k) --
         the `phase_frames` input of Unit2Control (vocoder.py:451,454)."""
         f0_new = core._f0_2d(core.as_f32(f0_new))
-        if f0_new.shape[1] < 1:
+        B, k = f0_new.shape
+        if k < 1:
             raise ValueError('begin() needs at least one new frame')
-        t = 0 if self._f0_tail is None else self._f0_tail.shape[1]
-        if t and self._f0_tail.shape[0] != f0_new.shape[0]:
-            raise ValueError('the number of clips must not change inside a stream (reset() first)')
-        f0_win = f0_new.contiguous() if t == 0 else torch.cat((self._f0_tail, f0_new), dim=1)
+        self._room(B, k, f0_new.device)
+        t, end = self._t, self._end
+        self._f0_buf[:, end:end + k] = f0_new
+        f0_win = self._f0_buf[:, end - t:end + k]
         phase_win, prefix = core.phase_stage_stream(f0_win, self.hop, self.sr, carry=self._carry,
                                                     initial_phase=self.initial_phase if self._carry is None else None)
         self._pending = (f0_win, prefix, t)
@@ -83,11 +108,17 @@ class CombSubFastStream:
         for r in rows:
             if tuple(r.shape) != (B, k, K):
                 raise ValueError(f'control rows must be (B, {k}, {K}); got {tuple(r.shape)}')
-        rows_win = torch.empty((B, W, 3 * K), dtype=torch.float32, device=f0_win.device)
-        if t:
-            rows_win[:, :t] = self._rows_tail
-        for i, r in enumerate(rows):
-            rows_win[:, t:, i * K:(i + 1) * K] = core.as_f32(r)
+        end = self._end
+        dst = self._rows_buf[:, end:end + k]
+        hm_, hp_, nm_ = rows
+        if (all(r.dtype == torch.float32 and r.is_cuda for r in rows) and hm_.stride() == hp_.stride() == nm_.stride() and hm_.stride(2) == 1
+                and hp_.data_ptr() - hm_.data_ptr() == 4 * K and nm_.data_ptr() - hp_.data_ptr() == 4 * K):
+            # the usual case: the three tensors are the split views of one (B,k,1539) tensor -> one copy
+            dst.copy_(hm_.as_strided((B, k, 3 * K), hm_.stride()))
+        else:
+            for i, r in enumerate(rows):
+                dst[:, :, i * K:(i + 1) * K] = core.as_f32(r)
+        rows_win = self._rows_buf[:, end - t:end + k]
         if (noise_u is None) != (self._noise_tail is None) and t:
             raise ValueError('either every block of a stream injects noise_u or none does')
         noise_win = None
@@ -108,8 +139,8 @@ class CombSubFastStream:
         self._last_tail = signal[:, hi * self.hop:]
         # state for the next block: its window starts at frame W - CONTEXT of this one
         keep = min(CONTEXT, W)
-        self._f0_tail = f0_win[:, W - keep:]
-        self._rows_tail = rows_win[:, W - keep:]
+        self._end = end + k
+        self._t = keep
         self._noise_tail = None if noise_win is None else noise_win[:, (W - keep) * self.hop:]
         self._carry = prefix[:, W - keep]
         self.frames_pushed += k
