@@ -321,17 +321,23 @@ def run_ours(args, rank, local_rank, world):
     e2e_steps = max(2, min(args.steps, 10))
     e2e_run(2, 0)
     torch.cuda.synchronize()
-    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.cuda.stream(s_in):
-        x0.record()
-    e2e_run(e2e_steps, 2000)
-    with torch.cuda.stream(s_out):
-        s_out.wait_stream(s_in)
-        s_out.wait_stream(s_cp)
-        x1.record()
-    barrier()
-    e2e_ms = x0.elapsed_time(x1)
+    # The leg is PCIe / host-memory bound and the host is shared with other tenants (one earlier run measured
+    # 12.8 instead of 6.6 ms/step on an otherwise identical box), so it is repeated three times and the
+    # fastest repeat is reported; all three are listed in the JSON line.
+    e2e_all = []
+    for rep in range(3):
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(s_in):
+            x0.record()
+        e2e_run(e2e_steps, 2000 + 100 * rep)
+        with torch.cuda.stream(s_out):
+            s_out.wait_stream(s_in)
+            s_out.wait_stream(s_cp)
+            x1.record()
+        barrier()
+        e2e_all.append(x0.elapsed_time(x1))
+    e2e_ms = min(e2e_all)
 
     # ---- reduce over ranks: max time, sum of samples ----------------------------------------
     t = torch.tensor([elapsed_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
@@ -362,8 +368,9 @@ def run_ours(args, rank, local_rank, world):
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': e2e_ms / e2e_steps,
                     'h2d_bytes_per_step': int(h_ctrl.numel() * 4 + h_f0.numel() * 4 + (h_u.numel() * 4 if h_u is not None else 0)),
                     'd2h_bytes_per_step': int(h_out.numel() * 4), 'steps': e2e_steps,
+                    'repeats_ms_per_step': [x / e2e_steps for x in e2e_all],
                     'how': 'pinned host buffers -> H2D -> stage A + stage B through the C ABI -> D2H; '
-                           'copies and compute of consecutive steps overlap on three streams'},
+                           'copies and compute of consecutive steps overlap on three streams; fastest of 3 repeats (this rank)'},
             'gpu_launches': launches, 'clocks': clocks,
         }
         if args.torch_port and model == 'combsubfast':
