@@ -535,6 +535,26 @@ def run_forward(args):
                 a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(); g.replay(); b_.record(); b_.synchronize()
                 ts.append(a.elapsed_time(b_))
+            # the public wrapper a caller uses (input copies + replay + output clone), host wall clock incl. the sync,
+            # next to the same call made eagerly
+            wall_graphed, wall_eager = None, None
+            if B == 1:
+                fast = vocoder.GraphedForward(model)
+                fast(units, f0, vol, spk)
+                torch.cuda.synchronize()
+                wg, we = [], []
+                for _ in range(iters):
+                    t0 = time.perf_counter()
+                    fast(units, f0, vol, spk)[0]
+                    torch.cuda.synchronize()
+                    wg.append((time.perf_counter() - t0) * 1e3)
+                for _ in range(iters):
+                    t0 = time.perf_counter()
+                    model(units, f0, vol, spk)[0]
+                    torch.cuda.synchronize()
+                    we.append((time.perf_counter() - t0) * 1e3)
+                wall_graphed = [float(np.percentile(wg, 50)), float(np.percentile(wg, 99))]
+                wall_eager = [float(np.percentile(we, 50)), float(np.percentile(we, 99))]
             tf32_ms = None
             if hasattr(model.unit2ctrl, 'matmul_tf32'):      # opt-in TF32 GEMMs in the control network
                 model.unit2ctrl.matmul_tf32 = True
@@ -550,7 +570,8 @@ def run_forward(args):
                 model.unit2ctrl.matmul_tf32 = False
         rows.append({'clips': B, 'frames': F, 'eager_ms': eager_ms, 'graph_ms_p50': float(np.percentile(ts, 50)),
                      'graph_ms_p99': float(np.percentile(ts, 99)), 'samples_per_s_graph': B * F * HOP / (np.percentile(ts, 50) * 1e-3),
-                     'eager_ms_tf32_gemm_opt_in': tf32_ms})
+                     'eager_ms_tf32_gemm_opt_in': tf32_ms, 'graphed_forward_wall_ms_p50_p99': wall_graphed,
+                     'eager_forward_wall_ms_p50_p99': wall_eager})
     print(json.dumps({'metric': 'full forward (stage A + PyTorch Unit2Control + stage B)', 'model': 'combsubfast',
                       'rows': rows}), flush=True)
 

@@ -32,8 +32,8 @@ _PROTOS = {
     'ddsp_b200_phase_stream': (C.c_int, [c_f32p, i64, i64, C.c_int, C.c_int, C.c_int, C.c_double, c_f32p, C.c_void_p, i64,
                                          c_f32p, C.c_void_p, C.c_void_p]),
     'ddsp_b200_combsubfast_stream': (C.c_int, [c_f32p, c_f32p, c_f32p, i64, i64, c_f32p, i64, i64, C.c_void_p, c_f32p,
-                                               u64, i64, c_f32p, C.c_int, C.c_int, C.c_int, C.c_double, c_f32p,
-                                               C.c_void_p]),
+                                               u64, C.c_void_p, i64, c_f32p, C.c_int, C.c_int, C.c_int, C.c_double,
+                                               c_f32p, C.c_void_p]),
     'ddsp_b200_combsubfast_backward': (C.c_int, [c_f32p, c_f32p, c_f32p, i64, i64, c_f32p, i64, i64, C.c_void_p,
                                                  c_f32p, u64, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_double,
                                                  c_f32p, c_f32p, c_f32p, i64, i64, C.c_void_p]),

@@ -183,9 +183,12 @@ def _common_views(tensors, names):
 
 
 def combsubfast_stage(harmonic_magnitude, harmonic_phase, noise_magnitude, f0_frames, prefix, block_size,
-                      sampling_rate, initial_phase=None, noise_u=None, seed=0, window=None, out=None, hop_offset=None):
+                      sampling_rate, initial_phase=None, noise_u=None, seed=0, window=None, out=None, hop_offset=None,
+                      seed_device=None):
     """Stage B of CombSubFast.forward (vocoder.py:455-492) -> signal (B,T).
-    `hop_offset` (streaming only): stream index of this block's first hop, see `phase_stage_stream`."""
+    `hop_offset` (streaming only): stream index of this block's first hop, see `phase_stage_stream`.
+    `seed_device` (CUDA graphs only): one-element int64 CUDA tensor added to `seed` on the device when the
+    kernel starts, so that a captured call draws fresh in-kernel noise on every replay."""
     hm, hp, nm = _common_views((harmonic_magnitude, harmonic_phase, noise_magnitude),
                                ('harmonic_magnitude', 'harmonic_phase', 'noise_magnitude'))
     f0 = _f0_2d(f0_frames)
@@ -207,7 +210,10 @@ def combsubfast_stage(harmonic_magnitude, harmonic_phase, noise_magnitude, f0_fr
     ip = _init_phase(initial_phase, B, dev)
     signal = out if out is not None else torch.empty((B, T), dtype=torch.float32, device=dev)
     with _OnDevice(dev) as _st:
-        if hop_offset is None:
+        if seed_device is not None and (not seed_device.is_cuda or seed_device.dtype != torch.int64
+                                        or seed_device.numel() != 1):
+            raise ValueError('seed_device must be a one-element int64 CUDA tensor')
+        if hop_offset is None and seed_device is None:
             _cabi.check(_cabi.lib().ddsp_b200_combsubfast(
                 hm.data_ptr(), hp.data_ptr(), nm.data_ptr(), hm.stride(0), hm.stride(1), f0.data_ptr(), f0.stride(0),
                 f0.stride(1), prefix.data_ptr(), _ptr(ip), _ptr(noise_u), int(seed) % _TWO62, _ptr(window), B, F, hop,
@@ -215,8 +221,8 @@ def combsubfast_stage(harmonic_magnitude, harmonic_phase, noise_magnitude, f0_fr
         else:
             _cabi.check(_cabi.lib().ddsp_b200_combsubfast_stream(
                 hm.data_ptr(), hp.data_ptr(), nm.data_ptr(), hm.stride(0), hm.stride(1), f0.data_ptr(), f0.stride(0),
-                f0.stride(1), prefix.data_ptr(), _ptr(noise_u), int(seed) % _TWO62, int(hop_offset), _ptr(window), B, F,
-                hop, float(sampling_rate), signal.data_ptr(), _st))
+                f0.stride(1), prefix.data_ptr(), _ptr(noise_u), int(seed) % _TWO62, _ptr(seed_device),
+                int(hop_offset or 0), _ptr(window), B, F, hop, float(sampling_rate), signal.data_ptr(), _st))
     return signal
 
 

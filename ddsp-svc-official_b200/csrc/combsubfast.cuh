@@ -42,6 +42,7 @@ struct CsfParams {
     const float* tables;                                  // device tables (twiddles + exact window)
     float* signal;                                        // (B,T)
     uint64_t seed;
+    const uint64_t* seed_device;                          // optional: added to `seed` when the kernel starts (CUDA graphs)
     uint32_t key_offset;                                  // streaming: noise key shift of hop_offset hops (0 otherwise)
     int B, F;
     // run partition: run r of a clip owns pairs [r*run_len + min(r,run_rem), ... + run_len + (r < run_rem));
@@ -201,7 +202,8 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             ctx[0] = b0;
             ctx[1] = pb;                                        // p_begin
             ctx[2] = pb + P.run_len + (r < P.run_rem ? 1 : 0);  // p_end
-            ctx[3] = (int)(noise_key(P.seed, (uint32_t)b0) + P.key_offset);
+            const uint64_t seed = P.seed + (P.seed_device ? __ldg(P.seed_device) : 0ull);
+            ctx[3] = (int)(noise_key(seed, (uint32_t)b0) + P.key_offset);
         }
         __syncwarp();
     }

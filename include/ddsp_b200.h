@@ -135,7 +135,10 @@ int ddsp_b200_combsubfast(const float *harmonic_magnitude, const float *harmonic
  *     (then initial_phase applies as in core.py:44-45).
  *   ddsp_b200_combsubfast_stream: `hop_offset` = stream index of this block's first hop; it only
  *     shifts the in-kernel noise stream (ignored with an injected noise_u) so that a hop that is
- *     synthesised again as context of the next block gets the same noise.
+ *     synthesised again as context of the next block gets the same noise.  `seed_device`: optional
+ *     (NULL) device pointer to one uint64 that is added to `seed` when the kernel starts, so a call
+ *     captured in a CUDA graph draws fresh noise on every replay (the caller bumps the counter
+ *     inside the graph).
  * A stream of blocks, each overlapping its predecessor by 3 frames and keeping hops 1..F-3 of
  * every block, equals one call over the concatenated frames to the last fp32 ulp or two (same
  * phase, excitation and noise; the pair-packed inverse FFT rounds differently when a block starts
@@ -148,9 +151,9 @@ int ddsp_b200_phase_stream(const float *f0_frames, int64_t fB, int64_t fF, int B
 int ddsp_b200_combsubfast_stream(const float *harmonic_magnitude, const float *harmonic_phase,
                                  const float *noise_magnitude, int64_t cB, int64_t cF,
                                  const float *f0_frames, int64_t fB, int64_t fF, const double *prefix,
-                                 const float *noise_u, uint64_t seed, int64_t hop_offset,
-                                 const float *window, int B, int F, int hop, double sr, float *signal,
-                                 void *stream);
+                                 const float *noise_u, uint64_t seed, const uint64_t *seed_device,
+                                 int64_t hop_offset, const float *window, int B, int F, int hop,
+                                 double sr, float *signal, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Gradient of stage B of CombSubFast.forward with respect to the three control tensors -- what
