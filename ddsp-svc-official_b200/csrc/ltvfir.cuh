@@ -516,23 +516,26 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                 const float2* zh = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2;   // last IR repeated (core.py:228)
                 const float2 wl = make_float2(tw4[lane].y, tw4[lane].w);        // W1024^lane = (cos, -sin)
                 float zr[32], zi[32];
+                // Ey and Oy are spectra of REAL sequences (the even / odd output samples), so
+                //   Zy[1024-k] = conj(Ey[k]) + j conj(Oy[k]):
+                // only bins k <= 512 are multiplied out (registers q = 0..15 of every lane hold k = lane + 32 q
+                // < 512; bin 512 is lane 0's register 16), the upper half arrives by one conjugate-pair exchange
+                // (bin 1024-k lives in lane 32-l, register 31-q; lane 0: its own register 32-q).
+                float pr[17], pi[17];                     // (Re, Im) of Zy[1024-k] for this lane's k = lane + 32 q
                 // tap-spectrum loads run kLook bins ahead of their use (software pipeline over the unrolled loop)
-                constexpr int kLook = 6;
+                constexpr int kLook = 4;
                 float2 zkq[kLook], zpq[kLook];
 #pragma unroll
-                for (int qq = 0; qq < kLook; ++qq) {
-                    const int q = (qq & 1) ? 31 - (qq >> 1) : (qq >> 1);
-                    zkq[qq] = __ldg(zh + lane + 32 * q);
-                    zpq[qq] = __ldg(zh + ((1024 - (lane + 32 * q)) & 1023));
+                for (int q = 0; q < kLook; ++q) {
+                    zkq[q] = __ldg(zh + lane + 32 * q);
+                    zpq[q] = __ldg(zh + ((1024 - (lane + 32 * q)) & 1023));
                 }
 #pragma unroll
-                for (int qq = 0; qq < 32; ++qq) {
-                    const int q = (qq & 1) ? 31 - (qq >> 1) : (qq >> 1);   // 0,31,1,30,...: registers die in pairs
-                    const float2 zk = zkq[qq % kLook], zp = zpq[qq % kLook];
-                    if (qq + kLook < 32) {
-                        const int qn = ((qq + kLook) & 1) ? 31 - ((qq + kLook) >> 1) : ((qq + kLook) >> 1);
-                        zkq[qq % kLook] = __ldg(zh + lane + 32 * qn);
-                        zpq[qq % kLook] = __ldg(zh + ((1024 - (lane + 32 * qn)) & 1023));
+                for (int q = 0; q < 17; ++q) {            // q = 16: bin 512, meaningful on lane 0 only (others: in-bounds dummies)
+                    const float2 zk = zkq[q % kLook], zp = zpq[q % kLook];
+                    if (q + kLook < 17) {
+                        zkq[q % kLook] = __ldg(zh + lane + 32 * (q + kLook));
+                        zpq[q % kLook] = __ldg(zh + ((1024 - (lane + 32 * (q + kLook))) & 1023));
                     }
                     float cr, ci;
                     LTV_PARTNER(X, q, cr, ci);
@@ -550,6 +553,19 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                     const float oyi = (Ear * Ohi + Eai * Ohr) + (Oar * Ehi + Oai * Ehr);
                     zr[q] = eyr - oyi;          // Ey + j Oy
                     zi[q] = eyi + oyr;
+                    pr[q] = eyr + oyi;          // conj(Ey) + j conj(Oy)
+                    pi[q] = oyr - eyi;
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float tr = __shfl_sync(kFullMask, pr[q], partner);
+                    const float ti = __shfl_sync(kFullMask, pi[q], partner);
+                    // lane 0: register 31-q holds bin 32 (31-q) = 1024 - 32 (q+1), the partner of its own bin q+1;
+                    // register 16 (q = 15) is bin 512 itself
+                    const float r0 = (q < 15) ? pr[q + 1] : zr[16];
+                    const float i0 = (q < 15) ? pi[q + 1] : zi[16];
+                    if (q < 15) { zr[31 - q] = lane0 ? r0 : tr; zi[31 - q] = lane0 ? i0 : ti; }
+                    else { zr[16] = lane0 ? r0 : tr; zi[16] = lane0 ? i0 : ti; }
                 }
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
