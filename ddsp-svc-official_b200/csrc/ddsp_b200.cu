@@ -458,8 +458,11 @@ int launch_ltv_ir(const ddsp::LtvParams& P, cudaStream_t st) {
 // 2) framing + convolution + overlap-add
 int launch_ltv_conv(const ddsp::LtvParams& P, cudaStream_t st) {
     if (P.runs_per_clip > 1) {
-        CUDA_TRY(cudaMemsetAsync(P.out, 0, (size_t)P.B * P.F * ddsp::kHop * sizeof(float), st));
-        ++g_launches;
+        // only the hops at run seams are accumulated with atomics (2 hops for L = 510, 3 for L = 1022)
+        const int n_seams = P.B * (P.runs_per_clip - 1), hops = P.n_mag == 256 ? 2 : 3;
+        ddsp::ltv_zero_seams_kernel<<<(unsigned)(n_seams * hops), 128, 0, st>>>(P.out, P.F, P.run_len, P.runs_per_clip,
+                                                                               P.n_mag - 1, hops, n_seams);
+        LAUNCH_CHECK();
     }
     const int64_t runs = (int64_t)P.B * P.runs_per_clip;
     const unsigned grid = (unsigned)((runs + ddsp::kLtvWarps - 1) / ddsp::kLtvWarps);

@@ -633,6 +633,25 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
     }
 }
 
+// Zero the output samples that receive atomic adds from two neighbouring runs: the first `hops` hops a run
+// (other than the first of its clip) retires, i.e. samples [512 (m_begin - 1) - D, + 512 hops) with
+// m_begin = r * run_len.  Everything else is written with plain stores, so the rest of `out` needs no clearing.
+// One CTA of 128 threads per (seam, hop).
+__global__ void __launch_bounds__(128) ltv_zero_seams_kernel(float* __restrict__ out, int F, int run_len,
+                                                             int runs_per_clip, int D, int hops, int n_seams) {
+    const int seam = blockIdx.x / hops, c = blockIdx.x % hops;
+    if (seam >= n_seams) return;
+    const int b = seam / (runs_per_clip - 1), r = seam % (runs_per_clip - 1) + 1;
+    const int64_t T = (int64_t)F * kHop;
+    const int64_t t0 = (int64_t)(r * run_len - 1 + c) * kHop - D;
+    float* ob = out + (int64_t)b * T;
+#pragma unroll
+    for (int i = 0; i < kHop / 128; ++i) {
+        const int64_t t = t0 + threadIdx.x + 128 * i;
+        if (t >= 0 && t < T) ob[t] = 0.0f;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kernel 2b: the convolution for L = 510 filters (n_mag = 256: all-pass and noise filters).
 // The Bartlett-windowed 1024-sample frame is the sum of its rising half (samples of hop m-1) and
