@@ -430,7 +430,7 @@ int ltv_params(ddsp::LtvParams& P, const float* audio, int audio_mode, uint64_t 
     P.audio = audio; P.audio_mode = audio_mode; P.seed = seed;
     P.mags = mags; P.mB = mB; P.mF = mF; P.n_mag = n_mag; P.encoding = encoding; P.mag_scale = mag_scale;
     P.window_mode = window_mode; P.f0_frames = f0_frames; P.fB = fB; P.fF = fF; P.sr15 = (float)(1.5 * sr);
-    P.spec = (float2*)spec_ws; P.out = out; P.B = B; P.F = F;
+    P.spec = (float2*)spec_ws; P.out = out; P.add_in = nullptr; P.sum_out = nullptr; P.B = B; P.F = F;
     const int frames = F + 1;
     const int64_t slots = (int64_t)sm_count() * ddsp::kLtvWarps;
     int run_len = (int)(((int64_t)B * frames + slots - 1) / slots);
@@ -468,6 +468,12 @@ int launch_ltv_conv(const ddsp::LtvParams& P, cudaStream_t st) {
     const unsigned grid = (unsigned)((runs + ddsp::kLtvWarps - 1) / ddsp::kLtvWarps);
     ltv_conv_select(P.audio_mode, P.n_mag)<<<grid, ddsp::kLtvThreads, ddsp::kLtvConvSmemBytes, st>>>(P);
     LAUNCH_CHECK();
+    if (P.sum_out && P.runs_per_clip > 1) {
+        const int n_seams = P.B * (P.runs_per_clip - 1);
+        ddsp::ltv_sum_seams_kernel<<<(unsigned)(n_seams * 2), 128, 0, st>>>(P.out, P.add_in, P.sum_out, P.F, P.run_len,
+                                                                           P.runs_per_clip, P.n_mag - 1, 2, n_seams);
+        LAUNCH_CHECK();
+    }
     return DDSP_B200_OK;
 }
 
@@ -487,12 +493,14 @@ int launch_ltv(const float* audio, int audio_mode, uint64_t seed, const float* m
 int launch_allpass_and_noise(const float* allpass_in, float* allpass_out, const float* group_delay,
                              const float* noise_u, uint64_t seed, const float* noise_magnitude, int64_t cB, int64_t cF,
                              double sr, int B, int F, float* noise_out, void* spec_a, void* spec_n, cudaStream_t st,
-                             int (*between)(void*), void* between_arg) {
+                             int (*between)(void*), void* between_arg, const float* sum_in, float* sum_out) {
     ddsp::LtvParams Pa, Pn;
     if (int rc = ltv_params(Pa, allpass_in, 0, 0, group_delay, cB, cF, 256, DDSP_B200_MAG_ALLPASS_TANH, 1.0f,
                             DDSP_B200_WINDOW_NONE, nullptr, 0, 0, sr, B, F, allpass_out, spec_a, st)) return rc;
     if (int rc = ltv_params(Pn, noise_u, noise_u ? 1 : 2, seed, noise_magnitude, cB, cF, 256, DDSP_B200_MAG_EXP,
                             1.0f / 128.0f, DDSP_B200_WINDOW_HANN, nullptr, 0, 0, sr, B, F, noise_out, spec_n, st)) return rc;
+    // the noise convolution runs last and writes signal = sum_in + noise beside the noise itself (vocoder.py:421,548)
+    Pn.add_in = sum_in; Pn.sum_out = sum_out;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     ddsp::LtvDualParams D;
@@ -719,8 +727,10 @@ int ddsp_b200_combsub(const float* group_delay, int n_mag_allpass, const float* 
                               m->f0, m->fB, m->fF, m->sr, m->B, m->F, m->harmonic, m->spec, m->st);
         };
         if (int rc = launch_allpass_and_noise(comb, h1, group_delay, noise_u, seed, noise_magnitude, cB, cF, sr, B, F,
-                                              noise, spec, spec_n, st, between, &mid)) return rc;
+                                              noise, spec, spec_n, st, between, &mid, harmonic, signal)) return rc;
         launches += g_launches; g_launches = 0;
+        g_launches += launches;
+        return DDSP_B200_OK;
     } else {
         // :540  all-pass (group delay), no window
         if (int rc = launch_ltv(comb, 0, 0, group_delay, cB, cF, n_mag_allpass, DDSP_B200_MAG_ALLPASS_TANH, 1.0f,
@@ -773,8 +783,10 @@ int ddsp_b200_sins(const float* amplitudes, int n_harmonics, const float* group_
     if (n_mag_allpass == 256 && n_mag_noise == 256) {
         // :415 all-pass and :418-419 noise: impulse responses from one shared Bluestein pass
         if (int rc = launch_allpass_and_noise(sinus, harmonic, group_delay, noise_u, seed, noise_magnitude, cB, cF, sr, B,
-                                              F, noise, spec, spec_n, st, nullptr, nullptr)) return rc;
+                                              F, noise, spec, spec_n, st, nullptr, nullptr, harmonic, signal)) return rc;
         launches += g_launches; g_launches = 0;
+        g_launches += launches;
+        return DDSP_B200_OK;
     } else {
         // :415  all-pass
         if (int rc = launch_ltv(sinus, 0, 0, group_delay, cB, cF, n_mag_allpass, DDSP_B200_MAG_ALLPASS_TANH, 1.0f,

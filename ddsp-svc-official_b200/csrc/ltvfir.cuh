@@ -57,6 +57,7 @@ struct LtvParams {
     const float* chirp;                 // tables for this L
     float2* spec;                       // workspace (B,F,1024) complex: tap spectra
     float* out;                         // (B,T)
+    const float* add_in; float* sum_out; // optional (L = 510 convolution): sum_out = add_in + out (vocoder.py:421,548)
     int B, F, run_len, runs_per_clip;
 };
 
@@ -652,6 +653,23 @@ __global__ void __launch_bounds__(128) ltv_zero_seams_kernel(float* __restrict__
     }
 }
 
+// sum_out = add_in + out on the seam hops (same geometry as ltv_zero_seams_kernel), after the convolution
+// kernel: there `out` is complete only once both neighbouring runs have added their part.
+__global__ void __launch_bounds__(128) ltv_sum_seams_kernel(const float* __restrict__ out, const float* __restrict__ add_in,
+                                                            float* __restrict__ sum_out, int F, int run_len,
+                                                            int runs_per_clip, int D, int hops, int n_seams) {
+    const int seam = blockIdx.x / hops, c = blockIdx.x % hops;
+    if (seam >= n_seams) return;
+    const int b = seam / (runs_per_clip - 1), r = seam % (runs_per_clip - 1) + 1;
+    const int64_t T = (int64_t)F * kHop;
+    const int64_t t0 = (int64_t)(r * run_len - 1 + c) * kHop - D;
+#pragma unroll
+    for (int i = 0; i < kHop / 128; ++i) {
+        const int64_t t = t0 + threadIdx.x + 128 * i;
+        if (t >= 0 && t < T) sum_out[(int64_t)b * T + t] = __fadd_rn(add_in[(int64_t)b * T + t], out[(int64_t)b * T + t]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kernel 2b: the convolution for L = 510 filters (n_mag = 256: all-pass and noise filters).
 // The Bartlett-windowed 1024-sample frame is the sum of its rising half (samples of hop m-1) and
@@ -781,10 +799,26 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
                 const bool complete = (m - 2 >= m_begin) || (m_begin == 0);
                 float* ob = P.out + (int64_t)CV_B * T;
                 const int64_t tb = t0 - D;
+                // finished samples also go out as sum_out = add_in + out when the caller asked for it (the models'
+                // signal = harmonic + noise); seam hops are summed by ltv_sum_seams_kernel after both runs added theirs
+                const float* ai = P.sum_out ? P.add_in + (int64_t)CV_B * T : nullptr;
+                float* so = P.sum_out ? P.sum_out + (int64_t)CV_B * T : nullptr;
                 if (complete && tb >= 0 && tb + kHop <= T) {       // the common case: a whole finished hop inside the clip
                     float* dst = ob + tb + lane;
+                    if (so) {
+                        float hv[16];
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) dst[32 * r] = blk0[32 * r];
+                        for (int r = 0; r < 16; ++r) hv[r] = __ldg(ai + tb + lane + 32 * r);
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            const float v = blk0[32 * r];
+                            dst[32 * r] = v;
+                            so[tb + lane + 32 * r] = __fadd_rn(hv[r], v);
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) dst[32 * r] = blk0[32 * r];
+                    }
                 } else {
 #pragma unroll
                     for (int r = 0; r < 16; ++r) {
@@ -792,7 +826,8 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
                         const int64_t t = tb + j;
                         if (t >= 0 && t < T) {
                             const float v = blk0[32 * r];
-                            if (complete) ob[t] = v; else atomicAdd(ob + t, v);
+                            if (complete) { ob[t] = v; if (so) so[t] = __fadd_rn(__ldg(ai + t), v); }
+                            else atomicAdd(ob + t, v);
                         }
                     }
                 }
@@ -814,7 +849,10 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
                 const int64_t t = tb + j;
                 if (t >= 0 && t < T) {
                     const float v = ring[(rs + j) & (kLtvRing - 1)];
-                    if (complete) ob[t] = v; else atomicAdd(ob + t, v);
+                    if (complete) {
+                        ob[t] = v;
+                        if (P.sum_out) P.sum_out[(int64_t)CV_B * T + t] = __fadd_rn(__ldg(P.add_in + (int64_t)CV_B * T + t), v);
+                    } else atomicAdd(ob + t, v);
                 }
             }
         }
