@@ -775,7 +775,7 @@ int ddsp_b200_sins(const float* amplitudes, int n_harmonics, const float* group_
     void* spec = (void*)(sinus + n);
     int launches = 0;
     // vocoder.py:397,402-412  oscillator bank with the Nyquist mask (fmax = sr/2)
-    ddsp::sins_osc_kernel<<<(unsigned)((int64_t)B * F), 128, 0, st>>>(amplitudes, cB, cF, n_harmonics, f0_frames, fB, fF,
+    ddsp::sins_osc_kernel<<<(unsigned)((int64_t)B * F), ddsp::kOscThreads, 0, st>>>(amplitudes, cB, cF, n_harmonics, f0_frames, fB, fF,
                                                                        F, (float)(sr / 2.0), phase_full, sinus);
     LAUNCH_CHECK();
     launches += g_launches; g_launches = 0;

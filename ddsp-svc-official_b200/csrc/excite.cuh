@@ -33,14 +33,19 @@ __global__ void __launch_bounds__(256) combtooth_kernel(const float* __restrict_
     for (int i = 0; i < 4; ++i) dst[i] = make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
 }
 
-// Sins oscillator bank.  One CTA of 128 threads per hop (512 samples, 4 per thread).
+// Sins oscillator bank.  One CTA of kOscThreads threads per hop (512 samples, 2*kOscPairs per thread).
 //   A[m,k] = fl(exp(a[m,k]) / 128) * ((f0[m]*k < sr/2) + 1e-7)            (vocoder.py:397,402)
 //   s[t]   = sum_k lerp(A[:,k])[t] * sin(k * theta[t])                     (vocoder.py:406-412)
 // sin(k*theta) comes from a two-term recurrence (see below); two samples ride in one packed
 // fp32x2 register pair.  n_harm must be even.
 constexpr int kSinsMaxHarm = 512;
+#ifndef SINS_PAIRS
+#define SINS_PAIRS 4                               // packed sample pairs per thread
+#endif
+constexpr int kOscPairs = SINS_PAIRS;
+constexpr int kOscThreads = kHop / (2 * kOscPairs);   // one CTA per hop
 
-__global__ void __launch_bounds__(128) sins_osc_kernel(const float* __restrict__ amp_ctrl, int64_t cB, int64_t cF,
+__global__ void __launch_bounds__(kOscThreads) sins_osc_kernel(const float* __restrict__ amp_ctrl, int64_t cB, int64_t cF,
                                                        int n_harm, const float* __restrict__ f0_frames, int64_t fB,
                                                        int64_t fF, int F, float fmax,
                                                        const float* __restrict__ phase_full,
@@ -67,10 +72,10 @@ __global__ void __launch_bounds__(128) sins_osc_kernel(const float* __restrict__
     // sin(k*theta) by Reinsch's stable recurrence:  d_{k+1} = d_k + delta*s_k,  s_{k+1} = s_k + d_{k+1},
     // delta = -4 sin^2(phi/2), which needs |phi| <= pi/2: theta in the outer half of [-pi,pi] is shifted by
     // +-pi, sin(k*theta) = (-1)^k sin(k*phi), i.e. the odd harmonics change sign (separate accumulators).
-    float2 lam[2], dl[2], sk[2], dk[2], acc_e[2], acc_o[2], sgn[2];
+    float2 lam[kOscPairs], dl[kOscPairs], sk[kOscPairs], dk[kOscPairs], acc_e[kOscPairs], acc_o[kOscPairs], sgn[kOscPairs];
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const int i0 = t + 256 * p, i1 = i0 + 128;
+    for (int p = 0; p < kOscPairs; ++p) {
+        const int i0 = t + 2 * kOscThreads * p, i1 = i0 + kOscThreads;
         lam[p] = make_float2((float)i0 * (1.0f / kHop), (float)i1 * (1.0f / kHop));
         float th[2] = {__ldg(phase_full + base + i0), __ldg(phase_full + base + i1)};
         float hx[2], gv[2];
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(128) sins_osc_kernel(const float* __restrict__
     for (int k = 0; k < n_harm; k += 2) {        // k, k+1 are harmonics k+1 (odd) and k+2 (even); n_harm is even
         const float4 a = amps[k], a2 = amps[k + 1];
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
+        for (int p = 0; p < kOscPairs; ++p) {
             acc_o[p] = fma2(fma2(lam[p], make_float2(a.z, a.w), make_float2(a.x, a.y)), sk[p], acc_o[p]);
             dk[p] = fma2(dl[p], sk[p], dk[p]);
             sk[p] = add2(sk[p], dk[p]);
@@ -113,10 +118,10 @@ __global__ void __launch_bounds__(128) sins_osc_kernel(const float* __restrict__
         }
     }
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < kOscPairs; ++p) {
         const float2 r = fma2(sgn[p], acc_o[p], acc_e[p]);
-        out[base + t + 256 * p] = r.x;
-        out[base + t + 256 * p + 128] = r.y;
+        out[base + t + 2 * kOscThreads * p] = r.x;
+        out[base + t + 2 * kOscThreads * p + kOscThreads] = r.y;
     }
 }
 
