@@ -254,8 +254,12 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
                 __syncwarp();
             } else {
                 float2* dst = P.spec + ((int64_t)ctx[0] * P.F + ctx[1]) * kLtvSpecFloat2 + lane;
+                // L = 510: H[k] of real taps is Hermitian -- only bins 0..512 are stored (ltv_conv510_kernel
+                // mirrors the rest); L = 1022: the raw even/odd-packed spectrum needs all 1024 bins
+                const bool half = IR_NMAG == 256;
 #pragma unroll
-                for (int q = 0; q < 32; ++q) dst[32 * q] = make_float2(DDSP_RE(X, q), DDSP_IM(X, q));
+                for (int q = 0; q < 32; ++q)
+                    if (!half || q < 16 || (q == 16 && lane == 0)) dst[32 * q] = make_float2(DDSP_RE(X, q), DDSP_IM(X, q));
             }
         }
     }
@@ -409,13 +413,17 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_dual_kernel(const LtvDu
                 const bool lane0 = lane == 0;
                 float2* da = P.spec_a + ((int64_t)ctx[0] * P.F + ctx[1]) * kLtvSpecFloat2 + lane;
                 float2* dn = P.spec_n + ((int64_t)ctx[0] * P.F + ctx[1]) * kLtvSpecFloat2 + lane;
+                // both spectra are Hermitian (real taps): only bins 0..512 are stored (registers 0..15 of every
+                // lane, bin 512 = lane 0's register 16); ltv_conv510_kernel mirrors the upper half
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
+                for (int q = 0; q < 17; ++q) {
                     float c, d;
                     LTV_PARTNER(X, q, c, d);
                     const float a = DDSP_RE(X, q), b = DDSP_IM(X, q);
-                    da[32 * q] = make_float2(a + c, b - d);
-                    dn[32 * q] = make_float2(b + d, c - a);
+                    if (q < 16 || lane0) {
+                        da[32 * q] = make_float2(a + c, b - d);
+                        dn[32 * q] = make_float2(b + d, c - a);
+                    }
                 }
             }
         }
@@ -722,10 +730,10 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
         for (int phase = 0; phase < 2; ++phase) {
             if (phase == 0) {
                 const float2* zh = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2;
-                {   // pull this frame's tap spectrum (8 KB) into L2 while the audio FFT runs
+                {   // pull this frame's tap spectrum (bins 0..512: 4 KB + one line) into L2 while the audio FFT runs
                     const char* pz = reinterpret_cast<const char*>(zh) + 128 * lane;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(pz));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pz + 4096));
+                    if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pz + 4096));
                 }
                 // z[n] = up[n] + j down[n], n = 32 n1 + lane < 512:
                 //   up[n] = x[t0 + n] * n/512, down[n] = x[t0 + 512 + n] * (512 - n)/512   (core.py:218-222)
@@ -761,19 +769,28 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
             warp_fft1024(X, plane, tw4, lane);
 
             if (phase == 0) {
-                const float2* zh = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2 + lane;   // last IR repeated (core.py:228)
+                // last IR repeated (core.py:228).  Only bins 0..512 of the Hermitian tap spectrum are stored:
+                // bin k = lane + 32 q >= 512 is read as conj(H[1024 - k]) (for k = 512 that is H[512] itself, real)
+                const float2* zlo = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2 + lane;
+                const float2* zhi = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2 + (1024 - lane);
                 constexpr int kLook = 8;
                 float2 hq[kLook];
 #pragma unroll
-                for (int q = 0; q < kLook; ++q) hq[q] = __ldg(zh + 32 * q);
+                for (int q = 0; q < kLook; ++q) hq[q] = __ldg(zlo + 32 * q);
                 float yr[32], yi[32];
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
                     const float2 h = hq[q % kLook];
-                    if (q + kLook < 32) hq[q % kLook] = __ldg(zh + 32 * (q + kLook));
+                    if (q + kLook < 32)
+                        hq[q % kLook] = (q + kLook < 16) ? __ldg(zlo + 32 * (q + kLook)) : __ldg(zhi - 32 * (q + kLook));
                     const float ar = DDSP_RE(X, q), ai = DDSP_IM(X, q);
-                    yr[q] = ar * h.x - ai * h.y;
-                    yi[q] = ar * h.y + ai * h.x;
+                    if (q < 16) {
+                        yr[q] = ar * h.x - ai * h.y;
+                        yi[q] = ar * h.y + ai * h.x;
+                    } else {                   // conj(h)
+                        yr[q] = ar * h.x + ai * h.y;
+                        yi[q] = ai * h.x - ar * h.y;
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
