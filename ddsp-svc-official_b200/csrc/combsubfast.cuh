@@ -28,7 +28,33 @@ constexpr int kCsfWarps = CSF_WARPS;                // warps per CTA (one CTA pe
 constexpr int kCsfThreads = kCsfWarps * 32;
 constexpr int kRingSlot = kHop + kHop / 32;         // 528 floats: one pad word per 32 samples
 constexpr int kStashFloat2 = 17 * 32;               // Y_m stash: 16 bins/lane (+ bin 512 on lane 0)
-constexpr int kCsfCtxInts = 8;                      // cold per-warp scalars parked in shared memory
+constexpr int kCsfCtxInts = 16;                     // cold per-warp scalars parked in shared memory (+ staged hop operands)
+// Experiment switches (profiles/r02_csf_variants.md); the defaults are the shipped configuration.
+#ifndef CSF_PRE
+#define CSF_PRE 0            // filter bins per lane staged by cp.async into the dead ring slot while the FFT runs
+#endif
+#ifndef CSF_HOP_AHEAD
+#define CSF_HOP_AHEAD 0      // f0 / prefix operands of the next hop staged by cp.async one step ahead
+#endif
+#ifndef CSF_RED_OLA
+#define CSF_RED_OLA 1        // hop shared with the previous pair finished by RED.ADD instead of load + add + store
+#endif
+#ifndef CSF_ZERO_FAST
+#define CSF_ZERO_FAST 0      // unvoiced zeroing (vocoder.py:460) only on hops that touch a non-positive f0 frame
+#endif
+#ifndef CSF_INT_PHASE
+#define CSF_INT_PHASE 1      // intra-lane phase in 32-bit fixed point on top of an fp64 lane base
+#endif
+#ifndef CSF_L1PF
+#define CSF_L1PF 0           // prefetch the lines of the first CSF_LOOK filter bins into L1 (not only L2) ahead of the FFT
+#endif
+#ifndef CSF_LOOK
+#define CSF_LOOK 6           // filter bins whose control loads are in flight ahead of their use
+#endif
+#ifndef CSF_NOALLOC
+#define CSF_NOALLOC 1        // control rows are read once: keep them out of L1
+#endif
+constexpr int kCsfPre = CSF_PRE;
 constexpr int kCsfWarpBytes = kPlaneFloats * 4 + 2 * kRingSlot * 4 + kStashFloat2 * 8 + kCsfCtxInts * 4;
 constexpr int kCsfSmemBytes = kTableBytes + kCsfWarps * kCsfWarpBytes;
 
@@ -77,20 +103,67 @@ __device__ __forceinline__ void csf_gen_hop(const CsfParams& P, int h, const Hop
         return;
     }
     float2 f2[8], rot2[8];
+#if CSF_INT_PHASE
+    hop_rotation_q32(in.x0, in.x1, in.base, P.inv_sr, lane, f2, rot2);
+    const float sr_scale = P.sr * 2.3283064365386963e-10f;      // rot2 holds rot * 2^32
+#else
     hop_rotation2(in.x0, in.x1, in.base, P.inv_sr, lane, f2, rot2);
+    const float sr_scale = P.sr;
+#endif
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         // vocoder.py:459  sinc(sr * rot / (f0 + 1e-3)), two samples per packed register pair
         const float2 den = add2(f2[j], bc2(1e-3f));
-        const float2 xs = fma2(mul2(bc2(P.sr), rot2[j]), make_float2(rcp_approx(den.x), rcp_approx(den.y)), bc2(1e-30f));
+        const float2 xs = fma2(mul2(bc2(sr_scale), rot2[j]), make_float2(rcp_approx(den.x), rcp_approx(den.y)), bc2(1e-30f));
         const float2 c = sinc2_xs(xs);
+#if CSF_ZERO_FAST
+        dst[2 * j] = c.x;
+        dst[2 * j + 1] = c.y;
+#else
         dst[2 * j] = (f2[j].x <= 0.0f) ? 0.0f : c.x;       // vocoder.py:460
         dst[2 * j + 1] = (f2[j].y <= 0.0f) ? 0.0f : c.y;
+#endif
     }
+#if CSF_ZERO_FAST
+    // vocoder.py:460 combtooth[f0 <= 0] = 0.  An interpolated sample can only be non-positive when one of the
+    // hop's two frame values is (warp-uniform test): voiced hops skip the per-sample compare + select.
+    if (in.x0 <= 0.0f || in.x1 <= 0.0f) {
+        const float lam0 = (float)(16 * lane) * (1.0f / kHop);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (lerp_torch(in.x0, in.x1, lam0 + (float)i * (1.0f / kHop)) <= 0.0f) dst[i] = 0.0f;
+    }
+#endif
+}
+
+// cp.async (LDGSTS): global -> shared without a register in between; completion via cp_async_wait_all().
+__device__ __forceinline__ uint32_t smem_u32(const volatile void* p) {
+    return (uint32_t)__cvta_generic_to_shared(const_cast<const void*>(p));
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// control rows are consumed exactly once: bypass L1 so that it keeps serving f0 / prefix / seam lines
+__device__ __forceinline__ float ldg_once(const float* p) {
+#if CSF_NOALLOC
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
 // Zero the seam hops (first output hop of every run that does not start a clip).
@@ -121,7 +194,7 @@ __device__ __forceinline__ void csf_load_frame(const CsfParams& P, Pts32& X, con
     const bool vA = (fm >= 1) && (fm - 1 < F), vB = fm < F;
     const int64_t baseA = vA ? (int64_t)(fm - 1) * kHop : 0, baseB = vB ? (int64_t)fm * kHop : 0;
     const float okA = vA ? 1.0f : 0.0f, okB = vB ? 1.0f : 0.0f;
-    const float sclA = okA * 1.1920928955078125e-7f, sclB = okB * 1.1920928955078125e-7f;   // 2^-23
+    const float sclA = okA * 4.6566128730773926e-10f, sclB = okB * 4.6566128730773926e-10f;   // 2^-31
     const float* u_b = HAS_U ? P.noise_u + (int64_t)b * F * kHop + lane : nullptr;
     uint32_t stA = 0, stB = 0;
     if (!HAS_U) {
@@ -147,10 +220,10 @@ __device__ __forceinline__ void csf_load_frame(const CsfParams& P, Pts32& X, con
         } else {
             uint32_t& st = (n1 < 16) ? stA : stB;
             st = noise_next(st);
-            const float v0 = (float)noise_s24(st);
+            const float v0 = noise_f31(st);
             st = noise_next(st);
-            const float v1 = (float)noise_s24(st);
-            // 2u - 1 = v * 2^-23 with v the centred 24-bit draw; sclA/sclB carry the 2^-23 (or 0)
+            const float v1 = noise_f31(st);
+            // 2u - 1 = v * 2^-31 with v = 2^8 * the centred 24-bit draw; sclA/sclB carry the 2^-31 (or 0)
             wz = mul2(make_float2(v0, v1), mul2(w, bc2(n1 < 16 ? sclA : sclB)));
         }
         X.R[brev5(n1)] = mul2(w, c);
@@ -190,6 +263,9 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
     // Per-warp scalars that are needed only a few times per step live in shared memory (volatile
     // reads) instead of registers: the FFT keeps 64 data registers live and anything else held
     // across it would be spilled to local memory, whose reloads miss the (tiny) L1 here.
+    //   ctx[0] clip, [1] first pair, [2] end pair, [3] noise key, [4] step,
+    //   ctx[8], [9] f0 frame values and [10..11] fp64 prefix of the NEXT hop (staged by cp.async),
+    //   ctx[12..13] f0 row pointer, [14..15] prefix row pointer of the clip
     volatile int* ctx = reinterpret_cast<volatile int*>(stash + kStashFloat2);
     {
         // runs are dealt round-robin over the CTAs so that every SM gets the same mix of long and short runs
@@ -204,6 +280,8 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             ctx[2] = pb + P.run_len + (r < P.run_rem ? 1 : 0);  // p_end
             const uint64_t seed = P.seed + (P.seed_device ? __ldg(P.seed_device) : 0ull);
             ctx[3] = (int)(noise_key(seed, (uint32_t)b0) + P.key_offset);
+            *reinterpret_cast<volatile uint64_t*>(ctx + 12) = (uint64_t)(P.f0_frames + (int64_t)b0 * P.fB);
+            *reinterpret_cast<volatile uint64_t*>(ctx + 14) = (uint64_t)(P.prefix + (int64_t)b0 * P.F);
         }
         __syncwarp();
     }
@@ -217,6 +295,26 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
     const int F = P.F;
     const int partner = (32 - lane) & 31;
     const bool lane0 = lane == 0;
+    const uint32_t ctx_s = smem_u32(ctx);
+
+    // Stage the operands of excitation hop h (two f0 frame values, the fp64 prefix) into ctx[8..11]:
+    // lanes 0..2 issue one cp.async each; the values are read after the next cp_async_wait_all + __syncwarp.
+    auto stage_hop = [&](int h) {
+        if (lane < 3) {
+            const int hc = min(max(h, 0), F - 1);
+            const float* f0_row = reinterpret_cast<const float*>(*reinterpret_cast<volatile uint64_t*>(ctx + 12));
+            const double* pre_row = reinterpret_cast<const double*>(*reinterpret_cast<volatile uint64_t*>(ctx + 14));
+            if (lane == 2) cp_async8(ctx_s + 40, pre_row + hc);
+            else cp_async4(ctx_s + 32 + 4 * lane, f0_row + (int64_t)min(hc + lane, F - 1) * P.fF);
+        }
+    };
+    auto staged_hop = [&]() {
+        HopIn in;
+        in.x0 = __int_as_float(ctx[8]);
+        in.x1 = __int_as_float(ctx[9]);
+        in.base = *reinterpret_cast<volatile double*>(ctx + 10);
+        return in;
+    };
 
     Pts32 X;
     // De-phase the four warps that share a scheduler (wid, wid+4, wid+8, wid+12) by 1 us each so that
@@ -233,27 +331,69 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
 #define CTX_STEP ctx[4]
     int p = CTX_PBEGIN;
     if (lane == 0) CTX_STEP = -1;
+#if CSF_HOP_AHEAD
+    stage_hop(2 * p - 1);
+    cp_async_wait_all();
+#endif
     __syncwarp();
+    // @section loop
 #pragma unroll 1
     for (;;) {
         const int s = CTX_STEP;
         const int fm = 2 * p + s;                           // frame handled by steps 0 and 1
         if (s < 2) {
+            // @section excite
             // ---- excitation hop fm (second half of frame fm; fm = 2p-1 on the priming step) ----
+#if CSF_HOP_AHEAD
+            csf_gen_hop(P, fm, staged_hop(), ring + (fm & 1) * kRingSlot, lane);
+#else
             // (f0 / prefix of consecutive hops share cache lines: after the first hop of a run these are L2 hits)
             csf_gen_hop(P, fm, csf_load_hop(P, CTX_B, fm), ring + (fm & 1) * kRingSlot, lane);
+#endif
             __syncwarp();
-            if (s < 0) { CTX_STEP = 0; __syncwarp(); continue; }
+            if (s < 0) {
+#if CSF_HOP_AHEAD
+                stage_hop(fm + 1);
+                cp_async_wait_all();
+#endif
+                CTX_STEP = 0; __syncwarp(); continue;
+            }
+            // @section frame
             {   // pull this frame's three control rows into L2 while the FFT runs (lanes 0..16: one line each)
                 const int64_t ro = (int64_t)CTX_B * P.cB + (int64_t)min(fm, F - 1) * P.cF + 32 * lane;
+#if CSF_L1PF
+                if (lane <= CSF_LOOK) { prefetch_l1(P.hm + ro); prefetch_l1(P.hp + ro); prefetch_l1(P.nm + ro); }
+                else
+#endif
                 if (lane <= 16) { prefetch_l2(P.hm + ro); prefetch_l2(P.hp + ro); prefetch_l2(P.nm + ro); }
             }
             csf_load_frame<HAS_U>(P, X, ring, win, fm, CTX_B, CTX_KEY, lane);
+#if CSF_PRE > 0 || CSF_HOP_AHEAD
+            __syncwarp();       // every lane has read hop fm-1 out of its ring slot: the slot is free until hop fm+1 is generated
+#endif
+#if CSF_PRE > 0
+            {   // the first kCsfPre filter bins of every lane travel global -> shared (the free ring slot) while
+                // the FFT runs, as (hm, hp, nm, -) quads: no register is held across the FFT
+                const int64_t ro = (int64_t)CTX_B * P.cB + (int64_t)min(fm, F - 1) * P.cF + lane;
+                const uint32_t st = smem_u32(ring + ((fm - 1) & 1) * kRingSlot) + 16 * lane;
+#pragma unroll
+                for (int q = 0; q < kCsfPre; ++q) {
+                    cp_async4(st + 512 * q, P.hm + ro + 32 * q);
+                    cp_async4(st + 512 * q + 4, P.hp + ro + 32 * q);
+                    cp_async4(st + 512 * q + 8, P.nm + ro + 32 * q);
+                }
+            }
+#endif
+#if CSF_HOP_AHEAD
+            stage_hop(fm + 1);
+#endif
         }
+        // @section fft
         // s == 2: re/im already hold the packed spectrum of the pair (swapped for the inverse)
 
         warp_fft1024(X, plane, tw4, lane);
 
+        // @section filter
         if (CTX_STEP < 2) {
             // ---- split the two real spectra, apply the filters (vocoder.py:472-481) ----------
             // last filter frame repeated (:473,476)
@@ -271,15 +411,31 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             float chm[kLook], chp[kLook], cnm[kLook];
 #pragma unroll
             for (int q = 0; q < kLook; ++q) {
-                chm[q] = __ldg(hm_r + 32 * q); chp[q] = __ldg(hp_r + 32 * q); cnm[q] = __ldg(nm_r + 32 * q);
+                const int off = (q + kCsfPre < 16) ? 32 * (q + kCsfPre) : k16;
+#if CSF_L1PF
+                chm[q] = __ldg(hm_r + off); chp[q] = __ldg(hp_r + off); cnm[q] = __ldg(nm_r + off);
+#else
+                chm[q] = ldg_once(hm_r + off); chp[q] = ldg_once(hp_r + off); cnm[q] = ldg_once(nm_r + off);
+#endif
             }
+#if CSF_PRE > 0 || CSF_HOP_AHEAD
+            cp_async_wait_all();
+#endif
+            const float4* staged = reinterpret_cast<const float4*>(ring + ((fm - 1) & 1) * kRingSlot) + lane;
 #pragma unroll
             for (int q = 0; q < 17; ++q) {
                 float a, bb, c, d;
-                const float vhm = chm[q % kLook], vhp = chp[q % kLook], vnm = cnm[q % kLook];
-                if (q + kLook < 17) {
-                    const int off = (q + kLook < 16) ? 32 * (q + kLook) : k16;   // bin 512: lane 0 (others: dummy)
-                    chm[q % kLook] = __ldg(hm_r + off); chp[q % kLook] = __ldg(hp_r + off); cnm[q % kLook] = __ldg(nm_r + off);
+                float vhm, vhp, vnm;
+                if (q < kCsfPre) {
+                    const float4 sv = staged[32 * q];
+                    vhm = sv.x; vhp = sv.y; vnm = sv.z;
+                } else {
+                    const int i = (q - kCsfPre) % kLook;
+                    vhm = chm[i]; vhp = chp[i]; vnm = cnm[i];
+                    if (q + kLook < 17) {
+                        const int off = (q + kLook < 16) ? 32 * (q + kLook) : k16;   // bin 512: lane 0 (others: dummy)
+                        chm[i] = ldg_once(hm_r + off); chp[i] = ldg_once(hp_r + off); cnm[i] = ldg_once(nm_r + off);
+                    }
                 }
                 if (q < 16) {
                     a = DDSP_RE(X, q); bb = DDSP_IM(X, q);
@@ -308,12 +464,14 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             // irfft ignores the imaginary part of the DC and Nyquist bins
             yi[0] = lane0 ? 0.0f : yi[0];
             yi[16] = 0.0f;
+            // @section stash
             if (CTX_STEP == 0) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) stash[q * 32 + lane] = make_float2(yr[q], yi[q]);
                 if (lane0) stash[16 * 32] = make_float2(yr[16], 0.0f);
                 CTX_STEP = 1;
             } else {
+                // @section pack
                 // ---- V = Y_m + j*Y_{m+1}; feed (Im V, Re V) to the forward FFT = inverse FFT ---
                 float xr[16], xi[16];
 #pragma unroll
@@ -341,11 +499,13 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                 CTX_STEP = 2;
             }
         } else {
+            // @section ola
             // ---- window (vocoder.py:486), overlap-add (:485-487), crop (:490) -----------------
             // after the swapped FFT: DDSP_IM(X, ) = Re v = frame 2p, DDSP_RE(X, ) = Im v = frame 2p+1
             // Hop 2p-1 (shared with the previous pair) was left in the output buffer by that pair as a
-            // partial sum and is completed here by read-modify-write (same thread wrote it); at a run
-            // seam both sides use atomic adds onto zeros instead.
+            // partial sum and is completed here by one reduction per sample (same thread stored the partial:
+            // program order on the same address; stored value + one addend is the same fp32 number as a
+            // load-add-store); at a run seam both sides add onto zeros instead.
             const int hopA = 2 * p - 1, hopB = 2 * p, hopC = 2 * p + 1;
             const int p_begin = CTX_PBEGIN, p_end = CTX_PEND;
             const bool first = p == p_begin, last = p + 1 >= p_end;
@@ -363,6 +523,12 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                 X.I[q] = mul2(X.I[q], w);
                 X.R[q] = mul2(X.R[q], w);
             }
+#if CSF_RED_OLA
+            if (!first || seam_head) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) atomicAdd(oA + 32 * q, X.I[q].x);
+            }
+#else
             if (first) {
                 if (seam_head) {
 #pragma unroll
@@ -375,6 +541,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
 #pragma unroll
                 for (int q = 0; q < 16; ++q) oA[32 * q] = __fadd_rn(prev[q], X.I[q].x);
             }
+#endif
             if (hopB < F) {
 #pragma unroll
                 for (int q = 0; q < 16; ++q) oB[32 * q] = __fadd_rn(X.I[q].y, X.R[q].x);

@@ -39,23 +39,25 @@ __host__ __device__ __forceinline__ uint32_t noise_key(uint64_t seed, uint32_t c
     return (uint32_t)(z >> 32) ^ (uint32_t)z;
 }
 // Noise stream layout: the 16 samples {hop*512 + 32*i + lane, i = 0..15} that one lane feeds into
-// the FFT form one short multiplicative-congruential stream (x <- 747796405 x mod 2^32, odd seed)
-// seeded by a strong hash of (clip key, hop, lane); one IMAD + one shift per sample instead of a
-// full hash.  Only the top 24 bits of each state are used.
+// the FFT form one short multiplicative-congruential stream seeded by a strong hash of (clip key, hop,
+// lane).  The state keeps its low byte clear: state = 256*s with s an odd 24-bit number, and
+// state <- 747796405 state mod 2^32 is s <- 747796405 s mod 2^24.  The draw is s itself (top 24 bits of
+// the state), so the centred value is the state read as a signed integer -- one IMAD + one exact
+// int->float conversion per sample, no shift.
 __host__ __device__ __forceinline__ uint32_t noise_seed(uint32_t key, uint32_t hop, uint32_t lane) {
     uint32_t x = (hop * 32u + lane) * 0x9E3779B1u + key;
     x ^= x >> 16; x *= 0x7feb352du;
     x ^= x >> 15; x *= 0x846ca68bu;
     x ^= x >> 16;
-    return x | 1u;              // odd: the stream is a multiplicative congruential sequence mod 2^32
+    return (x & 0xffffff00u) | 0x100u;
 }
 __host__ __device__ __forceinline__ uint32_t noise_next(uint32_t state) { return state * 747796405u; }
-// uniform integer in [0, 2^24) from an LCG state: its top 24 bits (the streams are 16 draws long and
-// seeded by a strong hash, so no further output mixing is needed); U = value * 2^-24
+// uniform integer in [0, 2^24) from a state: its top 24 bits; U = value * 2^-24
 __host__ __device__ __forceinline__ uint32_t noise_u24(uint32_t state) { return (state >> 8) ^ 0x800000u; }
 // the same draw as a centred integer v = u24 - 2^23 in [-2^23, 2^23):  2U - 1 == v * 2^-23 exactly
-// (one arithmetic shift of the state read as a signed integer)
 __host__ __device__ __forceinline__ int32_t noise_s24(uint32_t state) { return (int32_t)state >> 8; }
+// 2^8 * v as fp32 (exact: the low byte of the state is clear):  2U - 1 == noise_f31(state) * 2^-31
+__device__ __forceinline__ float noise_f31(uint32_t state) { return (float)(int32_t)state; }
 
 // Single-MUFU approximations (flush-to-zero forms: no denormal fix-up code around them).
 __device__ __forceinline__ float ex2_approx(float x) {

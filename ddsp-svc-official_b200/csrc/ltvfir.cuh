@@ -501,8 +501,8 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                         const bool ok = (n1 < 8) ? vA : vB;
                         if (amode == 2) {
                             uint32_t& st = (n1 < 8) ? stA : stB;
-                            st = noise_next(st); v0 = (float)noise_s24(st) * 1.1920928955078125e-7f;
-                            st = noise_next(st); v1 = (float)noise_s24(st) * 1.1920928955078125e-7f;
+                            st = noise_next(st); v0 = noise_f31(st) * 4.6566128730773926e-10f;
+                            st = noise_next(st); v1 = noise_f31(st) * 4.6566128730773926e-10f;
                             v0 = ok ? v0 : 0.0f;
                             v1 = ok ? v1 : 0.0f;
                         } else if (ok) {
@@ -749,8 +749,8 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
                         const int n = 32 * n1 + lane;
                         if (amode == 2) {
                             // lane l draws the samples 32 i + l of a hop, i = 0..15, from its (hop, lane) stream
-                            stA = noise_next(stA); v0 = (float)noise_s24(stA) * 1.1920928955078125e-7f;
-                            stB = noise_next(stB); v1 = (float)noise_s24(stB) * 1.1920928955078125e-7f;
+                            stA = noise_next(stA); v0 = noise_f31(stA) * 4.6566128730773926e-10f;
+                            stB = noise_next(stB); v1 = noise_f31(stB) * 4.6566128730773926e-10f;
                             v0 = vA ? v0 : 0.0f;
                             v1 = vB ? v1 : 0.0f;
                         } else {

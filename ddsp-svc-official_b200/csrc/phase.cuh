@@ -227,6 +227,39 @@ __device__ __forceinline__ void hop_rotation2(float x0, float x1, double base, d
         rot2[j] = make_float2(wrap_rot(fma(sl[2 * j], inv_sr, off)), wrap_rot(fma(sl[2 * j + 1], inv_sr, off)));
 }
 
+// Fixed-point variant for the fused CombSubFast kernels (forward and gradient).  The lane's first sample
+// takes its rotation from the exact fp64 hop prefix plus the closed-form sum of the interpolated f0 over
+// the samples before the lane; inside the lane the rotation advances in 32-bit fixed point (unit 2^-32
+// rotation; integer wrap-around is the reference's `rot - round(rot)`, core.py:46) by rn(f * 2^32/sr)
+// per sample.  What is ignored: the fp32 roundings of the individual upsampled samples inside ONE hop
+// (<= 512 * 2^-25 * f0 Hz*samples, i.e. < 3e-7 rotations worst case, ~1e-8 typical) -- they do not
+// accumulate because `base` is the exact prefix of every hop -- and the 2^-24 relative rounding of the 16
+// increments.  In the sinc argument sr*rot/f0 both stay below 1e-6, under the 3e-5 fp32 spacing the
+// reference's own argument has at low f0.  Returns f (bit-exact upsample) and rot * 2^32 as fp32.
+__device__ __forceinline__ void hop_rotation_q32(float x0, float x1, double base, double inv_sr, int lane,
+                                                 float2 (&f2)[8], float2 (&roti2)[8]) {
+    const double n = (double)(16 * lane);
+    const double dx = (double)x1 - (double)x0;
+    // sum_{k < n} (x0 + dx k/512) = n x0 + dx n(n-1)/1024   (n(n-1) and dx/1024 are exact)
+    const double excl = fma(dx * (1.0 / 1024.0), n * (n - 1.0), n * (double)x0);
+    double c = (base + excl) * inv_sr;
+    c -= rint(c);
+    uint32_t p = (uint32_t)__double2ll_rn(c * 4294967296.0);
+    const float k32 = (float)(4294967296.0 * inv_sr);
+    const float lam0 = (float)(16 * lane) * (1.0f / kHop);
+    float2 lam = make_float2(lam0, lam0 + 1.0f / kHop);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        f2[j] = fma2(sub2(bc2(1.0f), lam), bc2(x0), mul2(lam, bc2(x1)));      // lerp_torch on both halves
+        lam = add2(lam, bc2(2.0f / kHop));
+        const float2 d = mul2(f2[j], bc2(k32));
+        p += __float2uint_rn(d.x);
+        const float r0 = (float)(int32_t)p;
+        p += __float2uint_rn(d.y);
+        roti2[j] = make_float2(r0, (float)(int32_t)p);
+    }
+}
+
 __device__ __forceinline__ void hop_rotation(float x0, float x1, double base, double inv_sr, int lane,
                                              float (&f)[16], float (&rot)[16]) {
     float2 f2[8], rot2[8];

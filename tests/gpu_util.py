@@ -66,7 +66,7 @@ def hop_noise(k, hop):
     x ^= x >> 16; x = (x * 0x7feb352d) & 0xffffffff
     x ^= x >> 15; x = (x * 0x846ca68b) & 0xffffffff
     x ^= x >> 16
-    x |= 1
+    x = (x & 0xffffff00) | 0x100        # 24-bit stream in the top bits, odd; low byte clear (exact int->float)
     out = np.zeros(512, np.float32)
     for i in range(16):
         x = (x * 747796405) & 0xffffffff
