@@ -50,6 +50,9 @@ _PROTOS = {
                                       C.c_int, c_f32p, C.c_void_p]),
     'ddsp_b200_glu_dwconv_silu': (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p,
                                             C.c_void_p]),
+    'ddsp_b200_linear_tf32x3': (C.c_int, [c_f32p, i64, c_f32p, i64, c_f32p, c_f32p, i64, c_f32p, i64, C.c_int, C.c_int,
+                                          C.c_int, C.c_void_p]),
+    'ddsp_b200_tc_microbench': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ddsp_b200_apply_frame_mask': (C.c_int, [c_f32p, c_f32p, i64, i64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ddsp_b200_frequency_filter_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'ddsp_b200_frequency_filter': (C.c_int, [c_f32p, c_f32p, i64, i64, C.c_int, C.c_int, C.c_float, C.c_int, c_f32p,

@@ -124,22 +124,23 @@ class _SelfAttention(nn.Module):
             from . import core
             proj = self.fast_attention.projection_matrix
             if b * n * self.heads >= _FUSED_PROJECTION_MIN_ROWS:
-                # large batches: projection fused into the feature kernel, the (B,N,H,266) products stay on
-                # chip; the q/k Linear biases are added there too (bias-free GEMMs skip cuBLASLt's separate
-                # epilogue kernel)
-                q = core.performer_project_features(F.linear(x, self.to_q.weight), proj, self.heads, True,
+                # large batches: the three projections run on the tensor cores (3xTF32 tcgen05 GEMM, csrc/gemm_tc.cuh);
+                # the random-feature projection is fused into the feature kernel, the (B,N,H,266) products stay on
+                # chip; the q/k Linear biases are added there too
+                q = core.performer_project_features(core.linear(x, self.to_q.weight), proj, self.heads, True,
                                                     x_bias=self.to_q.bias)
-                k = core.performer_project_features(F.linear(x, self.to_k.weight), proj, self.heads, False,
+                k = core.performer_project_features(core.linear(x, self.to_k.weight), proj, self.heads, False,
                                                     x_bias=self.to_k.bias)
-                out = self.fast_attention.attend(q, k, split(self.to_v(x)))
+                out = self.fast_attention.attend(q, k, split(core.linear(x, self.to_v.weight, self.to_v.bias)))
                 out = out.transpose(1, 2).reshape(b * n, self.heads * _DIM_HEAD)
             elif b * n > _ATTENTION_KERNEL_MAX_FRAMES:
-                # mid-sized calls: a library GEMM + the one-pass feature kernel
-                q, k = self.to_q(x), self.to_k(x)
+                # mid-sized calls: tensor-core GEMMs + the one-pass feature kernel
+                q = core.linear(x, self.to_q.weight, self.to_q.bias)
+                k = core.linear(x, self.to_k.weight, self.to_k.bias)
                 scale = _DIM_HEAD ** -0.25
                 q, k = [core.performer_features(torch.matmul((scale * t).view(-1, _DIM_HEAD), proj.t()), t, self.heads, is_q)
                         for t, is_q in ((q, True), (k, False))]
-                out = self.fast_attention.attend(q, k, split(self.to_v(x)))
+                out = self.fast_attention.attend(q, k, split(core.linear(x, self.to_v.weight, self.to_v.bias)))
                 out = out.transpose(1, 2).reshape(b * n, self.heads * _DIM_HEAD)
             else:
                 # streaming blocks: the whole attention after the three (bias-free) projection GEMMs is one
@@ -147,6 +148,9 @@ class _SelfAttention(nn.Module):
                 q, k, v = F.linear(x, self._merged_qkv_weight()).chunk(3, dim=-1)      # one GEMM, three strided slices
                 out = core.performer_attention(q, k, v, proj, self.heads, self.to_q.bias, self.to_k.bias,
                                                self.to_v.bias).view(b * n, -1)
+            if b * n > _ATTENTION_KERNEL_MAX_FRAMES:
+                # bias and residual are added in the epilogue of the tensor-core GEMM
+                return core.linear(out, self.to_out.weight, self.to_out.bias, residual=residual).view(b, n, -1)
             if residual is None:
                 return self.to_out(out).view(b, n, -1)
             # residual + bias lands in a fresh buffer that the GEMM then accumulates into in place (no copy of C)
@@ -177,8 +181,12 @@ class _ConvModule(nn.Module):
         if _fused_ok(x):
             from . import core
             ln, _, pw1, _, dw, _, pw2, _, _ = self.net
-            u = F.linear(ln(x), pw1.weight.squeeze(-1))                            # channels last: no transposes
+            big = x.shape[0] * x.shape[1] > _ATTENTION_KERNEL_MAX_FRAMES
+            lin = core.linear if big else F.linear                                 # tensor cores for anything but streaming blocks
+            u = lin(ln(x), pw1.weight.squeeze(-1))                                 # channels last: no transposes
             s = core.glu_dwconv_silu(u, dw.weight, dw.bias, u_bias=pw1.bias)
+            if big:
+                return core.linear(s, pw2.weight.squeeze(-1), pw2.bias, residual=residual)
             if residual is None:
                 return F.linear(s, pw2.weight.squeeze(-1), pw2.bias)
             b, n, _ = x.shape
@@ -258,8 +266,16 @@ class Unit2Control(nn.Module):
             else:
                 spk = self.spk_embed(spk_id - 1)
             x = core.embed_sum(x, f0, phase, volume, self.f0_embed, self.phase_embed, self.volume_embed, spk)
-            e = self.dec_post(x)
             names, sizes = list(self.output_splits), list(self.output_splits.values())
+            if x.shape[0] * x.shape[1] > _ATTENTION_KERNEL_MAX_FRAMES:
+                # output projection on the tensor cores into a buffer whose row stride is padded to a multiple of 4
+                # floats (128-bit stores); the synthesizer consumes the strided views as they are
+                pcmer, norm, proj = self.dec_post
+                n_out = sum(sizes)
+                buf = torch.empty(x.shape[:-1] + ((n_out + 3) // 4 * 4,), dtype=torch.float32, device=x.device)
+                e = core.linear(norm(pcmer(x)), proj.weight, proj.bias, out=buf[..., :n_out])
+            else:
+                e = self.dec_post(x)
             return dict(zip(names, torch.split(e, sizes, dim=-1)))
         x = x + self.f0_embed((1 + f0 / 700).log()) + self.phase_embed(phase.unsqueeze(-1) / math.pi) \
             + self.volume_embed(volume.unsqueeze(-1))

@@ -458,6 +458,55 @@ def glu_dwconv_silu(u, weight, bias, u_bias=None):
     return out
 
 
+def linear(x, weight, bias=None, residual=None, out=None):
+    """`F.linear(x, weight, bias) (+ residual)` on the tensor cores with fp32-faithful 3xTF32 accumulation
+    (csrc/gemm_tc.cuh; replaces the nn.Linear / 1x1 Conv1d calls of ddsp/unit2control.py:56-62 and
+    ddsp/pcmer.py:41-63, :191-251).  x (..., K) whose leading dimensions collapse to rows with one stride,
+    weight (N, K) with contiguous rows; `residual` (..., N) is added in the epilogue; `out` may be given
+    (row stride a multiple of 4 floats for 128-bit stores) and may alias `residual`."""
+    x = _need_cuda_f32(x, 'x')
+    weight = _need_cuda_f32(weight, 'weight')
+    N, K = weight.shape
+    if x.shape[-1] != K:
+        raise ValueError(f'linear: x has {x.shape[-1]} features, weight expects {K}')
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1 or (x2.stride(0) & 3) or (x2.data_ptr() & 15):
+        x2 = x2.contiguous()
+    if weight.stride(1) != 1 or (weight.stride(0) & 3) or (weight.data_ptr() & 15):
+        weight = weight.contiguous()
+    M = x2.shape[0]
+    if K & 3:
+        raise ValueError('linear: the reduction length must be a multiple of 4 (16-byte rows for TMA)')
+    if out is None:
+        out = torch.empty(lead + (N,), dtype=torch.float32, device=x.device)
+    o2 = out.view(-1, N) if out.is_contiguous() else out.reshape(-1, out.shape[-1])[:, :N]
+    if o2.data_ptr() != out.data_ptr() or o2.stride(1) != 1:
+        raise ValueError('linear: `out` must have contiguous rows')
+    r2, ldr = None, 0
+    if residual is not None:
+        r2 = _need_cuda_f32(residual, 'residual').reshape(-1, N)
+        if r2.stride(1) != 1:
+            r2 = r2.contiguous()
+        ldr = r2.stride(0)
+    if bias is not None:
+        bias = _need_cuda_f32(bias, 'bias').contiguous()
+    with _OnDevice(x.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_linear_tf32x3(x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0),
+                                                        _ptr(bias), _ptr(r2), ldr, o2.data_ptr(), o2.stride(0), M, N, K, _st))
+    return out
+
+
+def tc_microbench(n, k, block_n, virtual_tiles, device='cuda'):
+    """Launch the tensor-pipe microbenchmark (operands resident in L2, nothing stored); returns nothing --
+    time it with CUDA events."""
+    a = torch.randn(128, k, device=device)
+    w = torch.randn(n, k, device=device)
+    c = torch.empty(128, n, device=device)
+    with _OnDevice(a.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_tc_microbench(a.data_ptr(), w.data_ptr(), c.data_ptr(), n, k, block_n, virtual_tiles, _st))
+
+
 def embed_sum(x, f0, phase, volume, f0_embed, phase_embed, volume_embed, spk_rows):
     """Input embedding sum of Unit2Control.forward (unit2control.py:80-95) in one kernel.
     x (B,N,C) any strides; f0 (B,N,1) or (B,N); phase, volume (B,N); *_embed: nn.Linear(1,C);

@@ -11,6 +11,7 @@
 #include "combsubfast_bwd.cuh"
 #include "control.cuh"
 #include "excite.cuh"
+#include "gemm_tc.cuh"
 #include "ltvfir.cuh"
 #include "phase.cuh"
 
@@ -801,6 +802,121 @@ int ddsp_b200_sins(const float* amplitudes, int n_harmonics, const float* group_
     if (int rc = launch_add(harmonic, noise, signal, n, st)) return rc;
     g_launches += launches;
     return DDSP_B200_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Linear layers of the control network on the tensor cores (csrc/gemm_tc.cuh)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time dependency on libcuda)
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// (rows, cols) fp32 matrix with row stride ld (elements), cols contiguous; box = 32 columns (128 bytes) x box_rows,
+// 128-byte swizzle, out-of-bounds elements read as zero
+int make_map_2d(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return DDSP_B200_ERR_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)ddsp::tc::kBK, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        g_last_cuda_error = (int)r;
+        return DDSP_B200_ERR_CUDA;
+    }
+    return 0;
+}
+
+template <int BN>
+int launch_linear(const float* A, int64_t lda, const float* W, int64_t ldw, ddsp::tc::LinearParams P, cudaStream_t st) {
+    using C = ddsp::tc::Cfg<BN>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return DDSP_B200_ERR_UNSUPPORTED;
+    if (!attr_set[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(ddsp::tc::linear_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      C::kSmemBytes));
+        attr_set[dev] = true;
+    }
+    CUtensorMap map_a, map_w;
+    if (int rc = make_map_2d(&map_a, A, P.M, P.K, lda, ddsp::tc::kBM)) return rc;
+    if (int rc = make_map_2d(&map_w, W, P.N, P.K, ldw, BN)) return rc;
+    P.tiles_m = (P.M + ddsp::tc::kBM - 1) / ddsp::tc::kBM;
+    P.tiles_n = (P.N + BN - 1) / BN;
+    const int64_t tiles = P.virtual_tiles > 0 ? P.virtual_tiles : (int64_t)P.tiles_m * P.tiles_n;
+    const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+    ddsp::tc::linear_tf32x3_kernel<BN><<<grid, ddsp::tc::kThreads, C::kSmemBytes, st>>>(map_a, map_w, P);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int linear_dispatch(const float* A, int64_t lda, const float* W, int64_t ldw, ddsp::tc::LinearParams P, int block_n,
+                    cudaStream_t st) {
+    if (block_n == 0) {
+        // least padded work; ties go to the wider tile (fewer re-reads of A)
+        int best = 256;
+        int64_t best_cost = ((P.N + 255) / 256) * 256;
+        for (int bn : {224, 128, 64}) {
+            const int64_t cost = (int64_t)((P.N + bn - 1) / bn) * bn;
+            if (cost < best_cost) { best_cost = cost; best = bn; }
+        }
+        block_n = best;
+    }
+    switch (block_n) {
+        case 256: return launch_linear<256>(A, lda, W, ldw, P, st);
+        case 224: return launch_linear<224>(A, lda, W, ldw, P, st);
+        case 128: return launch_linear<128>(A, lda, W, ldw, P, st);
+        case 64: return launch_linear<64>(A, lda, W, ldw, P, st);
+        default: return DDSP_B200_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ddsp_b200_linear_tf32x3(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                            const float* residual, int64_t ldr, float* C, int64_t ldc, int M, int N, int K, void* stream) {
+    g_launches = 0;
+    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || lda < K || ldw < K || ldc < N || (residual && ldr < N))
+        return DDSP_B200_ERR_INVALID_ARGUMENT;
+    // TMA: 16-byte aligned base addresses and row strides
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15) || (lda & 3) || (ldw & 3))
+        return DDSP_B200_ERR_UNSUPPORTED;
+    ddsp::tc::LinearParams P = {};
+    P.bias = bias; P.residual = residual; P.C = C; P.ldr = ldr; P.ldc = ldc;
+    P.M = M; P.N = N; P.K = K; P.store_output = 1; P.virtual_tiles = 0;
+    return linear_dispatch(A, lda, W, ldw, P, 0, (cudaStream_t)stream);
+}
+
+int ddsp_b200_tc_microbench(const float* A, const float* W, float* C, int N, int K, int block_n, int virtual_tiles,
+                            void* stream) {
+    g_launches = 0;
+    if (!A || !W || !C || N <= 0 || K <= 0 || virtual_tiles <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    ddsp::tc::LinearParams P = {};
+    P.C = C; P.ldc = N; P.M = ddsp::tc::kBM; P.N = N; P.K = K; P.store_output = 0; P.virtual_tiles = virtual_tiles;
+    return linear_dispatch(A, K, W, K, P, block_n, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -259,6 +259,25 @@ int ddsp_b200_embed_sum(const float *x, int64_t xB, int64_t xN, int64_t xC, cons
                         const float *b_volume, const float *spk, int64_t sB, int B, int N, int C,
                         float *out, void *stream);
 
+/* Linear layer on the tensor cores, fp32-faithful ("3xTF32": each operand split into two TF32 terms, three
+ * tcgen05.mma per k-step accumulate hi*hi + hi*lo + lo*hi in fp32 TMEM; csrc/gemm_tc.cuh):
+ *   C[m,n] = sum_k A[m,k] * W[n,k] (+ bias[n]) (+ residual[m,n])
+ * Replaces the nn.Linear / 1x1 Conv1d calls of the control network (ddsp/unit2control.py:56-62,
+ * ddsp/pcmer.py:41-63, :191-251).  A: (M,K) row stride lda; W: (N,K) = nn.Linear.weight, row stride ldw;
+ * bias (N) and residual (M,N; row stride ldr) optional (NULL); C: (M,N) row stride ldc; may alias residual.
+ * A and W must be 16-byte aligned with lda, ldw multiples of 4 (TMA); C / residual of any 4-byte alignment
+ * (128-bit stores are used when ldc, ldr are multiples of 4 and the bases 16-byte aligned). */
+int ddsp_b200_linear_tf32x3(const float *A, int64_t lda, const float *W, int64_t ldw, const float *bias,
+                            const float *residual, int64_t ldr, float *C, int64_t ldc, int M, int N,
+                            int K, void *stream);
+
+/* Tensor-pipe microbenchmark of the same kernel: `virtual_tiles` output tiles of 128 x block_n with reduction
+ * length K that all read tile 0 of A (128,K) and W (N,K) (operands stay in L2) and store nothing -- the
+ * rate at which the TMA -> split -> 3 x tcgen05.mma -> TMEM-drain pipeline runs without HBM traffic.  Used to
+ * measure a DFT-32 pass (N = K = 64) as a go / no-go for a tensor-core FFT in the synthesizer kernel. */
+int ddsp_b200_tc_microbench(const float *A, const float *W, float *C, int N, int K, int block_n,
+                            int virtual_tiles, void *stream);
+
 /* Number of kernel launches the last call of each entry point enqueued on this thread
  * (bench.py reports it as gpu_launches). */
 int ddsp_b200_last_launch_count(void);
