@@ -273,7 +273,9 @@ class Unit2Control(nn.Module):
                 pcmer, norm, proj = self.dec_post
                 n_out = sum(sizes)
                 buf = torch.empty(x.shape[:-1] + ((n_out + 3) // 4 * 4,), dtype=torch.float32, device=x.device)
-                e = core.linear(norm(pcmer(x)), proj.weight, proj.bias, out=buf[..., :n_out])
+                # weight_norm keeps (weight_g, weight_v) and rebuilds `weight` only inside Module.__call__
+                w = torch._weight_norm(proj.weight_v, proj.weight_g, 0) if hasattr(proj, 'weight_g') else proj.weight
+                e = core.linear(norm(pcmer(x)), w, proj.bias, out=buf[..., :n_out])
             else:
                 e = self.dec_post(x)
             return dict(zip(names, torch.split(e, sizes, dim=-1)))

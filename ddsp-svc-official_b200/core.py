@@ -10,6 +10,7 @@ import math
 import torch
 
 from . import _cabi
+from . import _torchext
 
 _TWO62 = 1 << 62
 
@@ -55,6 +56,17 @@ def as_f32(t):
 
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
+
+
+def _op(fn, *args):
+    """Call an operator of the PyTorch-extension host; ValueError / TypeError pass through (shape, dtype), every
+    other failure (CPU tensor, unsupported configuration, CUDA error) surfaces as DDSPB200Error like the ctypes path."""
+    try:
+        return fn(*args)
+    except (ValueError, TypeError):
+        raise
+    except RuntimeError as e:
+        raise _cabi.DDSPB200Error(str(e)) from None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -130,6 +142,11 @@ def phase_stage(f0_frames, block_size, sampling_rate, initial_phase=None, infer=
 
     Returns (phase_frames (B,F) fp32, prefix (B,F) fp64 workspace for stage B,
     phase (B,T) fp32 at sample rate if `full_rate` else None)."""
+    ops = _torchext.ops()
+    if ops is not None:     # the PyTorch-extension host: checks, allocation and the C-ABI call in C++
+        ip = None if initial_phase is None else torch.as_tensor(initial_phase, dtype=torch.float32, device=f0_frames.device)
+        pf, prefix, full = _op(ops.phase, f0_frames, int(block_size), float(sampling_rate), ip, bool(infer), bool(full_rate), None)
+        return pf, prefix, (full if full_rate else None)
     f0 = _f0_2d(f0_frames)
     B, F = f0.shape
     hop = int(block_size)
@@ -152,6 +169,11 @@ def phase_stage_stream(f0_frames, block_size, sampling_rate, carry=None, initial
     `carry` (B,) float64 view (any stride): the prefix the stream reached at this block's first frame --
     a column of the previous block's `prefix`; None at stream start (then `initial_phase` applies).
     Returns (phase_frames (B,F) fp32, prefix (B,F) fp64)."""
+    ops = _torchext.ops()
+    if ops is not None and carry is not None:
+        ip = None if initial_phase is None else torch.as_tensor(initial_phase, dtype=torch.float32, device=f0_frames.device)
+        pf, prefix, _ = _op(ops.phase, f0_frames, int(block_size), float(sampling_rate), ip, True, False, carry)
+        return pf, prefix
     f0 = _f0_2d(f0_frames)
     B, F = f0.shape
     dev = f0.device
@@ -189,6 +211,10 @@ def combsubfast_stage(harmonic_magnitude, harmonic_phase, noise_magnitude, f0_fr
     `hop_offset` (streaming only): stream index of this block's first hop, see `phase_stage_stream`.
     `seed_device` (CUDA graphs only): one-element int64 CUDA tensor added to `seed` on the device when the
     kernel starts, so that a captured call draws fresh in-kernel noise on every replay."""
+    ops = _torchext.ops()
+    if ops is not None:     # (initial_phase is carried by `prefix`)
+        return _op(ops.combsubfast, harmonic_magnitude, harmonic_phase, noise_magnitude, f0_frames, prefix, int(block_size),
+                               float(sampling_rate), noise_u, int(seed) % _TWO62, window, seed_device, int(hop_offset or 0), out)
     hm, hp, nm = _common_views((harmonic_magnitude, harmonic_phase, noise_magnitude),
                                ('harmonic_magnitude', 'harmonic_phase', 'noise_magnitude'))
     f0 = _f0_2d(f0_frames)
@@ -327,6 +353,10 @@ def _check_noise(noise_u, B, T):
 def combsub_stage(group_delay, harmonic_magnitude, noise_magnitude, f0_frames, prefix, block_size, sampling_rate,
                   noise_u=None, seed=0):
     """Stage B of CombSub.forward (old) (vocoder.py:521-548) -> (signal, harmonic, noise), each (B,T)."""
+    ops = _torchext.ops()
+    if ops is not None:
+        return _op(ops.combsub, group_delay, harmonic_magnitude, noise_magnitude, f0_frames, prefix, int(block_size),
+                           float(sampling_rate), noise_u, int(seed) % _TWO62)
     gd, hm, nm = _common_views((group_delay, harmonic_magnitude, noise_magnitude),
                                ('group_delay', 'harmonic_magnitude', 'noise_magnitude'))
     f0 = _f0_2d(f0_frames)
@@ -352,6 +382,10 @@ def sins_stage(amplitudes, group_delay, noise_magnitude, f0_frames, phase, block
                seed=0):
     """Stage B of Sins.forward (vocoder.py:397-421) -> (signal, harmonic, noise), each (B,T).
     `phase` is the full-rate phase (B,T) from `phase_stage(..., full_rate=True)`."""
+    ops = _torchext.ops()
+    if ops is not None:
+        return _op(ops.sins, amplitudes, group_delay, noise_magnitude, f0_frames, phase, int(block_size), float(sampling_rate),
+                        noise_u, int(seed) % _TWO62)
     am, gd, nm = _common_views((amplitudes, group_delay, noise_magnitude),
                                ('amplitudes', 'group_delay', 'noise_magnitude'))
     f0 = _f0_2d(f0_frames)

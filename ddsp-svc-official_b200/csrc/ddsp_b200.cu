@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <initializer_list>
 #include <mutex>
 
@@ -72,21 +73,31 @@ __device__ __align__(16) float g_chirp[3][ddsp::kChirpFloats];     // L=510, L=1
 const float* g_chirp_ptr[64][3] = {{nullptr, nullptr, nullptr}};
 
 std::mutex g_init_mutex;
-bool g_device_ready[64] = {false};
+// 0 = nothing set up, 1 = attributes + FFT / window tables, 2 = + Bluestein chirp tables (frequency_filter models)
+std::atomic<int> g_device_level[64];
 const float* g_tables_ptr[64] = {nullptr};
 
-// One-time per-device setup: opt-in shared memory sizes and the constant tables.  This is the
-// only place the library synchronises (once per device, on the first call).
-int ensure_device_ready(cudaStream_t st, const float** tables) {
+// One-time per-device setup: opt-in shared memory sizes and the constant tables.  This is the only place the
+// library synchronises (once per device and level, on the first call that needs it); afterwards an entry point
+// reads one atomic and takes no lock.  The chirp tables (an O(N^2) fp64 DFT, ~1 ms) are built only for callers
+// of the frequency_filter path.
+int ensure_device_ready(cudaStream_t st, const float** tables, int level = 2) {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return DDSP_B200_ERR_UNSUPPORTED;
+    if (g_device_level[dev].load(std::memory_order_acquire) >= level) {
+        *tables = g_tables_ptr[dev];
+        return 0;
+    }
     std::lock_guard<std::mutex> lock(g_init_mutex);
-    if (!g_device_ready[dev]) {
+    int have = g_device_level[dev].load(std::memory_order_acquire);
+    if (have < level) {
         // the one-time setup synchronises the stream, which a capturing stream cannot do: ask for one warm-up call
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         CUDA_TRY(cudaStreamIsCapturing(st, &cap));
         if (cap != cudaStreamCaptureStatusNone) return DDSP_B200_ERR_CAPTURE;
+    }
+    if (have < 1) {
         CUDA_TRY(cudaFuncSetAttribute(ddsp::combsubfast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       ddsp::kCsfSmemBytes));
         CUDA_TRY(cudaFuncSetAttribute(ddsp::combsubfast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -109,6 +120,12 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
         CUDA_TRY(cudaGetSymbolAddress((void**)&ptr, g_tables));
         ddsp::fft_tables_kernel<<<4, 256, 0, st>>>(reinterpret_cast<float4*>(ptr), ptr + 2048);
         CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(st));
+        g_tables_ptr[dev] = ptr;
+        have = 1;
+        g_device_level[dev].store(1, std::memory_order_release);
+    }
+    if (have < level) {
         for (LtvKernel fn : {ltv_ir_select(DDSP_B200_MAG_ALLPASS_TANH, DDSP_B200_WINDOW_NONE),
                              ltv_ir_select(DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_DYNAMIC),
                              ltv_ir_select(DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_HANN), ltv_ir_select(-1, -1)})
@@ -130,8 +147,7 @@ int ensure_device_ready(cudaStream_t st, const float** tables) {
             g_chirp_ptr[dev][v] = base;
         }
         CUDA_TRY(cudaStreamSynchronize(st));
-        g_tables_ptr[dev] = ptr;
-        g_device_ready[dev] = true;
+        g_device_level[dev].store(2, std::memory_order_release);
     }
     *tables = g_tables_ptr[dev];
     return 0;
@@ -310,7 +326,7 @@ static int combsubfast_impl(const float* harmonic_magnitude, const float* harmon
     if (hop != ddsp::kHop) return DDSP_B200_ERR_UNSUPPORTED;
     if ((int64_t)F * hop >= (1ll << 24)) return DDSP_B200_ERR_UNSUPPORTED;
     ddsp::CsfParams P;
-    if (int rc = ensure_device_ready((cudaStream_t)stream, &P.tables)) return rc;
+    if (int rc = ensure_device_ready((cudaStream_t)stream, &P.tables, 1)) return rc;
     P.hm = harmonic_magnitude; P.hp = harmonic_phase; P.nm = noise_magnitude;
     P.cB = cB; P.cF = cF;
     P.f0_frames = f0_frames; P.fB = fB; P.fF = fF;
@@ -380,7 +396,7 @@ int ddsp_b200_combsubfast_backward(const float* harmonic_magnitude, const float*
     cudaStream_t st = (cudaStream_t)stream;
     ddsp::CsbParams PB;
     ddsp::CsfParams& P = PB.fwd;
-    if (int rc = ensure_device_ready(st, &P.tables)) return rc;
+    if (int rc = ensure_device_ready(st, &P.tables, 1)) return rc;
     P.hm = harmonic_magnitude; P.hp = harmonic_phase; P.nm = noise_magnitude;
     P.cB = cB; P.cF = cF;
     P.f0_frames = f0_frames; P.fB = fB; P.fF = fF;
@@ -570,7 +586,7 @@ int ddsp_b200_performer_project_features(const float* x, const float* x_bias, co
     if (!x || !projection || !out || B <= 0 || N <= 0 || H <= 0 || M <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
     if (M < 256 || M > ddsp::kPpfCols || ((uintptr_t)x & 15) || ((uintptr_t)x_bias & 15)) return DDSP_B200_ERR_UNSUPPORTED;
     const float* tables = nullptr;
-    if (int rc = ensure_device_ready((cudaStream_t)stream, &tables)) return rc;     // shared-memory opt-in
+    if (int rc = ensure_device_ready((cudaStream_t)stream, &tables, 1)) return rc;     // shared-memory opt-in
     const int64_t groups = ((int64_t)B * N * H + ddsp::kPpfRows - 1) / ddsp::kPpfRows;
     const unsigned grid = (unsigned)grid_for(groups, ddsp::kPpfWarps, (int64_t)sm_count() * 2);
     const float normalizer = 0.35355339059327373f;             // 64^-0.25 (pcmer.py:137)
@@ -603,7 +619,7 @@ int ddsp_b200_performer_attention(const float* q, const float* k, const float* v
     if (M > ddsp::kPpfCols || B > 65535) return DDSP_B200_ERR_UNSUPPORTED;
     const float* tables = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = ensure_device_ready(st, &tables)) return rc;     // shared-memory opt-in
+    if (int rc = ensure_device_ready(st, &tables, 1)) return rc;     // shared-memory opt-in
     const float ratio = 1.0f / sqrtf((float)M);
     if (N <= 2 * ddsp::kPasRows) {
         ddsp::performer_attention_small_kernel<<<dim3(H, B), ddsp::kPasThreads, ddsp::kPasSmemBytes, st>>>(
