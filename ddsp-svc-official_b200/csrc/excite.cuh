@@ -42,6 +42,9 @@ constexpr int kSinsMaxHarm = 512;
 #ifndef SINS_PAIRS
 #define SINS_PAIRS 4                               // packed sample pairs per thread
 #endif
+#ifndef SINS_SKIP_MASKED
+#define SINS_SKIP_MASKED 1                         // skip harmonics that are above Nyquist in both frames of a hop
+#endif
 constexpr int kOscPairs = SINS_PAIRS;
 constexpr int kOscThreads = kHop / (2 * kOscPairs);   // one CTA per hop
 
@@ -51,6 +54,9 @@ __global__ void __launch_bounds__(kOscThreads) sins_osc_kernel(const float* __re
                                                        const float* __restrict__ phase_full,
                                                        float* __restrict__ out) {
     __shared__ float4 amps[kSinsMaxHarm];      // (A0, A0, dA, dA) per harmonic
+    __shared__ int k_live;                      // harmonics below Nyquist in at least one of the hop's two frames
+    if (threadIdx.x == 0) k_live = 0;
+    __syncthreads();
     const int hop = blockIdx.x % F, b = blockIdx.x / F;
     const int m1 = min(hop + 1, F - 1);         // hold-last (core.py:17)
     const float f0a = __ldg(f0_frames + (int64_t)b * fB + (int64_t)hop * fF);
@@ -65,8 +71,21 @@ __global__ void __launch_bounds__(kOscThreads) sins_osc_kernel(const float* __re
         const float A1 = __fmul_rn(__fmul_rn(expf(__ldg(rb + k)), 0.0078125f), mb);
         const float dA = A1 - A0;
         amps[k] = make_float4(A0, A0, dA, dA);
+#if SINS_SKIP_MASKED
+        if (ma > 0.5f || mb > 0.5f) atomicMax(&k_live, k + 1);
+#endif
     }
     __syncthreads();
+#if SINS_SKIP_MASKED
+    // Harmonics above Nyquist in BOTH frames of the hop carry the mask weight 1e-7 (core.py:27) throughout the hop:
+    // their sum is below 1.3e-7 of full scale for any amplitudes a trained network emits (sum_k exp(a_k)/128 ~ 1)
+    // and the loop stops at the last harmonic that is live in either frame (f0 = 800 Hz: 27 of 128).  The mask
+    // values of the live harmonics -- including the partially masked ones at a frame boundary -- are the
+    // reference's, bit for bit.
+    const int n_loop = min(n_harm, (k_live + 1) & ~1);
+#else
+    const int n_loop = n_harm;
+#endif
     const int64_t base = ((int64_t)b * F + hop) * kHop;
     const int t = threadIdx.x;
     // sin(k*theta) by Reinsch's stable recurrence:  d_{k+1} = d_k + delta*s_k,  s_{k+1} = s_k + d_{k+1},
@@ -105,7 +124,7 @@ __global__ void __launch_bounds__(kOscThreads) sins_osc_kernel(const float* __re
         acc_o[p] = make_float2(0.0f, 0.0f);
     }
 #pragma unroll 4
-    for (int k = 0; k < n_harm; k += 2) {        // k, k+1 are harmonics k+1 (odd) and k+2 (even); n_harm is even
+    for (int k = 0; k < n_loop; k += 2) {        // k, k+1 are harmonics k+1 (odd) and k+2 (even); n_harm is even
         const float4 a = amps[k], a2 = amps[k + 1];
 #pragma unroll
         for (int p = 0; p < kOscPairs; ++p) {

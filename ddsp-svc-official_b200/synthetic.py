@@ -41,3 +41,34 @@ def make_inputs(B, F, sum_k, seed=1234, zero_f0_fraction=0.0, hop=HOP, ctrl_std=
     if noise:
         out['U'] = rng.random((B, F * hop), dtype=np.float32)
     return out
+
+
+def synthetic_state_dict(template, seed=0):
+    """Deterministic stand-in for a trained checkpoint: for every floating entry of `template` (a state_dict, only
+    names / shapes / dtypes are used) a tensor drawn from a numpy PCG64 stream keyed by (seed, crc32(name)), scaled
+    like an initialised network (matrices ~ N(0, 1/fan_in), biases ~ 0.1 N(0,1), norm gains ~ 1 + 0.1 N(0,1),
+    weight-norm gains positive, FAVOR+ projection ~ N(0,1)).  Integer entries and the synthesis `window` are kept.
+    The reference module (tests/golden/make_golden_control.py) and the drop-in (tests) both `load_state_dict` the
+    result with strict=True, so the same weights run through both without shipping megabytes of parameters."""
+    import zlib
+
+    import torch
+    out = {}
+    for name, t in template.items():
+        if not torch.is_floating_point(t) or t.dim() == 0 or name == 'window':
+            out[name] = t.clone()
+            continue
+        rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
+        x = rng.standard_normal(tuple(t.shape))
+        if name.endswith('projection_matrix'):
+            pass
+        elif name.endswith('weight_g'):
+            x = 0.5 + 0.2 * np.abs(x)
+        elif t.dim() >= 2:
+            x = x / np.sqrt(max(1, t.numel() // t.shape[0]))
+        elif name.endswith('bias'):
+            x = 0.1 * x
+        else:
+            x = 1.0 + 0.1 * x
+        out[name] = torch.from_numpy(x).to(t.dtype)
+    return out

@@ -2,9 +2,8 @@
 state_dict keys as the reference's `ddsp/vocoder.py:343-550`, with the DSP (everything except
 `Unit2Control`) running as hand-written sm_100a kernels.
 
-`unit2ctrl` (the control network, not part of the hand-written path) is the reference's own
-`ddsp.unit2control.Unit2Control` when the reference repo is importable, else the state_dict-compatible
-PyTorch re-statement `ddsp_b200.control.Unit2Control`, or any module passed as `unit2ctrl=` with the
+`unit2ctrl` (the control network) is the state_dict-compatible `ddsp_b200.control.Unit2Control` (fused kernels and
+tensor-core Linears under no_grad, plain torch ops under autograd), or any module passed as `unit2ctrl=` with the
 same call signature returning the dict of control tensors.
 """
 import os
@@ -27,12 +26,13 @@ class DotDict(dict):
 
 
 def _make_unit2ctrl(n_unit, n_spk, output_splits, c):
-    """The control network is the reference's own `ddsp.unit2control.Unit2Control` when the reference
-    repo (and its extorch / fast-transformers dependencies) is importable; otherwise the
-    state_dict-compatible plain-PyTorch re-statement in `ddsp_b200.control`."""
-    try:
+    """The control network: `ddsp_b200.control.Unit2Control`, state_dict-compatible with the reference's
+    `ddsp/unit2control.py` + `ddsp/pcmer.py` (strict load; pinned to the reference in tests/test_module_parity.py) with its
+    fused / tensor-core inference path.  DDSP_B200_REFERENCE_CONTROL=1 selects the reference's own class instead when the
+    reference repo (and its extorch / fast-transformers dependencies) is importable."""
+    if os.environ.get('DDSP_B200_REFERENCE_CONTROL') == '1':
         from ddsp.unit2control import Unit2Control      # the reference's control network
-    except Exception:
+    else:
         from .control import Unit2Control
     return Unit2Control(n_unit, n_spk, output_splits, c)
 
@@ -54,10 +54,44 @@ class _SynthBase(torch.nn.Module):
         return (torch.initial_seed() * 0x9E3779B1 + self._noise_calls) & ((1 << 62) - 1)
 
     @staticmethod
-    def _forward_only(ctrls):
-        if torch.is_grad_enabled() and any(t.requires_grad for t in ctrls.values()):
-            raise RuntimeError('this ddsp_b200 synthesizer is forward-only (only CombSubFast has a backward): call under '
-                               'torch.no_grad() as main.py:145 / gui.py:125 / solver.py:28 do')
+    def _wants_grad(ctrls):
+        return torch.is_grad_enabled() and any(t.requires_grad for t in ctrls.values())
+
+
+class _FilterStageB(torch.autograd.Function):
+    """Stage B of the `frequency_filter` synthesizers (Sins, CombSub-old) under autograd, so that the drop-in modules
+    train (solver.py:111-113).  Forward: the hand-written kernels.  Backward: stage B is re-evaluated with the stock
+    torch ops of `ddsp_b200.diffsynth` (the same function, pinned to the reference's own gradients in
+    tests/test_diffsynth.py) under autograd and its gradients w.r.t. the three control tensors are returned; f0,
+    phase and the (explicitly drawn) noise are data, as in the reference graph."""
+
+    @staticmethod
+    def forward(ctx, kind, c0, c1, c2, f0_frames, aux, phase_full, hop, sr, noise_u):
+        if kind == 'sins':
+            outs = core.sins_stage(c0, c1, c2, f0_frames, phase_full, hop, sr, noise_u=noise_u)
+        else:
+            outs = core.combsub_stage(c0, c1, c2, f0_frames, aux, hop, sr, noise_u=noise_u)
+        ctx.save_for_backward(c0, c1, c2, f0_frames, phase_full, noise_u)
+        ctx.cfg = (kind, hop, sr)
+        return outs
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_signal, g_harmonic, g_noise):
+        from . import diffsynth
+        c0, c1, c2, f0_frames, phase_full, noise_u = ctx.saved_tensors
+        kind, hop, sr = ctx.cfg
+        with torch.enable_grad():
+            p = [t.detach().requires_grad_(True) for t in (c0, c1, c2)]
+            if kind == 'sins':
+                outs = diffsynth.sins_stage(p[0], p[1], p[2], f0_frames, phase_full, noise_u, hop, sr)
+            else:
+                rot = phase_full / (2 * 3.141592653589793)
+                outs = diffsynth.combsub_stage(p[0], p[1], p[2], f0_frames, rot, noise_u, hop, sr)
+            grads = [g for g in (g_signal, g_harmonic, g_noise)]
+            pairs = [(o, g) for o, g in zip(outs, grads) if g is not None]
+            torch.autograd.backward([o for o, _ in pairs], [g for _, g in pairs])
+        return (None, p[0].grad, p[1].grad, p[2].grad, None, None, None, None, None, None)
 
 
 class _CombSubFastStageB(torch.autograd.Function):
@@ -126,10 +160,20 @@ class CombSub(_SynthBase):
     def forward(self, units_frames, f0_frames, volume_frames, spk_id, spk_mix_dict=None, initial_phase=None,
                 infer=True, noise_u=None, **kwargs):
         f0_frames = core.as_f32(f0_frames)
-        phase_frames, prefix, _ = core.phase_stage(f0_frames, self._hop, self._sr, initial_phase, infer)   # :515-517
+        grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.unit2ctrl.parameters())
+        phase_frames, prefix, phase_full = core.phase_stage(f0_frames, self._hop, self._sr, initial_phase, infer,
+                                                            full_rate=grad)                                   # :515-517
         ctrls = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id, spk_mix_dict=spk_mix_dict)
-        self._forward_only(ctrls)
         ctrls = {k: core.as_f32(v) for k, v in ctrls.items()}
+        if self._wants_grad(ctrls):
+            if phase_full is None:
+                phase_full = core.phase_stage(f0_frames, self._hop, self._sr, initial_phase, infer, full_rate=True)[2]
+            if noise_u is None:     # torch.rand_like of vocoder.py:545, drawn here so that forward and backward share it
+                noise_u = torch.rand(f0_frames.shape[0], f0_frames.shape[1] * self._hop, device=f0_frames.device)
+            signal, harmonic, noise = _FilterStageB.apply('combsub', ctrls['group_delay'], ctrls['harmonic_magnitude'],
+                                                          ctrls['noise_magnitude'], f0_frames, prefix, phase_full,
+                                                          self._hop, self._sr, noise_u)
+            return signal, phase_frames.unsqueeze(-1), (harmonic, noise)
         signal, harmonic, noise = core.combsub_stage(ctrls['group_delay'], ctrls['harmonic_magnitude'],
                                                      ctrls['noise_magnitude'], f0_frames, prefix, self._hop, self._sr,
                                                      noise_u=noise_u, seed=self._next_seed())                  # :521-548
@@ -153,8 +197,14 @@ class Sins(_SynthBase):
         f0_frames = core.as_f32(f0_frames)
         phase_frames, _, phase = core.phase_stage(f0_frames, self._hop, self._sr, initial_phase, infer, full_rate=True)
         ctrls = self.unit2ctrl(units_frames, f0_frames, phase_frames, volume_frames, spk_id, spk_mix_dict=spk_mix_dict)
-        self._forward_only(ctrls)
         ctrls = {k: core.as_f32(v) for k, v in ctrls.items()}
+        if self._wants_grad(ctrls):
+            if noise_u is None:     # torch.rand_like of vocoder.py:418
+                noise_u = torch.rand(phase.shape, device=phase.device)
+            signal, harmonic, noise = _FilterStageB.apply('sins', ctrls['amplitudes'], ctrls['group_delay'],
+                                                          ctrls['noise_magnitude'], f0_frames, None, phase, self._hop,
+                                                          self._sr, noise_u)
+            return signal, phase.unsqueeze(-1), (harmonic, noise)
         signal, harmonic, noise = core.sins_stage(ctrls['amplitudes'], ctrls['group_delay'], ctrls['noise_magnitude'],
                                                   f0_frames, phase, self._hop, self._sr, noise_u=noise_u,
                                                   seed=self._next_seed())                                     # :397-421

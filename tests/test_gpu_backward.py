@@ -178,12 +178,58 @@ def test_module_trains_like_the_port():
     assert losses[-1] < losses[0], losses
 
 
-def test_other_models_still_refuse_autograd():
+@pytest.mark.parametrize('model', ['combsub', 'sins'])
+def test_filter_models_train(golden_dir, model):
+    """solver.py:111-113 with the Sins / CombSub-old drop-ins: forward through the kernels, gradients of the control
+    tensors from ddsp_b200.diffsynth -- checked against the gradients autograd gave through the reference module."""
+    from ddsp_b200 import vocoder
+    g = dict(np.load(os.path.join(golden_dir, f'{model}_grad_small.npz')))
+    splits = {'combsub': (256, 512, 256), 'sins': (128, 256, 256)}[model]
+    names = {'combsub': ('group_delay', 'harmonic_magnitude', 'noise_magnitude'),
+             'sins': ('amplitudes', 'group_delay', 'noise_magnitude')}[model]
+    ctrl = dev(g['ctrl']).requires_grad_(True)
+
+    class Fixed(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.dummy = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, *a, **k):
+            return dict(zip(names, torch.split(ctrl, list(splits), dim=-1)))
+    if model == 'combsub':
+        m = vocoder.CombSub(44100, 512, 256, 512, 256, n_unit=4, unit2ctrl=Fixed()).cuda()
+    else:
+        m = vocoder.Sins(44100, 512, 128, 256, 256, n_unit=4, unit2ctrl=Fixed()).cuda()
+    B, Fr = g['f0_frames'].shape
+    sig, _, (harm, noise) = m(torch.zeros(B, Fr, 4, device='cuda'), dev(g['f0_frames'])[..., None], torch.zeros(B, Fr, device='cuda'),
+                              torch.ones(B, 1, dtype=torch.long, device='cuda'), infer=False, noise_u=dev(g['U']))
+    assert sig.requires_grad
+    assert np.abs(sig.detach().cpu().numpy() - g['signal64']).max() < 5e-5
+    (sig * dev(g['R'])).sum().backward()
+    ref = g['grad64']
+    err = np.abs(ctrl.grad.cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err < 1e-4, err
+
+
+def test_filter_model_with_control_network_takes_an_optimiser_step():
     from ddsp_b200.vocoder import Sins
+    from ddsp_b200.loss import RSSLoss
+    torch.manual_seed(0)
     m = Sins(44100, 512, 128, 256, 256, n_unit=8).cuda()
-    with pytest.raises(RuntimeError, match='forward-only'):
-        m(torch.randn(1, 4, 8, device='cuda'), torch.full((1, 4, 1), 200.0, device='cuda'),
-          torch.rand(1, 4, device='cuda'), torch.ones(1, 1, dtype=torch.long, device='cuda'))
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+    loss_fn = RSSLoss(256, 1024, 2, device='cuda')
+    units = torch.randn(2, 12, 8, device='cuda')
+    f0 = torch.full((2, 12, 1), 220.0, device='cuda')
+    vol = torch.rand(2, 12, device='cuda')
+    spk = torch.ones(2, 1, dtype=torch.long, device='cuda')
+    target = torch.randn(2, 12 * 512, device='cuda') * 0.05
+    sig, _, _ = m(units, f0, vol, spk, infer=False)
+    loss = loss_fn(sig, target)
+    opt.zero_grad()
+    loss.backward()
+    n_grad = sum(1 for p in m.parameters() if p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0)
+    assert n_grad > 50
+    opt.step()
 
 
 def test_backward_error_cases():
