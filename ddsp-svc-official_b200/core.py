@@ -295,8 +295,9 @@ def frequency_filter(audio, magnitudes, hann_window=True, half_width_frames=None
                      sampling_rate=44100, encoding=None, mag_scale=1.0):
     """Apply a per-frame linear-phase LTV-FIR (reference ddsp/core.py:331-336).
 
-    audio (B,T) float32; magnitudes (B,F,n_mag) real float32 or complex64, n_mag in {256, 512},
-    T = 512*F.  `half_width_frames` (B,F,1) selects the dynamic cosine window exactly as in the
+    audio (B,T) float32; magnitudes (B,F,n_mag) real float32 or complex64, n_mag in {256, 512} (complex with
+    n_mag = 512 only with a zero imaginary part, the reference's `torch.complex(x, zeros)` idiom), T = 512*F (other hop
+    sizes raise).  `half_width_frames` (B,F,1) selects the dynamic cosine window exactly as in the
     reference; it must be the synthesizer's `1.5*sr/(f0_frames+1e-3)` (vocoder.py:542) -- pass the
     generating `f0_frames` instead and the kernel derives it.  `encoding`/`mag_scale` let the
     synthesizer modules hand over raw control tensors (exp / all-pass) without materialising the
@@ -307,7 +308,17 @@ def frequency_filter(audio, magnitudes, hann_window=True, half_width_frames=None
     if magnitudes.shape[0] != B:
         raise ValueError(f'Batch size of audio ({B}) and impulse response ({magnitudes.shape[0]}) must be the same.')
     if encoding is None:
-        if magnitudes.is_complex():
+        if magnitudes.is_complex() and magnitudes.shape[-1] == 512:
+            # The reference's own call with n_mag = 512 is `torch.complex(src_param, zeros)` (vocoder.py:541): the L = 1022
+            # kernels evaluate real (symmetric) magnitude responses.  A zero imaginary part is verified here (one device
+            # sync; this mirror is not on the modules' hot path) and the real part handed on; a genuinely complex 512-bin
+            # response is not supported.
+            if bool((magnitudes.imag != 0).any()):
+                raise _cabi.DDSPB200Error('frequency_filter: complex magnitudes with n_mag = 512 must have a zero imaginary '
+                                          'part (vocoder.py:541); only n_mag = 256 takes arbitrary complex responses')
+            magnitudes = magnitudes.real.to(torch.float32)
+            encoding, n_mag = MAG_REAL, 512
+        elif magnitudes.is_complex():
             magnitudes = torch.view_as_real(magnitudes.to(torch.complex64).contiguous()).reshape(
                 magnitudes.shape[0], magnitudes.shape[1], -1)
             encoding, n_mag = MAG_COMPLEX, magnitudes.shape[-1] // 2

@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(128) csf_zero_seams_kernel(float* __restrict__
 // -> real part, noise excitation (injected U or the in-kernel stream) -> imaginary part.
 template <bool HAS_U>
 __device__ __forceinline__ void csf_load_frame(const CsfParams& P, Pts32& X, const float* __restrict__ ring,
-                                               const float* __restrict__ win, int fm, int b, uint32_t key, int lane) {
+                                               const float* __restrict__ win, int fm, int b, uint32_t key, uint32_t key2,
+                                               int lane) {
     const int F = P.F;
     const float* slotA = ring + ((fm - 1) & 1) * kRingSlot + lane;   // hop fm-1
     const float* slotB = ring + (fm & 1) * kRingSlot + lane;         // hop fm
@@ -198,8 +199,8 @@ __device__ __forceinline__ void csf_load_frame(const CsfParams& P, Pts32& X, con
     const float* u_b = HAS_U ? P.noise_u + (int64_t)b * F * kHop + lane : nullptr;
     uint32_t stA = 0, stB = 0;
     if (!HAS_U) {
-        stA = noise_seed(key, (uint32_t)(fm - 1), (uint32_t)lane);
-        stB = noise_seed(key, (uint32_t)fm, (uint32_t)lane);
+        stA = noise_seed(key, key2, (uint32_t)(fm - 1), (uint32_t)lane);
+        stB = noise_seed(key, key2, (uint32_t)fm, (uint32_t)lane);
     }
     // samples 32*n1 + lane for n1 = 2j, 2j+1 land in the two halves of one packed register
     // (register index brev5(2j) and brev5(2j) + 16), so each window pair feeds packed multiplies
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
     // Per-warp scalars that are needed only a few times per step live in shared memory (volatile
     // reads) instead of registers: the FFT keeps 64 data registers live and anything else held
     // across it would be spilled to local memory, whose reloads miss the (tiny) L1 here.
-    //   ctx[0] clip, [1] first pair, [2] end pair, [3] noise key, [4] step,
+    //   ctx[0] clip, [1] first pair, [2] end pair, [3] noise key (low word + hop offset), [4] step, [5] noise key (high word),
     //   ctx[8], [9] f0 frame values and [10..11] fp64 prefix of the NEXT hop (staged by cp.async),
     //   ctx[12..13] f0 row pointer, [14..15] prefix row pointer of the clip
     volatile int* ctx = reinterpret_cast<volatile int*>(stash + kStashFloat2);
@@ -279,7 +280,9 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             ctx[1] = pb;                                        // p_begin
             ctx[2] = pb + P.run_len + (r < P.run_rem ? 1 : 0);  // p_end
             const uint64_t seed = P.seed + (P.seed_device ? __ldg(P.seed_device) : 0ull);
-            ctx[3] = (int)(noise_key(seed, (uint32_t)b0) + P.key_offset);
+            const uint64_t k64 = noise_key64(seed, (uint32_t)b0);
+            ctx[3] = (int)((uint32_t)k64 + P.key_offset);
+            ctx[5] = (int)(uint32_t)(k64 >> 32);
             *reinterpret_cast<volatile uint64_t*>(ctx + 12) = (uint64_t)(P.f0_frames + (int64_t)b0 * P.fB);
             *reinterpret_cast<volatile uint64_t*>(ctx + 14) = (uint64_t)(P.prefix + (int64_t)b0 * P.F);
         }
@@ -289,6 +292,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
 #define CTX_PBEGIN ctx[1]
 #define CTX_PEND ctx[2]
 #define CTX_KEY ((uint32_t)ctx[3])
+#define CTX_KEY2 ((uint32_t)ctx[5])
     // Seams between runs: the hop shared by the last frame of run r-1 and the first frame of run r
     // receives one atomic add from each side onto zeros written by csf_zero_seams_kernel
     // (0 + a + b is the same fp32 number in either order, so the result does not depend on timing).
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
 #endif
                 if (lane <= 16) { prefetch_l2(P.hm + ro); prefetch_l2(P.hp + ro); prefetch_l2(P.nm + ro); }
             }
-            csf_load_frame<HAS_U>(P, X, ring, win, fm, CTX_B, CTX_KEY, lane);
+            csf_load_frame<HAS_U>(P, X, ring, win, fm, CTX_B, CTX_KEY, CTX_KEY2, lane);
 #if CSF_PRE > 0 || CSF_HOP_AHEAD
             __syncwarp();       // every lane has read hop fm-1 out of its ring slot: the slot is free until hop fm+1 is generated
 #endif

@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(kCsbThreads, 1) combsubfast_backward_kernel(co
             ctx[0] = b0;
             ctx[1] = pb;
             ctx[2] = pb + P.run_len + (r < P.run_rem ? 1 : 0);
-            ctx[3] = (int)noise_key(P.seed, (uint32_t)b0);
+            const uint64_t k64 = noise_key64(P.seed, (uint32_t)b0);
+            ctx[3] = (int)(uint32_t)k64;
+            ctx[5] = (int)(uint32_t)(k64 >> 32);
         }
         __syncwarp();
     }
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(kCsbThreads, 1) combsubfast_backward_kernel(co
                 const int64_t rp = (int64_t)b * P.cB + (int64_t)min(fm, F - 1) * P.cF + 32 * lane;
                 if (lane <= 16) { prefetch_l2(P.hm + rp); prefetch_l2(P.hp + rp); prefetch_l2(P.nm + rp); }
             }
-            csf_load_frame<HAS_U>(P, X, ring, win, fm, b, (uint32_t)ctx[3], lane);
+            csf_load_frame<HAS_U>(P, X, ring, win, fm, b, (uint32_t)ctx[3], (uint32_t)ctx[5], lane);
         } else {
             // ---- q_2p -> real part, q_2p+1 -> imaginary part --------------------------------------
             // frame m spans output hops m-1 (first half) and m (second half); hops outside [0,F) carry no gradient

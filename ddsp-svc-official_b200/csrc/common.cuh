@@ -30,13 +30,15 @@ __device__ __forceinline__ float lerp_torch(float x0, float x1, float w1) {
 }
 
 // Counter-based uniform noise used when no `noise_u` tensor is injected.
-// lowbias32 finaliser over (sample index, per-clip key); returns U in [0,1) on a 2^-24 grid.
-__host__ __device__ __forceinline__ uint32_t noise_key(uint64_t seed, uint32_t clip) {
+// A clip owns a 64-bit key (splitmix64 of seed and clip index): the low word enters the per-(hop, lane) stream seed
+// linearly (so that a streaming hop offset folds into it on the host), the high word is added between the two
+// multiply-xorshift rounds of the hash.  Two clips draw the same (shifted) streams only if BOTH words line up,
+// i.e. with probability ~2^-64 per pair instead of ~2^-32 * frames with a single additive key.
+__host__ __device__ __forceinline__ uint64_t noise_key64(uint64_t seed, uint32_t clip) {
     uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(clip + 1);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    return (uint32_t)(z >> 32) ^ (uint32_t)z;
+    return z ^ (z >> 31);
 }
 // Noise stream layout: the 16 samples {hop*512 + 32*i + lane, i = 0..15} that one lane feeds into
 // the FFT form one short multiplicative-congruential stream seeded by a strong hash of (clip key, hop,
@@ -44,9 +46,10 @@ __host__ __device__ __forceinline__ uint32_t noise_key(uint64_t seed, uint32_t c
 // state <- 747796405 state mod 2^32 is s <- 747796405 s mod 2^24.  The draw is s itself (top 24 bits of
 // the state), so the centred value is the state read as a signed integer -- one IMAD + one exact
 // int->float conversion per sample, no shift.
-__host__ __device__ __forceinline__ uint32_t noise_seed(uint32_t key, uint32_t hop, uint32_t lane) {
+__host__ __device__ __forceinline__ uint32_t noise_seed(uint32_t key, uint32_t key2, uint32_t hop, uint32_t lane) {
     uint32_t x = (hop * 32u + lane) * 0x9E3779B1u + key;
     x ^= x >> 16; x *= 0x7feb352du;
+    x += key2;
     x ^= x >> 15; x *= 0x846ca68bu;
     x ^= x >> 16;
     return (x & 0xffffff00u) | 0x100u;

@@ -457,7 +457,9 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
         const int mb = (int)(run % P.runs_per_clip) * P.run_len;
         if (lane == 0) {
             ctx[0] = b0; ctx[1] = mb; ctx[2] = min(P.F + 1, mb + P.run_len);
-            ctx[3] = (int)noise_key(P.seed, (uint32_t)b0);
+            const uint64_t k64 = noise_key64(P.seed, (uint32_t)b0);
+            ctx[3] = (int)(uint32_t)k64;
+            ctx[5] = (int)(uint32_t)(k64 >> 32);
         }
         __syncwarp();
     }
@@ -490,9 +492,9 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                 // z[n] = a[2n] + j a[2n+1], n = 32 n1 + lane < 512; a = bartlett * frame (core.py:218-222)
                 const bool vA = m >= 1, vB = m < F;
                 const float* src = P.audio + (int64_t)CV_B * T;
-                const uint32_t key = (uint32_t)ctx[3];
-                uint32_t stA = noise_seed(key, (uint32_t)(m - 1), (uint32_t)lane);
-                uint32_t stB = noise_seed(key, (uint32_t)m, (uint32_t)lane);
+                const uint32_t key = (uint32_t)ctx[3], key2 = (uint32_t)ctx[5];
+                uint32_t stA = noise_seed(key, key2, (uint32_t)(m - 1), (uint32_t)lane);
+                uint32_t stB = noise_seed(key, key2, (uint32_t)m, (uint32_t)lane);
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) {
                     float v0 = 0.0f, v1 = 0.0f;
@@ -710,7 +712,9 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
         const int mb = (int)(run % P.runs_per_clip) * P.run_len;
         if (lane == 0) {
             ctx[0] = b0; ctx[1] = mb; ctx[2] = min(P.F + 1, mb + P.run_len);
-            ctx[3] = (int)noise_key(P.seed, (uint32_t)b0);
+            const uint64_t k64 = noise_key64(P.seed, (uint32_t)b0);
+            ctx[3] = (int)(uint32_t)k64;
+            ctx[5] = (int)(uint32_t)(k64 >> 32);
         }
         __syncwarp();
     }
@@ -739,9 +743,9 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
                 //   up[n] = x[t0 + n] * n/512, down[n] = x[t0 + 512 + n] * (512 - n)/512   (core.py:218-222)
                 const bool vA = m >= 1, vB = m < F;
                 const float* src = P.audio + (int64_t)CV_B * T + lane;
-                const uint32_t key = (uint32_t)ctx[3];
-                uint32_t stA = noise_seed(key, (uint32_t)(m - 1), (uint32_t)lane);
-                uint32_t stB = noise_seed(key, (uint32_t)m, (uint32_t)lane);
+                const uint32_t key = (uint32_t)ctx[3], key2 = (uint32_t)ctx[5];
+                uint32_t stA = noise_seed(key, key2, (uint32_t)(m - 1), (uint32_t)lane);
+                uint32_t stB = noise_seed(key, key2, (uint32_t)m, (uint32_t)lane);
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) {
                     float v0 = 0.0f, v1 = 0.0f;

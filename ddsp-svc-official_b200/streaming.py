@@ -41,10 +41,15 @@ class CombSubFastStream:
         self.sr = float(sampling_rate)
         self.window = window
         self.seed = int(seed)
+        self._utterance = -1
         self.initial_phase = initial_phase
         self.reset()
 
     def reset(self):
+        # a new utterance draws new noise: the stream seed moves on every reset() / flush() (re-synthesised hops inside one
+        # utterance keep their noise through the hop index, not through the seed)
+        self._utterance += 1
+        self._seed_now = (self.seed + 0x9E3779B97F4A7C15 * self._utterance) & ((1 << 62) - 1)
         self.frames_pushed = 0          # frames handed to finish() so far
         self.hops_emitted = 0
         # f0 and control rows of the stream live in one linear device buffer each; the window of a block is
@@ -130,7 +135,7 @@ class CombSubFastStream:
         hm, hp, nm = torch.split(rows_win, K, dim=-1)
         first_hop = self.frames_pushed - t                 # stream index of the window's first hop
         signal = core.combsubfast_stage(hm, hp, nm, f0_win, prefix, self.hop, self.sr, noise_u=noise_win,
-                                        seed=self.seed, window=self.window, hop_offset=first_hop)
+                                        seed=self._seed_now, window=self.window, hop_offset=first_hop)
         # hop j of the window is final for j <= W-3 (and for j >= 1 unless the window starts the stream: lo is
         # 1 in the steady state, 0 while the window still begins at frame 0)
         lo = self.hops_emitted - first_hop

@@ -49,9 +49,14 @@ class _SynthBase(torch.nn.Module):
         self._noise_calls = 0
         self._seed_device = None        # set by GraphedForward: device counter added to the noise seed per replay
 
+    _instances = 0          # every module draws from its own seed sequence (two models with equal call counts must differ)
+
     def _next_seed(self):
+        if self._noise_calls == 0:
+            _SynthBase._instances += 1
+            self._instance = _SynthBase._instances
         self._noise_calls += 1
-        return (torch.initial_seed() * 0x9E3779B1 + self._noise_calls) & ((1 << 62) - 1)
+        return ((torch.initial_seed() * 0x9E3779B1 + self._instance) * 0x2545F4914F6CDD1D + self._noise_calls) & ((1 << 62) - 1)
 
     @staticmethod
     def _wants_grad(ctrls):

@@ -103,6 +103,12 @@ int ddsp_b200_frequency_filter(const float *audio, const float *mags, int64_t mB
  * = fl32(2*pi)*rot[:, ::hop]; prefix (B,F) fp64 = sum of the upsampled fp32 f0 over all samples
  * before each frame (consumed by stage B); phase_full (B,T) or NULL (Sins: 2*pi*rot at sample
  * rate, vocoder.py:392).  hop must be 512.
+ * `precise` mirrors fo_to_rot's flag (the forwards pass `infer`) and is accepted for signature compatibility only:
+ * this fused stage ALWAYS accumulates in fp64.  The reference's precise=False (training, core.py:40) is an fp32
+ * `cumsum` whose rounding depends on the scan order of the backend (torch CPU and CUDA already differ) and drifts by
+ * whole rotations on long clips; the fp64 result is the value both approximate.  Callers that need the fp32
+ * arithmetic itself use ddsp_b200_fo_to_rot(precise = 0).  `initial_phase` (radians, per clip or NULL) enters the
+ * prefix here; the stage-B entry points take the prefix and ignore their own `initial_phase` argument.
  * ---------------------------------------------------------------------------------------- */
 int ddsp_b200_phase(const float *f0_frames, int64_t fB, int64_t fF, int B, int F, int hop, double sr,
                     const float *initial_phase, int precise, float *phase_frames, double *prefix,

@@ -48,22 +48,24 @@ def assert_waveform(out, ref, max_abs=MAX_ABS_TOL, snr=SNR_TOL_DB, what=''):
     return err, s
 
 
-# ---- host restatement of the in-kernel counter-based noise (csrc/common.cuh: noise_key / noise_seed /
+# ---- host restatement of the in-kernel counter-based noise (csrc/common.cuh: noise_key64 / noise_seed /
 # noise_next / noise_u24).  Integer work, so the comparison with the kernels is bit-exact.
-def noise_key(seed, clip):
+def noise_key64(seed, clip):
     m = (1 << 64) - 1
     z = (seed + 0x9E3779B97F4A7C15 * (clip + 1)) & m
     z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
     z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
-    z = z ^ (z >> 31)
-    return ((z >> 32) ^ z) & 0xffffffff
+    return z ^ (z >> 31)
 
 
-def hop_noise(k, hop):
-    """(512,) uniforms of one hop: lane l owns samples 32*i + l, an LCG stream seeded per (hop, lane)."""
+def hop_noise(k64, hop):
+    """(512,) uniforms of one hop: lane l owns samples 32*i + l, a 24-bit multiplicative stream seeded per (hop, lane)
+    from the clip's 64-bit key (low word additive before the first hash round, high word between the rounds)."""
+    key, key2 = k64 & 0xffffffff, k64 >> 32
     lane = np.arange(32, dtype=np.uint64)
-    x = ((hop * 32 + lane) * 0x9E3779B1 + k) & 0xffffffff
+    x = ((hop * 32 + lane) * 0x9E3779B1 + key) & 0xffffffff
     x ^= x >> 16; x = (x * 0x7feb352d) & 0xffffffff
+    x = (x + key2) & 0xffffffff
     x ^= x >> 15; x = (x * 0x846ca68b) & 0xffffffff
     x ^= x >> 16
     x = (x & 0xffffff00) | 0x100        # 24-bit stream in the top bits, odd; low byte clear (exact int->float)
@@ -77,4 +79,4 @@ def hop_noise(k, hop):
 
 def in_kernel_noise(seed, B, F):
     """(B, F*512) uniforms the kernels draw for `seed` when no noise tensor is injected."""
-    return np.stack([np.concatenate([hop_noise(noise_key(seed, b), h) for h in range(F)]) for b in range(B)])
+    return np.stack([np.concatenate([hop_noise(noise_key64(seed, b), h) for h in range(F)]) for b in range(B)])

@@ -47,6 +47,19 @@ def test_frequency_filter_allpass_complex(gold):
     assert_waveform(y2, gold['ff_ap_y'], max_abs=3e-5, snr=85, what='frequency_filter/allpass (tanh control)')
 
 
+def test_frequency_filter_replays_the_reference_call_sequence(gold):
+    """vocoder.py:541-542 verbatim through the mirror: `frequency_filter(x, torch.complex(src_param, zeros), hann_window=True,
+    half_width_frames=1.5*sr/(f0_frames+1e-3))` with n_mag = 512 -- complex magnitudes with a zero imaginary part."""
+    from ddsp_b200 import _cabi
+    f0f = torch.from_numpy(gold['ff_f0f'].astype(np.float32)).cuda()
+    src = dev(gold['ff_mags2'])
+    y = core.frequency_filter(dev(gold['ff_audio']), torch.complex(src, torch.zeros_like(src)), hann_window=True,
+                              half_width_frames=1.5 * 44100 / (f0f + 1e-3)).cpu().numpy()
+    assert_waveform(y, gold['ff_dyn_y'], max_abs=3e-5, snr=90, what='frequency_filter/reference call sequence')
+    with pytest.raises(_cabi.DDSPB200Error):
+        core.frequency_filter(dev(gold['ff_audio']), torch.complex(src, torch.ones_like(src)), hann_window=True)
+
+
 @pytest.mark.parametrize('B,F,n_mag', [(1, 1, 256), (2, 3, 256), (1, 9, 512), (3, 40, 256), (2, 33, 512)])
 def test_frequency_filter_vs_oracle_ragged_runs(B, F, n_mag):
     """Frame counts that do not divide into runs evenly, single-frame clips, seams between runs."""
