@@ -542,6 +542,124 @@ def linear(x, weight, bias=None, residual=None, out=None):
     return out
 
 
+def split_tf32(w):
+    """(hi, lo) with hi = w rounded to TF32 (the kernel's rounding: add half a TF32 ulp to the bit pattern, clear the low
+    13 bits) and lo = w - hi (exact): static weights are split once here instead of in shared memory on every tile."""
+    w = _need_cuda_f32(w, 'weight').contiguous()
+    hi = ((w.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    return hi, w - hi
+
+
+def linear_ex(x, weight, bias=None, residual=None, out=None, weight_lo=None, ln=None, ln_out=None):
+    """`linear` through the second-generation GEMM (csrc/gemm_attn.cuh): TMA-store epilogue, optional pre-split weight
+    (`weight` = hi, `weight_lo` = lo from `split_tf32`) and optional fused LayerNorm: `ln = (gamma, beta, eps)` makes the
+    call return `(out, layer_norm(out))` -- the normalised copy is produced while the row is still in tensor memory
+    (pcmer.py:25,44: every LayerNorm of PCmer follows a residual GEMM)."""
+    x = _need_cuda_f32(x, 'x')
+    weight = _need_cuda_f32(weight, 'weight')
+    N, K = weight.shape
+    if x.shape[-1] != K:
+        raise ValueError(f'linear: x has {x.shape[-1]} features, weight expects {K}')
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1 or (x2.stride(0) & 3) or (x2.data_ptr() & 15):
+        x2 = x2.contiguous()
+    if weight.stride(1) != 1 or (weight.stride(0) & 3) or (weight.data_ptr() & 15):
+        if weight_lo is not None:
+            raise ValueError('linear_ex: a pre-split weight must be contiguous')
+        weight = weight.contiguous()
+    if weight_lo is not None and (weight_lo.shape != weight.shape or weight_lo.stride() != weight.stride()):
+        raise ValueError('linear_ex: weight_lo must match weight')
+    M = x2.shape[0]
+    if K & 3:
+        raise ValueError('linear: the reduction length must be a multiple of 4 (16-byte rows for TMA)')
+    if out is None:
+        out = torch.empty(lead + (N,), dtype=torch.float32, device=x.device)
+    o2 = out.view(-1, N) if out.is_contiguous() else out.reshape(-1, out.shape[-1])[:, :N]
+    if o2.data_ptr() != out.data_ptr() or o2.stride(1) != 1:
+        raise ValueError('linear: `out` must have contiguous rows')
+    r2, ldr = None, 0
+    if residual is not None:
+        r2 = _need_cuda_f32(residual, 'residual').reshape(-1, N)
+        if r2.stride(1) != 1:
+            r2 = r2.contiguous()
+        ldr = r2.stride(0)
+    if bias is not None:
+        bias = _need_cuda_f32(bias, 'bias').contiguous()
+    g = b_ = None
+    eps = 0.0
+    l2 = None
+    if ln is not None:
+        g, b_, eps = ln
+        g = _need_cuda_f32(g, 'ln gamma').contiguous()
+        b_ = _need_cuda_f32(b_, 'ln beta').contiguous()
+        if ln_out is None:
+            ln_out = torch.empty(lead + (N,), dtype=torch.float32, device=x.device)
+        l2 = ln_out.view(-1, N)
+    with _OnDevice(x.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_linear_tf32x3_ex(
+            x2.data_ptr(), x2.stride(0), weight.data_ptr(), _ptr(weight_lo), weight.stride(0), _ptr(bias), _ptr(r2), ldr,
+            o2.data_ptr(), o2.stride(0), _ptr(g), _ptr(b_), float(eps), _ptr(l2), l2.stride(0) if l2 is not None else 0,
+            M, N, K, _st))
+    return (out, ln_out) if ln is not None else out
+
+
+_FAVOR_FEATURES, _FAVOR_PAD, _FAVOR_VT_ROWS = 266, 272, 80
+_favor_ws = {}
+
+
+def favor_workspace(B, H, F, device):
+    """Buffers of the tensor-core attention path, allocated once per (B, H, F, device) and reused by every layer and
+    call: q, k (B,H,F,64); vt (B,H,80,Fp) with its row of ones; q' (B*H,F,272); k'^T (B*H,272,Fp) zero-initialised
+    (its pad rows / columns are never written); ctxT (B*H,80,272)."""
+    key = (B, H, F, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _favor_ws.get(key)
+    if ws is None:
+        Fp = (F + 3) // 4 * 4
+        Z = B * H
+        f32 = dict(dtype=torch.float32, device=device)
+        vt = torch.zeros((B, H, _FAVOR_VT_ROWS, Fp), **f32)
+        vt[:, :, 64, :F] = 1.0
+        ws = {'Fp': Fp, 'q': torch.empty((B, H, F, 64), **f32), 'k': torch.empty((B, H, F, 64), **f32), 'vt': vt,
+              'qf': torch.empty((Z, F, _FAVOR_PAD), **f32), 'kt': torch.zeros((Z, _FAVOR_PAD, Fp), **f32),
+              'ctx': torch.empty((Z, _FAVOR_VT_ROWS, _FAVOR_PAD), **f32)}
+        if len(_favor_ws) >= 4:
+            _favor_ws.clear()
+        _favor_ws[key] = ws
+    return ws
+
+
+def favor_attention(x, w_qkv, w_qkv_lo, b_qkv, proj_scaled, heads, eps=1e-4):
+    """Non-causal Performer self-attention (pcmer.py:191-251 up to, not including, `to_out`) as five tensor-core
+    launches: merged q|k|v projection with head-split / transposed stores, the FAVOR+ feature GEMM for q and for k,
+    the context GEMM and the normalised output GEMM.  x (B,F,C) layer-normed input; w_qkv (3*H*64, C) = [W_q; W_k; W_v]
+    (optionally pre-split: w_qkv = hi, w_qkv_lo = lo), b_qkv (3*H*64); proj_scaled = 64^-0.25 * projection_matrix
+    (266, 64).  Returns the head-merged attention output (B, F, H*64)."""
+    x = _need_cuda_f32(x, 'x')
+    B, F, Cc = x.shape
+    H = int(heads)
+    if proj_scaled.shape != (_FAVOR_FEATURES, 64) or w_qkv.shape != (3 * H * 64, Cc):
+        raise ValueError('favor_attention: dim_head 64 / 266 features / merged (3*H*64, C) weight expected')
+    x2 = x.reshape(B * F, Cc)
+    if x2.stride(1) != 1 or (x2.stride(0) & 3) or (x2.data_ptr() & 15):
+        x2 = x2.contiguous()
+    ws = favor_workspace(B, H, F, x.device)
+    Fp, Z = ws['Fp'], B * H
+    out = torch.empty((B, F, H * 64), dtype=torch.float32, device=x.device)
+    L = _cabi.lib()
+    launches = 0
+    with _OnDevice(x.device) as _st:
+        _cabi.check(L.ddsp_b200_qkv_heads(x2.data_ptr(), x2.stride(0), w_qkv.data_ptr(), _ptr(w_qkv_lo), w_qkv.stride(0),
+                                          _ptr(b_qkv), ws['q'].data_ptr(), ws['k'].data_ptr(), ws['vt'].data_ptr(), B, F, Fp, H, Cc, _st))
+        _cabi.check(L.ddsp_b200_favor_features(ws['q'].data_ptr(), proj_scaled.data_ptr(), _FAVOR_FEATURES, 1, float(eps),
+                                               ws['qf'].data_ptr(), Z, F, Fp, _st))
+        _cabi.check(L.ddsp_b200_favor_features(ws['k'].data_ptr(), proj_scaled.data_ptr(), _FAVOR_FEATURES, 0, float(eps),
+                                               ws['kt'].data_ptr(), Z, F, Fp, _st))
+        _cabi.check(L.ddsp_b200_favor_context(ws['vt'].data_ptr(), ws['kt'].data_ptr(), ws['ctx'].data_ptr(), Z, Fp, _st))
+        _cabi.check(L.ddsp_b200_favor_output(ws['qf'].data_ptr(), ws['ctx'].data_ptr(), out.data_ptr(), B, H, F, _st))
+    return out
+
+
 def tc_microbench(n, k, block_n, virtual_tiles, device='cuda'):
     """Launch the tensor-pipe microbenchmark (operands resident in L2, nothing stored); returns nothing --
     time it with CUDA events."""

@@ -12,6 +12,7 @@
 #include "combsubfast_bwd.cuh"
 #include "control.cuh"
 #include "excite.cuh"
+#include "gemm_attn.cuh"
 #include "gemm_tc.cuh"
 #include "ltvfir.cuh"
 #include "phase.cuh"
@@ -933,6 +934,198 @@ int ddsp_b200_tc_microbench(const float* A, const float* W, float* C, int N, int
     ddsp::tc::LinearParams P = {};
     P.C = C; P.ldc = N; P.M = ddsp::tc::kBM; P.N = N; P.K = K; P.store_output = 0; P.virtual_tiles = virtual_tiles;
     return linear_dispatch(A, K, W, K, P, block_n, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Second-generation tensor-core path of the control network (csrc/gemm_attn.cuh): batched 3xTF32 GEMM with fused
+// epilogues (bias / residual / LayerNorm, head-split q|k|v, attention normalisation) and the FAVOR+ feature GEMM
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// fp32 tensor of rank 3 or 4 (innermost dimension contiguous), box = 32 floats (one 128-byte swizzle row) x box_rows x 1 (x 1)
+int make_map_nd(CUtensorMap* m, const float* base, int rank, const int64_t* dims, const int64_t* strides_elems, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return DDSP_B200_ERR_UNSUPPORTED;
+    cuuint64_t d[4];
+    cuuint64_t sb[3];
+    cuuint32_t box[4] = {(cuuint32_t)ddsp::tc::kBK, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    for (int i = 0; i < rank; ++i) d[i] = (cuuint64_t)dims[i];
+    for (int i = 0; i + 1 < rank; ++i) {
+        if (strides_elems[i] & 3) return DDSP_B200_ERR_UNSUPPORTED;
+        sb[i] = (cuuint64_t)strides_elems[i] * sizeof(float);
+    }
+    if (reinterpret_cast<uintptr_t>(base) & 15) return DDSP_B200_ERR_UNSUPPORTED;
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), d, sb, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        g_last_cuda_error = (int)r;
+        return DDSP_B200_ERR_CUDA;
+    }
+    return 0;
+}
+// (rows x cols) matrices with row stride ld, Z of them batch_stride apart
+int make_map_3(CUtensorMap* m, const float* base, int64_t cols, int64_t rows, int64_t Z, int64_t ld, int64_t batch_stride,
+               int box_rows) {
+    const int64_t dims[3] = {cols, rows, Z};
+    const int64_t strides[2] = {ld, Z > 1 ? batch_stride : ld * rows};
+    return make_map_nd(m, base, 3, dims, strides, box_rows);
+}
+
+template <typename K>
+int set_smem_once(K kernel, int bytes, bool* flags) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return DDSP_B200_ERR_UNSUPPORTED;
+    if (!flags[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        flags[dev] = true;
+    }
+    return 0;
+}
+
+template <int BN, int EPI>
+int launch_gemm3x(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& wlo, const CUtensorMap& c, const CUtensorMap& c2,
+                  ddsp::tc::GemmParams P, cudaStream_t st) {
+    using C = ddsp::tc::GCfg<BN>;
+    static bool attr_set[64] = {false};
+    if (int rc = set_smem_once(ddsp::tc::gemm3x_kernel<BN, EPI>, C::kSmemBytes, attr_set)) return rc;
+    P.tiles_m = (P.M + ddsp::tc::kBM - 1) / ddsp::tc::kBM;
+    P.tiles_n = (P.N + BN - 1) / BN;
+    const int64_t tiles = (int64_t)P.Z * P.tiles_m * P.tiles_n;
+    if (tiles > 0x7fffffffLL) return DDSP_B200_ERR_UNSUPPORTED;
+    const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+    ddsp::tc::gemm3x_kernel<BN, EPI><<<grid, ddsp::tc::kThreads, C::kSmemBytes, st>>>(a, w, wlo, c, c2, P);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ddsp_b200_linear_tf32x3_ex(const float* A, int64_t lda, const float* W, const float* W_lo, int64_t ldw, const float* bias,
+                               const float* residual, int64_t ldr, float* C, int64_t ldc, const float* ln_gamma,
+                               const float* ln_beta, float ln_eps, float* C_ln, int64_t ldc_ln, int M, int N, int K,
+                               void* stream) {
+    g_launches = 0;
+    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || lda < K || ldw < K || ldc < N || (residual && ldr < N))
+        return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if ((ln_gamma != nullptr) != (C_ln != nullptr) || (ln_gamma && !ln_beta) || (ln_gamma && ldc_ln < N))
+        return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (ln_gamma && (N > 256 || (N & 31))) return DDSP_B200_ERR_UNSUPPORTED;
+    if (residual && ((N & 31) || (ldr & 3) || (reinterpret_cast<uintptr_t>(residual) & 15))) return DDSP_B200_ERR_UNSUPPORTED;
+    if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return DDSP_B200_ERR_UNSUPPORTED;
+    ddsp::tc::GemmParams P = {};
+    P.Z = 1; P.M = M; P.N = N; P.K = K;
+    P.w_presplit = W_lo ? 1 : 0;
+    P.bias = bias; P.residual = residual; P.ldr = ldr;
+    P.ln_gamma = ln_gamma; P.ln_beta = ln_beta; P.ln_eps = ln_eps;
+    int bn = 256;
+    if (!ln_gamma) {
+        int64_t best_cost = ((N + 255) / 256) * 256;
+        for (int cand : {224, 128}) {
+            const int64_t cost = (int64_t)((N + cand - 1) / cand) * cand;
+            if (cost < best_cost) { best_cost = cost; bn = cand; }
+        }
+    }
+    CUtensorMap ma, mw, mwl, mc, mc2;
+    if (int rc = make_map_3(&ma, A, K, M, 1, lda, 0, ddsp::tc::kBM)) return rc;
+    if (int rc = make_map_3(&mw, W, K, N, 1, ldw, 0, bn)) return rc;
+    if (int rc = make_map_3(&mwl, W_lo ? W_lo : W, K, N, 1, ldw, 0, bn)) return rc;
+    if (int rc = make_map_3(&mc, C, N, M, 1, ldc, 0, 32)) return rc;
+    if (int rc = make_map_3(&mc2, C_ln ? C_ln : C, N, M, 1, C_ln ? ldc_ln : ldc, 0, 32)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (bn) {
+        case 256: return launch_gemm3x<256, ddsp::tc::EPI_PLAIN>(ma, mw, mwl, mc, mc2, P, st);
+        case 224: return launch_gemm3x<224, ddsp::tc::EPI_PLAIN>(ma, mw, mwl, mc, mc2, P, st);
+        default: return launch_gemm3x<128, ddsp::tc::EPI_PLAIN>(ma, mw, mwl, mc, mc2, P, st);
+    }
+}
+
+int ddsp_b200_qkv_heads(const float* A, int64_t lda, const float* W, const float* W_lo, int64_t ldw, const float* bias,
+                        float* q, float* k, float* vt, int B, int F, int Fp, int H, int K, void* stream) {
+    g_launches = 0;
+    if (!A || !W || !q || !k || !vt || B <= 0 || F <= 0 || H <= 0 || K <= 0 || lda < K || ldw < K || Fp < F)
+        return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if ((H & 3) || (Fp & 3) || (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) || (int64_t)B * F > 0x7fffffffLL)
+        return DDSP_B200_ERR_UNSUPPORTED;
+    ddsp::tc::GemmParams P = {};
+    P.Z = 1; P.M = B * F; P.N = 3 * H * 64; P.K = K;
+    P.w_presplit = W_lo ? 1 : 0;
+    P.bias = bias; P.vt = vt; P.q = q; P.k = k; P.frames = F; P.frames_pad = Fp; P.heads = H;
+    CUtensorMap ma, mw, mwl, mq, mk;
+    if (int rc = make_map_3(&ma, A, K, P.M, 1, lda, 0, ddsp::tc::kBM)) return rc;
+    if (int rc = make_map_3(&mw, W, K, P.N, 1, ldw, 0, 256)) return rc;
+    if (int rc = make_map_3(&mwl, W_lo ? W_lo : W, K, P.N, 1, ldw, 0, 256)) return rc;
+    const int64_t dims[4] = {64, F, H, B};
+    const int64_t strides[3] = {64, (int64_t)F * 64, (int64_t)H * F * 64};
+    if (int rc = make_map_nd(&mq, q, 4, dims, strides, 32)) return rc;
+    if (int rc = make_map_nd(&mk, k, 4, dims, strides, 32)) return rc;
+    return launch_gemm3x<256, ddsp::tc::EPI_QKV>(ma, mw, mwl, mq, mk, P, (cudaStream_t)stream);
+}
+
+int ddsp_b200_favor_features(const float* x, const float* proj_scaled, int n_features, int is_query, float eps, float* out,
+                             int Z, int F, int Fp, void* stream) {
+    g_launches = 0;
+    if (!x || !proj_scaled || !out || Z <= 0 || F <= 0 || Fp < F) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (n_features != ddsp::tc::kFeat || (Fp & 3)) return DDSP_B200_ERR_UNSUPPORTED;
+    ddsp::tc::FeatParams P = {};
+    P.x = x; P.kt = out; P.Z = Z; P.F = F; P.Fp = Fp; P.eps = eps;
+    P.tiles_m = (F + ddsp::tc::kBM - 1) / ddsp::tc::kBM;
+    const int64_t tiles = (int64_t)Z * P.tiles_m;
+    if (tiles > 0x7fffffffLL) return DDSP_B200_ERR_UNSUPPORTED;
+    CUtensorMap ma, mw, mc;
+    if (int rc = make_map_3(&ma, x, 64, F, Z, 64, (int64_t)F * 64, ddsp::tc::kBM)) return rc;
+    if (int rc = make_map_3(&mw, proj_scaled, 64, n_features, 1, 64, 0, 136)) return rc;
+    if (is_query) {
+        if (int rc = make_map_3(&mc, out, ddsp::tc::kFeatPad, F, Z, ddsp::tc::kFeatPad, (int64_t)F * ddsp::tc::kFeatPad, 32)) return rc;
+    } else {
+        mc = ma;
+    }
+    const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr_q[64] = {false}, attr_k[64] = {false};
+    if (is_query) {
+        if (int rc = set_smem_once(ddsp::tc::favor_features_kernel<true>, ddsp::tc::kFeatSmemBytes, attr_q)) return rc;
+        ddsp::tc::favor_features_kernel<true><<<grid, ddsp::tc::kThreads, ddsp::tc::kFeatSmemBytes, st>>>(ma, mw, mc, P);
+    } else {
+        if (int rc = set_smem_once(ddsp::tc::favor_features_kernel<false>, ddsp::tc::kFeatSmemBytes, attr_k)) return rc;
+        ddsp::tc::favor_features_kernel<false><<<grid, ddsp::tc::kThreads, ddsp::tc::kFeatSmemBytes, st>>>(ma, mw, mc, P);
+    }
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int ddsp_b200_favor_context(const float* vt, const float* kt, float* ctxT, int Z, int Fp, void* stream) {
+    g_launches = 0;
+    if (!vt || !kt || !ctxT || Z <= 0 || Fp <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (Fp & 3) return DDSP_B200_ERR_UNSUPPORTED;
+    using namespace ddsp::tc;
+    GemmParams P = {};
+    P.Z = Z; P.M = kVtRows; P.N = kFeatPad; P.K = Fp; P.w_batched = 1;
+    CUtensorMap ma, mw, mc;
+    if (int rc = make_map_3(&ma, vt, Fp, kVtRows, Z, Fp, (int64_t)kVtRows * Fp, kBM)) return rc;
+    if (int rc = make_map_3(&mw, kt, Fp, kFeatPad, Z, Fp, (int64_t)kFeatPad * Fp, 96)) return rc;
+    if (int rc = make_map_3(&mc, ctxT, kFeatPad, kVtRows, Z, kFeatPad, (int64_t)kVtRows * kFeatPad, 32)) return rc;
+    return launch_gemm3x<96, EPI_PLAIN>(ma, mw, mw, mc, mc, P, (cudaStream_t)stream);   // 3 column tiles of 96 = 288 >= 272
+}
+
+int ddsp_b200_favor_output(const float* qf, const float* ctxT, float* out, int B, int H, int F, void* stream) {
+    g_launches = 0;
+    if (!qf || !ctxT || !out || B <= 0 || H <= 0 || F <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    using namespace ddsp::tc;
+    const int Z = B * H;
+    GemmParams P = {};
+    P.Z = Z; P.M = F; P.N = kVtRows; P.K = kFeatPad; P.w_batched = 1; P.heads = H; P.frames = F;
+    CUtensorMap ma, mw, mc;
+    if (int rc = make_map_3(&ma, qf, kFeatPad, F, Z, kFeatPad, (int64_t)F * kFeatPad, kBM)) return rc;
+    if (int rc = make_map_3(&mw, ctxT, kFeatPad, kVtRows, Z, kFeatPad, (int64_t)kVtRows * kFeatPad, kVtRows)) return rc;
+    if (int rc = make_map_3(&mc, out, (int64_t)H * 64, F, B, (int64_t)H * 64, (int64_t)F * H * 64, 32)) return rc;
+    return launch_gemm3x<kVtRows, EPI_OUT>(ma, mw, mw, mc, mc, P, (cudaStream_t)stream);
 }
 
 }  // extern "C"

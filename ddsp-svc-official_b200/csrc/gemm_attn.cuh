@@ -1,0 +1,689 @@
+// gemm_attn.cuh -- the control network's GEMM-shaped work on the 5th-generation tensor cores, second generation of
+// csrc/gemm_tc.cuh: one batched 3xTF32 tcgen05 GEMM with fused epilogues, and the FAVOR+ feature map as a GEMM
+// epilogue.  Together they replace every nn.Linear / 1x1 Conv1d / LayerNorm / einsum of one PCmer layer
+// (ddsp/pcmer.py:20-78, :124-160, :191-251) -- SURVEY section 8 row (f1).
+//
+//   gemm3x_kernel<BN, EPI>      C[z] = A[z] (M x K) * W[z]^T (N x K), operands K-major, fp32-faithful split
+//                               accumulation (hi*hi + hi*lo + lo*hi in the fp32 TMEM accumulator)
+//       EPI_PLAIN   + bias + residual, rows leave through TMA stores (coalesced, clipped at the tensor edge);
+//                   optionally LayerNorm(C) as a second output while the row is still in TMEM (N <= BN)
+//       EPI_QKV     merged q|k|v projection: q, k stored head-major (B,H,F,64); v stored transposed (B,H,80,Fp)
+//                   next to a row of ones, so that the context GEMM also yields sum_n k'
+//       EPI_OUT     attention output: columns 0..63 divided by column 64 (= q' . k_sum) + 1e-8, heads merged
+//   favor_features_kernel<Q>    dash = x * (scale * projection)^T with the projection resident in shared memory,
+//                               epilogue = the softmax-kernel feature map (pcmer.py:124-160); q' row-major
+//                               (B*H, F, 272), k' transposed (B*H, 272, Fp)
+//
+// Non-causal linear attention (pcmer.py:69-78) then is two batched GEMMs:
+//   ctxT[z] (80 x 272)  = [v^T; 1; 0][z] (80 x Fp) * k'^T[z] (272 x Fp)^T          row 64 = k_sum
+//   out[z]  (F x 80)    = q'[z] (F x 272) * ctxT[z] (80 x 272)^T                    column 64 = q' . k_sum
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace ddsp {
+namespace tc {
+
+enum { EPI_PLAIN = 0, EPI_QKV = 1, EPI_OUT = 2 };
+
+constexpr int kFeat = 266;          // int(64 * ln 64) random features (pcmer.py:166)
+constexpr int kFeatPad = 272;       // padded to a multiple of 16 (UMMA N) / 16 bytes
+constexpr int kVtRows = 80;         // 64 rows of v^T + the row of ones + zero padding to a multiple of 16
+
+struct GemmParams {
+    int Z, M, N, K;                 // per-batch problem
+    int tiles_m, tiles_n;           // per batch
+    int w_presplit;                 // W arrives as two tensors (hi, lo) split once on the host side
+    int w_batched;                  // W has a batch coordinate (else the same W for every batch)
+    const float* bias;              // (N) or null
+    const float* residual;          // (M, N), row stride ldr, or null            (Z == 1)
+    int64_t ldr;
+    const float* ln_gamma;          // LayerNorm over the N columns as second output (tiles_n == 1), or null
+    const float* ln_beta;
+    float ln_eps;
+    // EPI_QKV / EPI_OUT
+    float* vt;                      // (B, H, 80, Fp)
+    float* q; float* k;             // (B, H, F, 64): the same tensors map_c / map_c2 describe (EPI_QKV)
+    int frames, frames_pad, heads;
+};
+
+// ---- PTX wrappers (beyond gemm_tc.cuh) ------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_n(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+// One warp's 32 rows x 32 columns (a row per lane) leave through a 128-byte-swizzled staging slice and one TMA
+// store: coalesced 128-byte rows in global memory, rows / columns beyond the tensor edge are clipped by the TMA
+// unit.  Two slices per warp alternate; `wait_read<1>` makes sure the store that last read this slice is done.
+struct RowStore {
+    uint32_t base;      // shared address of this warp's two 4-KB slices (1024-byte aligned)
+    int count;
+    int lane;
+    __device__ __forceinline__ uint32_t begin() {
+        const uint32_t buf = base + (count & 1) * 4096;
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        return buf;
+    }
+    __device__ __forceinline__ void fill(uint32_t buf, const float (&v)[32]) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            st_shared_v4(buf + lane * 128 + ((c ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        ++count;
+    }
+    __device__ __forceinline__ void drain() {
+        if (lane == 0) bulk_wait_all<0>();
+        __syncwarp();
+    }
+};
+
+template <int BN>
+struct GCfg {
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128: multiple of 16 in [16, 256]");
+    static constexpr int kABytes = kBM * 128;
+    static constexpr int kWBytes = BN * 128;
+    static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;   // A_hi | A_lo | W_hi | W_lo
+    static constexpr int kStoreBytes = 4 * 2 * 4096;                // four epilogue warps x two staging slices
+    static constexpr int kBarBytes = 256;
+    static constexpr int kBudget = 227 * 1024 - 1024 - kBarBytes - kStoreBytes;
+    static constexpr int kStages = kBudget / kStageBytes < 2 ? 2 : (kBudget / kStageBytes > 6 ? 6 : kBudget / kStageBytes);
+    static constexpr int kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static constexpr int kTmemCols = 2 * kAccCols;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + kBarBytes + 1024;
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+              const __grid_constant__ CUtensorMap map_w_lo, const __grid_constant__ CUtensorMap map_c,
+              const __grid_constant__ CUtensorMap map_c2, const GemmParams P) {
+    using C = GCfg<BN>;
+    static_assert(EPI != EPI_PLAIN || BN % 32 == 0, "the row-store epilogue works in chunks of 32 columns");
+    static_assert(EPI != EPI_QKV || BN % 64 == 0, "head-split epilogue: a column tile holds whole heads");
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* store_smem = smem + C::kStages * C::kStageBytes;
+    unsigned char* bars = store_smem + C::kStoreBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bars);
+    uint64_t* split_bar = full_bar + C::kStages;
+    uint64_t* empty_bar = split_bar + C::kStages;
+    uint64_t* acc_full = empty_bar + C::kStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    static_assert((3 * C::kStages + 4) * 8 + 4 <= C::kBarBytes, "barrier block too small");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_kb = (P.K + kBK - 1) / kBK;
+    const int tiles_per_z = P.tiles_m * P.tiles_n;
+    const int n_tiles = P.Z * tiles_per_z;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_w);
+        if (P.w_presplit) tma_prefetch_desc(&map_w_lo);
+        tma_prefetch_desc(&map_c);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < C::kStages; ++s) {
+                mbar_init(s32(full_bar + s), 1);
+                mbar_init(s32(split_bar + s), 128);
+                mbar_init(s32(empty_bar + s), 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(s32(acc_full + a), 1);
+                mbar_init(s32(acc_empty + a), 128);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<C::kTmemCols>(s32(tmem_slot));
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx = C::kABytes + (P.w_presplit ? 2 : 1) * C::kWBytes;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int z = tile / tiles_per_z, rem = tile - z * tiles_per_z;
+                const int m0 = (rem / P.tiles_n) * kBM, n0 = (rem % P.tiles_n) * BN;
+                const int wz = P.w_batched ? z : 0;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(s32(empty_bar + stage), phase ^ 1);
+                    const uint32_t st = s32(smem + stage * C::kStageBytes);
+                    mbar_arrive_expect_tx(s32(full_bar + stage), tx);
+                    tma_load_3d(st, &map_a, kb * kBK, m0, z, s32(full_bar + stage));
+                    tma_load_3d(st + 2 * C::kABytes, &map_w, kb * kBK, n0, wz, s32(full_bar + stage));
+                    if (P.w_presplit)
+                        tma_load_3d(st + 2 * C::kABytes + C::kWBytes, &map_w_lo, kb * kBK, n0, wz, s32(full_bar + stage));
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = umma_idesc_tf32_n(BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(s32(acc_empty + acc), acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem_base + acc * C::kAccCols;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(s32(split_bar + stage), phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t st = s32(smem + stage * C::kStageBytes);
+                    const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + C::kABytes);
+                    const uint64_t w_hi = umma_desc_sw128(st + 2 * C::kABytes), w_lo = umma_desc_sw128(st + 2 * C::kABytes + C::kWBytes);
+#pragma unroll
+                    for (int kk = 0; kk < kBK / 8; ++kk) {
+                        const uint64_t o = (uint64_t)(2 * kk);
+                        umma_tf32(d, a_lo + o, w_hi + o, idesc, (kb | kk) != 0);
+                        umma_tf32(d, a_hi + o, w_lo + o, idesc, 1);
+                        umma_tf32(d, a_hi + o, w_hi + o, idesc, 1);
+                    }
+                    umma_commit(s32(empty_bar + stage));
+                    if (kb == n_kb - 1) umma_commit(s32(acc_full + acc));
+                }
+                __syncwarp();
+                if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= kSplitWarp0) {
+        // ===== splitter: x -> hi (in place) + lo =====
+        const int t = threadIdx.x - kSplitWarp0 * 32;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(s32(full_bar + stage), phase);
+                float4* a_hi = reinterpret_cast<float4*>(smem + stage * C::kStageBytes);
+                float4* a_lo = a_hi + C::kABytes / 16;
+                float4* w_hi = a_lo + C::kABytes / 16;
+                float4* w_lo = w_hi + C::kWBytes / 16;
+#pragma unroll 4
+                for (int i = t; i < C::kABytes / 16; i += 128) {
+                    const float4 x = a_hi[i];
+                    float4 h;
+                    h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
+                    a_hi[i] = h;
+                    a_lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                }
+                if (!P.w_presplit) {
+#pragma unroll 4
+                    for (int i = t; i < C::kWBytes / 16; i += 128) {
+                        const float4 x = w_hi[i];
+                        float4 h;
+                        h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
+                        w_hi[i] = h;
+                        w_lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(s32(split_bar + stage));
+                if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int row_in_tile = q * 32 + lane;
+        RowStore rs;
+        rs.base = s32(store_smem + (warp - kEpiWarp0) * 8192);
+        rs.count = 0;
+        rs.lane = lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int z = tile / tiles_per_z, rem = tile - z * tiles_per_z;
+            const int m0 = (rem / P.tiles_n) * kBM, n0 = (rem % P.tiles_n) * BN;
+            const int row = m0 + row_in_tile;
+            mbar_wait(s32(acc_full + acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::kAccCols;
+            uint32_t r[32];
+            float v[32];
+
+            if constexpr (EPI == EPI_PLAIN) {
+                const bool row_ok = row < P.M;
+                const float* rrow = (P.residual && row_ok) ? P.residual + (int64_t)row * P.ldr : nullptr;
+                const bool ln = P.ln_gamma != nullptr;
+                float sum = 0.0f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    const int n = n0 + c0;
+                    if (n >= P.N) break;
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (P.bias) {
+                        if (n + 32 <= P.N) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + n + j));
+                                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += (n + j < P.N) ? __ldg(P.bias + n + j) : 0.0f;
+                        }
+                    }
+                    if (rrow) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 e = *reinterpret_cast<const float4*>(rrow + n + j);
+                            v[j] += e.x; v[j + 1] += e.y; v[j + 2] += e.z; v[j + 3] += e.w;
+                        }
+                    }
+                    if (ln) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { sum += v[j]; r[j] = __float_as_uint(v[j]); }
+                        tmem_st32(taddr + c0, r);
+                    }
+                    const uint32_t buf = rs.begin();
+                    rs.fill(buf, v);
+                    if (lane == 0) { tma_store_3d(&map_c, buf, n, m0 + q * 32, z); bulk_commit(); }
+                }
+                if (ln) {
+                    // LayerNorm of the finished row (torch.nn.LayerNorm: biased variance, eps inside the sqrt), two more
+                    // passes over the row parked in TMEM: exact mean first, then the centred sum of squares
+                    tmem_st_wait();
+                    const float inv_n = 1.0f / (float)P.N;
+                    const float mean = sum * inv_n;
+                    float ssq = 0.0f;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < P.N; c0 += 32) {
+                        tmem_ld32(taddr + c0, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { const float dlt = __uint_as_float(r[j]) - mean; ssq = fmaf(dlt, dlt, ssq); }
+                    }
+                    const float rstd = rsqrtf(ssq * inv_n + P.ln_eps);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < P.N; c0 += 32) {
+                        tmem_ld32(taddr + c0, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 g = __ldg(reinterpret_cast<const float4*>(P.ln_gamma + c0 + j));
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(P.ln_beta + c0 + j));
+                            v[j] = fmaf((__uint_as_float(r[j]) - mean) * rstd, g.x, b.x);
+                            v[j + 1] = fmaf((__uint_as_float(r[j + 1]) - mean) * rstd, g.y, b.y);
+                            v[j + 2] = fmaf((__uint_as_float(r[j + 2]) - mean) * rstd, g.z, b.z);
+                            v[j + 3] = fmaf((__uint_as_float(r[j + 3]) - mean) * rstd, g.w, b.w);
+                        }
+                        const uint32_t buf = rs.begin();
+                        rs.fill(buf, v);
+                        if (lane == 0) { tma_store_3d(&map_c2, buf, c0, m0 + q * 32, z); bulk_commit(); }
+                    }
+                }
+            } else if constexpr (EPI == EPI_QKV) {
+                // N = 3 * heads * 64: column block -> (q | k | v, head); BN is a multiple of 64
+                const int F = P.frames, H = P.heads;
+                const int inner = H * 64;
+                const int which = n0 / inner;                       // 0 q, 1 k, 2 v (tiles never straddle: inner % BN == 0)
+                const int r0 = m0 + q * 32;                         // first row of this warp's slice
+                const int b0 = r0 / F, f0 = r0 - b0 * F;
+                const int bb = row / F, ff = row - bb * F;
+                const int n_clips = P.M / F;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    const int n = n0 + c0;
+                    const int col = n - which * inner;
+                    const int h = col >> 6, e0 = col & 63;
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (P.bias) b = __ldg(reinterpret_cast<const float4*>(P.bias + n + j));
+                        v[j] = __uint_as_float(r[j]) + b.x;
+                        v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+                        v[j + 2] = __uint_as_float(r[j + 2]) + b.z;
+                        v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+                    }
+                    if (which < 2) {
+                        const uint32_t buf = rs.begin();
+                        rs.fill(buf, v);
+                        // a slice that runs past the end of its clip continues in the next clip: the TMA store clips the
+                        // tail rows, and the few rows of the next clip are stored directly (a TMA store must not start at a
+                        // negative coordinate)
+                        const bool straddle = f0 + 32 > F;
+                        if (lane == 0) {
+                            if (b0 < n_clips) {
+                                if (which == 0) tma_store_4d(&map_c, buf, e0, f0, h, b0);
+                                else tma_store_4d(&map_c2, buf, e0, f0, h, b0);
+                            }
+                            bulk_commit();
+                        }
+                        if (straddle && bb > b0 && row < P.M) {
+                            float* dst = (which == 0 ? P.q : P.k) + ((((int64_t)bb * H + h) * F + ff) * 64 + e0);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                    } else if (row < P.M) {
+                        // v^T: lanes hold consecutive frames -> 128-byte coalesced stores along the frame axis
+                        float* dst = P.vt + (((int64_t)bb * H + h) * kVtRows + e0) * P.frames_pad + ff;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) dst[(int64_t)j * P.frames_pad] = v[j];
+                    }
+                }
+            } else {   // EPI_OUT
+                // batch z = (clip, head); accumulator columns 0..63 = sum_j q'_j ctx_j, column 64 = q' . k_sum
+                const int H = P.heads;
+                const int b = z / H, h = z - b * H;
+                tmem_ld32(taddr + 64, r);
+                tmem_ld_wait();
+                const float d_inv = 1.0f / (__uint_as_float(r[0]) + 1e-8f);           // pcmer.py:72
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * d_inv;
+                    const uint32_t buf = rs.begin();
+                    rs.fill(buf, v);
+                    if (lane == 0) { tma_store_3d(&map_c, buf, h * 64 + c0, m0 + q * 32, b); bulk_commit(); }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(s32(acc_empty + acc));
+        }
+        rs.drain();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+// ---- FAVOR+ feature map as a GEMM epilogue ---------------------------------------------------------------------------
+// x: (Z, F, 64) rows of one head (q or k with its Linear bias already added), W = 64^-0.25 * projection (266 x 64),
+// resident in shared memory as hi | lo, both k-blocks.  Per 128-row tile: dash = x W^T in TMEM (272 columns, two
+// MMAs of N = 256 and N = 16 per k-step), then
+//   q: ratio * (exp(dash - diag - max_j dash) + eps)      -> (Z, F, 272) row-major through TMA stores
+//   k: ratio * exp(dash - diag + eps)                     -> (Z, 272, Fp) transposed, lanes = consecutive frames
+// with diag = |x|^2 / (2 sqrt(64)), ratio = 266^-0.5 (pcmer.py:124-160).  Columns 266..271 of q' are written as
+// zeros; rows 266..271 of k'^T are never written (the buffer is zero-initialised once by the host side).
+struct FeatParams {
+    const float* x;             // (Z, F, 64)
+    float* kt;                  // k: (Z, 272, Fp)
+    int Z, F, Fp;
+    int tiles_m;                // per batch
+    float eps;
+};
+
+constexpr int kFeatWBytes = kFeatPad * 128;                                  // one k-block of W (hi or lo)
+constexpr int kFeatABytes = kBM * 128;
+constexpr int kFeatSmemW = 4 * kFeatWBytes;                                  // hi kb0 | hi kb1 | lo kb0 | lo kb1
+constexpr int kFeatSmemA = 4 * kFeatABytes;                                  // hi kb0 | hi kb1 | lo kb0 | lo kb1
+constexpr int kFeatStoreBytes = 4 * 4096;                                    // one staging slice per epilogue warp
+constexpr int kFeatSmemBytes = kFeatSmemW + kFeatSmemA + kFeatStoreBytes + 256 + 1024;
+static_assert(kFeatSmemBytes <= 227 * 1024, "shared memory budget");
+
+template <bool IS_Q>
+__global__ void __launch_bounds__(kThreads, 1)
+favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                      const __grid_constant__ CUtensorMap map_c, const FeatParams P) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* w_smem = smem;
+    unsigned char* a_smem = smem + kFeatSmemW;
+    unsigned char* store_smem = a_smem + kFeatSmemA;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(store_smem + kFeatStoreBytes);
+    uint64_t* w_bar = bars;            // TMA -> everyone (W landed)
+    uint64_t* full_bar = bars + 1;     // TMA -> splitter
+    uint64_t* split_bar = bars + 2;    // splitter -> MMA
+    uint64_t* empty_bar = bars + 3;    // MMA -> TMA
+    uint64_t* acc_full = bars + 4;     // MMA -> epilogue
+    uint64_t* acc_empty = bars + 5;    // epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = P.Z * P.tiles_m;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(s32(w_bar), 1);
+            mbar_init(s32(full_bar), 1);
+            mbar_init(s32(split_bar), 128);
+            mbar_init(s32(empty_bar), 1);
+            mbar_init(s32(acc_full), 1);
+            mbar_init(s32(acc_empty), 128);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<512>(s32(tmem_slot));
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // resident projection: both k-blocks of all 272 rows (rows 266..271 are out of bounds: zero-filled)
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_w);
+        mbar_arrive_expect_tx(s32(w_bar), 2 * kFeatWBytes);
+        for (int kb = 0; kb < 2; ++kb) {      // box = 136 rows (17 swizzle atoms): two boxes per k-block
+            tma_load_3d(s32(w_smem + kb * kFeatWBytes), &map_w, kb * kBK, 0, 0, s32(w_bar));
+            tma_load_3d(s32(w_smem + kb * kFeatWBytes + 136 * 128), &map_w, kb * kBK, 136, 0, s32(w_bar));
+        }
+    }
+    mbar_wait(s32(w_bar), 0);
+    {
+        float4* hi = reinterpret_cast<float4*>(w_smem);
+        float4* lo = hi + 2 * kFeatWBytes / 16;
+        for (int i = threadIdx.x; i < 2 * kFeatWBytes / 16; i += kThreads) {
+            const float4 x = hi[i];
+            float4 h;
+            h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
+            hi[i] = h;
+            lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        }
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ===== TMA producer: one A tile (two k-blocks) at a time =====
+        if (lane == 0) {
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int z = tile / P.tiles_m, m0 = (tile - z * P.tiles_m) * kBM;
+                mbar_wait(s32(empty_bar), phase ^ 1);
+                mbar_arrive_expect_tx(s32(full_bar), 2 * kFeatABytes);
+                tma_load_3d(s32(a_smem), &map_a, 0, m0, z, s32(full_bar));
+                tma_load_3d(s32(a_smem + kFeatABytes), &map_a, kBK, m0, z, s32(full_bar));
+                phase ^= 1;
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc256 = umma_idesc_tf32_n(256), idesc16 = umma_idesc_tf32_n(16);
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(s32(acc_empty), phase ^ 1);
+            mbar_wait(s32(split_bar), phase);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint64_t a_hi = umma_desc_sw128(s32(a_smem + kb * kFeatABytes));
+                    const uint64_t a_lo = umma_desc_sw128(s32(a_smem + (2 + kb) * kFeatABytes));
+                    const uint32_t wh = s32(w_smem + kb * kFeatWBytes), wl = s32(w_smem + (2 + kb) * kFeatWBytes);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t idesc = half ? idesc16 : idesc256;
+                        const uint32_t d = tmem_base + half * 256;
+                        const uint64_t w_hi = umma_desc_sw128(wh + half * 256 * 128), w_lo = umma_desc_sw128(wl + half * 256 * 128);
+#pragma unroll
+                        for (int kk = 0; kk < kBK / 8; ++kk) {
+                            const uint64_t o = (uint64_t)(2 * kk);
+                            umma_tf32(d, a_lo + o, w_hi + o, idesc, (kb | kk) != 0);
+                            umma_tf32(d, a_hi + o, w_lo + o, idesc, 1);
+                            umma_tf32(d, a_hi + o, w_hi + o, idesc, 1);
+                        }
+                    }
+                }
+                umma_commit(s32(empty_bar));
+                umma_commit(s32(acc_full));
+            }
+            __syncwarp();
+            phase ^= 1;
+        }
+    } else if (warp >= kSplitWarp0) {
+        // ===== splitter =====
+        const int t = threadIdx.x - kSplitWarp0 * 32;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(s32(full_bar), phase);
+            float4* hi = reinterpret_cast<float4*>(a_smem);
+            float4* lo = hi + 2 * kFeatABytes / 16;
+#pragma unroll 4
+            for (int i = t; i < 2 * kFeatABytes / 16; i += 128) {
+                const float4 x = hi[i];
+                float4 h;
+                h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
+                hi[i] = h;
+                lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+            }
+            fence_proxy_async();
+            mbar_arrive(s32(split_bar));
+            phase ^= 1;
+        }
+    } else {
+        // ===== epilogue =====
+        const int q = warp & 3;
+        const int row_in_tile = q * 32 + lane;
+        const uint32_t stage_buf = s32(store_smem + (warp - kEpiWarp0) * 4096);
+        const float ratio = rsqrtf((float)kFeat);
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int z = tile / P.tiles_m, m0 = (tile - z * P.tiles_m) * kBM;
+            const int f = m0 + row_in_tile;
+            const bool ok = f < P.F;
+            // diag = |x|^2 * 64^-0.5 / 2 from the fp32 row itself (L2-resident: TMA has just read it)
+            float ss = 0.0f;
+            if (ok) {
+                const float4* xr = reinterpret_cast<const float4*>(P.x + ((int64_t)z * P.F + f) * 64);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float4 t4 = __ldg(xr + i);
+                    ss = fmaf(t4.x, t4.x, fmaf(t4.y, t4.y, fmaf(t4.z, t4.z, fmaf(t4.w, t4.w, ss))));
+                }
+            }
+            const float diag = 0.0625f * ss;
+            mbar_wait(s32(acc_full), phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+            uint32_t r[32];
+            float v[32];
+            float mx = -3.0e38f;
+            if (IS_Q) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < kFeatPad; c0 += 32) {
+                    tmem_ld32(taddr + c0, r);            // (the last chunk reads 16 columns beyond the accumulator: ignored)
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < kFeat) mx = fmaxf(mx, __uint_as_float(r[j]));
+                }
+            }
+            const float shift = IS_Q ? -(diag + mx) : (P.eps - diag);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kFeatPad; c0 += 32) {
+                tmem_ld32(taddr + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float e = __expf(__uint_as_float(r[j]) + shift);
+                    const float val = IS_Q ? ratio * (e + P.eps) : ratio * e;
+                    v[j] = (c0 + j < kFeat) ? val : 0.0f;
+                }
+                if (IS_Q) {
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        st_shared_v4(stage_buf + lane * 128 + ((c ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_3d(&map_c, stage_buf, c0, m0 + q * 32, z); bulk_commit(); }
+                } else if (ok) {
+                    float* dst = P.kt + ((int64_t)z * kFeatPad + c0) * P.Fp + f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < kFeat) dst[(int64_t)j * P.Fp] = v[j];
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(s32(acc_empty));
+            phase ^= 1;
+        }
+        if (IS_Q) {
+            if (lane == 0) bulk_wait_all<0>();
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace tc
+}  // namespace ddsp

@@ -277,6 +277,38 @@ int ddsp_b200_linear_tf32x3(const float *A, int64_t lda, const float *W, int64_t
                             const float *residual, int64_t ldr, float *C, int64_t ldc, int M, int N,
                             int K, void *stream);
 
+/* Second generation of the same GEMM (csrc/gemm_attn.cuh): rows leave through TMA stores (coalesced), the weight may
+ * arrive already split into its two TF32 terms (W = hi, W_lo = W - hi; NULL: split in shared memory), and
+ * LayerNorm(C) over the N <= 256 columns (torch.nn.LayerNorm: biased variance, ln_eps inside the sqrt;
+ * ddsp/pcmer.py:25, :44, ddsp/unit2control.py:58) can be written as a second output C_ln while the finished row
+ * is still in tensor memory.  ln_gamma / ln_beta / C_ln NULL: no LayerNorm.  C, C_ln, residual: 16-byte aligned
+ * with row strides that are multiples of 4. */
+int ddsp_b200_linear_tf32x3_ex(const float *A, int64_t lda, const float *W, const float *W_lo, int64_t ldw,
+                               const float *bias, const float *residual, int64_t ldr, float *C, int64_t ldc,
+                               const float *ln_gamma, const float *ln_beta, float ln_eps, float *C_ln,
+                               int64_t ldc_ln, int M, int N, int K, void *stream);
+
+/* Performer (FAVOR+) self-attention of one PCmer layer as tensor-core GEMMs     ddsp/pcmer.py:69-78,124-160,191-251
+ * (non-causal; dim_head 64, 266 random features padded to 272; Z = B * heads; Fp = frames rounded up to a multiple of 4)
+ *
+ * ddsp_b200_qkv_heads:      [q | k | v] = A (B*F, K) * [W_q; W_k; W_v]^T + bias in one GEMM; q, k stored head-major
+ *                           (B,H,F,64); v stored transposed into rows 0..63 of vt (B,H,80,Fp) -- the caller presets
+ *                           row 64 to ones and rows 65..79 / columns >= F to zero once.
+ * ddsp_b200_favor_features: x (Z,F,64) -> softmax-kernel features of dash = x * proj_scaled^T with
+ *                           proj_scaled = 64^-0.25 * projection_matrix (266,64):
+ *                             query: out (Z,F,272)   = 266^-0.5 (exp(dash - |x|^2/16 - max_j dash) + eps), pad columns 0
+ *                             key:   out (Z,272,Fp)  = 266^-0.5  exp(dash - |x|^2/16 + eps), transposed; pad rows /
+ *                                    columns are never written (zero-initialise the buffer once)
+ * ddsp_b200_favor_context:  ctxT[z] (80,272) = vt[z] (80,Fp) * kt[z] (272,Fp)^T   (row 64 = sum over frames of k')
+ * ddsp_b200_favor_output:   out (B,F,H*64): out[b,f,h*64+e] = (q'[z,f,:] . ctxT[z,e,:]) / (q'[z,f,:] . ctxT[z,64,:] + 1e-8) */
+int ddsp_b200_qkv_heads(const float *A, int64_t lda, const float *W, const float *W_lo, int64_t ldw,
+                        const float *bias, float *q, float *k, float *vt, int B, int F, int Fp, int H, int K,
+                        void *stream);
+int ddsp_b200_favor_features(const float *x, const float *proj_scaled, int n_features, int is_query, float eps,
+                             float *out, int Z, int F, int Fp, void *stream);
+int ddsp_b200_favor_context(const float *vt, const float *kt, float *ctxT, int Z, int Fp, void *stream);
+int ddsp_b200_favor_output(const float *qf, const float *ctxT, float *out, int B, int H, int F, void *stream);
+
 /* Tensor-pipe microbenchmark of the same kernel: `virtual_tiles` output tiles of 128 x block_n with reduction
  * length K that all read tile 0 of A (128,K) and W (N,K) (operands stay in L2) and store nothing -- the
  * rate at which the TMA -> split -> 3 x tcgen05.mma -> TMEM-drain pipeline runs without HBM traffic.  Used to
