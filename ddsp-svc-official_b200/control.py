@@ -68,6 +68,25 @@ def _softmax_features(x, proj, is_query, eps=1e-4):
     return ratio * torch.exp(dash - diag + eps)
 
 
+def _split_cached(owner, slot, tensors, build=None):
+    """(hi, lo) TF32 split of a weight (or of `build(*tensors)`), cached on `owner` until one of `tensors` changes
+    (in-place update, load_state_dict, .to())."""
+    from . import core
+    key = tuple((t._version, t.data_ptr()) for t in tensors)
+    cache = owner.__dict__.setdefault('_tc_cache', {})
+    hit = cache.get(slot)
+    if hit is None or hit[0] != key:
+        w = build(*[t.detach() for t in tensors]) if build is not None else tensors[0].detach()
+        hit = (key,) + tuple(core.split_tf32(w.reshape(w.shape[0], -1).contiguous()))
+        cache[slot] = hit
+    return hit[1], hit[2]
+
+
+def _tc_path(x):
+    """Calls larger than a GUI block run every GEMM-shaped step of the network on the tensor cores (csrc/gemm_attn.cuh)."""
+    return _fused_ok(x) and x.shape[0] * x.shape[1] > _ATTENTION_KERNEL_MAX_FRAMES and x.shape[-1] == _DIM
+
+
 def _fused_ok(x):
     """The fused CUDA stages (csrc/control.cuh) are inference-only and fp32-only; everything else --
     CPU tensors, autograd, other dtypes -- takes the plain PyTorch ops below."""
@@ -114,6 +133,23 @@ class _SelfAttention(nn.Module):
             self._qkv_cache = torch.cat([w.detach() for w in ws])
             self._qkv_key = key
         return self._qkv_cache
+
+    def forward_tc(self, xn, residual, ln):
+        """Tensor-core path: xn = LayerNorm(x) -> attention -> `to_out` with bias + residual in the epilogue.  Returns
+        (residual + attention, LayerNorm_ln(residual + attention)); writes the first in place over `residual`."""
+        from . import core
+        fa = self.fast_attention
+        w_hi, w_lo = _split_cached(self, 'qkv', (self.to_q.weight, self.to_k.weight, self.to_v.weight), lambda a, b, c: torch.cat([a, b, c]))
+        cache = self.__dict__['_tc_cache']
+        bkey = tuple((t._version, t.data_ptr()) for t in (self.to_q.bias, self.to_k.bias, self.to_v.bias, fa.projection_matrix))
+        if cache.get('aux', (None,))[0] != bkey:
+            cache['aux'] = (bkey, torch.cat([self.to_q.bias.detach(), self.to_k.bias.detach(), self.to_v.bias.detach()]).contiguous(),
+                            (_DIM_HEAD ** -0.25 * fa.projection_matrix.detach()).contiguous())
+        _, b_qkv, proj_scaled = cache['aux']
+        att = core.favor_attention(xn, w_hi, w_lo, b_qkv, proj_scaled, self.heads)
+        o_hi, o_lo = _split_cached(self, 'out', (self.to_out.weight,))
+        return core.linear_ex(att, o_hi, self.to_out.bias, residual=residual, out=residual, weight_lo=o_lo,
+                              ln=(ln.weight, ln.bias, ln.eps))
 
     def forward(self, x, residual=None):
         """`residual` (fused path only): returns residual + attention(x), with the output bias and the
@@ -175,6 +211,18 @@ class _ConvModule(nn.Module):
             nn.Dropout(0.0),
         )
 
+    def forward_tc(self, xn, residual, next_ln):
+        """Tensor-core path: xn = this module's LayerNorm(x) (already produced by the previous GEMM's epilogue).
+        Returns (residual + module, next_ln(residual + module)) -- or only the first when `next_ln` is None."""
+        from . import core
+        _, _, pw1, _, dw, _, pw2, _, _ = self.net
+        w1_hi, w1_lo = _split_cached(self, 'pw1', (pw1.weight,))
+        u = core.linear_ex(xn, w1_hi, weight_lo=w1_lo)                          # bias added on load by the next kernel
+        s = core.glu_dwconv_silu(u, dw.weight, dw.bias, u_bias=pw1.bias)
+        w2_hi, w2_lo = _split_cached(self, 'pw2', (pw2.weight,))
+        ln = None if next_ln is None else (next_ln.weight, next_ln.bias, next_ln.eps)
+        return core.linear_ex(s, w2_hi, pw2.bias, residual=residual, out=residual, weight_lo=w2_lo, ln=ln)
+
     def forward(self, x, residual=None):
         """`residual` (fused path only): returns residual + module(x) with bias and residual folded into the
         last GEMM."""
@@ -216,6 +264,17 @@ class PCmer(nn.Module):
 
     def forward(self, x):
         return self.net(x)
+
+    def forward_tc(self, x, post_ln):
+        """Tensor-core path over all layers; every LayerNorm but the first is produced by the epilogue of the GEMM
+        that finishes its input (pcmer.py:25-37).  Returns post_ln(PCmer(x)); x is overwritten (residual stream)."""
+        layers = list(self.net)
+        xn = F.layer_norm(x, (x.shape[-1],), layers[0].norm.weight, layers[0].norm.bias, layers[0].norm.eps)
+        for i, layer in enumerate(layers):
+            x, xn = layer.attn.forward_tc(xn, x, layer.local_mixer.net[0])
+            nxt = layers[i + 1].norm if i + 1 < len(layers) else post_ln
+            x, xn = layer.local_mixer.forward_tc(xn, x, nxt)
+        return xn
 
 
 class Unit2Control(nn.Module):
@@ -267,15 +326,20 @@ class Unit2Control(nn.Module):
                 spk = self.spk_embed(spk_id - 1)
             x = core.embed_sum(x, f0, phase, volume, self.f0_embed, self.phase_embed, self.volume_embed, spk)
             names, sizes = list(self.output_splits), list(self.output_splits.values())
-            if x.shape[0] * x.shape[1] > _ATTENTION_KERNEL_MAX_FRAMES:
+            if _tc_path(x):
                 # output projection on the tensor cores into a buffer whose row stride is padded to a multiple of 4
                 # floats (128-bit stores); the synthesizer consumes the strided views as they are
                 pcmer, norm, proj = self.dec_post
                 n_out = sum(sizes)
                 buf = torch.empty(x.shape[:-1] + ((n_out + 3) // 4 * 4,), dtype=torch.float32, device=x.device)
                 # weight_norm keeps (weight_g, weight_v) and rebuilds `weight` only inside Module.__call__
-                w = torch._weight_norm(proj.weight_v, proj.weight_g, 0) if hasattr(proj, 'weight_g') else proj.weight
-                e = core.linear(norm(pcmer(x)), w, proj.bias, out=buf[..., :n_out])
+                if hasattr(proj, 'weight_g'):
+                    w_hi, w_lo = _split_cached(self, 'proj', (proj.weight_v, proj.weight_g), lambda v, g: torch._weight_norm(v, g, 0))
+                else:
+                    w_hi, w_lo = _split_cached(self, 'proj', (proj.weight,))
+                if not x.is_contiguous():
+                    x = x.contiguous()
+                e = core.linear_ex(pcmer.forward_tc(x, norm), w_hi, proj.bias, out=buf[..., :n_out], weight_lo=w_lo)
             else:
                 e = self.dec_post(x)
             return dict(zip(names, torch.split(e, sizes, dim=-1)))
