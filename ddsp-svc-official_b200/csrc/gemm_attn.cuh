@@ -85,6 +85,23 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, fl
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// The tensor core reads an fp32 word as TF32 by ignoring its low 13 mantissa bits, so the raw tile IS the high term
+// (hi = x truncated to TF32) and only the low term lo = x - hi (exact in fp32, |lo| < 2^-10 |x|) has to be written:
+// one 128-bit shared load + one 128-bit shared store per four elements.
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ void split_tile_lo(uint32_t raw, uint32_t lo, int n_vec, int t) {
+#pragma unroll 4
+    for (int i = t; i < n_vec; i += 128) {
+        const float4 x = ld_shared_v4(raw + 16 * i);
+        st_shared_v4(lo + 16 * i, tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+    }
+}
+
 __host__ __device__ constexpr uint32_t umma_idesc_tf32_n(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 }
@@ -247,28 +264,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < n_kb; ++kb) {
                 mbar_wait(s32(full_bar + stage), phase);
-                float4* a_hi = reinterpret_cast<float4*>(smem + stage * C::kStageBytes);
-                float4* a_lo = a_hi + C::kABytes / 16;
-                float4* w_hi = a_lo + C::kABytes / 16;
-                float4* w_lo = w_hi + C::kWBytes / 16;
-#pragma unroll 4
-                for (int i = t; i < C::kABytes / 16; i += 128) {
-                    const float4 x = a_hi[i];
-                    float4 h;
-                    h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
-                    a_hi[i] = h;
-                    a_lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-                }
-                if (!P.w_presplit) {
-#pragma unroll 4
-                    for (int i = t; i < C::kWBytes / 16; i += 128) {
-                        const float4 x = w_hi[i];
-                        float4 h;
-                        h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
-                        w_hi[i] = h;
-                        w_lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-                    }
-                }
+                const uint32_t st = s32(smem + stage * C::kStageBytes);
+                split_tile_lo(st, st + C::kABytes, C::kABytes / 16, t);
+                if (!P.w_presplit) split_tile_lo(st + 2 * C::kABytes, st + 2 * C::kABytes + C::kWBytes, C::kWBytes / 16, t);
                 fence_proxy_async();
                 mbar_arrive(s32(split_bar + stage));
                 if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -525,14 +523,10 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
     mbar_wait(s32(w_bar), 0);
     {
-        float4* hi = reinterpret_cast<float4*>(w_smem);
-        float4* lo = hi + 2 * kFeatWBytes / 16;
+        const uint32_t hi = s32(w_smem), lo = hi + 2 * kFeatWBytes;
         for (int i = threadIdx.x; i < 2 * kFeatWBytes / 16; i += kThreads) {
-            const float4 x = hi[i];
-            float4 h;
-            h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
-            hi[i] = h;
-            lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+            const float4 x = ld_shared_v4(hi + 16 * i);
+            st_shared_v4(lo + 16 * i, tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
         }
         fence_proxy_async();
     }
@@ -591,16 +585,7 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             mbar_wait(s32(full_bar), phase);
-            float4* hi = reinterpret_cast<float4*>(a_smem);
-            float4* lo = hi + 2 * kFeatABytes / 16;
-#pragma unroll 4
-            for (int i = t; i < 2 * kFeatABytes / 16; i += 128) {
-                const float4 x = hi[i];
-                float4 h;
-                h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
-                hi[i] = h;
-                lo[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-            }
+            split_tile_lo(s32(a_smem), s32(a_smem) + 2 * kFeatABytes, 2 * kFeatABytes / 16, t);
             fence_proxy_async();
             mbar_arrive(s32(split_bar));
             phase ^= 1;
@@ -630,36 +615,50 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             mbar_wait(s32(acc_full), phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-            uint32_t r[32];
-            float v[32];
+            // TMEM reads are software-pipelined: the load of chunk c+1 is in flight while chunk c is processed
+            // (tcgen05.wait::ld covers every load issued before it, so the next load is issued right after the wait)
+            uint32_t ra[32], rb[32];
+            constexpr int kChunks = (kFeatPad + 31) / 32;      // 9; the last one reads 16 columns beyond the accumulator (ignored)
+            constexpr float kLog2e = 1.4426950408889634f;
             float mx = -3.0e38f;
             if (IS_Q) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < kFeatPad; c0 += 32) {
-                    tmem_ld32(taddr + c0, r);            // (the last chunk reads 16 columns beyond the accumulator: ignored)
+                tmem_ld32(taddr, ra);
+#pragma unroll
+                for (int c = 0; c < kChunks; ++c) {
+                    uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+                    uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
                     tmem_ld_wait();
+                    tmem_ld32(taddr + (c + 1 < kChunks ? 32 * (c + 1) : 0), nxt);        // last iteration: chunk 0 for the second pass
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (c0 + j < kFeat) mx = fmaxf(mx, __uint_as_float(r[j]));
+                        if (32 * c + j < kFeat) mx = fmaxf(mx, __uint_as_float(cur[j]));
                 }
+            } else {
+                tmem_ld32(taddr, (kChunks & 1) ? rb : ra);
             }
-            const float shift = IS_Q ? -(diag + mx) : (P.eps - diag);
-#pragma unroll 1
-            for (int c0 = 0; c0 < kFeatPad; c0 += 32) {
-                tmem_ld32(taddr + c0, r);
+            // exp(dash + shift) = 2^(dash * log2e + shift * log2e): one FFMA + one MUFU.EX2 per element, then ratio * (e + eps)
+            const float shift2 = (IS_Q ? -(diag + mx) : (P.eps - diag)) * kLog2e;
+            const float add = IS_Q ? ratio * P.eps : 0.0f;
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+                // after the (odd number of) pass-1 iterations chunk 0 sits in the buffer pass 1 would have used next
+                uint32_t(&cur)[32] = ((c + kChunks) & 1) ? rb : ra;
+                uint32_t(&nxt)[32] = ((c + kChunks) & 1) ? ra : rb;
                 tmem_ld_wait();
+                if (c + 1 < kChunks) tmem_ld32(taddr + 32 * (c + 1), nxt);
+                float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float e = __expf(__uint_as_float(r[j]) + shift);
-                    const float val = IS_Q ? ratio * (e + P.eps) : ratio * e;
-                    v[j] = (c0 + j < kFeat) ? val : 0.0f;
+                    const float e = ex2_approx(fmaf(__uint_as_float(cur[j]), kLog2e, shift2));
+                    v[j] = (32 * c + j < kFeat) ? fmaf(e, ratio, add) : 0.0f;
                 }
+                const int c0 = 32 * c;
                 if (IS_Q) {
                     if (lane == 0) bulk_wait_read<0>();
                     __syncwarp();
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        st_shared_v4(stage_buf + lane * 128 + ((c ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    for (int k4 = 0; k4 < 8; ++k4)
+                        st_shared_v4(stage_buf + lane * 128 + ((k4 ^ (lane & 7)) << 4), v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) { tma_store_3d(&map_c, stage_buf, c0, m0 + q * 32, z); bulk_commit(); }

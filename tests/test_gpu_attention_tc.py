@@ -57,7 +57,8 @@ def test_linear_ex_fused_layer_norm(M):
     y, yn = core.linear_ex(x, w, b, r, ln=(gamma, beta, 1e-5))
     ref = x.double() @ w.double().t() + b.double() + r.double()
     refn = torch.nn.functional.layer_norm(ref, (256,), gamma.double(), beta.double(), 1e-5)
-    assert (y.double() - ref).abs().max().item() < 2e-5
+    # values up to ~13; the fp32 TMEM accumulator rounds once per MMA (3 x K/8 accumulations): a few 1e-6 relative
+    assert (y.double() - ref).abs().max().item() < 4e-5
     assert (yn.double() - refn).abs().max().item() < 2e-5
     # in place on the residual stream, as the control network calls it
     r2 = r.clone()
