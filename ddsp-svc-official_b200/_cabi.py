@@ -54,6 +54,9 @@ _PROTOS = {
                                           C.c_int, C.c_void_p]),
     'ddsp_b200_linear_tf32x3_ex': (C.c_int, [c_f32p, i64, c_f32p, c_f32p, i64, c_f32p, c_f32p, i64, c_f32p, i64, c_f32p, c_f32p,
                                              C.c_float, c_f32p, i64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ddsp_b200_linear_glu': (C.c_int, [c_f32p, i64, c_f32p, c_f32p, i64, c_f32p, c_f32p, i64, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p]),
+    'ddsp_b200_dwconv_silu': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
     'ddsp_b200_qkv_heads': (C.c_int, [c_f32p, i64, c_f32p, c_f32p, i64, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ddsp_b200_favor_features': (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_float, c_f32p, C.c_int, C.c_int, C.c_int,

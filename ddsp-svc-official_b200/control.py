@@ -19,6 +19,7 @@ Structure (the module / parameter names are dictated by the checkpoint layout):
     ConvModule  : LN - T - Conv1x1(256->1024) - GLU - depthwise Conv(k31) - SiLU - Conv1x1(512->256) - T   pcmer.py:41-63
 """
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -77,7 +78,9 @@ def _split_cached(owner, slot, tensors, build=None):
     hit = cache.get(slot)
     if hit is None or hit[0] != key:
         w = build(*[t.detach() for t in tensors]) if build is not None else tensors[0].detach()
-        hit = (key,) + tuple(core.split_tf32(w.reshape(w.shape[0], -1).contiguous()))
+        w = w.reshape(w.shape[0], -1).contiguous()
+        # DDSP_B200_NO_PRESPLIT=1 (experiments): leave the split to the kernel's splitter warps (half the weight bytes per tile)
+        hit = (key, w, None) if os.environ.get('DDSP_B200_NO_PRESPLIT') == '1' else (key,) + tuple(core.split_tf32(w))
         cache[slot] = hit
     return hit[1], hit[2]
 
@@ -216,9 +219,13 @@ class _ConvModule(nn.Module):
         Returns (residual + module, next_ln(residual + module)) -- or only the first when `next_ln` is None."""
         from . import core
         _, _, pw1, _, dw, _, pw2, _, _ = self.net
-        w1_hi, w1_lo = _split_cached(self, 'pw1', (pw1.weight,))
-        u = core.linear_ex(xn, w1_hi, weight_lo=w1_lo)                          # bias added on load by the next kernel
-        s = core.glu_dwconv_silu(u, dw.weight, dw.bias, u_bias=pw1.bias)
+        # pointwise conv + GLU in one GEMM (weight rows interleaved per column tile), then depthwise conv + SiLU
+        w1_hi, w1_lo = _split_cached(self, 'pw1', (pw1.weight,), lambda w: core.glu_interleave(w))
+        cache = self.__dict__['_tc_cache']
+        bkey = (pw1.bias._version, pw1.bias.data_ptr())
+        if cache.get('pw1_bias', (None,))[0] != bkey:
+            cache['pw1_bias'] = (bkey, core.glu_interleave(pw1.weight.detach(), pw1.bias.detach())[1])
+        s = core.dwconv_silu(core.linear_glu(xn, w1_hi, cache['pw1_bias'][1], weight_lo=w1_lo), dw.weight, dw.bias)
         w2_hi, w2_lo = _split_cached(self, 'pw2', (pw2.weight,))
         ln = None if next_ln is None else (next_ln.weight, next_ln.bias, next_ln.eps)
         return core.linear_ex(s, w2_hi, pw2.bias, residual=residual, out=residual, weight_lo=w2_lo, ln=ln)

@@ -604,6 +604,50 @@ def linear_ex(x, weight, bias=None, residual=None, out=None, weight_lo=None, ln=
     return (out, ln_out) if ln is not None else out
 
 
+def glu_interleave(weight, bias=None):
+    """Row order the GLU-fused GEMM expects (include/ddsp_b200.h, ddsp_b200_linear_glu): per 256-row tile t the 128 value
+    channels 128 t.. followed by their 128 gate channels N/2 + 128 t..  weight (N, K) [, bias (N)] -> permuted copies."""
+    N = weight.shape[0]
+    if N % 256:
+        raise ValueError('glu_interleave: N must be a multiple of 256')
+    half = N // 2
+    idx = torch.arange(N, device=weight.device).view(N // 256, 2, 128)
+    perm = (idx[:, 0] % 128 + 128 * torch.arange(N // 256, device=weight.device).view(-1, 1))
+    perm = torch.stack([perm, perm + half], dim=1).reshape(-1)
+    w = weight.reshape(N, -1)[perm].contiguous()
+    return (w, bias[perm].contiguous()) if bias is not None else w
+
+
+def linear_glu(x, weight_il, bias_il=None, weight_lo=None):
+    """GLU(F.linear(x, W, b)) (pcmer.py:52-53 in channels-last layout) with the gating done in the GEMM epilogue:
+    `weight_il` / `bias_il` / `weight_lo` in the interleaved row order of `glu_interleave`.  x (..., K) -> (..., N/2)."""
+    x = _need_cuda_f32(x, 'x')
+    N, K = weight_il.shape
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1 or (x2.stride(0) & 3) or (x2.data_ptr() & 15):
+        x2 = x2.contiguous()
+    out = torch.empty(lead + (N // 2,), dtype=torch.float32, device=x.device)
+    with _OnDevice(x.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_linear_glu(x2.data_ptr(), x2.stride(0), weight_il.data_ptr(), _ptr(weight_lo),
+                                                     weight_il.stride(0), _ptr(bias_il), out.data_ptr(), N // 2, x2.shape[0], N, K, _st))
+    return out
+
+
+def dwconv_silu(g, weight, bias):
+    """Depthwise Conv1d(k=31, 'same') -> SiLU on a channels-last tensor g (B,T,C) (pcmer.py:54-55)."""
+    g = _need_cuda_f32(g, 'g').contiguous()
+    B, T, C = g.shape
+    weight = _need_cuda_f32(weight, 'weight').reshape(C, -1).contiguous()
+    if weight.shape[1] != 31:
+        raise ValueError('depthwise kernel size must be 31')
+    bias = _need_cuda_f32(bias, 'bias').contiguous()
+    out = torch.empty_like(g)
+    with _OnDevice(g.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_dwconv_silu(g.data_ptr(), weight.data_ptr(), bias.data_ptr(), B, T, C, out.data_ptr(), _st))
+    return out
+
+
 _FAVOR_FEATURES, _FAVOR_PAD, _FAVOR_VT_ROWS = 266, 272, 80
 _favor_ws = {}
 

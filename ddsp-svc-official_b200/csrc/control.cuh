@@ -605,4 +605,40 @@ __global__ void __launch_bounds__(256) glu_dwconv_silu_kernel(const float* __res
     }
 }
 
+// Depthwise Conv1d(k=31, 'same') + SiLU on a gated channels-last tensor (the GLU already applied by the epilogue of the
+// producing GEMM, csrc/gemm_attn.cuh EPI_GLU).  A thread owns one channel and kDw2Run consecutive frames: the 31 taps and
+// a sliding window of inputs stay in registers, every input is loaded once per thread (lanes = consecutive channels:
+// 128-byte coalesced rows; the 30-frame halo of neighbouring runs comes out of L1 / L2).
+constexpr int kDw2Run = 32;
+
+__global__ void __launch_bounds__(256) dwconv_silu_kernel(const float* __restrict__ g, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ out, int T, int C) {
+    const int c = blockIdx.x * 256 + threadIdx.x, t0 = blockIdx.y * kDw2Run, b = blockIdx.z;
+    if (c >= C) return;
+    float wr[kDwTaps];
+#pragma unroll
+    for (int j = 0; j < kDwTaps; ++j) wr[j] = __ldg(w + (int64_t)c * kDwTaps + j);
+    const float bs = __ldg(bias + c);
+    float acc[kDw2Run];
+#pragma unroll
+    for (int o = 0; o < kDw2Run; ++o) acc[o] = bs;
+    const float* gb = g + (int64_t)b * T * C + c;
+#pragma unroll
+    for (int i = 0; i < kDw2Run + kDwTaps - 1; ++i) {
+        const int t = t0 + i - kDwPad;
+        const float val = (t >= 0 && t < T) ? __ldg(gb + (int64_t)t * C) : 0.0f;
+#pragma unroll
+        for (int o = 0; o < kDw2Run; ++o) {
+            const int j = i - o;
+            if (j >= 0 && j < kDwTaps) acc[o] = fmaf(wr[j], val, acc[o]);
+        }
+    }
+    float* ob = out + (int64_t)b * T * C + c;
+#pragma unroll
+    for (int o = 0; o < kDw2Run; ++o) {
+        const int t = t0 + o;
+        if (t < T) ob[(int64_t)t * C] = __fdividef(acc[o], 1.0f + __expf(-acc[o]));
+    }
+}
+
 }  // namespace ddsp

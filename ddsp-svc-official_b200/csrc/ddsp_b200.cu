@@ -673,6 +673,17 @@ int ddsp_b200_glu_dwconv_silu(const float* u, const float* u_bias, const float* 
     return DDSP_B200_OK;
 }
 
+int ddsp_b200_dwconv_silu(const float* g, const float* weight, const float* bias, int B, int T, int C, float* out,
+                          void* stream) {
+    g_launches = 0;
+    if (!g || !weight || !bias || !out || B <= 0 || T <= 0 || C <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (B > 65535) return DDSP_B200_ERR_UNSUPPORTED;
+    const dim3 grid((C + 255) / 256, (T + ddsp::kDw2Run - 1) / ddsp::kDw2Run, B);
+    ddsp::dwconv_silu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, weight, bias, out, T, C);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
 size_t ddsp_b200_frequency_filter_workspace_bytes(int B, int F, int n_mag) {
     (void)n_mag;
     if (B <= 0 || F <= 0) return 0;
@@ -1044,6 +1055,23 @@ int ddsp_b200_linear_tf32x3_ex(const float* A, int64_t lda, const float* W, cons
         case 224: return launch_gemm3x<224, ddsp::tc::EPI_PLAIN>(ma, mw, mwl, mc, mc2, P, st);
         default: return launch_gemm3x<128, ddsp::tc::EPI_PLAIN>(ma, mw, mwl, mc, mc2, P, st);
     }
+}
+
+int ddsp_b200_linear_glu(const float* A, int64_t lda, const float* W, const float* W_lo, int64_t ldw, const float* bias,
+                         float* C, int64_t ldc, int M, int N, int K, void* stream) {
+    g_launches = 0;
+    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || lda < K || ldw < K || ldc < N / 2) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if ((N & 255) || (bias && (reinterpret_cast<uintptr_t>(bias) & 15))) return DDSP_B200_ERR_UNSUPPORTED;
+    ddsp::tc::GemmParams P = {};
+    P.Z = 1; P.M = M; P.N = N; P.K = K;
+    P.w_presplit = W_lo ? 1 : 0;
+    P.bias = bias;
+    CUtensorMap ma, mw, mwl, mc;
+    if (int rc = make_map_3(&ma, A, K, M, 1, lda, 0, ddsp::tc::kBM)) return rc;
+    if (int rc = make_map_3(&mw, W, K, N, 1, ldw, 0, 256)) return rc;
+    if (int rc = make_map_3(&mwl, W_lo ? W_lo : W, K, N, 1, ldw, 0, 256)) return rc;
+    if (int rc = make_map_3(&mc, C, N / 2, M, 1, ldc, 0, 32)) return rc;
+    return launch_gemm3x<256, ddsp::tc::EPI_GLU>(ma, mw, mwl, mc, mc, P, (cudaStream_t)stream);
 }
 
 int ddsp_b200_qkv_heads(const float* A, int64_t lda, const float* W, const float* W_lo, int64_t ldw, const float* bias,

@@ -10,6 +10,9 @@
 //       EPI_QKV     merged q|k|v projection: q, k stored head-major (B,H,F,64); v stored transposed (B,H,80,Fp)
 //                   next to a row of ones, so that the context GEMM also yields sum_n k'
 //       EPI_OUT     attention output: columns 0..63 divided by column 64 (= q' . k_sum) + 1e-8, heads merged
+//       EPI_GLU     first pointwise conv of the conformer module with GLU fused (pcmer.py:52-53): the weight rows are
+//                   interleaved per column tile (128 value channels | their 128 gate channels), the epilogue writes
+//                   (a + b_a) * sigmoid(g + b_g) -- half the columns, no (B,N,1024) tensor in HBM
 //   favor_features_kernel<Q>    dash = x * (scale * projection)^T with the projection resident in shared memory,
 //                               epilogue = the softmax-kernel feature map (pcmer.py:124-160); q' row-major
 //                               (B*H, F, 272), k' transposed (B*H, 272, Fp)
@@ -23,7 +26,7 @@
 namespace ddsp {
 namespace tc {
 
-enum { EPI_PLAIN = 0, EPI_QKV = 1, EPI_OUT = 2 };
+enum { EPI_PLAIN = 0, EPI_QKV = 1, EPI_OUT = 2, EPI_GLU = 3 };
 
 constexpr int kFeat = 266;          // int(64 * ln 64) random features (pcmer.py:166)
 constexpr int kFeatPad = 272;       // padded to a multiple of 16 (UMMA N) / 16 bytes
@@ -418,6 +421,36 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 #pragma unroll
                         for (int j = 0; j < 32; ++j) dst[(int64_t)j * P.frames_pad] = v[j];
                     }
+                }
+            } else if constexpr (EPI == EPI_GLU) {
+                // column tile nt = [value channels 128 nt .. 128 nt + 127 | gate channels of the same range]; bias in the
+                // same interleaved order.  Output (M, N / 2): channel 128 nt + c.
+                static_assert(BN == 256, "GLU epilogue: 128 value + 128 gate columns per tile");
+                uint32_t rg[32];
+#pragma unroll 1
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld32(taddr + 128 + c0, rg);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+                        if (P.bias) {
+                            ba = __ldg(reinterpret_cast<const float4*>(P.bias + n0 + c0 + j));
+                            bg = __ldg(reinterpret_cast<const float4*>(P.bias + n0 + 128 + c0 + j));
+                        }
+                        const float a0 = __uint_as_float(r[j]) + ba.x, a1 = __uint_as_float(r[j + 1]) + ba.y;
+                        const float a2 = __uint_as_float(r[j + 2]) + ba.z, a3 = __uint_as_float(r[j + 3]) + ba.w;
+                        const float g0 = __uint_as_float(rg[j]) + bg.x, g1 = __uint_as_float(rg[j + 1]) + bg.y;
+                        const float g2 = __uint_as_float(rg[j + 2]) + bg.z, g3 = __uint_as_float(rg[j + 3]) + bg.w;
+                        v[j] = __fdividef(a0, 1.0f + __expf(-g0));
+                        v[j + 1] = __fdividef(a1, 1.0f + __expf(-g1));
+                        v[j + 2] = __fdividef(a2, 1.0f + __expf(-g2));
+                        v[j + 3] = __fdividef(a3, 1.0f + __expf(-g3));
+                    }
+                    const uint32_t buf = rs.begin();
+                    rs.fill(buf, v);
+                    if (lane == 0) { tma_store_3d(&map_c, buf, (n0 >> 1) + c0, m0 + q * 32, z); bulk_commit(); }
                 }
             } else {   // EPI_OUT
                 // batch z = (clip, head); accumulator columns 0..63 = sum_j q'_j ctx_j, column 64 = q' . k_sum

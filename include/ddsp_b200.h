@@ -288,6 +288,19 @@ int ddsp_b200_linear_tf32x3_ex(const float *A, int64_t lda, const float *W, cons
                                const float *ln_gamma, const float *ln_beta, float ln_eps, float *C_ln,
                                int64_t ldc_ln, int M, int N, int K, void *stream);
 
+/* First pointwise convolution of the conformer module with the GLU fused into the GEMM epilogue  (ddsp/pcmer.py:52-53):
+ *   C[m, 128 t + c] = (y[m, 256 t + c] + bias[256 t + c]) * sigmoid(y[m, 256 t + 128 + c] + bias[256 t + 128 + c]),
+ *   y = A (M,K) * W^T, W (N,K) with N a multiple of 256 and its rows (and `bias`) interleaved per 256-column tile:
+ *   rows 256 t .. 256 t + 127 = value channels 128 t .. 128 t + 127, rows 256 t + 128 .. 256 t + 255 = their gate
+ *   channels (N/2 + 128 t ...).  C: (M, N/2), row stride ldc (multiple of 4, 16-byte aligned base). */
+int ddsp_b200_linear_glu(const float *A, int64_t lda, const float *W, const float *W_lo, int64_t ldw,
+                         const float *bias, float *C, int64_t ldc, int M, int N, int K, void *stream);
+
+/* Depthwise Conv1d(k=31, 'same') -> SiLU on an already gated channels-last tensor g (B,T,C) -> out (B,T,C)
+ * (ddsp/pcmer.py:54-55; the second half of ddsp_b200_glu_dwconv_silu). */
+int ddsp_b200_dwconv_silu(const float *g, const float *w, const float *bias, int B, int T, int C, float *out,
+                          void *stream);
+
 /* Performer (FAVOR+) self-attention of one PCmer layer as tensor-core GEMMs     ddsp/pcmer.py:69-78,124-160,191-251
  * (non-causal; dim_head 64, 266 random features padded to 272; Z = B * heads; Fp = frames rounded up to a multiple of 4)
  *

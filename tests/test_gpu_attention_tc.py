@@ -134,3 +134,23 @@ def test_favor_attention_large_arguments():
     assert torch.isfinite(out).all()
     rel = ((out.double() - ref).abs().max() / ref.abs().max()).item()
     assert rel < 1e-4, rel
+
+
+@pytest.mark.parametrize('B,T', [(2, 300), (1, 33), (3, 862)])
+def test_linear_glu_and_dwconv_silu_match_the_module(B, T):
+    """pcmer.py:52-55: Conv1d(256 -> 1024, 1) -> GLU -> depthwise Conv1d(k=31, same) -> SiLU, channels-last."""
+    from ddsp_b200 import core
+    torch.manual_seed(B * 100 + T)
+    x = torch.randn(B, T, 256, device='cuda')
+    pw1 = torch.nn.Conv1d(256, 1024, 1).cuda()
+    dw = torch.nn.Conv1d(512, 512, 31, padding='same', groups=512).cuda()
+    with torch.no_grad():
+        ref_u = torch.nn.functional.linear(x.double(), pw1.weight.double().squeeze(-1), pw1.bias.double())
+        ref_g = torch.nn.functional.glu(ref_u, dim=-1).transpose(1, 2)
+        ref = torch.nn.functional.silu(torch.nn.functional.conv1d(ref_g, dw.weight.double(), dw.bias.double(), padding=15, groups=512))
+        w_il, b_il = core.glu_interleave(pw1.weight.detach(), pw1.bias.detach())
+        hi, lo = core.split_tf32(w_il)
+        for g in (core.linear_glu(x, w_il, b_il), core.linear_glu(x, hi, b_il, weight_lo=lo)):
+            assert (g.double() - ref_g.transpose(1, 2)).abs().max().item() < 2e-5
+        y = core.dwconv_silu(g, dw.weight, dw.bias)
+    assert (y.double() - ref.transpose(1, 2)).abs().max().item() < 3e-5
