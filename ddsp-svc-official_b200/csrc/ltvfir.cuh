@@ -37,7 +37,8 @@ constexpr int kLtvWarps = 16;                      // warps per CTA, both kernel
 constexpr int kLtvThreads = kLtvWarps * 32;
 constexpr int kLtvRing = 2048;                     // floats: overlap-add ring of the convolution kernel
 constexpr int kLtvCtxInts = 8;                     // cold per-warp scalars parked in shared memory (see combsubfast.cuh)
-constexpr int kLtvIrSmemBytes = 512 * 16 + kLtvWarps * (kPlaneFloats * 4 + kLtvCtxInts * 4);
+constexpr int kLtvChirpBytes = (512 * 2 + 1024 * 2) * 4;   // c[m] (512 complex) + chirp spectrum (1024 complex), parked in shared memory
+constexpr int kLtvIrSmemBytes = 512 * 16 + kLtvChirpBytes + kLtvWarps * (kPlaneFloats * 4 + kLtvCtxInts * 4);
 constexpr int kLtvConvWarpBytes = kPlaneFloats * 4 + kLtvRing * 4 + kLtvCtxInts * 4;
 constexpr int kLtvConvSmemBytes = 512 * 16 + kLtvWarps * kLtvConvWarpBytes;
 constexpr int kLtvSpecFloat2 = 1024;               // workspace per frame: raw FFT-1024 of the even/odd-packed taps
@@ -87,12 +88,16 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float4* tw4 = reinterpret_cast<const float4*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float* plane = reinterpret_cast<float*>(smem_raw + 512 * 16) + wid * (kPlaneFloats + kLtvCtxInts);
+    const float2* chirp_s = reinterpret_cast<const float2*>(smem_raw + 512 * 16);      // [0,512): c[m]; [512,1536): chirp spectrum
+    float* plane = reinterpret_cast<float*>(smem_raw + 512 * 16 + kLtvChirpBytes) + wid * (kPlaneFloats + kLtvCtxInts);
     volatile int* ctx = reinterpret_cast<volatile int*>(plane + kPlaneFloats);
     {
         const float4* src = reinterpret_cast<const float4*>(P.tw_tables);
         float4* dst = reinterpret_cast<float4*>(smem_raw);
         for (int e = threadIdx.x; e < 512; e += kLtvThreads) dst[e] = __ldg(src + e);
+        const float4* csrc = reinterpret_cast<const float4*>(P.chirp);
+        float4* cdst = reinterpret_cast<float4*>(smem_raw + 512 * 16);
+        for (int e = threadIdx.x; e < kLtvChirpBytes / 16; e += kLtvThreads) cdst[e] = __ldg(csrc + e);
         __syncthreads();
     }
 #define IR_NMAG (P.n_mag)
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
             if (phase == 0) {
                 // a'[k] = w_k X[k] c[k] / (L*1024), k = 32 n1 + lane < n_mag   (irfft, core.py:316)
                 const int n_mag = IR_NMAG, L = IR_L;
-                const float2* chirp_c = reinterpret_cast<const float2*>(P.chirp);
+                const float2* chirp_c = chirp_s;
                 const float* row = P.mags + (int64_t)ctx[0] * P.mB + (int64_t)ctx[1] * P.mF;
                 const float scale = 1.0f / ((float)L * 1024.0f);
                 float carry = 0.0f;                                      // allpass: running phase in turns
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
                         const bool edge = (k == 0) || (k == n_mag - 1);
                         const float wgt = edge ? scale : 2.0f * scale;
                         xi = edge ? 0.0f : xi;
-                        const float2 c = __ldg(chirp_c + k);
+                        const float2 c = chirp_c[k];
                         const float ar = xr * wgt, ai = xi * wgt;
                         xr = ar * c.x - ai * c.y;
                         xi = ar * c.y + ai * c.x;
@@ -191,12 +196,11 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
 
             if (phase == 0) {
                 // times the chirp spectrum, then inverse FFT (real/imag swapped through the forward FFT)
-                const float2* chirp_d = reinterpret_cast<const float2*>(P.chirp) + 512;
+                const float2* chirp_d = chirp_s + 512;
                 float pr[32], pi[32];
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
-                    if ((q & 7) == 0) asm volatile("" ::: "memory");      // keep at most 8 table loads in flight (registers)
-                    const float2 dh = __ldg(chirp_d + lane + 32 * q);
+                    const float2 dh = chirp_d[lane + 32 * q];
                     const float ur = DDSP_RE(X, q), ui = DDSP_IM(X, q);
                     pr[q] = ur * dh.x - ui * dh.y;
                     pi[q] = ur * dh.y + ui * dh.x;
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
                 const int L = IR_L, D = IR_D;
                 const int n_out = (L == 510) ? 510 : 512;          // IR samples produced by the chirp convolution
                 const bool sym = L != 510;                          // L=1022: real magnitudes -> IR symmetric, mirror it
-                const float2* chirp_c = reinterpret_cast<const float2*>(P.chirp);
+                const float2* chirp_c = chirp_s;
                 const float two_pi_over_L = DDSP_TWO_PI_F / (float)L;
                 float hw_inv = 0.0f;
                 if (win_mode == DDSP_B200_WINDOW_DYNAMIC) {
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
                 for (int q = 0; q < 16; ++q) {
                     const int n = lane + 32 * q;
                     if (n < n_out) {
-                        const float2 c = __ldg(chirp_c + n);
+                        const float2 c = chirp_c[n];
                         const float ir = DDSP_IM(X, q) * c.x - DDSP_RE(X, q) * c.y;   // Re(c * conv)
                         // tap positions: i = (n + D) mod L holds lag +n; for symmetric IRs also lag -n
 #pragma unroll
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
 // (packed as real / imaginary part and split by conjugate symmetry).  3 FFTs for two filters instead of 6.  Used by CombSub (vocoder.py:540,545-546) and Sins (:415,418-419).
 // ---------------------------------------------------------------------------------------------
 constexpr int kLtvDualWarpFloats = kPlaneFloats + kLtvCtxInts;           // plane (also holds the packed taps) + ctx
-constexpr int kLtvDualSmemBytes = 512 * 16 + kLtvWarps * kLtvDualWarpFloats * 4;
+constexpr int kLtvDualSmemBytes = 512 * 16 + kLtvChirpBytes + kLtvWarps * kLtvDualWarpFloats * 4;
 
 struct LtvDualParams {
     const float* gd; const float* nm; int64_t mB, mF;   // group_delay / noise_magnitude control rows (B,F,256)
@@ -288,17 +292,23 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_dual_kernel(const LtvDu
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float4* tw4 = reinterpret_cast<const float4*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float* plane = reinterpret_cast<float*>(smem_raw + 512 * 16) + wid * kLtvDualWarpFloats;
+    float* plane = reinterpret_cast<float*>(smem_raw + 512 * 16 + kLtvChirpBytes) + wid * kLtvDualWarpFloats;
     volatile int* ctx = reinterpret_cast<volatile int*>(plane + kPlaneFloats);
+    // chirp tables parked in shared memory: c[m] (512 complex), then the 1024-bin chirp spectrum
+    const float2* chirp_c = reinterpret_cast<const float2*>(smem_raw + 512 * 16);
+    const float2* chirp_d = chirp_c + 512;
     {
         const float4* src = reinterpret_cast<const float4*>(P.tw_tables);
         float4* dst = reinterpret_cast<float4*>(smem_raw);
         for (int e = threadIdx.x; e < 512; e += kLtvThreads) dst[e] = __ldg(src + e);
+        float4* cdst = reinterpret_cast<float4*>(smem_raw + 512 * 16);
+        const float4* c1 = reinterpret_cast<const float4*>(P.chirp_c);
+        const float4* c2 = reinterpret_cast<const float4*>(P.chirp_d_dual);
+        for (int e = threadIdx.x; e < 256; e += kLtvThreads) cdst[e] = __ldg(c1 + e);
+        for (int e = threadIdx.x; e < 512; e += kLtvThreads) cdst[256 + e] = __ldg(c2 + e);
         __syncthreads();
     }
     constexpr int L = 510, D = 255, NM = 256;
-    const float2* chirp_c = reinterpret_cast<const float2*>(P.chirp_c);
-    const float2* chirp_d = reinterpret_cast<const float2*>(P.chirp_d_dual);
     const int64_t n_frames = (int64_t)P.B * P.F;
 
     __nanosleep((unsigned)(wid >> 2) * LTV_STAGGER_NS);
@@ -348,7 +358,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_dual_kernel(const LtvDu
                         if (k == 0 || k == NM - 1) xi = 0.0f;             // irfft ignores Im of DC / Nyquist
                         // V = Xa + j Xn  (Xn real)
                         const float ar = xr * scale, ai = (xi + pm.y) * scale;
-                        const float2 c = __ldg(chirp_c + k);
+                        const float2 c = chirp_c[k];
                         vr[n1] = ar * c.x - ai * c.y;
                         vi[n1] = ar * c.y + ai * c.x;
                     }
@@ -377,7 +387,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_dual_kernel(const LtvDu
                 float pr[32], pi[32];
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
-                    const float2 dh = __ldg(chirp_d + lane + 32 * q);
+                    const float2 dh = chirp_d[lane + 32 * q];
                     const float ur = DDSP_RE(X, q), ui = DDSP_IM(X, q);
                     pr[q] = ur * dh.x - ui * dh.y;
                     pi[q] = ur * dh.y + ui * dh.x;
@@ -394,7 +404,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_dual_kernel(const LtvDu
                 for (int q = 0; q < 16; ++q) {
                     const int n = lane + 32 * q;
                     if (n < L) {
-                        const float2 c = __ldg(chirp_c + n);
+                        const float2 c = chirp_c[n];
                         const float cr = DDSP_IM(X, q), ci = DDSP_RE(X, q);      // conv = cr + j ci (swapped FFT)
                         const float sa = cr * c.x - ci * c.y, sn = cr * c.y + ci * c.x;
                         const int lag = (n <= L - D - 1) ? n : n - L;
