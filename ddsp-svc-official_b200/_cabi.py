@@ -65,6 +65,15 @@ _PROTOS = {
     'ddsp_b200_favor_output': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ddsp_b200_tc_microbench': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ddsp_b200_apply_frame_mask': (C.c_int, [c_f32p, c_f32p, i64, i64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ddsp_b200_apply_volume_mask': (C.c_int, [c_f32p, c_f32p, i64, i64, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ddsp_b200_phase_stream_full': (C.c_int, [c_f32p, i64, i64, C.c_int, C.c_int, C.c_int, C.c_double, c_f32p, C.c_void_p, i64,
+                                              c_f32p, C.c_void_p, c_f32p, C.c_void_p]),
+    'ddsp_b200_combsub_stream': (C.c_int, [c_f32p, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, i64, i64, c_f32p, i64, i64,
+                                           C.c_void_p, c_f32p, u64, i64, C.c_int, C.c_int, C.c_int, C.c_double, c_f32p,
+                                           c_f32p, c_f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'ddsp_b200_sins_stream': (C.c_int, [c_f32p, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, i64, i64, c_f32p, i64, i64,
+                                        c_f32p, c_f32p, u64, i64, C.c_int, C.c_int, C.c_int, C.c_double, c_f32p, c_f32p, c_f32p,
+                                        C.c_void_p, C.c_size_t, C.c_void_p]),
     'ddsp_b200_frequency_filter_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'ddsp_b200_frequency_filter': (C.c_int, [c_f32p, c_f32p, i64, i64, C.c_int, C.c_int, C.c_float, C.c_int, c_f32p,
                                              i64, i64, C.c_double, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,

@@ -163,14 +163,14 @@ def phase_stage(f0_frames, block_size, sampling_rate, initial_phase=None, infer=
     return phase_frames, prefix, phase_full
 
 
-def phase_stage_stream(f0_frames, block_size, sampling_rate, carry=None, initial_phase=None):
+def phase_stage_stream(f0_frames, block_size, sampling_rate, carry=None, initial_phase=None, full_rate=False):
     """Stage A for a block that continues a stream (gui.py:373-388).
 
     `carry` (B,) float64 view (any stride): the prefix the stream reached at this block's first frame --
     a column of the previous block's `prefix`; None at stream start (then `initial_phase` applies).
-    Returns (phase_frames (B,F) fp32, prefix (B,F) fp64)."""
+    Returns (phase_frames (B,F) fp32, prefix (B,F) fp64) and, with `full_rate` (Sins), the sample-rate phase (B,T)."""
     ops = _torchext.ops()
-    if ops is not None and carry is not None:
+    if ops is not None and carry is not None and not full_rate:
         ip = None if initial_phase is None else torch.as_tensor(initial_phase, dtype=torch.float32, device=f0_frames.device)
         pf, prefix, _ = _op(ops.phase, f0_frames, int(block_size), float(sampling_rate), ip, True, False, carry)
         return pf, prefix
@@ -185,6 +185,13 @@ def phase_stage_stream(f0_frames, block_size, sampling_rate, carry=None, initial
         if not carry.is_cuda or carry.dtype != torch.float64 or carry.dim() != 1 or carry.numel() != B:
             raise ValueError('carry must be a CUDA float64 tensor with one entry per clip')
         cptr, cstride = carry.data_ptr(), carry.stride(0)
+    if full_rate:
+        phase_full = torch.empty((B, F * int(block_size)), dtype=torch.float32, device=dev)
+        with _OnDevice(dev) as _st:
+            _cabi.check(_cabi.lib().ddsp_b200_phase_stream_full(f0.data_ptr(), f0.stride(0), f0.stride(1), B, F, int(block_size),
+                                                                float(sampling_rate), _ptr(ip), cptr, cstride,
+                                                                phase_frames.data_ptr(), prefix.data_ptr(), phase_full.data_ptr(), _st))
+        return phase_frames, prefix, phase_full
     with _OnDevice(dev) as _st:
         _cabi.check(_cabi.lib().ddsp_b200_phase_stream(f0.data_ptr(), f0.stride(0), f0.stride(1), B, F, int(block_size),
                                                        float(sampling_rate), _ptr(ip), cptr, cstride,
@@ -362,10 +369,11 @@ def _check_noise(noise_u, B, T):
 
 
 def combsub_stage(group_delay, harmonic_magnitude, noise_magnitude, f0_frames, prefix, block_size, sampling_rate,
-                  noise_u=None, seed=0):
-    """Stage B of CombSub.forward (old) (vocoder.py:521-548) -> (signal, harmonic, noise), each (B,T)."""
+                  noise_u=None, seed=0, hop_offset=0):
+    """Stage B of CombSub.forward (old) (vocoder.py:521-548) -> (signal, harmonic, noise), each (B,T).
+    `hop_offset` (streaming): stream index of the first hop, so that the in-kernel noise of a hop repeats."""
     ops = _torchext.ops()
-    if ops is not None:
+    if ops is not None and not hop_offset:
         return _op(ops.combsub, group_delay, harmonic_magnitude, noise_magnitude, f0_frames, prefix, int(block_size),
                            float(sampling_rate), noise_u, int(seed) % _TWO62)
     gd, hm, nm = _common_views((group_delay, harmonic_magnitude, noise_magnitude),
@@ -381,20 +389,20 @@ def combsub_stage(group_delay, harmonic_magnitude, noise_magnitude, f0_frames, p
                      dtype=torch.uint8, device=dev)
     signal, harmonic, noise = (torch.empty((B, T), dtype=torch.float32, device=dev) for _ in range(3))
     with _OnDevice(dev) as _st:
-        _cabi.check(L.ddsp_b200_combsub(
+        _cabi.check(L.ddsp_b200_combsub_stream(
             gd.data_ptr(), gd.shape[-1], hm.data_ptr(), hm.shape[-1], nm.data_ptr(), nm.shape[-1], gd.stride(0),
-            gd.stride(1), f0.data_ptr(), f0.stride(0), f0.stride(1), prefix.data_ptr(), 0, _ptr(noise_u),
-            int(seed) % _TWO62, B, F, hop, float(sampling_rate), signal.data_ptr(), harmonic.data_ptr(),
+            gd.stride(1), f0.data_ptr(), f0.stride(0), f0.stride(1), prefix.data_ptr(), _ptr(noise_u),
+            int(seed) % _TWO62, int(hop_offset), B, F, hop, float(sampling_rate), signal.data_ptr(), harmonic.data_ptr(),
             noise.data_ptr(), ws.data_ptr(), ws.numel(), _st))
     return signal, harmonic, noise
 
 
 def sins_stage(amplitudes, group_delay, noise_magnitude, f0_frames, phase, block_size, sampling_rate, noise_u=None,
-               seed=0):
+               seed=0, hop_offset=0):
     """Stage B of Sins.forward (vocoder.py:397-421) -> (signal, harmonic, noise), each (B,T).
-    `phase` is the full-rate phase (B,T) from `phase_stage(..., full_rate=True)`."""
+    `phase` is the full-rate phase (B,T) from `phase_stage(..., full_rate=True)`; `hop_offset` as in `combsub_stage`."""
     ops = _torchext.ops()
-    if ops is not None:
+    if ops is not None and not hop_offset:
         return _op(ops.sins, amplitudes, group_delay, noise_magnitude, f0_frames, phase, int(block_size), float(sampling_rate),
                         noise_u, int(seed) % _TWO62)
     am, gd, nm = _common_views((amplitudes, group_delay, noise_magnitude),
@@ -411,10 +419,10 @@ def sins_stage(amplitudes, group_delay, noise_magnitude, f0_frames, phase, block
                      dtype=torch.uint8, device=dev)
     signal, harmonic, noise = (torch.empty((B, T), dtype=torch.float32, device=dev) for _ in range(3))
     with _OnDevice(dev) as _st:
-        _cabi.check(L.ddsp_b200_sins(
+        _cabi.check(L.ddsp_b200_sins_stream(
             am.data_ptr(), am.shape[-1], gd.data_ptr(), gd.shape[-1], nm.data_ptr(), nm.shape[-1], am.stride(0),
             am.stride(1), f0.data_ptr(), f0.stride(0), f0.stride(1), phase.data_ptr(), _ptr(noise_u),
-            int(seed) % _TWO62, B, F, hop, float(sampling_rate), signal.data_ptr(), harmonic.data_ptr(),
+            int(seed) % _TWO62, int(hop_offset), B, F, hop, float(sampling_rate), signal.data_ptr(), harmonic.data_ptr(),
             noise.data_ptr(), ws.data_ptr(), ws.numel(), _st))
     return signal, harmonic, noise
 
@@ -433,6 +441,23 @@ def apply_frame_mask_(signal, mask_frames, block_size=512):
     with _OnDevice(signal.device) as _st:
         _cabi.check(_cabi.lib().ddsp_b200_apply_frame_mask(signal.data_ptr(), m.data_ptr(), m.stride(0), m.stride(1),
                                                            B, F, int(block_size), _st))
+    return signal
+
+
+def apply_volume_mask_(signal, volume_frames, threshold_db=-60.0, block_size=512):
+    """The callers' whole silence-mask epilogue in one in-place pass (main.py:112-116,159; gui.py:108-112,127):
+    `mask = volume > 10**(threshold_db/20)`, padded by 4 frames with its edge values, 9-frame running maximum,
+    `signal *= upsample(mask, block_size)`.  signal (B,T) fp32 contiguous; volume_frames (B,F) or (B,F,1)."""
+    signal = _need_cuda_f32(signal, 'signal')
+    if not signal.is_contiguous():
+        raise ValueError('signal must be contiguous (it is modified in place)')
+    v = _f0_2d(volume_frames)
+    B, F = v.shape
+    if tuple(signal.shape) != (B, F * int(block_size)):
+        raise ValueError('signal must be (B, Frame*block_size)')
+    with _OnDevice(signal.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_apply_volume_mask(signal.data_ptr(), v.data_ptr(), v.stride(0), v.stride(1),
+                                                            10.0 ** (float(threshold_db) / 20.0), B, F, int(block_size), _st))
     return signal
 
 

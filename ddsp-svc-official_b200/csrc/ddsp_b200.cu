@@ -21,6 +21,7 @@ namespace {
 
 thread_local int g_last_cuda_error = 0;
 thread_local int g_launches = 0;
+thread_local int64_t g_noise_hop_offset = 0;     // set by the *_stream entry points of the frequency_filter models
 
 inline int cuda_fail(cudaError_t e) {
     g_last_cuda_error = (int)e;
@@ -315,6 +316,14 @@ int ddsp_b200_phase_stream(const float* f0_frames, int64_t fB, int64_t fF, int B
                       nullptr, stream);
 }
 
+int ddsp_b200_phase_stream_full(const float* f0_frames, int64_t fB, int64_t fF, int B, int F, int hop, double sr,
+                                const float* initial_phase, const double* carry, int64_t carry_stride,
+                                float* phase_frames, double* prefix, float* phase_full, void* stream) {
+    if (carry && (carry == prefix || carry_stride < 0)) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    return phase_impl(f0_frames, fB, fF, B, F, hop, sr, initial_phase, carry, carry_stride, phase_frames, prefix,
+                      phase_full, stream);
+}
+
 static int combsubfast_impl(const float* harmonic_magnitude, const float* harmonic_phase, const float* noise_magnitude,
                             int64_t cB, int64_t cF, const float* f0_frames, int64_t fB, int64_t fF,
                             const double* prefix, const float* noise_u, uint64_t seed,
@@ -446,6 +455,7 @@ int ltv_params(ddsp::LtvParams& P, const float* audio, int audio_mode, uint64_t 
     CUDA_TRY(cudaGetDevice(&dev));
     P.chirp = g_chirp_ptr[dev][n_mag == 256 ? 0 : 1];
     P.audio = audio; P.audio_mode = audio_mode; P.seed = seed;
+    P.key_offset = (uint32_t)((uint64_t)g_noise_hop_offset * 32ull) * 0x9E3779B1u;     // same folding as combsubfast_impl
     P.mags = mags; P.mB = mB; P.mF = mF; P.n_mag = n_mag; P.encoding = encoding; P.mag_scale = mag_scale;
     P.window_mode = window_mode; P.f0_frames = f0_frames; P.fB = fB; P.fF = fF; P.sr15 = (float)(1.5 * sr);
     P.spec = (float2*)spec_ws; P.out = out; P.add_in = nullptr; P.sum_out = nullptr; P.B = B; P.F = F;
@@ -559,6 +569,18 @@ int ddsp_b200_apply_frame_mask(float* signal, const float* mask_frames, int64_t 
     const int64_t n4 = (int64_t)B * F * (hop / 4);
     ddsp::apply_frame_mask_kernel<<<(unsigned)grid_for(n4, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<float4*>(signal), mask_frames, mB, mF, B, F);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int ddsp_b200_apply_volume_mask(float* signal, const float* volume_frames, int64_t vB, int64_t vF, double threshold, int B,
+                                int F, int hop, void* stream) {
+    g_launches = 0;
+    if (!signal || !volume_frames || B <= 0 || F <= 0 || ((uintptr_t)signal & 15)) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (hop != ddsp::kHop) return DDSP_B200_ERR_UNSUPPORTED;
+    const int64_t n4 = (int64_t)B * F * (hop / 4);
+    ddsp::apply_volume_mask_kernel<<<(unsigned)grid_for(n4, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4*>(signal), volume_frames, vB, vF, threshold, B, F);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }
@@ -830,6 +852,34 @@ int ddsp_b200_sins(const float* amplitudes, int n_harmonics, const float* group_
     if (int rc = launch_add(harmonic, noise, signal, n, st)) return rc;
     g_launches += launches;
     return DDSP_B200_OK;
+}
+
+int ddsp_b200_combsub_stream(const float* group_delay, int n_mag_allpass, const float* harmonic_magnitude, int n_mag_harmonic,
+                             const float* noise_magnitude, int n_mag_noise, int64_t cB, int64_t cF, const float* f0_frames,
+                             int64_t fB, int64_t fF, const double* prefix, const float* noise_u, uint64_t seed,
+                             int64_t hop_offset, int B, int F, int hop, double sr, float* signal, float* harmonic,
+                             float* noise, void* workspace, size_t workspace_bytes, void* stream) {
+    if (hop_offset < 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    g_noise_hop_offset = hop_offset;
+    const int rc = ddsp_b200_combsub(group_delay, n_mag_allpass, harmonic_magnitude, n_mag_harmonic, noise_magnitude, n_mag_noise,
+                                     cB, cF, f0_frames, fB, fF, prefix, nullptr, noise_u, seed, B, F, hop, sr, signal, harmonic,
+                                     noise, workspace, workspace_bytes, stream);
+    g_noise_hop_offset = 0;
+    return rc;
+}
+
+int ddsp_b200_sins_stream(const float* amplitudes, int n_harmonics, const float* group_delay, int n_mag_allpass,
+                          const float* noise_magnitude, int n_mag_noise, int64_t cB, int64_t cF, const float* f0_frames,
+                          int64_t fB, int64_t fF, const float* phase_full, const float* noise_u, uint64_t seed,
+                          int64_t hop_offset, int B, int F, int hop, double sr, float* signal, float* harmonic, float* noise,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    if (hop_offset < 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    g_noise_hop_offset = hop_offset;
+    const int rc = ddsp_b200_sins(amplitudes, n_harmonics, group_delay, n_mag_allpass, noise_magnitude, n_mag_noise, cB, cF,
+                                  f0_frames, fB, fF, phase_full, noise_u, seed, B, F, hop, sr, signal, harmonic, noise,
+                                  workspace, workspace_bytes, stream);
+    g_noise_hop_offset = 0;
+    return rc;
 }
 
 }  // extern "C"

@@ -165,6 +165,37 @@ __global__ void __launch_bounds__(256) apply_frame_mask_kernel(float4* __restric
     }
 }
 
+// The whole silence-mask epilogue of main.py:112-116,159 / gui.py:108-112,127 in one in-place pass:
+//   mask = (volume > threshold)  ->  edge-padded 9-frame maximum  ->  upsample  ->  signal *= mask
+// (the comparison is made in double like numpy's float32-array > python-float; edge padding == index clamping).
+__global__ void __launch_bounds__(256) apply_volume_mask_kernel(float4* __restrict__ signal, const float* __restrict__ volume,
+                                                                int64_t vB, int64_t vF, double threshold, int B, int F) {
+    const int64_t n4 = (int64_t)B * F * (kHop / 4);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t hop_id = i / (kHop / 4);
+        const int j = (int)(i % (kHop / 4)) * 4;
+        const int b = (int)(hop_id / F), h = (int)(hop_id % F);
+        const float* row = volume + (int64_t)b * vB;
+        // frames h-4 .. h+5 cover the 9-frame windows of mask[h] and mask[h+1]
+        bool any_lo = false, any_hi = false;          // window of h: d = -4..4; window of h+1: d = -3..5
+#pragma unroll
+        for (int d = -4; d <= 5; ++d) {
+            const bool on = (double)__ldg(row + (int64_t)min(max(h + d, 0), F - 1) * vF) > threshold;
+            if (d <= 4) any_lo |= on;
+            if (d >= -3) any_hi |= on;
+        }
+        // mask[h+1] with hold-last at the end (core.py:17): frame F is frame F-1, whose window is d = -4..4 around F-1
+        if (h + 1 > F - 1) any_hi = any_lo;
+        const float x0 = any_lo ? 1.0f : 0.0f, x1 = any_hi ? 1.0f : 0.0f;
+        float4 v = signal[i];
+        v.x = __fmul_rn(v.x, lerp_torch(x0, x1, (float)(j + 0) * (1.0f / kHop)));
+        v.y = __fmul_rn(v.y, lerp_torch(x0, x1, (float)(j + 1) * (1.0f / kHop)));
+        v.z = __fmul_rn(v.z, lerp_torch(x0, x1, (float)(j + 2) * (1.0f / kHop)));
+        v.w = __fmul_rn(v.w, lerp_torch(x0, x1, (float)(j + 3) * (1.0f / kHop)));
+        signal[i] = v;
+    }
+}
+
 __global__ void __launch_bounds__(256) add_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                                   float4* __restrict__ out, int64_t n4) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {

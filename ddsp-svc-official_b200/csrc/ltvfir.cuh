@@ -50,6 +50,7 @@ struct LtvParams {
     const float* audio;                 // (B,T) contiguous, or U when audio_mode==1, unused when 2
     int audio_mode;                     // 0: samples, 1: uniform U -> 2U-1 (vocoder.py:418,545), 2: in-kernel noise
     uint64_t seed;
+    uint32_t key_offset;                // streaming: noise key shift of the block's first hop (0 otherwise)
     const float* mags; int64_t mB, mF;  // (B,F,n_mag) control / magnitude rows
     int n_mag, encoding; float mag_scale;
     int window_mode;
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
         if (lane == 0) {
             ctx[0] = b0; ctx[1] = mb; ctx[2] = min(P.F + 1, mb + P.run_len);
             const uint64_t k64 = noise_key64(P.seed, (uint32_t)b0);
-            ctx[3] = (int)(uint32_t)k64;
+            ctx[3] = (int)((uint32_t)k64 + P.key_offset);
             ctx[5] = (int)(uint32_t)(k64 >> 32);
         }
         __syncwarp();
@@ -723,7 +724,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
         if (lane == 0) {
             ctx[0] = b0; ctx[1] = mb; ctx[2] = min(P.F + 1, mb + P.run_len);
             const uint64_t k64 = noise_key64(P.seed, (uint32_t)b0);
-            ctx[3] = (int)(uint32_t)k64;
+            ctx[3] = (int)((uint32_t)k64 + P.key_offset);
             ctx[5] = (int)(uint32_t)(k64 >> 32);
         }
         __syncwarp();

@@ -17,7 +17,8 @@ same excitation, same noise; equal to the last fp32 ulp or two (measured 7e-8) r
 the inverse FFT handles STFT frames in pairs and which frames share a pair depends on the parity of a
 block's first frame (tests/test_gpu_stream.py); `flush()` hands out the last two hops with the
 reference's hold-last ending.
-Only CombSubFast streams: the `frequency_filter` models need an (L-1)-sample tail per filter as well.
+`FilterModelStream` (below) does the same for the `frequency_filter` models Sins and CombSub (old), whose (L-1)-tap
+filters reach further: 1 + 2 (Sins) or 2 + 3 (CombSub) frames are re-synthesised around every block.
 """
 import torch
 
@@ -211,4 +212,116 @@ class StreamingCombSubFast:
     def flush(self):
         out = self.stream.flush()
         self._phase_hist = None
+        return out
+
+
+class FilterModelStream:
+    """Stage-level stream for the `frequency_filter` models (`Sins`, vocoder.py:381-423; `CombSub` old, :504-550):
+
+        audio = stream.push(c0, c1, c2, f0_new)        # (B, 512*n) finished samples of (signal, harmonic, noise)
+        tail  = stream.flush()                          # the hops still held back; resets the stream
+
+    `model` = 'sins': c0, c1, c2 = amplitudes, group_delay, noise_magnitude; 'combsub': group_delay,
+    harmonic_magnitude, noise_magnitude -- rows of the k new frames, (B,k,K) each.
+
+    The LTV-FIR output y[t] = sum_s x[s] h_s[t + L/2 - s] (core.py:185-336) needs input samples up to L/2 on either side,
+    and a sample of hop h needs frame h+1 (interpolated f0 and impulse response).  With the block's window starting `LEFT`
+    frames before the first hop still owed and the newest `RIGHT` hops held back, every hop handed out equals what ONE call
+    over all frames pushed so far produces (to the last ulp or two: the overlap-add order follows the run partition of the
+    call):  CombSub chains a 510-tap and a 1022-tap filter -> LEFT = 2, RIGHT = 3;  Sins has 510-tap filters only ->
+    LEFT = 1, RIGHT = 2.  The phase is carried as the fp64 prefix (`ddsp_b200_phase_stream`), the in-kernel noise by hop
+    index (`hop_offset`), so re-synthesised hops repeat exactly."""
+
+    GEOMETRY = {'sins': (1, 2), 'combsub': (2, 3)}
+
+    def __init__(self, model, block_size=512, sampling_rate=44100, seed=0, initial_phase=None):
+        if model not in self.GEOMETRY:
+            raise ValueError("model must be 'sins' or 'combsub'")
+        self.model = model
+        self.left, self.right = self.GEOMETRY[model]
+        self.hop = int(block_size)
+        self.sr = float(sampling_rate)
+        self.seed = int(seed)
+        self.initial_phase = initial_phase
+        self._utterance = -1
+        self.reset()
+
+    def reset(self):
+        self._utterance += 1
+        self._seed_now = (self.seed + 0x9E3779B97F4A7C15 * self._utterance) & ((1 << 62) - 1)
+        self.frames_pushed = 0
+        self.hops_emitted = 0
+        self._f0 = None                 # (B,w) frames kept: the next window's left part
+        self._rows = None               # list of three (B,w,K)
+        self._noise = None              # (B,w*hop) injected noise of the kept frames (parity mode)
+        self._first = 0                 # stream index of the first kept frame
+        self._carry = None              # (B,) fp64: prefix at the first kept frame
+        self._held = None               # the hops held back, ended the hold-last way (for flush())
+
+    def _synth(self, rows, f0_win, noise_win, first):
+        B, W = f0_win.shape
+        if self.model == 'sins':
+            _, prefix, phase = core.phase_stage_stream(f0_win, self.hop, self.sr, carry=self._carry,
+                                                       initial_phase=self.initial_phase if self._carry is None else None,
+                                                       full_rate=True)
+            out = core.sins_stage(rows[0], rows[1], rows[2], f0_win, phase, self.hop, self.sr, noise_u=noise_win,
+                                  seed=self._seed_now, hop_offset=first)
+        else:
+            _, prefix = core.phase_stage_stream(f0_win, self.hop, self.sr, carry=self._carry,
+                                                initial_phase=self.initial_phase if self._carry is None else None)
+            out = core.combsub_stage(rows[0], rows[1], rows[2], f0_win, prefix, self.hop, self.sr, noise_u=noise_win,
+                                     seed=self._seed_now, hop_offset=first)
+        return out, prefix
+
+    def push(self, c0, c1, c2, f0_new, noise_u=None):
+        """k new frames in, the newly finished hops out as (signal, harmonic, noise), each (B, 512*n) -- n = k in the
+        steady state, k - RIGHT on the first push (possibly 0 samples)."""
+        f0_new = core._f0_2d(core.as_f32(f0_new))
+        B, k = f0_new.shape
+        if k < 1:
+            raise ValueError('push() needs at least one new frame')
+        new_rows = [core.as_f32(r) for r in (c0, c1, c2)]
+        for r in new_rows:
+            if r.shape[0] != B or r.shape[1] != k:
+                raise ValueError('control rows must be (B, k, K) for the k new frames')
+        if self._f0 is not None and self._f0.shape[0] != B:
+            raise ValueError('the number of clips must not change inside a stream (reset() first)')
+        if (noise_u is None) != (self._noise is None) and self._f0 is not None:
+            raise ValueError('either every block of a stream injects noise_u or none does')
+        if noise_u is not None:
+            noise_u = core._need_cuda_f32(noise_u, 'noise_u')
+            if tuple(noise_u.shape) != (B, k * self.hop):
+                raise ValueError('noise_u must be (B, k*block_size)')
+        if self._f0 is None:
+            f0_win, rows, noise_win = f0_new.contiguous(), [r.contiguous() for r in new_rows], noise_u
+        else:
+            f0_win = torch.cat((self._f0, f0_new), dim=1)
+            rows = [torch.cat((a, b), dim=1) for a, b in zip(self._rows, new_rows)]
+            noise_win = None if noise_u is None else torch.cat((self._noise, noise_u), dim=1)
+        first = self._first
+        W = f0_win.shape[1]
+        (signal, harmonic, noise), prefix = self._synth(rows, f0_win, noise_win, first)
+        n_total = first + W                                  # frames pushed so far
+        lo = self.hops_emitted - first                       # window hop of the first hop still owed
+        hi = max(lo, W - self.right)
+        hop = self.hop
+        out = tuple(t[:, lo * hop:hi * hop] for t in (signal, harmonic, noise))
+        self._held = tuple(t[:, hi * hop:] for t in (signal, harmonic, noise))
+        self.hops_emitted += hi - lo
+        self.frames_pushed = n_total
+        # keep the frames from LEFT before the first hop still owed
+        keep_from = max(0, self.hops_emitted - self.left - first)
+        self._f0 = f0_win[:, keep_from:].contiguous()
+        self._rows = [r[:, keep_from:].contiguous() for r in rows]
+        self._noise = None if noise_win is None else noise_win[:, keep_from * hop:].contiguous()
+        self._carry = prefix[:, keep_from].clone()
+        self._first = first + keep_from
+        return out
+
+    def flush(self):
+        """The hops still held back, ending the way one call over all pushed frames ends.  Resets the stream."""
+        if self._held is None:
+            raise RuntimeError('flush() on an empty stream')
+        out = self._held
+        self.reset()
         return out

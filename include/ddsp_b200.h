@@ -215,6 +215,35 @@ int ddsp_b200_sins(const float *amplitudes, int n_harmonics, const float *group_
 int ddsp_b200_apply_frame_mask(float *signal, const float *mask_frames, int64_t mB, int64_t mF, int B,
                                int F, int hop, void *stream);
 
+/* The whole silence-mask epilogue of the callers in one in-place pass            main.py:112-116,159 / gui.py:108-112,127
+ *   mask = (volume > threshold) -> padded with its edge values by 4 frames -> 9-frame running maximum
+ *        -> upsample(mask, block_size) -> signal *= mask
+ * volume_frames: (B,F) view (element strides vB, vF), threshold = 10^(dB/20) compared in double as numpy does;
+ * signal (B, F*hop) contiguous, 16-byte aligned, modified in place. */
+int ddsp_b200_apply_volume_mask(float *signal, const float *volume_frames, int64_t vB, int64_t vF,
+                                double threshold, int B, int F, int hop, void *stream);
+
+/* Streaming forms of the frequency_filter models (ddsp/vocoder.py:381-423, :504-550): the same computation on a window
+ * of frames that continues a stream -- `prefix` / `phase_full` come from ddsp_b200_phase_stream(_full) with the
+ * carried fp64 prefix, and `hop_offset` is the stream index of the window's first hop, so that the in-kernel noise of
+ * a re-synthesised hop repeats.  ddsp_b200.streaming.FilterModelStream re-synthesises the few frames whose output the
+ * (L-1)-tap filters had not finished (2 + 3 frames for CombSub, 1 + 2 for Sins) and emits only finished hops. */
+int ddsp_b200_phase_stream_full(const float *f0_frames, int64_t fB, int64_t fF, int B, int F, int hop, double sr,
+                                const float *initial_phase, const double *carry, int64_t carry_stride,
+                                float *phase_frames, double *prefix, float *phase_full, void *stream);
+int ddsp_b200_combsub_stream(const float *group_delay, int n_mag_allpass, const float *harmonic_magnitude,
+                             int n_mag_harmonic, const float *noise_magnitude, int n_mag_noise, int64_t cB,
+                             int64_t cF, const float *f0_frames, int64_t fB, int64_t fF, const double *prefix,
+                             const float *noise_u, uint64_t seed, int64_t hop_offset, int B, int F, int hop,
+                             double sr, float *signal, float *harmonic, float *noise, void *workspace,
+                             size_t workspace_bytes, void *stream);
+int ddsp_b200_sins_stream(const float *amplitudes, int n_harmonics, const float *group_delay, int n_mag_allpass,
+                          const float *noise_magnitude, int n_mag_noise, int64_t cB, int64_t cF,
+                          const float *f0_frames, int64_t fB, int64_t fF, const float *phase_full,
+                          const float *noise_u, uint64_t seed, int64_t hop_offset, int B, int F, int hop, double sr,
+                          float *signal, float *harmonic, float *noise, void *workspace, size_t workspace_bytes,
+                          void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Control network (ddsp/unit2control.py, ddsp/pcmer.py) -- fused elementwise stages between the
  * library GEMMs.  Not part of the synthesizer path; see DESIGN.md section 7.

@@ -171,3 +171,72 @@ def test_stream_block_under_cuda_graph():
         graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# frequency_filter models (Sins, CombSub old): carried phase + re-synthesised context frames
+SPLITS = {'combsub': (256, 512, 256), 'sins': (128, 256, 256)}
+
+
+def _filter_one_shot(model, d, U, seed):
+    a, b, c = SPLITS[model]
+    ctrl = dev(d['ctrl'])
+    c0, c1, c2 = torch.split(ctrl, [a, b, c], dim=-1)
+    f0 = dev(d['f0_frames'])
+    _, prefix, phase = core.phase_stage(f0, 512, 44100, None, True, full_rate=(model == 'sins'))
+    if model == 'sins':
+        return core.sins_stage(c0, c1, c2, f0, phase, 512, 44100, noise_u=U, seed=seed)
+    return core.combsub_stage(c0, c1, c2, f0, prefix, 512, 44100, noise_u=U, seed=seed)
+
+
+@pytest.mark.parametrize('model', ['sins', 'combsub'])
+@pytest.mark.parametrize('blocks', [[30], [1] * 10, [9] * 5, [2, 1, 7, 26, 3]])
+@pytest.mark.parametrize('inject', [True, False])
+def test_filter_model_stream_equals_one_call(model, blocks, inject):
+    from ddsp_b200.streaming import FilterModelStream
+    F = sum(blocks)
+    a, b, c = SPLITS[model]
+    d = make_inputs(2, F, a + b + c, seed=11 + F)
+    U = dev(d['U']) if inject else None
+    ref = _filter_one_shot(model, d, U, seed=5)
+    ctrl = dev(d['ctrl'])
+    c0, c1, c2 = torch.split(ctrl, [a, b, c], dim=-1)
+    f0 = dev(d['f0_frames'])
+    s = FilterModelStream(model, 512, 44100, seed=5)
+    outs, pos = [], 0
+    for k in blocks:
+        e = pos + k
+        outs.append(s.push(c0[:, pos:e], c1[:, pos:e], c2[:, pos:e], f0[:, pos:e],
+                           noise_u=None if U is None else U[:, pos * 512:e * 512]))
+        assert s.frames_pushed == e and s.hops_emitted == max(0, e - s.right)
+        assert outs[-1][0].shape[1] == 512 * (max(0, e - s.right) - max(0, pos - s.right))
+        pos = e
+    outs.append(s.flush())
+    for i, name in enumerate(('signal', 'harmonic', 'noise')):
+        got = torch.cat([o[i] for o in outs], dim=1)
+        assert got.shape == ref[i].shape
+        err = float((got - ref[i]).abs().max())
+        # the overlap-add order inside a call follows its run partition: a few fp32 ulps of O(1) signals
+        assert err <= 3e-6, (name, err)
+
+
+def test_apply_volume_mask_matches_the_callers_numpy_code():
+    """main.py:112-116,159: threshold -> edge padding by 4 -> 9-frame maximum -> upsample -> multiply."""
+    from oracle import ddsp_oracle as O
+    rng = np.random.default_rng(3)
+    B, F = 3, 57
+    vol = (10.0 ** rng.uniform(-5, -1, size=(B, F))).astype(np.float32)
+    vol[0, :6] = 1e-6
+    vol[1, -3:] = 1e-6
+    vol[2, 20:45] = 1e-7
+    sig = rng.standard_normal((B, F * 512)).astype(np.float32)
+    thr_db = -60.0
+    expect = np.empty_like(sig)
+    for b in range(B):
+        mask = (vol[b] > 10 ** (float(thr_db) / 20)).astype('float')
+        mask = np.pad(mask, (4, 4), constant_values=(mask[0], mask[-1]))
+        mask = np.array([np.max(mask[n: n + 9]) for n in range(len(mask) - 8)])
+        up = O.upsample(mask[None, :, None].astype(np.float32), 512)[0, :, 0]
+        expect[b] = sig[b] * up
+    got = core.apply_volume_mask_(dev(sig.copy()), dev(vol), thr_db)
+    assert np.array_equal(got.cpu().numpy(), expect)
