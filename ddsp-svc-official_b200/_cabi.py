@@ -74,6 +74,13 @@ _PROTOS = {
     'ddsp_b200_sins_stream': (C.c_int, [c_f32p, C.c_int, c_f32p, C.c_int, c_f32p, C.c_int, i64, i64, c_f32p, i64, i64,
                                         c_f32p, c_f32p, u64, i64, C.c_int, C.c_int, C.c_int, C.c_double, c_f32p, c_f32p, c_f32p,
                                         C.c_void_p, C.c_size_t, C.c_void_p]),
+    'ddsp_b200_mel_spectrogram': (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p, C.c_void_p,
+                                            C.c_int, C.c_float, c_f32p, C.c_int, C.c_void_p]),
+    'ddsp_b200_sinc_resample': (C.c_int, [c_f32p, C.c_int, C.c_int, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int, C.c_void_p]),
+    'ddsp_b200_interp_frames': (C.c_int, [c_f32p, i64, i64, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, C.c_double,
+                                          c_f32p, C.c_int, C.c_void_p]),
+    'ddsp_b200_sola_splice': (C.c_int, [c_f32p, C.c_int, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p,
+                                        C.c_void_p]),
     'ddsp_b200_frequency_filter_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'ddsp_b200_frequency_filter': (C.c_int, [c_f32p, c_f32p, i64, i64, C.c_int, C.c_int, C.c_float, C.c_int, c_f32p,
                                              i64, i64, C.c_double, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,

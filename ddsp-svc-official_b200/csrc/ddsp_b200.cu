@@ -12,6 +12,7 @@
 #include "combsubfast_bwd.cuh"
 #include "control.cuh"
 #include "excite.cuh"
+#include "frontend.cuh"
 #include "gemm_attn.cuh"
 #include "gemm_tc.cuh"
 #include "ltvfir.cuh"
@@ -1204,6 +1205,87 @@ int ddsp_b200_favor_output(const float* qf, const float* ctxT, float* out, int B
     if (int rc = make_map_3(&mw, ctxT, kFeatPad, kVtRows, Z, kFeatPad, (int64_t)kVtRows * kFeatPad, kVtRows)) return rc;
     if (int rc = make_map_3(&mc, out, (int64_t)H * 64, F, B, (int64_t)H * 64, (int64_t)F * H * 64, 32)) return rc;
     return launch_gemm3x<kVtRows, EPI_OUT>(ma, mw, mw, mc, mc, P, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Downstream of the synthesizer: enhancer front-end and the GUI's SOLA splice (csrc/frontend.cuh)
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ddsp_b200_mel_spectrogram(const float* audio, int B, int T, int n_fft, int win_size, int hop, const float* mel_basis,
+                              const int* band_start, const int* band_end, int n_mels, float clip_val, float* out,
+                              int n_frames, void* stream) {
+    g_launches = 0;
+    if (!audio || !mel_basis || !band_start || !band_end || !out || B <= 0 || T <= 0 || hop <= 0 || n_mels <= 0)
+        return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (n_fft != ddsp::kMelFft || win_size != ddsp::kMelFft || hop > ddsp::kMelFft) return DDSP_B200_ERR_UNSUPPORTED;
+    const int pad_left = (win_size - hop) / 2;
+    int pad_right = (win_size - hop + 1) / 2;
+    if (win_size - T - pad_left > pad_right) pad_right = win_size - T - pad_left;
+    const int expect = 1 + (T + pad_left + pad_right - n_fft) / hop;
+    if (n_frames != expect) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    ddsp::MelParams P;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = ensure_device_ready(st, &P.tw_tables, 1)) return rc;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(ddsp::mel_spectrogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kMelSmemBytes));
+        attr_set[dev] = true;
+    }
+    P.audio = audio; P.B = B; P.T = T; P.n_frames = n_frames; P.hop = hop; P.pad_left = pad_left;
+    P.reflect = pad_right < T ? 1 : 0;
+    P.mel_basis = mel_basis; P.band_start = band_start; P.band_end = band_end; P.n_mels = n_mels; P.clip_val = clip_val;
+    P.out = out;
+    int64_t grid = ((int64_t)B * n_frames + ddsp::kMelWarps - 1) / ddsp::kMelWarps;
+    if (grid > 2 * sm_count()) grid = 2 * sm_count();
+    ddsp::mel_spectrogram_kernel<<<(unsigned)grid, ddsp::kMelWarps * 32, ddsp::kMelSmemBytes, st>>>(P);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int ddsp_b200_sinc_resample(const float* x, int B, int T, const float* kernel_t, int orig, int nw, int width, float* y,
+                            int T_out, void* stream) {
+    g_launches = 0;
+    if (!x || !kernel_t || !y || B <= 0 || T <= 0 || orig <= 0 || nw <= 0 || width < 0 || T_out <= 0)
+        return DDSP_B200_ERR_INVALID_ARGUMENT;
+    const int K = 2 * width + orig;
+    const size_t smem = (size_t)((ddsp::kResTileI - 1) * orig + K) * sizeof(float);
+    if (smem > 48 * 1024 || B > 65535) return DDSP_B200_ERR_UNSUPPORTED;
+    const int64_t n_i = ((int64_t)T_out + nw - 1) / nw;
+    const dim3 grid((unsigned)((n_i + ddsp::kResTileI - 1) / ddsp::kResTileI), (unsigned)B);
+    ddsp::sinc_resample_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, T, kernel_t, orig, nw, width, K, y, T_out);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int ddsp_b200_interp_frames(const float* f0, int64_t fB, int64_t fN, int B, int n, float scale, double hop_over_sr,
+                            double real_factor, double dt_out, float* out, int n_out, void* stream) {
+    g_launches = 0;
+    if (!f0 || !out || B <= 0 || n <= 0 || n_out <= 0 || !(hop_over_sr > 0) || !(real_factor > 0) || !(dt_out > 0))
+        return DDSP_B200_ERR_INVALID_ARGUMENT;
+    const int64_t tot = (int64_t)B * n_out;
+    ddsp::interp_frames_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, (cudaStream_t)stream>>>(f0, fB, fN, B, n, scale, hop_over_sr,
+                                                                                              real_factor, dt_out, out, n_out);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int ddsp_b200_sola_splice(const float* x, int n, float* sola_buffer, const float* fade_in, const float* fade_out, int block,
+                          int crossfade, int search, float* out, int* shift_out, void* stream) {
+    g_launches = 0;
+    if (!x || !sola_buffer || !fade_in || !fade_out || !out || !shift_out || block <= 0 || crossfade <= 0 || search < 0)
+        return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (n < block + crossfade + search || block < crossfade) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    const size_t smem = (size_t)crossfade * sizeof(float) + ddsp::kSolaThreads * (sizeof(float) + sizeof(int));
+    if (smem > 48 * 1024) return DDSP_B200_ERR_UNSUPPORTED;
+    ddsp::sola_splice_kernel<<<1, ddsp::kSolaThreads, smem, (cudaStream_t)stream>>>(x, sola_buffer, fade_in, fade_out, block,
+                                                                                   crossfade, search, out, shift_out);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
 }
 
 }  // extern "C"

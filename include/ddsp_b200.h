@@ -358,6 +358,33 @@ int ddsp_b200_favor_output(const float *qf, const float *ctxT, float *out, int B
 int ddsp_b200_tc_microbench(const float *A, const float *W, float *C, int N, int K, int block_n,
                             int virtual_tiles, void *stream);
 
+/* ---- downstream of the synthesizer: enhancer front-end and GUI splice ----------------------
+ *
+ * ddsp_b200_mel_spectrogram   nsf_hifigan/nvSTFT.py:65-116 (STFT.get_mel, keyshift = 0, speed = 1, center = False):
+ *     reflect padding by (win-hop)/2 | (win-hop+1)/2, STFT with the periodic Hann window, sqrt(re^2 + im^2 + 1e-9),
+ *     mel_basis (n_mels, n_fft/2+1) product, log(max(., clip_val)).  audio (B,T) -> out (B, n_mels, n_frames),
+ *     n_frames = 1 + (T + pads - n_fft) / hop.  n_fft = win_size = 2048 (the 44.1 kHz NSF-HiFiGAN setting).
+ *     band_start / band_end (n_mels, int32): first and one-past-last non-zero bin of every mel filter.
+ * ddsp_b200_sinc_resample     torchaudio.transforms.Resample(orig, new, lowpass_filter_width) as called at
+ *     enhancer.py:47,69 and gui.py:398-401: y[i*nw + j] = sum_k kernel[j][k] * xpad[i*orig + k]; kernel_t is the
+ *     table of torchaudio's _get_sinc_resample_kernel TRANSPOSED to (K = 2*width + orig, nw); orig / nw already divided
+ *     by their gcd; y (B, T_out), T_out = ceil(nw * T / orig).
+ * ddsp_b200_interp_frames     enhancer.py:57-63: out[b,i] = np.interp(dt_out * i, (hop_over_sr * k) / real_factor,
+ *     f0[b,k] * scale) in double, ends held; f0 (B,n) view with element strides (fB, fN); out (B, n_out).
+ * ddsp_b200_sola_splice       gui.py:408-426 (no phase vocoder): shift = first argmax over d = 0..search of the
+ *     normalised cross-correlation of x[d : d+crossfade] with sola_buffer; out[i] = x[shift+i] (crossfaded with the
+ *     buffer over the first `crossfade` samples), i < block; sola_buffer <- x[shift+block : shift+block+crossfade];
+ *     *shift_out = shift (device memory).  x has n >= block + crossfade + search samples. */
+int ddsp_b200_mel_spectrogram(const float *audio, int B, int T, int n_fft, int win_size, int hop,
+                              const float *mel_basis, const int *band_start, const int *band_end, int n_mels,
+                              float clip_val, float *out, int n_frames, void *stream);
+int ddsp_b200_sinc_resample(const float *x, int B, int T, const float *kernel_t, int orig, int nw, int width,
+                            float *y, int T_out, void *stream);
+int ddsp_b200_interp_frames(const float *f0, int64_t fB, int64_t fN, int B, int n, float scale, double hop_over_sr,
+                            double real_factor, double dt_out, float *out, int n_out, void *stream);
+int ddsp_b200_sola_splice(const float *x, int n, float *sola_buffer, const float *fade_in, const float *fade_out,
+                          int block, int crossfade, int search, float *out, int *shift_out, void *stream);
+
 /* Number of kernel launches the last call of each entry point enqueued on this thread
  * (bench.py reports it as gpu_launches). */
 int ddsp_b200_last_launch_count(void);
