@@ -61,8 +61,8 @@ _PROTOS = {
                                       C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ddsp_b200_favor_features': (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_float, c_f32p, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p]),
-    'ddsp_b200_favor_context': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_void_p]),
-    'ddsp_b200_favor_output': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ddsp_b200_favor_context': (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_void_p]),
+    'ddsp_b200_favor_output': (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ddsp_b200_tc_microbench': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ddsp_b200_apply_frame_mask': (C.c_int, [c_f32p, c_f32p, i64, i64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ddsp_b200_apply_volume_mask': (C.c_int, [c_f32p, c_f32p, i64, i64, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p]),

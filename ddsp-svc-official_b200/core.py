@@ -691,7 +691,7 @@ def favor_workspace(B, H, F, device):
         vt[:, :, 64, :F] = 1.0
         ws = {'Fp': Fp, 'q': torch.empty((B, H, F, 64), **f32), 'k': torch.empty((B, H, F, 64), **f32), 'vt': vt,
               'qf': torch.empty((Z, F, _FAVOR_PAD), **f32), 'kt': torch.zeros((Z, _FAVOR_PAD, Fp), **f32),
-              'ctx': torch.empty((Z, _FAVOR_VT_ROWS, _FAVOR_PAD), **f32)}
+              'ctx': torch.empty((Z, _FAVOR_VT_ROWS, _FAVOR_PAD), **f32), 'ctx_lo': torch.empty((Z, _FAVOR_VT_ROWS, _FAVOR_PAD), **f32)}
         if len(_favor_ws) >= 4:
             _favor_ws.clear()
         _favor_ws[key] = ws
@@ -724,8 +724,8 @@ def favor_attention(x, w_qkv, w_qkv_lo, b_qkv, proj_scaled, heads, eps=1e-4):
                                                ws['qf'].data_ptr(), Z, F, Fp, _st))
         _cabi.check(L.ddsp_b200_favor_features(ws['k'].data_ptr(), proj_scaled.data_ptr(), _FAVOR_FEATURES, 0, float(eps),
                                                ws['kt'].data_ptr(), Z, F, Fp, _st))
-        _cabi.check(L.ddsp_b200_favor_context(ws['vt'].data_ptr(), ws['kt'].data_ptr(), ws['ctx'].data_ptr(), Z, Fp, _st))
-        _cabi.check(L.ddsp_b200_favor_output(ws['qf'].data_ptr(), ws['ctx'].data_ptr(), out.data_ptr(), B, H, F, _st))
+        _cabi.check(L.ddsp_b200_favor_context(ws['vt'].data_ptr(), ws['kt'].data_ptr(), ws['ctx'].data_ptr(), ws['ctx_lo'].data_ptr(), Z, Fp, _st))
+        _cabi.check(L.ddsp_b200_favor_output(ws['qf'].data_ptr(), ws['ctx'].data_ptr(), ws['ctx_lo'].data_ptr(), out.data_ptr(), B, H, F, _st))
     return out
 
 

@@ -1179,7 +1179,7 @@ int ddsp_b200_favor_features(const float* x, const float* proj_scaled, int n_fea
     return DDSP_B200_OK;
 }
 
-int ddsp_b200_favor_context(const float* vt, const float* kt, float* ctxT, int Z, int Fp, void* stream) {
+int ddsp_b200_favor_context(const float* vt, const float* kt, float* ctxT, float* ctxT_lo, int Z, int Fp, void* stream) {
     g_launches = 0;
     if (!vt || !kt || !ctxT || Z <= 0 || Fp <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
     if (Fp & 3) return DDSP_B200_ERR_UNSUPPORTED;
@@ -1190,10 +1190,16 @@ int ddsp_b200_favor_context(const float* vt, const float* kt, float* ctxT, int Z
     if (int rc = make_map_3(&ma, vt, Fp, kVtRows, Z, Fp, (int64_t)kVtRows * Fp, kBM)) return rc;
     if (int rc = make_map_3(&mw, kt, Fp, kFeatPad, Z, Fp, (int64_t)kFeatPad * Fp, 96)) return rc;
     if (int rc = make_map_3(&mc, ctxT, kFeatPad, kVtRows, Z, kFeatPad, (int64_t)kVtRows * kFeatPad, 32)) return rc;
-    return launch_gemm3x<96, EPI_PLAIN>(ma, mw, mw, mc, mc, P, (cudaStream_t)stream);   // 3 column tiles of 96 = 288 >= 272
+    CUtensorMap mc2 = mc;
+    if (ctxT_lo) {
+        if (int rc = make_map_3(&mc2, ctxT_lo, kFeatPad, kVtRows, Z, kFeatPad, (int64_t)kVtRows * kFeatPad, 32)) return rc;
+        P.split_out = 1;
+    }
+    return launch_gemm3x<96, EPI_PLAIN>(ma, mw, mw, mc, mc2, P, (cudaStream_t)stream);   // 3 column tiles of 96 = 288 >= 272
 }
 
-int ddsp_b200_favor_output(const float* qf, const float* ctxT, float* out, int B, int H, int F, void* stream) {
+int ddsp_b200_favor_output(const float* qf, const float* ctxT, const float* ctxT_lo, float* out, int B, int H, int F,
+                           void* stream) {
     g_launches = 0;
     if (!qf || !ctxT || !out || B <= 0 || H <= 0 || F <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
     using namespace ddsp::tc;
@@ -1204,7 +1210,12 @@ int ddsp_b200_favor_output(const float* qf, const float* ctxT, float* out, int B
     if (int rc = make_map_3(&ma, qf, kFeatPad, F, Z, kFeatPad, (int64_t)F * kFeatPad, kBM)) return rc;
     if (int rc = make_map_3(&mw, ctxT, kFeatPad, kVtRows, Z, kFeatPad, (int64_t)kVtRows * kFeatPad, kVtRows)) return rc;
     if (int rc = make_map_3(&mc, out, (int64_t)H * 64, F, B, (int64_t)H * 64, (int64_t)F * H * 64, 32)) return rc;
-    return launch_gemm3x<kVtRows, EPI_OUT>(ma, mw, mw, mc, mc, P, (cudaStream_t)stream);
+    CUtensorMap mwl = mw;
+    if (ctxT_lo) {
+        if (int rc = make_map_3(&mwl, ctxT_lo, kFeatPad, kVtRows, Z, kFeatPad, (int64_t)kVtRows * kFeatPad, kVtRows)) return rc;
+        P.w_presplit = 1;
+    }
+    return launch_gemm3x<kVtRows, EPI_OUT>(ma, mw, mwl, mc, mc, P, (cudaStream_t)stream);
 }
 
 }  // extern "C"

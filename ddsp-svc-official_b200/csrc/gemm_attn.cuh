@@ -43,6 +43,7 @@ struct GemmParams {
     const float* ln_gamma;          // LayerNorm over the N columns as second output (tiles_n == 1), or null
     const float* ln_beta;
     float ln_eps;
+    int split_out;                  // EPI_PLAIN: also write the low TF32 term of C through map_c2 (C itself is the high term)
     // EPI_QKV / EPI_OUT
     float* vt;                      // (B, H, 80, Fp)
     float* q; float* k;             // (B, H, F, 64): the same tensors map_c / map_c2 describe (EPI_QKV)
@@ -239,18 +240,37 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             tc_fence_after();
             const uint32_t d = tmem_base + acc * C::kAccCols;
             for (int kb = 0; kb < n_kb; ++kb) {
+                const uint32_t st = s32(smem + stage * C::kStageBytes);
+                const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + C::kABytes);
+                const uint64_t w_hi = umma_desc_sw128(st + 2 * C::kABytes), w_lo = umma_desc_sw128(st + 2 * C::kABytes + C::kWBytes);
+                // The raw tile is the high term, so with a pre-split weight two of the three products (hi*hi, hi*lo) can
+                // start the moment TMA has landed; only lo*hi waits for the splitter -- its latency hides behind them.
+                if (P.w_presplit) {
+                    mbar_wait(s32(full_bar + stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < kBK / 8; ++kk) {
+                            const uint64_t o = (uint64_t)(2 * kk);
+                            umma_tf32(d, a_hi + o, w_lo + o, idesc, (kb | kk) != 0);
+                            umma_tf32(d, a_hi + o, w_hi + o, idesc, 1);
+                        }
+                    }
+                    __syncwarp();
+                }
                 mbar_wait(s32(split_bar + stage), phase);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t st = s32(smem + stage * C::kStageBytes);
-                    const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + C::kABytes);
-                    const uint64_t w_hi = umma_desc_sw128(st + 2 * C::kABytes), w_lo = umma_desc_sw128(st + 2 * C::kABytes + C::kWBytes);
 #pragma unroll
                     for (int kk = 0; kk < kBK / 8; ++kk) {
                         const uint64_t o = (uint64_t)(2 * kk);
-                        umma_tf32(d, a_lo + o, w_hi + o, idesc, (kb | kk) != 0);
-                        umma_tf32(d, a_hi + o, w_lo + o, idesc, 1);
-                        umma_tf32(d, a_hi + o, w_hi + o, idesc, 1);
+                        if (P.w_presplit) {
+                            umma_tf32(d, a_lo + o, w_hi + o, idesc, 1);
+                        } else {
+                            umma_tf32(d, a_lo + o, w_hi + o, idesc, (kb | kk) != 0);
+                            umma_tf32(d, a_hi + o, w_lo + o, idesc, 1);
+                            umma_tf32(d, a_hi + o, w_hi + o, idesc, 1);
+                        }
                     }
                     umma_commit(s32(empty_bar + stage));
                     if (kb == n_kb - 1) umma_commit(s32(acc_full + acc));
@@ -336,6 +356,15 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     const uint32_t buf = rs.begin();
                     rs.fill(buf, v);
                     if (lane == 0) { tma_store_3d(&map_c, buf, n, m0 + q * 32, z); bulk_commit(); }
+                    if (P.split_out) {
+                        // the consumer GEMM reads C as the high term (the tensor core ignores the low 13 mantissa bits);
+                        // its low term leaves here, so that the consumer needs no splitter pass over this operand
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = tf32_lo(v[j]);
+                        const uint32_t buf2 = rs.begin();
+                        rs.fill(buf2, v);
+                        if (lane == 0) { tma_store_3d(&map_c2, buf2, n, m0 + q * 32, z); bulk_commit(); }
+                    }
                 }
                 if (ln) {
                     // LayerNorm of the finished row (torch.nn.LayerNorm: biased variance, eps inside the sqrt), two more

@@ -341,15 +341,19 @@ int ddsp_b200_dwconv_silu(const float *g, const float *w, const float *bias, int
  *                             query: out (Z,F,272)   = 266^-0.5 (exp(dash - |x|^2/16 - max_j dash) + eps), pad columns 0
  *                             key:   out (Z,272,Fp)  = 266^-0.5  exp(dash - |x|^2/16 + eps), transposed; pad rows /
  *                                    columns are never written (zero-initialise the buffer once)
- * ddsp_b200_favor_context:  ctxT[z] (80,272) = vt[z] (80,Fp) * kt[z] (272,Fp)^T   (row 64 = sum over frames of k')
+ * ddsp_b200_favor_context:  ctxT[z] (80,272) = vt[z] (80,Fp) * kt[z] (272,Fp)^T   (row 64 = sum over frames of k');
+ *                           ctxT_lo (optional, same shape) receives ctxT minus its TF32 truncation, which
+ *                           ddsp_b200_favor_output then takes as the pre-split low term of its second operand
  * ddsp_b200_favor_output:   out (B,F,H*64): out[b,f,h*64+e] = (q'[z,f,:] . ctxT[z,e,:]) / (q'[z,f,:] . ctxT[z,64,:] + 1e-8) */
 int ddsp_b200_qkv_heads(const float *A, int64_t lda, const float *W, const float *W_lo, int64_t ldw,
                         const float *bias, float *q, float *k, float *vt, int B, int F, int Fp, int H, int K,
                         void *stream);
 int ddsp_b200_favor_features(const float *x, const float *proj_scaled, int n_features, int is_query, float eps,
                              float *out, int Z, int F, int Fp, void *stream);
-int ddsp_b200_favor_context(const float *vt, const float *kt, float *ctxT, int Z, int Fp, void *stream);
-int ddsp_b200_favor_output(const float *qf, const float *ctxT, float *out, int B, int H, int F, void *stream);
+int ddsp_b200_favor_context(const float *vt, const float *kt, float *ctxT, float *ctxT_lo, int Z, int Fp,
+                            void *stream);
+int ddsp_b200_favor_output(const float *qf, const float *ctxT, const float *ctxT_lo, float *out, int B, int H,
+                           int F, void *stream);
 
 /* Tensor-pipe microbenchmark of the same kernel: `virtual_tiles` output tiles of 128 x block_n with reduction
  * length K that all read tile 0 of A (128,K) and W (N,K) (operands stay in L2) and store nothing -- the

@@ -43,12 +43,12 @@ run('featk', lambda: L.ddsp_b200_favor_features(ws['k'].data_ptr(), ps.data_ptr(
 kf = feat(kr, False)
 gk = ws['kt'].view(B, H, 272, Fp)
 print('kt rel err', ((gk[:, :, :266, :F].double() - kf.transpose(2, 3)).abs().max() / kf.abs().max()).item(), 'pad', gk[:, :, 266:].abs().max().item(), gk[..., F:].abs().max().item() if Fp > F else 0)
-run('ctx', lambda: L.ddsp_b200_favor_context(ws['vt'].data_ptr(), ws['kt'].data_ptr(), ws['ctx'].data_ptr(), Z, Fp, st))
+run('ctx', lambda: L.ddsp_b200_favor_context(ws['vt'].data_ptr(), ws['kt'].data_ptr(), ws['ctx'].data_ptr(), ws['ctx_lo'].data_ptr(), Z, Fp, st))
 ctx_ref = torch.einsum('bhen,bhjn->bhej', ws['vt'].double(), gk.double())
 gc = ws['ctx'].view(B, H, 80, 272)
 print('ctx rel err', ((gc.double() - ctx_ref).abs().max() / ctx_ref.abs().max()).item())
 out = torch.empty(B, F, H * 64, device='cuda')
-run('out', lambda: L.ddsp_b200_favor_output(ws['qf'].data_ptr(), ws['ctx'].data_ptr(), out.data_ptr(), B, H, F, st))
+run('out', lambda: L.ddsp_b200_favor_output(ws['qf'].data_ptr(), ws['ctx'].data_ptr(), ws['ctx_lo'].data_ptr(), out.data_ptr(), B, H, F, st))
 num = torch.einsum('bhnj,bhej->bhne', got.double(), gc.double())
 ref = (num[..., :64] / (num[..., 64:65] + 1e-8)).transpose(1, 2).reshape(B, F, H * 64)
 print('out err', (out.double() - ref).abs().max().item(), 'scale', ref.abs().max().item())

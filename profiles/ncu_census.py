@@ -54,6 +54,11 @@ def main():
             cur.append(r)
     rec = {'source_hash': shash, 'capture': os.path.basename(rep), 'units_per_launch': units, 'kernels': {}}
     tot_dram = 0.0
+    # the source page lists every profiled launch once per view (SASS, and again when source correlation is imported):
+    # keep one block per launch so that they line up with the rows of the raw page
+    if len(rows) and len(blocks) % len(raw[2:]) == 0 and len(blocks) > len(raw[2:]):
+        step = len(blocks) // len(raw[2:])
+        names, blocks = names[::step], blocks[::step]
     sel = [(n, b) for n, b in zip(names, blocks) if pat is None or pat.search(n)]
     for idx, (name, b) in enumerate(sel):
         iS, iE = shdr.index('Source'), shdr.index('Instructions Executed')
@@ -69,11 +74,22 @@ def main():
                 slots += n
         short = re.sub(r'[<(].*', '', name).replace('void ', '').replace('ddsp::', '')
         k = kernels[idx] if idx < len(kernels) else {}      # raw page and source page list the launches in the same order
-        rec['kernels'][short] = {'instructions_per_unit': inst / units, 'fma_pipe_slots_per_unit': slots / units,
-                                 'dram_bytes_per_launch': k.get('dram_bytes'), 'ncu_time_us': k.get('time_us'),
-                                 'issue_active_pct': k.get('issue_active_pct')}
+        cur = rec['kernels'].get(short)
+        if cur is None:
+            rec['kernels'][short] = {'launches': 1, 'instructions_per_unit': inst / units, 'fma_pipe_slots_per_unit': slots / units,
+                                     'dram_bytes_per_launch': k.get('dram_bytes'), 'ncu_time_us': k.get('time_us'),
+                                     'issue_active_pct': k.get('issue_active_pct')}
+        else:       # the same kernel launched again inside the step (e.g. the two L = 510 convolutions): totals per step
+            cur['launches'] += 1
+            cur['instructions_per_unit'] += inst / units
+            cur['fma_pipe_slots_per_unit'] += slots / units
+            cur['dram_bytes_per_launch'] = (cur['dram_bytes_per_launch'] or 0.0) + (k.get('dram_bytes') or 0.0)
+            cur['ncu_time_us'] = (cur['ncu_time_us'] or 0.0) + (k.get('time_us') or 0.0)
         tot_dram += k.get('dram_bytes') or 0.0
     rec['dram_bytes_per_launch'] = tot_dram
+    rec['instructions_per_unit'] = sum(v['instructions_per_unit'] for v in rec['kernels'].values())
+    rec['fma_pipe_slots_per_unit'] = sum(v['fma_pipe_slots_per_unit'] for v in rec['kernels'].values())
+    rec['ncu_time_us'] = sum(v['ncu_time_us'] or 0.0 for v in rec['kernels'].values())
     if model == 'combsubfast' and rec['kernels']:
         k0 = next(iter(rec['kernels'].values()))
         rec['instructions_per_pair'] = k0['instructions_per_unit']

@@ -27,4 +27,4 @@ for i in range(iters):
     else:
         core.sins_stage(c0, c1, c2, f0, phase, 512, 44100, seed=i)
 torch.cuda.synchronize()
-print('source_hash', source_hash())
+print('source_hash', source_hash(model))

@@ -28,12 +28,22 @@ FMA_SCALAR = ('FFMA', 'FMUL', 'FADD', 'IMAD', 'FSEL_NOT', )
 FMA_PACKED = ('FFMA2', 'FMUL2', 'FADD2')
 
 
-def source_hash():
+# the headers a model's synthesizer kernels are compiled from (a census record is tied to THESE files: edits to the
+# control-network or front-end kernels do not invalidate it)
+MODEL_SOURCES = {
+    'combsubfast': ('common.cuh', 'fft32.cuh', 'phase.cuh', 'combsubfast.cuh'),
+    'combsub': ('common.cuh', 'fft32.cuh', 'phase.cuh', 'excite.cuh', 'ltvfir.cuh'),
+    'sins': ('common.cuh', 'fft32.cuh', 'phase.cuh', 'excite.cuh', 'ltvfir.cuh'),
+}
+
+
+def source_hash(model=None):
+    """Hash of the kernel sources of `model` (all of csrc/ when None)."""
     h = hashlib.sha256()
-    for f in sorted(os.listdir(CSRC)):
-        if f.endswith(('.cu', '.cuh')):
-            with open(os.path.join(CSRC, f), 'rb') as fh:
-                h.update(fh.read())
+    files = MODEL_SOURCES[model] if model else sorted(f for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh')))
+    for f in files:
+        with open(os.path.join(CSRC, f), 'rb') as fh:
+            h.update(fh.read())
     return h.hexdigest()[:16]
 
 
