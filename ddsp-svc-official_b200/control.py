@@ -7,8 +7,8 @@ This is NOT part of the hand-written synthesizer path: the GEMMs and convolution
 ops (cuBLAS / cuDNN), exactly like the reference's own control network.  Under `torch.no_grad()` on
 CUDA the memory-bound chains between the GEMMs run as two fused kernels of `csrc/control.cuh`
 (FAVOR+ feature map; GLU -> depthwise conv -> SiLU in channels-last layout); with autograd enabled or
-on CPU the plain ops below run.  Only the non-causal configuration (`c: false`, the value in every
-shipped config) is implemented.
+on CPU the plain ops below run.  The causal configuration (`c: true`; no shipped config sets it) runs on the plain
+ops only: causal convolutions and chunked causal linear attention.
 
 Structure (the module / parameter names are dictated by the checkpoint layout):
     unit_prenet : T - Conv1d(k3) - GroupNorm(4) - LeakyReLU - Conv1d(k3) - T        unit2control.py:38-45
@@ -96,16 +96,46 @@ def _fused_ok(x):
     return x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
 
 
+class _CausalConv1d(nn.Conv1d):
+    """`extorch.Conv1dEx(..., padding="same", causal=True)` (unit2control.py:40,43, pcmer.py:54): the output frame n sees the
+    input frames n-k+1 .. n only (left padding by kernel_size - 1).  extorch is an un-vendored, unpinned dependency that
+    is not installed here: this follows its documented meaning (parity unpinned for c=True)."""
+
+    def __init__(self, c_in, c_out, kernel_size, groups=1):
+        super().__init__(c_in, c_out, kernel_size, padding=0, groups=groups)
+
+    def forward(self, x):
+        return super().forward(F.pad(x, (self.kernel_size[0] - 1, 0)))
+
+
+def _causal_attend(q, k, v, eps=1e-6, chunk=128):
+    """Causal linear attention (pcmer.py:141-160, `fast_transformers.causal_product.CausalDotProduct`):
+    out_n = sum_{m<=n} (q_n . k_m) v_m / (q_n . (sum_{m<=n} k_m + eps)), evaluated chunk-wise: inside a chunk the masked
+    score matrix, across chunks the running (features x dim) state -- O(N) memory, differentiable plain ops."""
+    b, h, n, j = q.shape
+    k_cum = k.cumsum(dim=-2) + eps
+    d_inv = 1.0 / torch.einsum('bhnj,bhnj->bhn', q, k_cum)
+    state = q.new_zeros(b, h, j, v.shape[-1])
+    outs = []
+    for s0 in range(0, n, chunk):
+        qc, kc, vc = q[:, :, s0:s0 + chunk], k[:, :, s0:s0 + chunk], v[:, :, s0:s0 + chunk]
+        scores = torch.einsum('bhnj,bhmj->bhnm', qc, kc).tril_()
+        outs.append(torch.einsum('bhnm,bhme->bhne', scores, vc) + torch.einsum('bhnj,bhje->bhne', qc, state))
+        state = state + torch.einsum('bhmj,bhme->bhje', kc, vc)
+    return torch.cat(outs, dim=2) * d_inv.unsqueeze(-1)
+
+
 class _FastAttention(nn.Module):
-    def __init__(self, dim_head):
+    def __init__(self, dim_head, causal=False):
         super().__init__()
         n_features = int(dim_head * math.log(dim_head))
+        self.causal = causal
         self.register_buffer('projection_matrix', _orthogonal_gaussian_features(n_features, dim_head))
 
     def forward(self, q, k, v):
         q = _softmax_features(q, self.projection_matrix, True)
         k = _softmax_features(k, self.projection_matrix, False)
-        return self.attend(q, k, v)
+        return _causal_attend(q, k, v) if self.causal else self.attend(q, k, v)
 
     @staticmethod
     def attend(q, k, v):
@@ -117,11 +147,12 @@ class _FastAttention(nn.Module):
 
 
 class _SelfAttention(nn.Module):
-    def __init__(self, dim, heads):
+    def __init__(self, dim, heads, causal=False):
         super().__init__()
         inner = _DIM_HEAD * heads
         self.heads = heads
-        self.fast_attention = _FastAttention(_DIM_HEAD)
+        self.causal = causal
+        self.fast_attention = _FastAttention(_DIM_HEAD, causal)
         self.to_q = nn.Linear(dim, inner)
         self.to_k = nn.Linear(dim, inner)
         self.to_v = nn.Linear(dim, inner)
@@ -159,7 +190,7 @@ class _SelfAttention(nn.Module):
         residual folded into the output GEMM (addmm, beta = 1) instead of two more elementwise passes."""
         b, n, _ = x.shape
         split = lambda t: t.view(b, n, self.heads, _DIM_HEAD).transpose(1, 2)      # noqa: E731
-        if _fused_ok(x):
+        if _fused_ok(x) and not self.causal:
             from . import core
             proj = self.fast_attention.projection_matrix
             if b * n * self.heads >= _FUSED_PROJECTION_MIN_ROWS:
@@ -199,14 +230,16 @@ class _SelfAttention(nn.Module):
 
 
 class _ConvModule(nn.Module):
-    def __init__(self, dim, expansion=2, kernel_size=31):
+    def __init__(self, dim, expansion=2, kernel_size=31, causal=False):
         super().__init__()
         inner = dim * expansion
+        self.causal = causal
         self.net = nn.Sequential(
             nn.LayerNorm(dim),
             _Swap(1, 2),
             nn.Conv1d(dim, inner * 2, 1),
             nn.GLU(dim=1),
+            _CausalConv1d(inner, inner, kernel_size, groups=inner) if causal else
             nn.Conv1d(inner, inner, kernel_size, padding='same', groups=inner),
             nn.SiLU(),
             nn.Conv1d(inner, dim, 1),
@@ -233,7 +266,7 @@ class _ConvModule(nn.Module):
     def forward(self, x, residual=None):
         """`residual` (fused path only): returns residual + module(x) with bias and residual folded into the
         last GEMM."""
-        if _fused_ok(x):
+        if _fused_ok(x) and not self.causal:
             from . import core
             ln, _, pw1, _, dw, _, pw2, _, _ = self.net
             big = x.shape[0] * x.shape[1] > _ATTENTION_KERNEL_MAX_FRAMES
@@ -250,14 +283,15 @@ class _ConvModule(nn.Module):
 
 
 class _EncoderLayer(nn.Module):
-    def __init__(self, heads, dim):
+    def __init__(self, heads, dim, causal=False):
         super().__init__()
+        self.causal = causal
         self.norm = nn.LayerNorm(dim)
-        self.attn = _SelfAttention(dim, heads)
-        self.local_mixer = _ConvModule(dim)
+        self.attn = _SelfAttention(dim, heads, causal)
+        self.local_mixer = _ConvModule(dim, causal=causal)
 
     def forward(self, x):
-        if _fused_ok(x):
+        if _fused_ok(x) and not self.causal:
             x = self.attn(self.norm(x), residual=x)
             return self.local_mixer(x, residual=x)
         x = x + self.attn(self.norm(x))
@@ -265,9 +299,10 @@ class _EncoderLayer(nn.Module):
 
 
 class PCmer(nn.Module):
-    def __init__(self, num_layers, num_heads, dim_model):
+    def __init__(self, num_layers, num_heads, dim_model, causal=False):
         super().__init__()
-        self.net = nn.Sequential(*[_EncoderLayer(num_heads, dim_model) for _ in range(num_layers)])
+        self.causal = causal
+        self.net = nn.Sequential(*[_EncoderLayer(num_heads, dim_model, causal) for _ in range(num_layers)])
 
     def forward(self, x):
         return self.net(x)
@@ -290,14 +325,14 @@ class Unit2Control(nn.Module):
 
     def __init__(self, ndim_feat_i, n_spk, output_splits, c=False):
         super().__init__()
-        if c:
-            raise NotImplementedError('causal control network (c: true) is not implemented; no shipped config uses it')
+        self.causal = bool(c)
+        conv = (lambda i, o: _CausalConv1d(i, o, 3)) if c else (lambda i, o: nn.Conv1d(i, o, 3, padding='same'))
         self.unit_prenet = nn.Sequential(
             _Swap(1, 2),
-            nn.Conv1d(ndim_feat_i, _DIM, 3, padding='same'),
+            conv(ndim_feat_i, _DIM),
             nn.GroupNorm(4, _DIM),
             nn.LeakyReLU(),
-            nn.Conv1d(_DIM, _DIM, 3, padding='same'),
+            conv(_DIM, _DIM),
             _Swap(1, 2),
         )
         self.f0_embed = nn.Linear(1, _DIM)
@@ -305,7 +340,7 @@ class Unit2Control(nn.Module):
         self.volume_embed = nn.Linear(1, _DIM)
         self.spk_embed = nn.Embedding(n_spk, _DIM)
         n_out = sum(output_splits.values())
-        self.dec_post = nn.Sequential(PCmer(3, _HEADS, _DIM), nn.LayerNorm(_DIM), weight_norm(nn.Linear(_DIM, n_out)))
+        self.dec_post = nn.Sequential(PCmer(3, _HEADS, _DIM, self.causal), nn.LayerNorm(_DIM), weight_norm(nn.Linear(_DIM, n_out)))
         self.output_splits = dict(output_splits)
 
     # Opt-in: run the fp32 GEMMs of the network on the TF32 tensor cores (the reference's cuDNN
@@ -333,7 +368,7 @@ class Unit2Control(nn.Module):
                 spk = self.spk_embed(spk_id - 1)
             x = core.embed_sum(x, f0, phase, volume, self.f0_embed, self.phase_embed, self.volume_embed, spk)
             names, sizes = list(self.output_splits), list(self.output_splits.values())
-            if _tc_path(x):
+            if _tc_path(x) and not self.causal:
                 # output projection on the tensor cores into a buffer whose row stride is padded to a multiple of 4
                 # floats (128-bit stores); the synthesizer consumes the strided views as they are
                 pcmer, norm, proj = self.dec_post
