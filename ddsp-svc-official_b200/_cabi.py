@@ -57,11 +57,11 @@ _PROTOS = {
     'ddsp_b200_linear_glu': (C.c_int, [c_f32p, i64, c_f32p, c_f32p, i64, c_f32p, c_f32p, i64, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p]),
     'ddsp_b200_dwconv_silu': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
-    'ddsp_b200_qkv_heads': (C.c_int, [c_f32p, i64, c_f32p, c_f32p, i64, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int,
+    'ddsp_b200_qkv_heads': (C.c_int, [c_f32p, i64, c_f32p, c_f32p, i64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ddsp_b200_favor_features': (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_float, c_f32p, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p]),
-    'ddsp_b200_favor_context': (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_void_p]),
+    'ddsp_b200_favor_context': (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_void_p]),
     'ddsp_b200_favor_output': (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ddsp_b200_tc_microbench': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ddsp_b200_apply_frame_mask': (C.c_int, [c_f32p, c_f32p, i64, i64, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -719,12 +719,12 @@ def favor_attention(x, w_qkv, w_qkv_lo, b_qkv, proj_scaled, heads, eps=1e-4):
     launches = 0
     with _OnDevice(x.device) as _st:
         _cabi.check(L.ddsp_b200_qkv_heads(x2.data_ptr(), x2.stride(0), w_qkv.data_ptr(), _ptr(w_qkv_lo), w_qkv.stride(0),
-                                          _ptr(b_qkv), ws['q'].data_ptr(), ws['k'].data_ptr(), ws['vt'].data_ptr(), B, F, Fp, H, Cc, _st))
+                                          _ptr(b_qkv), ws['q'].data_ptr(), ws['k'].data_ptr(), ws['vt'].data_ptr(), 0, B, F, Fp, H, Cc, _st))
         _cabi.check(L.ddsp_b200_favor_features(ws['q'].data_ptr(), proj_scaled.data_ptr(), _FAVOR_FEATURES, 1, float(eps),
                                                ws['qf'].data_ptr(), Z, F, Fp, _st))
         _cabi.check(L.ddsp_b200_favor_features(ws['k'].data_ptr(), proj_scaled.data_ptr(), _FAVOR_FEATURES, 0, float(eps),
                                                ws['kt'].data_ptr(), Z, F, Fp, _st))
-        _cabi.check(L.ddsp_b200_favor_context(ws['vt'].data_ptr(), ws['kt'].data_ptr(), ws['ctx'].data_ptr(), ws['ctx_lo'].data_ptr(), Z, Fp, _st))
+        _cabi.check(L.ddsp_b200_favor_context(ws['vt'].data_ptr(), 0, ws['kt'].data_ptr(), ws['ctx'].data_ptr(), ws['ctx_lo'].data_ptr(), Z, Fp, _st))
         _cabi.check(L.ddsp_b200_favor_output(ws['qf'].data_ptr(), ws['ctx'].data_ptr(), ws['ctx_lo'].data_ptr(), out.data_ptr(), B, H, F, _st))
     return out
 

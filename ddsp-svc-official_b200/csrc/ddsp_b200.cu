@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <initializer_list>
 #include <mutex>
 
@@ -1051,7 +1052,7 @@ int set_smem_once(K kernel, int bytes, bool* flags) {
 
 template <int BN, int EPI>
 int launch_gemm3x(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& wlo, const CUtensorMap& c, const CUtensorMap& c2,
-                  ddsp::tc::GemmParams P, cudaStream_t st) {
+                  ddsp::tc::GemmParams P, cudaStream_t st, const CUtensorMap* a_lo = nullptr) {
     using C = ddsp::tc::GCfg<BN>;
     static bool attr_set[64] = {false};
     if (int rc = set_smem_once(ddsp::tc::gemm3x_kernel<BN, EPI>, C::kSmemBytes, attr_set)) return rc;
@@ -1060,7 +1061,7 @@ int launch_gemm3x(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap&
     const int64_t tiles = (int64_t)P.Z * P.tiles_m * P.tiles_n;
     if (tiles > 0x7fffffffLL) return DDSP_B200_ERR_UNSUPPORTED;
     const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-    ddsp::tc::gemm3x_kernel<BN, EPI><<<grid, ddsp::tc::kThreads, C::kSmemBytes, st>>>(a, w, wlo, c, c2, P);
+    ddsp::tc::gemm3x_kernel<BN, EPI><<<grid, ddsp::tc::kThreads, C::kSmemBytes, st>>>(a, a_lo ? *a_lo : a, w, wlo, c, c2, P);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }
@@ -1087,7 +1088,9 @@ int ddsp_b200_linear_tf32x3_ex(const float* A, int64_t lda, const float* W, cons
     P.bias = bias; P.residual = residual; P.ldr = ldr;
     P.ln_gamma = ln_gamma; P.ln_beta = ln_beta; P.ln_eps = ln_eps;
     int bn = 256;
-    if (!ln_gamma) {
+    static const int forced_bn = [] { const char* e = getenv("DDSP_B200_GEMM_BN"); return e ? atoi(e) : 0; }();   // experiments
+    if (!ln_gamma && (forced_bn == 128 || forced_bn == 224 || forced_bn == 256)) bn = forced_bn;
+    else if (!ln_gamma) {
         int64_t best_cost = ((N + 255) / 256) * 256;
         for (int cand : {224, 128}) {
             const int64_t cost = (int64_t)((N + cand - 1) / cand) * cand;
@@ -1126,7 +1129,7 @@ int ddsp_b200_linear_glu(const float* A, int64_t lda, const float* W, const floa
 }
 
 int ddsp_b200_qkv_heads(const float* A, int64_t lda, const float* W, const float* W_lo, int64_t ldw, const float* bias,
-                        float* q, float* k, float* vt, int B, int F, int Fp, int H, int K, void* stream) {
+                        float* q, float* k, float* vt, float* vt_lo, int B, int F, int Fp, int H, int K, void* stream) {
     g_launches = 0;
     if (!A || !W || !q || !k || !vt || B <= 0 || F <= 0 || H <= 0 || K <= 0 || lda < K || ldw < K || Fp < F)
         return DDSP_B200_ERR_INVALID_ARGUMENT;
@@ -1135,7 +1138,7 @@ int ddsp_b200_qkv_heads(const float* A, int64_t lda, const float* W, const float
     ddsp::tc::GemmParams P = {};
     P.Z = 1; P.M = B * F; P.N = 3 * H * 64; P.K = K;
     P.w_presplit = W_lo ? 1 : 0;
-    P.bias = bias; P.vt = vt; P.q = q; P.k = k; P.frames = F; P.frames_pad = Fp; P.heads = H;
+    P.bias = bias; P.vt = vt; P.vt_lo = vt_lo; P.q = q; P.k = k; P.frames = F; P.frames_pad = Fp; P.heads = H;
     CUtensorMap ma, mw, mwl, mq, mk;
     if (int rc = make_map_3(&ma, A, K, P.M, 1, lda, 0, ddsp::tc::kBM)) return rc;
     if (int rc = make_map_3(&mw, W, K, P.N, 1, ldw, 0, 256)) return rc;
@@ -1179,7 +1182,8 @@ int ddsp_b200_favor_features(const float* x, const float* proj_scaled, int n_fea
     return DDSP_B200_OK;
 }
 
-int ddsp_b200_favor_context(const float* vt, const float* kt, float* ctxT, float* ctxT_lo, int Z, int Fp, void* stream) {
+int ddsp_b200_favor_context(const float* vt, const float* vt_lo, const float* kt, float* ctxT, float* ctxT_lo, int Z, int Fp,
+                            void* stream) {
     g_launches = 0;
     if (!vt || !kt || !ctxT || Z <= 0 || Fp <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
     if (Fp & 3) return DDSP_B200_ERR_UNSUPPORTED;
@@ -1195,7 +1199,12 @@ int ddsp_b200_favor_context(const float* vt, const float* kt, float* ctxT, float
         if (int rc = make_map_3(&mc2, ctxT_lo, kFeatPad, kVtRows, Z, kFeatPad, (int64_t)kVtRows * kFeatPad, 32)) return rc;
         P.split_out = 1;
     }
-    return launch_gemm3x<96, EPI_PLAIN>(ma, mw, mw, mc, mc2, P, (cudaStream_t)stream);   // 3 column tiles of 96 = 288 >= 272
+    CUtensorMap mal;
+    if (vt_lo) {
+        if (int rc = make_map_3(&mal, vt_lo, Fp, kVtRows, Z, Fp, (int64_t)kVtRows * Fp, kBM)) return rc;
+        P.a_presplit = 1;
+    }
+    return launch_gemm3x<96, EPI_PLAIN>(ma, mw, mw, mc, mc2, P, (cudaStream_t)stream, vt_lo ? &mal : nullptr);   // 3 column tiles of 96 = 288 >= 272
 }
 
 int ddsp_b200_favor_output(const float* qf, const float* ctxT, const float* ctxT_lo, float* out, int B, int H, int F,

@@ -36,6 +36,7 @@ struct GemmParams {
     int Z, M, N, K;                 // per-batch problem
     int tiles_m, tiles_n;           // per batch
     int w_presplit;                 // W arrives as two tensors (hi, lo) split once on the host side
+    int a_presplit;                 // A arrives as two tensors (raw = hi, lo) written by the producing epilogue
     int w_batched;                  // W has a batch coordinate (else the same W for every batch)
     const float* bias;              // (N) or null
     const float* residual;          // (M, N), row stride ldr, or null            (Z == 1)
@@ -46,6 +47,7 @@ struct GemmParams {
     int split_out;                  // EPI_PLAIN: also write the low TF32 term of C through map_c2 (C itself is the high term)
     // EPI_QKV / EPI_OUT
     float* vt;                      // (B, H, 80, Fp)
+    float* vt_lo;                   // optional: low TF32 term of v^T, same layout (pre-split operand of the context GEMM)
     float* q; float* k;             // (B, H, F, 64): the same tensors map_c / map_c2 describe (EPI_QKV)
     int frames, frames_pad, heads;
 };
@@ -155,9 +157,9 @@ struct GCfg {
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-              const __grid_constant__ CUtensorMap map_w_lo, const __grid_constant__ CUtensorMap map_c,
-              const __grid_constant__ CUtensorMap map_c2, const GemmParams P) {
+gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a_lo,
+              const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w_lo,
+              const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2, const GemmParams P) {
     using C = GCfg<BN>;
     static_assert(EPI != EPI_PLAIN || BN % 32 == 0, "the row-store epilogue works in chunks of 32 columns");
     static_assert(EPI != EPI_QKV || BN % 64 == 0, "head-split epilogue: a column tile holds whole heads");
@@ -210,7 +212,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx = C::kABytes + (P.w_presplit ? 2 : 1) * C::kWBytes;
+            const uint32_t tx = (P.a_presplit ? 2 : 1) * C::kABytes + (P.w_presplit ? 2 : 1) * C::kWBytes;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int z = tile / tiles_per_z, rem = tile - z * tiles_per_z;
                 const int m0 = (rem / P.tiles_n) * kBM, n0 = (rem % P.tiles_n) * BN;
@@ -220,6 +222,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     const uint32_t st = s32(smem + stage * C::kStageBytes);
                     mbar_arrive_expect_tx(s32(full_bar + stage), tx);
                     tma_load_3d(st, &map_a, kb * kBK, m0, z, s32(full_bar + stage));
+                    if (P.a_presplit) tma_load_3d(st + C::kABytes, &map_a_lo, kb * kBK, m0, z, s32(full_bar + stage));
                     tma_load_3d(st + 2 * C::kABytes, &map_w, kb * kBK, n0, wz, s32(full_bar + stage));
                     if (P.w_presplit)
                         tma_load_3d(st + 2 * C::kABytes + C::kWBytes, &map_w_lo, kb * kBK, n0, wz, s32(full_bar + stage));
@@ -243,34 +246,29 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 const uint32_t st = s32(smem + stage * C::kStageBytes);
                 const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + C::kABytes);
                 const uint64_t w_hi = umma_desc_sw128(st + 2 * C::kABytes), w_lo = umma_desc_sw128(st + 2 * C::kABytes + C::kWBytes);
-                // The raw tile is the high term, so with a pre-split weight two of the three products (hi*hi, hi*lo) can
-                // start the moment TMA has landed; only lo*hi waits for the splitter -- its latency hides behind them.
-                if (P.w_presplit) {
-                    mbar_wait(s32(full_bar + stage), phase);
-                    tc_fence_after();
-                    if (elect_one()) {
+                // The raw tile is the high term: hi*hi -- and every product whose low operand arrived pre-split -- can start
+                // the moment TMA has landed; only the products that need a low term from the splitter wait for it, so the
+                // splitter's latency hides behind the early MMAs.
+                mbar_wait(s32(full_bar + stage), phase);
+                tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < kBK / 8; ++kk) {
-                            const uint64_t o = (uint64_t)(2 * kk);
-                            umma_tf32(d, a_hi + o, w_lo + o, idesc, (kb | kk) != 0);
-                            umma_tf32(d, a_hi + o, w_hi + o, idesc, 1);
-                        }
+                    for (int kk = 0; kk < kBK / 8; ++kk) {
+                        const uint64_t o = (uint64_t)(2 * kk);
+                        umma_tf32(d, a_hi + o, w_hi + o, idesc, (kb | kk) != 0);
+                        if (P.w_presplit) umma_tf32(d, a_hi + o, w_lo + o, idesc, 1);
+                        if (P.a_presplit) umma_tf32(d, a_lo + o, w_hi + o, idesc, 1);
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
                 mbar_wait(s32(split_bar + stage), phase);
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < kBK / 8; ++kk) {
                         const uint64_t o = (uint64_t)(2 * kk);
-                        if (P.w_presplit) {
-                            umma_tf32(d, a_lo + o, w_hi + o, idesc, 1);
-                        } else {
-                            umma_tf32(d, a_lo + o, w_hi + o, idesc, (kb | kk) != 0);
-                            umma_tf32(d, a_hi + o, w_lo + o, idesc, 1);
-                            umma_tf32(d, a_hi + o, w_hi + o, idesc, 1);
-                        }
+                        if (!P.w_presplit) umma_tf32(d, a_hi + o, w_lo + o, idesc, 1);
+                        if (!P.a_presplit) umma_tf32(d, a_lo + o, w_hi + o, idesc, 1);
                     }
                     umma_commit(s32(empty_bar + stage));
                     if (kb == n_kb - 1) umma_commit(s32(acc_full + acc));
@@ -288,7 +286,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             for (int kb = 0; kb < n_kb; ++kb) {
                 mbar_wait(s32(full_bar + stage), phase);
                 const uint32_t st = s32(smem + stage * C::kStageBytes);
-                split_tile_lo(st, st + C::kABytes, C::kABytes / 16, t);
+                if (!P.a_presplit) split_tile_lo(st, st + C::kABytes, C::kABytes / 16, t);
                 if (!P.w_presplit) split_tile_lo(st + 2 * C::kABytes, st + 2 * C::kABytes + C::kWBytes, C::kWBytes / 16, t);
                 fence_proxy_async();
                 mbar_arrive(s32(split_bar + stage));
@@ -368,7 +366,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 }
                 if (ln) {
                     // LayerNorm of the finished row (torch.nn.LayerNorm: biased variance, eps inside the sqrt), two more
-                    // passes over the row parked in TMEM: exact mean first, then the centred sum of squares
+                    // passes over the row parked in TMEM: exact mean first, then the centred sum of squares (a one-pass
+                    // shifted variance was measured: no faster -- the epilogue hides behind the next tile's main loop --
+                    // and 2x the error)
                     tmem_st_wait();
                     const float inv_n = 1.0f / (float)P.N;
                     const float mean = sum * inv_n;
@@ -446,9 +446,15 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         }
                     } else if (row < P.M) {
                         // v^T: lanes hold consecutive frames -> 128-byte coalesced stores along the frame axis
-                        float* dst = P.vt + (((int64_t)bb * H + h) * kVtRows + e0) * P.frames_pad + ff;
+                        const int64_t off = (((int64_t)bb * H + h) * kVtRows + e0) * P.frames_pad + ff;
+                        float* dst = P.vt + off;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) dst[(int64_t)j * P.frames_pad] = v[j];
+                        if (P.vt_lo) {
+                            float* dlo = P.vt_lo + off;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) dlo[(int64_t)j * P.frames_pad] = tf32_lo(v[j]);
+                        }
                     }
                 }
             } else if constexpr (EPI == EPI_GLU) {

@@ -335,7 +335,9 @@ int ddsp_b200_dwconv_silu(const float *g, const float *w, const float *bias, int
  *
  * ddsp_b200_qkv_heads:      [q | k | v] = A (B*F, K) * [W_q; W_k; W_v]^T + bias in one GEMM; q, k stored head-major
  *                           (B,H,F,64); v stored transposed into rows 0..63 of vt (B,H,80,Fp) -- the caller presets
- *                           row 64 to ones and rows 65..79 / columns >= F to zero once.
+ *                           row 64 to ones and rows 65..79 / columns >= F to zero once.  vt_lo (optional, same layout,
+ *                           zero-initialised once) receives v^T minus its TF32 truncation: the pre-split low term
+ *                           ddsp_b200_favor_context takes for its first operand.
  * ddsp_b200_favor_features: x (Z,F,64) -> softmax-kernel features of dash = x * proj_scaled^T with
  *                           proj_scaled = 64^-0.25 * projection_matrix (266,64):
  *                             query: out (Z,F,272)   = 266^-0.5 (exp(dash - |x|^2/16 - max_j dash) + eps), pad columns 0
@@ -346,12 +348,12 @@ int ddsp_b200_dwconv_silu(const float *g, const float *w, const float *bias, int
  *                           ddsp_b200_favor_output then takes as the pre-split low term of its second operand
  * ddsp_b200_favor_output:   out (B,F,H*64): out[b,f,h*64+e] = (q'[z,f,:] . ctxT[z,e,:]) / (q'[z,f,:] . ctxT[z,64,:] + 1e-8) */
 int ddsp_b200_qkv_heads(const float *A, int64_t lda, const float *W, const float *W_lo, int64_t ldw,
-                        const float *bias, float *q, float *k, float *vt, int B, int F, int Fp, int H, int K,
-                        void *stream);
+                        const float *bias, float *q, float *k, float *vt, float *vt_lo, int B, int F, int Fp, int H,
+                        int K, void *stream);
 int ddsp_b200_favor_features(const float *x, const float *proj_scaled, int n_features, int is_query, float eps,
                              float *out, int Z, int F, int Fp, void *stream);
-int ddsp_b200_favor_context(const float *vt, const float *kt, float *ctxT, float *ctxT_lo, int Z, int Fp,
-                            void *stream);
+int ddsp_b200_favor_context(const float *vt, const float *vt_lo, const float *kt, float *ctxT, float *ctxT_lo,
+                            int Z, int Fp, void *stream);
 int ddsp_b200_favor_output(const float *qf, const float *ctxT, const float *ctxT_lo, float *out, int B, int H,
                            int F, void *stream);
 

@@ -23,7 +23,7 @@ def run(name, fn):
     except Exception as e:
         print(name, 'rc', rc, 'FAILED', str(e)[:100], flush=True)
         sys.exit(1)
-run('qkv', lambda: L.ddsp_b200_qkv_heads(x2.data_ptr(), 256, w.data_ptr(), 0, 256, bias.data_ptr(), ws['q'].data_ptr(), ws['k'].data_ptr(), ws['vt'].data_ptr(), B, F, Fp, H, 256, st))
+run('qkv', lambda: L.ddsp_b200_qkv_heads(x2.data_ptr(), 256, w.data_ptr(), 0, 256, bias.data_ptr(), ws['q'].data_ptr(), ws['k'].data_ptr(), ws['vt'].data_ptr(), 0, B, F, Fp, H, 256, st))
 qkv = torch.nn.functional.linear(x.double(), w.double(), bias.double()).view(B, F, 3, H, 64)
 qr = qkv[:, :, 0].permute(0, 2, 1, 3); kr = qkv[:, :, 1].permute(0, 2, 1, 3); vr = qkv[:, :, 2].permute(0, 2, 3, 1)
 print('q err', (ws['q'].double() - qr).abs().max().item(), 'k err', (ws['k'].double() - kr).abs().max().item(),
@@ -43,7 +43,7 @@ run('featk', lambda: L.ddsp_b200_favor_features(ws['k'].data_ptr(), ps.data_ptr(
 kf = feat(kr, False)
 gk = ws['kt'].view(B, H, 272, Fp)
 print('kt rel err', ((gk[:, :, :266, :F].double() - kf.transpose(2, 3)).abs().max() / kf.abs().max()).item(), 'pad', gk[:, :, 266:].abs().max().item(), gk[..., F:].abs().max().item() if Fp > F else 0)
-run('ctx', lambda: L.ddsp_b200_favor_context(ws['vt'].data_ptr(), ws['kt'].data_ptr(), ws['ctx'].data_ptr(), ws['ctx_lo'].data_ptr(), Z, Fp, st))
+run('ctx', lambda: L.ddsp_b200_favor_context(ws['vt'].data_ptr(), 0, ws['kt'].data_ptr(), ws['ctx'].data_ptr(), ws['ctx_lo'].data_ptr(), Z, Fp, st))
 ctx_ref = torch.einsum('bhen,bhjn->bhej', ws['vt'].double(), gk.double())
 gc = ws['ctx'].view(B, H, 80, 272)
 print('ctx rel err', ((gc.double() - ctx_ref).abs().max() / ctx_ref.abs().max()).item())
