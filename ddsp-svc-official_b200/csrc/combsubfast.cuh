@@ -54,6 +54,9 @@ constexpr int kCsfCtxInts = 16;                     // cold per-warp scalars par
 #ifndef CSF_NOALLOC
 #define CSF_NOALLOC 1        // control rows are read once: keep them out of L1
 #endif
+#ifndef CSF_BALANCE
+#define CSF_BALANCE 1        // long runs spread evenly over the schedulers (see slot_to_run)
+#endif
 constexpr int kCsfPre = CSF_PRE;
 constexpr int kCsfWarpBytes = kPlaneFloats * 4 + 2 * kRingSlot * 4 + kStashFloat2 * 8 + kCsfCtxInts * 4;
 constexpr int kCsfSmemBytes = kTableBytes + kCsfWarps * kCsfWarpBytes;
@@ -269,11 +272,16 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
     //   ctx[12..13] f0 row pointer, [14..15] prefix row pointer of the clip
     volatile int* ctx = reinterpret_cast<volatile int*>(stash + kStashFloat2);
     {
-        // runs are dealt round-robin over the CTAs so that every SM gets the same mix of long and short runs
-        const int64_t run = (int64_t)wid * gridDim.x + blockIdx.x;
-        if (run >= (int64_t)P.B * P.runs_per_clip) return;
-        const int b0 = (int)(run / P.runs_per_clip);
-        const int r = (int)(run % P.runs_per_clip);
+        // runs are dealt over the warp slots so that every scheduler gets the same mix of long and short runs
+        const int64_t slot = (int64_t)wid * gridDim.x + blockIdx.x;
+        if (slot >= (int64_t)P.B * P.runs_per_clip) return;
+        int b0, r;
+#if CSF_BALANCE
+        slot_to_run(slot, P.B, P.runs_per_clip, P.run_rem, b0, r);
+#else
+        b0 = (int)(slot / P.runs_per_clip);
+        r = (int)(slot % P.runs_per_clip);
+#endif
         const int pb = csf_run_begin(r, P.run_len, P.run_rem);
         if (lane == 0) {
             ctx[0] = b0;

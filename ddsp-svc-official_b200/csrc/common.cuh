@@ -22,6 +22,25 @@ __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y
 __device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }            // folds into a broadcast immediate
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return fma2(b, bc2(-1.0f), a); }
 
+// Run partition shared by the run-based kernels (combsubfast_kernel, ltv_conv*_kernel): a clip is cut into `R` runs of
+// consecutive units (frame pairs / frames), the first `rem` of them one unit longer than the rest.
+__host__ __device__ __forceinline__ int run_begin(int r, int len, int rem) { return r * len + (r < rem ? r : rem); }
+// Warp slot -> run.  Slots are numbered wid * gridDim.x + blockIdx.x, so the four warps a scheduler owns (wid, wid + 4,
+// wid + 8, wid + 12) hold slots a multiple of 4 * gridDim.x apart.  All LONG runs come first in slot order and the short
+// ones after them: every scheduler then gets its long runs in its low warps and no scheduler carries more than
+// ceil(4 * long share) of them.  (Dealing run = clip * R + r straight onto the slots put 16 long runs on 100 of the 148
+// CTAs and 16 short ones on the other 48 at the headline shape, because 37 runs per clip divides 148.)
+__device__ __forceinline__ void slot_to_run(int64_t slot, int B, int R, int rem, int& b, int& r) {
+    const int64_t n_long = (int64_t)B * rem;
+    if (slot < n_long) {
+        b = (int)(slot / rem); r = (int)(slot % rem);
+    } else {
+        const int64_t i = slot - n_long;
+        const int S = R - rem;
+        b = (int)(i / S); r = rem + (int)(i % S);
+    }
+}
+
 // torch upsample_linear1d(align_corners=True) arithmetic for one sample (core.py:17):
 // fma(w0, x0, fl32(w1*x1)) with w1 = j/hop (exact for power-of-two hop), w0 = 1 - w1.
 __device__ __forceinline__ float lerp_torch(float x0, float x1, float w1) {

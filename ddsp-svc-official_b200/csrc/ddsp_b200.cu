@@ -463,12 +463,14 @@ int ltv_params(ddsp::LtvParams& P, const float* audio, int audio_mode, uint64_t 
     P.spec = (float2*)spec_ws; P.out = out; P.add_in = nullptr; P.sum_out = nullptr; P.B = B; P.F = F;
     const int frames = F + 1;
     const int64_t slots = (int64_t)sm_count() * ddsp::kLtvWarps;
-    int run_len = (int)(((int64_t)B * frames + slots - 1) / slots);
-    if (run_len < 4) run_len = frames < 4 ? frames : 4;     // keep the 3-hop seams a minority of the work
-    if (run_len > frames) run_len = frames;
-    while (run_len < frames && (int64_t)B * ((frames + run_len - 1) / run_len) > slots) ++run_len;   // one resident wave
-    P.run_len = run_len;
-    P.runs_per_clip = (frames + run_len - 1) / run_len;
+    // one resident wave: as many runs per clip as the chip's warp slots allow, each at least 4 frames long (keeps the
+    // 3-hop seams a minority of the work), the first run_rem of them one frame longer than the rest
+    int64_t R = slots / B;
+    if (R > frames / 4) R = frames / 4;
+    if (R < 1) R = 1;
+    P.runs_per_clip = (int)R;
+    P.run_len = frames / (int)R;
+    P.run_rem = frames % (int)R;
     return DDSP_B200_OK;
 }
 
@@ -490,7 +492,7 @@ int launch_ltv_conv(const ddsp::LtvParams& P, cudaStream_t st) {
     if (P.runs_per_clip > 1) {
         // only the hops at run seams are accumulated with atomics (2 hops for L = 510, 3 for L = 1022)
         const int n_seams = P.B * (P.runs_per_clip - 1), hops = P.n_mag == 256 ? 2 : 3;
-        ddsp::ltv_zero_seams_kernel<<<(unsigned)(n_seams * hops), 128, 0, st>>>(P.out, P.F, P.run_len, P.runs_per_clip,
+        ddsp::ltv_zero_seams_kernel<<<(unsigned)(n_seams * hops), 128, 0, st>>>(P.out, P.F, P.run_len, P.run_rem, P.runs_per_clip,
                                                                                P.n_mag - 1, hops, n_seams);
         LAUNCH_CHECK();
     }
@@ -500,7 +502,7 @@ int launch_ltv_conv(const ddsp::LtvParams& P, cudaStream_t st) {
     LAUNCH_CHECK();
     if (P.sum_out && P.runs_per_clip > 1) {
         const int n_seams = P.B * (P.runs_per_clip - 1);
-        ddsp::ltv_sum_seams_kernel<<<(unsigned)(n_seams * 2), 128, 0, st>>>(P.out, P.add_in, P.sum_out, P.F, P.run_len,
+        ddsp::ltv_sum_seams_kernel<<<(unsigned)(n_seams * 2), 128, 0, st>>>(P.out, P.add_in, P.sum_out, P.F, P.run_len, P.run_rem,
                                                                            P.runs_per_clip, P.n_mag - 1, 2, n_seams);
         LAUNCH_CHECK();
     }

@@ -60,7 +60,7 @@ struct LtvParams {
     float2* spec;                       // workspace (B,F,1024) complex: tap spectra
     float* out;                         // (B,T)
     const float* add_in; float* sum_out; // optional (L = 510 convolution): sum_out = add_in + out (vocoder.py:421,548)
-    int B, F, run_len, runs_per_clip;
+    int B, F, run_len, run_rem, runs_per_clip;   // run r of a clip: frames [run_begin(r), + run_len + (r < run_rem))
 };
 
 __device__ __forceinline__ float bartlett1024(int i) {      // torch.bartlett_window(1024), periodic (core.py:221)
@@ -462,12 +462,13 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
         __syncthreads();
     }
     {
-        const int64_t run = (int64_t)blockIdx.x * kLtvWarps + wid;
-        if (run >= (int64_t)P.B * P.runs_per_clip) return;
-        const int b0 = (int)(run / P.runs_per_clip);
-        const int mb = (int)(run % P.runs_per_clip) * P.run_len;
+        const int64_t slot = (int64_t)wid * gridDim.x + blockIdx.x;     // long runs evenly over the schedulers (slot_to_run)
+        if (slot >= (int64_t)P.B * P.runs_per_clip) return;
+        int b0, r;
+        slot_to_run(slot, P.B, P.runs_per_clip, P.run_rem, b0, r);
+        const int mb = run_begin(r, P.run_len, P.run_rem);
         if (lane == 0) {
-            ctx[0] = b0; ctx[1] = mb; ctx[2] = min(P.F + 1, mb + P.run_len);
+            ctx[0] = b0; ctx[1] = mb; ctx[2] = mb + P.run_len + (r < P.run_rem ? 1 : 0);
             const uint64_t k64 = noise_key64(P.seed, (uint32_t)b0);
             ctx[3] = (int)((uint32_t)k64 + P.key_offset);
             ctx[5] = (int)(uint32_t)(k64 >> 32);
@@ -657,15 +658,15 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
 
 // Zero the output samples that receive atomic adds from two neighbouring runs: the first `hops` hops a run
 // (other than the first of its clip) retires, i.e. samples [512 (m_begin - 1) - D, + 512 hops) with
-// m_begin = r * run_len.  Everything else is written with plain stores, so the rest of `out` needs no clearing.
+// m_begin = run_begin(r).  Everything else is written with plain stores, so the rest of `out` needs no clearing.
 // One CTA of 128 threads per (seam, hop).
-__global__ void __launch_bounds__(128) ltv_zero_seams_kernel(float* __restrict__ out, int F, int run_len,
+__global__ void __launch_bounds__(128) ltv_zero_seams_kernel(float* __restrict__ out, int F, int run_len, int run_rem,
                                                              int runs_per_clip, int D, int hops, int n_seams) {
     const int seam = blockIdx.x / hops, c = blockIdx.x % hops;
     if (seam >= n_seams) return;
     const int b = seam / (runs_per_clip - 1), r = seam % (runs_per_clip - 1) + 1;
     const int64_t T = (int64_t)F * kHop;
-    const int64_t t0 = (int64_t)(r * run_len - 1 + c) * kHop - D;
+    const int64_t t0 = (int64_t)(run_begin(r, run_len, run_rem) - 1 + c) * kHop - D;
     float* ob = out + (int64_t)b * T;
 #pragma unroll
     for (int i = 0; i < kHop / 128; ++i) {
@@ -677,13 +678,13 @@ __global__ void __launch_bounds__(128) ltv_zero_seams_kernel(float* __restrict__
 // sum_out = add_in + out on the seam hops (same geometry as ltv_zero_seams_kernel), after the convolution
 // kernel: there `out` is complete only once both neighbouring runs have added their part.
 __global__ void __launch_bounds__(128) ltv_sum_seams_kernel(const float* __restrict__ out, const float* __restrict__ add_in,
-                                                            float* __restrict__ sum_out, int F, int run_len,
+                                                            float* __restrict__ sum_out, int F, int run_len, int run_rem,
                                                             int runs_per_clip, int D, int hops, int n_seams) {
     const int seam = blockIdx.x / hops, c = blockIdx.x % hops;
     if (seam >= n_seams) return;
     const int b = seam / (runs_per_clip - 1), r = seam % (runs_per_clip - 1) + 1;
     const int64_t T = (int64_t)F * kHop;
-    const int64_t t0 = (int64_t)(r * run_len - 1 + c) * kHop - D;
+    const int64_t t0 = (int64_t)(run_begin(r, run_len, run_rem) - 1 + c) * kHop - D;
 #pragma unroll
     for (int i = 0; i < kHop / 128; ++i) {
         const int64_t t = t0 + threadIdx.x + 128 * i;
@@ -717,12 +718,13 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
         __syncthreads();
     }
     {
-        const int64_t run = (int64_t)blockIdx.x * kLtvWarps + wid;
-        if (run >= (int64_t)P.B * P.runs_per_clip) return;
-        const int b0 = (int)(run / P.runs_per_clip);
-        const int mb = (int)(run % P.runs_per_clip) * P.run_len;
+        const int64_t slot = (int64_t)wid * gridDim.x + blockIdx.x;     // long runs evenly over the schedulers (slot_to_run)
+        if (slot >= (int64_t)P.B * P.runs_per_clip) return;
+        int b0, r;
+        slot_to_run(slot, P.B, P.runs_per_clip, P.run_rem, b0, r);
+        const int mb = run_begin(r, P.run_len, P.run_rem);
         if (lane == 0) {
-            ctx[0] = b0; ctx[1] = mb; ctx[2] = min(P.F + 1, mb + P.run_len);
+            ctx[0] = b0; ctx[1] = mb; ctx[2] = mb + P.run_len + (r < P.run_rem ? 1 : 0);
             const uint64_t k64 = noise_key64(P.seed, (uint32_t)b0);
             ctx[3] = (int)((uint32_t)k64 + P.key_offset);
             ctx[5] = (int)(uint32_t)(k64 >> 32);
