@@ -29,24 +29,22 @@ constexpr int kCsfThreads = kCsfWarps * 32;
 constexpr int kRingSlot = kHop + kHop / 32;         // 528 floats: one pad word per 32 samples
 constexpr int kStashFloat2 = 17 * 32;               // Y_m stash: 16 bins/lane (+ bin 512 on lane 0)
 constexpr int kCsfCtxInts = 16;                     // cold per-warp scalars parked in shared memory (+ staged hop operands)
-// Experiment switches (profiles/r02_csf_variants.md); the defaults are the shipped configuration.
-#ifndef CSF_PRE
-#define CSF_PRE 0            // filter bins per lane staged by cp.async into the dead ring slot while the FFT runs
-#endif
-#ifndef CSF_HOP_AHEAD
-#define CSF_HOP_AHEAD 0      // f0 / prefix operands of the next hop staged by cp.async one step ahead
-#endif
+// Experiment switches; the defaults are the shipped configuration.  Measured and dropped (profiles/r02_csf_variants_*.txt,
+// git history): filter bins / hop operands staged by per-lane cp.async (+5 % / +3 % time), L1 prefetch of the first
+// filter lines (+1 %), unvoiced zeroing only on hops that touch a non-positive frame (+6 %: spills), control values of
+// the first 1..6 filter bins or the next hop's operands loaded BEFORE the FFT and held in registers across it (+3 % .. +19 %
+// even without spills: the FFT needs every temporary register it can get, profiles/r02_csf_variants_e_early_loads.txt).
 #ifndef CSF_RED_OLA
 #define CSF_RED_OLA 1        // hop shared with the previous pair finished by RED.ADD instead of load + add + store
-#endif
-#ifndef CSF_ZERO_FAST
-#define CSF_ZERO_FAST 0      // unvoiced zeroing (vocoder.py:460) only on hops that touch a non-positive f0 frame
 #endif
 #ifndef CSF_INT_PHASE
 #define CSF_INT_PHASE 1      // intra-lane phase in 32-bit fixed point on top of an fp64 lane base
 #endif
-#ifndef CSF_L1PF
-#define CSF_L1PF 0           // prefetch the lines of the first CSF_LOOK filter bins into L1 (not only L2) ahead of the FFT
+#ifndef CSF_BULK
+#define CSF_BULK 1           // filter rows of a frame travel global -> shared by three bulk async copies issued mid-FFT
+#endif
+#ifndef CSF_L2PF
+#define CSF_L2PF (!CSF_BULK) // rows pulled into L2 one FFT ahead of the per-lane loads; with the bulk copies it only costs issue slots (178.6 -> 174.5 us without; one cp.async.bulk.prefetch.L2 per row instead: 181.5 us)
 #endif
 #ifndef CSF_LOOK
 #define CSF_LOOK 6           // filter bins whose control loads are in flight ahead of their use
@@ -54,10 +52,12 @@ constexpr int kCsfCtxInts = 16;                     // cold per-warp scalars par
 #ifndef CSF_NOALLOC
 #define CSF_NOALLOC 1        // control rows are read once: keep them out of L1
 #endif
+#ifndef CSF_DBG_SKIP
+#define CSF_DBG_SKIP 0       // timing experiments only (wrong output): 1 no FFT, 2 no excitation, 4 no filter arithmetic, 8 no framing, 16 no output stores
+#endif
 #ifndef CSF_BALANCE
 #define CSF_BALANCE 1        // long runs spread evenly over the schedulers (see slot_to_run)
 #endif
-constexpr int kCsfPre = CSF_PRE;
 constexpr int kCsfWarpBytes = kPlaneFloats * 4 + 2 * kRingSlot * 4 + kStashFloat2 * 8 + kCsfCtxInts * 4;
 constexpr int kCsfSmemBytes = kTableBytes + kCsfWarps * kCsfWarpBytes;
 
@@ -119,37 +119,46 @@ __device__ __forceinline__ void csf_gen_hop(const CsfParams& P, int h, const Hop
         const float2 den = add2(f2[j], bc2(1e-3f));
         const float2 xs = fma2(mul2(bc2(sr_scale), rot2[j]), make_float2(rcp_approx(den.x), rcp_approx(den.y)), bc2(1e-30f));
         const float2 c = sinc2_xs(xs);
-#if CSF_ZERO_FAST
-        dst[2 * j] = c.x;
-        dst[2 * j + 1] = c.y;
-#else
         dst[2 * j] = (f2[j].x <= 0.0f) ? 0.0f : c.x;       // vocoder.py:460
         dst[2 * j + 1] = (f2[j].y <= 0.0f) ? 0.0f : c.y;
-#endif
     }
-#if CSF_ZERO_FAST
-    // vocoder.py:460 combtooth[f0 <= 0] = 0.  An interpolated sample can only be non-positive when one of the
-    // hop's two frame values is (warp-uniform test): voiced hops skip the per-sample compare + select.
-    if (in.x0 <= 0.0f || in.x1 <= 0.0f) {
-        const float lam0 = (float)(16 * lane) * (1.0f / kHop);
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (lerp_torch(in.x0, in.x1, lam0 + (float)i * (1.0f / kHop)) <= 0.0f) dst[i] = 0.0f;
-    }
-#endif
 }
 
-// cp.async (LDGSTS): global -> shared without a register in between; completion via cp_async_wait_all().
-__device__ __forceinline__ uint32_t smem_u32(const volatile void* p) {
+// ---- bulk async copy (TMA engine, no tensor map) of the three filter rows of one frame -------------------------------
+// A row is 513 floats = 2052 B at a 4-byte-aligned address; cp.async.bulk wants 16-byte-aligned addresses and sizes, so
+// the copy covers the 16-byte-aligned window around the row: 2064 B from (address & ~15).  The <= 12 B read in front of /
+// behind the row lie in the same 16-byte granule as valid bytes of the row (never on another page).
+constexpr int kRowWindowBytes = 2064;
+__device__ __forceinline__ uint32_t csf_s32(const volatile void* p) {
     return (uint32_t)__cvta_generic_to_shared(const_cast<const void*>(p));
 }
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void csf_mbar_init(uint32_t bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void csf_mbar_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void csf_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "CSF_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra CSF_DONE_%=;\n\t"
+        "bra CSF_WAIT_%=;\n\t"
+        "CSF_DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// row -> shared window; the row's first float sits at window + csf_row_skew(row)
+__device__ __forceinline__ void csf_bulk_row(uint32_t dst, const float* row, uint32_t bar) {
+    const uint64_t src = reinterpret_cast<uint64_t>(row) & ~15ull;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "n"(kRowWindowBytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ int csf_row_skew(const float* row) { return (int)((reinterpret_cast<uint64_t>(row) & 15ull) >> 2); }
 
 // control rows are consumed exactly once: bypass L1 so that it keeps serving f0 / prefix / seam lines
 __device__ __forceinline__ float ldg_once(const float* p) {
@@ -164,9 +173,6 @@ __device__ __forceinline__ float ldg_once(const float* p) {
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
 // Zero the seam hops (first output hop of every run that does not start a clip).
@@ -268,8 +274,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
     // reads) instead of registers: the FFT keeps 64 data registers live and anything else held
     // across it would be spilled to local memory, whose reloads miss the (tiny) L1 here.
     //   ctx[0] clip, [1] first pair, [2] end pair, [3] noise key (low word + hop offset), [4] step, [5] noise key (high word),
-    //   ctx[8], [9] f0 frame values and [10..11] fp64 prefix of the NEXT hop (staged by cp.async),
-    //   ctx[12..13] f0 row pointer, [14..15] prefix row pointer of the clip
+    //   ctx[6..7] mbarrier of the filter-row copies
     volatile int* ctx = reinterpret_cast<volatile int*>(stash + kStashFloat2);
     {
         // runs are dealt over the warp slots so that every scheduler gets the same mix of long and short runs
@@ -291,8 +296,9 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             const uint64_t k64 = noise_key64(seed, (uint32_t)b0);
             ctx[3] = (int)((uint32_t)k64 + P.key_offset);
             ctx[5] = (int)(uint32_t)(k64 >> 32);
-            *reinterpret_cast<volatile uint64_t*>(ctx + 12) = (uint64_t)(P.f0_frames + (int64_t)b0 * P.fB);
-            *reinterpret_cast<volatile uint64_t*>(ctx + 14) = (uint64_t)(P.prefix + (int64_t)b0 * P.F);
+#if CSF_BULK
+            csf_mbar_init(csf_s32(ctx + 6));                    // ctx[6..7]: the warp's mbarrier for the filter-row copies
+#endif
         }
         __syncwarp();
     }
@@ -307,26 +313,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
     const int F = P.F;
     const int partner = (32 - lane) & 31;
     const bool lane0 = lane == 0;
-    const uint32_t ctx_s = smem_u32(ctx);
 
-    // Stage the operands of excitation hop h (two f0 frame values, the fp64 prefix) into ctx[8..11]:
-    // lanes 0..2 issue one cp.async each; the values are read after the next cp_async_wait_all + __syncwarp.
-    auto stage_hop = [&](int h) {
-        if (lane < 3) {
-            const int hc = min(max(h, 0), F - 1);
-            const float* f0_row = reinterpret_cast<const float*>(*reinterpret_cast<volatile uint64_t*>(ctx + 12));
-            const double* pre_row = reinterpret_cast<const double*>(*reinterpret_cast<volatile uint64_t*>(ctx + 14));
-            if (lane == 2) cp_async8(ctx_s + 40, pre_row + hc);
-            else cp_async4(ctx_s + 32 + 4 * lane, f0_row + (int64_t)min(hc + lane, F - 1) * P.fF);
-        }
-    };
-    auto staged_hop = [&]() {
-        HopIn in;
-        in.x0 = __int_as_float(ctx[8]);
-        in.x1 = __int_as_float(ctx[9]);
-        in.base = *reinterpret_cast<volatile double*>(ctx + 10);
-        return in;
-    };
 
     Pts32 X;
     // De-phase the four warps that share a scheduler (wid, wid+4, wid+8, wid+12) by 1 us each so that
@@ -343,10 +330,6 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
 #define CTX_STEP ctx[4]
     int p = CTX_PBEGIN;
     if (lane == 0) CTX_STEP = -1;
-#if CSF_HOP_AHEAD
-    stage_hop(2 * p - 1);
-    cp_async_wait_all();
-#endif
     __syncwarp();
     // @section loop
 #pragma unroll 1
@@ -356,54 +339,51 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
         if (s < 2) {
             // @section excite
             // ---- excitation hop fm (second half of frame fm; fm = 2p-1 on the priming step) ----
-#if CSF_HOP_AHEAD
-            csf_gen_hop(P, fm, staged_hop(), ring + (fm & 1) * kRingSlot, lane);
+#if CSF_DBG_SKIP & 2
+            if (fm == -12345) csf_gen_hop(P, fm, csf_load_hop(P, CTX_B, fm), ring + (fm & 1) * kRingSlot, lane);
 #else
             // (f0 / prefix of consecutive hops share cache lines: after the first hop of a run these are L2 hits)
             csf_gen_hop(P, fm, csf_load_hop(P, CTX_B, fm), ring + (fm & 1) * kRingSlot, lane);
 #endif
             __syncwarp();
             if (s < 0) {
-#if CSF_HOP_AHEAD
-                stage_hop(fm + 1);
-                cp_async_wait_all();
-#endif
                 CTX_STEP = 0; __syncwarp(); continue;
             }
             // @section frame
             {   // pull this frame's three control rows into L2 while the FFT runs (lanes 0..16: one line each)
                 const int64_t ro = (int64_t)CTX_B * P.cB + (int64_t)min(fm, F - 1) * P.cF + 32 * lane;
-#if CSF_L1PF
-                if (lane <= CSF_LOOK) { prefetch_l1(P.hm + ro); prefetch_l1(P.hp + ro); prefetch_l1(P.nm + ro); }
-                else
-#endif
+#if CSF_L2PF == 1
                 if (lane <= 16) { prefetch_l2(P.hm + ro); prefetch_l2(P.hp + ro); prefetch_l2(P.nm + ro); }
+#endif
             }
+#if CSF_DBG_SKIP & 8
+            if (fm == -12345)
+#endif
             csf_load_frame<HAS_U>(P, X, ring, win, fm, CTX_B, CTX_KEY, CTX_KEY2, lane);
-#if CSF_PRE > 0 || CSF_HOP_AHEAD
-            __syncwarp();       // every lane has read hop fm-1 out of its ring slot: the slot is free until hop fm+1 is generated
-#endif
-#if CSF_PRE > 0
-            {   // the first kCsfPre filter bins of every lane travel global -> shared (the free ring slot) while
-                // the FFT runs, as (hm, hp, nm, -) quads: no register is held across the FFT
-                const int64_t ro = (int64_t)CTX_B * P.cB + (int64_t)min(fm, F - 1) * P.cF + lane;
-                const uint32_t st = smem_u32(ring + ((fm - 1) & 1) * kRingSlot) + 16 * lane;
-#pragma unroll
-                for (int q = 0; q < kCsfPre; ++q) {
-                    cp_async4(st + 512 * q, P.hm + ro + 32 * q);
-                    cp_async4(st + 512 * q + 4, P.hp + ro + 32 * q);
-                    cp_async4(st + 512 * q + 8, P.nm + ro + 32 * q);
-                }
-            }
-#endif
-#if CSF_HOP_AHEAD
-            stage_hop(fm + 1);
-#endif
         }
         // @section fft
         // s == 2: re/im already hold the packed spectrum of the pair (swapped for the inverse)
 
+#if CSF_DBG_SKIP & 1
+#elif CSF_BULK
+        // Between the two passes of the FFT the transpose plane is free (until the next transform) and so is the ring
+        // slot of hop fm-1 (until hop fm+1 is generated): lane 0 starts the copies of this frame's three filter rows into
+        // them -- hm | hp into the plane, nm into the slot.  They land while the second pass runs; no register is held.
+        warp_fft1024(X, plane, tw4, lane, [&] {
+            if (lane0 && CTX_STEP < 2) {
+                const uint32_t bar = csf_s32(ctx + 6);
+                const int fr = 2 * p + CTX_STEP;
+                const int64_t ro = (int64_t)CTX_B * P.cB + (int64_t)min(fr, F - 1) * P.cF;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the warp's generic accesses before the async writes
+                csf_mbar_expect(bar, 3 * kRowWindowBytes);
+                csf_bulk_row(csf_s32(plane), P.hm + ro, bar);
+                csf_bulk_row(csf_s32(plane) + kRowWindowBytes, P.hp + ro, bar);
+                csf_bulk_row(csf_s32(ring + ((fr - 1) & 1) * kRingSlot), P.nm + ro, bar);
+            }
+        });
+#else
         warp_fft1024(X, plane, tw4, lane);
+#endif
 
         // @section filter
         if (CTX_STEP < 2) {
@@ -411,44 +391,42 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             // last filter frame repeated (:473,476)
             const int64_t ro = (int64_t)CTX_B * P.cB + (int64_t)min(fm, F - 1) * P.cF + lane;
             const int k16 = 512 - lane;                                       // bin 512 (used by lane 0 only): every lane reads that one word
+            float yr[17], yi[17];
+#if CSF_BULK
+            // the rows were copied into shared memory while the FFT ran (parity of the barrier = step: two copies per pair)
+            const float* hm_r = plane + csf_row_skew(P.hm + ro - lane) + lane;
+            const float* hp_r = plane + kRowWindowBytes / 4 + csf_row_skew(P.hp + ro - lane) + lane;
+            const float* nm_r = ring + ((fm - 1) & 1) * kRingSlot + csf_row_skew(P.nm + ro - lane) + lane;
+            csf_mbar_wait(csf_s32(ctx + 6), (uint32_t)(CTX_STEP & 1));
+#else
             const float* hm_r = P.hm + ro;
             const float* hp_r = P.hp + ro;
             const float* nm_r = P.nm + ro;
-            float yr[17], yi[17];
-            // control loads run kLook bins ahead of their use (software pipeline over the unrolled loop)
-#ifndef CSF_LOOK
-#define CSF_LOOK 4
 #endif
+            // control loads run kLook bins ahead of their use (software pipeline over the unrolled loop)
+#if !CSF_BULK
             constexpr int kLook = CSF_LOOK;
             float chm[kLook], chp[kLook], cnm[kLook];
 #pragma unroll
             for (int q = 0; q < kLook; ++q) {
-                const int off = (q + kCsfPre < 16) ? 32 * (q + kCsfPre) : k16;
-#if CSF_L1PF
-                chm[q] = __ldg(hm_r + off); chp[q] = __ldg(hp_r + off); cnm[q] = __ldg(nm_r + off);
-#else
+                const int off = (q < 16) ? 32 * q : k16;
                 chm[q] = ldg_once(hm_r + off); chp[q] = ldg_once(hp_r + off); cnm[q] = ldg_once(nm_r + off);
-#endif
             }
-#if CSF_PRE > 0 || CSF_HOP_AHEAD
-            cp_async_wait_all();
 #endif
-            const float4* staged = reinterpret_cast<const float4*>(ring + ((fm - 1) & 1) * kRingSlot) + lane;
 #pragma unroll
             for (int q = 0; q < 17; ++q) {
                 float a, bb, c, d;
-                float vhm, vhp, vnm;
-                if (q < kCsfPre) {
-                    const float4 sv = staged[32 * q];
-                    vhm = sv.x; vhp = sv.y; vnm = sv.z;
-                } else {
-                    const int i = (q - kCsfPre) % kLook;
-                    vhm = chm[i]; vhp = chp[i]; vnm = cnm[i];
-                    if (q + kLook < 17) {
-                        const int off = (q + kLook < 16) ? 32 * (q + kLook) : k16;   // bin 512: lane 0 (others: dummy)
-                        chm[i] = ldg_once(hm_r + off); chp[i] = ldg_once(hp_r + off); cnm[i] = ldg_once(nm_r + off);
-                    }
+#if CSF_BULK
+                const int off = (q < 16) ? 32 * q : k16;                         // bin 512: lane 0 (others: dummy)
+                const float vhm = hm_r[off], vhp = hp_r[off], vnm = nm_r[off];
+#else
+                const int i = q % kLook;
+                const float vhm = chm[i], vhp = chp[i], vnm = cnm[i];
+                if (q + kLook < 17) {
+                    const int off = (q + kLook < 16) ? 32 * (q + kLook) : k16;   // bin 512: lane 0 (others: dummy)
+                    chm[i] = ldg_once(hm_r + off); chp[i] = ldg_once(hp_r + off); cnm[i] = ldg_once(nm_r + off);
                 }
+#endif
                 if (q < 16) {
                     a = DDSP_RE(X, q); bb = DDSP_IM(X, q);
                     c = __shfl_sync(kFullMask, DDSP_RE(X, 31 - q), partner);
@@ -466,6 +444,10 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                 const float2 NrCi = fma2(bc2(d), make_float2(1.0f, -1.0f), bc2(bb));
                 // H = exp(hm + j*pi*hp) (vocoder.py:472), N = exp(nm)/128 (:475); the 1/2 of the
                 // split and the 1/1024 of irfft are folded in as exact powers of two.
+#if CSF_DBG_SKIP & 4
+                yr[q] = a + c + vhm; yi[q] = bb + d + vhp + vnm;
+                continue;
+#endif
                 const float g = ex2_approx(fmaf(vhm, DDSP_LOG2E_F, -11.0f));
                 const float nf = ex2_approx(fmaf(vnm, DDSP_LOG2E_F, -18.0f));
                 const float ang = DDSP_PI_F * vhp;
@@ -518,6 +500,10 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             // partial sum and is completed here by one reduction per sample (same thread stored the partial:
             // program order on the same address; stored value + one addend is the same fp32 number as a
             // load-add-store); at a run seam both sides add onto zeros instead.
+#if CSF_DBG_SKIP & 16
+            if (X.I[3].x == 1.2345f)
+#endif
+            {
             const int hopA = 2 * p - 1, hopB = 2 * p, hopC = 2 * p + 1;
             const int p_begin = CTX_PBEGIN, p_end = CTX_PEND;
             const bool first = p == p_begin, last = p + 1 >= p_end;
@@ -567,7 +553,8 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                     for (int q = 0; q < 16; ++q) atomicAdd(oC + 32 * q, X.R[q].y);
                 }
             }
-            if (++p >= p_end) break;
+            }
+            if (++p >= CTX_PEND) break;
             CTX_STEP = 0;
         }
         __syncwarp();

@@ -161,8 +161,11 @@ constexpr int kPlaneFloats = 32 * kPlaneStride;  // 1088 floats = 4352 B per war
 //   out: X[lane + 32*k2] at register-index k2 (natural order)
 // `plane` is this warp's private 32x34-float transpose buffer, `tw4` the CTA-wide twiddle table.
 // The inverse transform is obtained by calling it with real and imaginary parts swapped.
+// `mid()` runs between the two passes, after the last access to `plane`: the buffer is free from there until the next
+// transform (combsubfast_kernel starts the bulk copy of the next filter rows into it at that point).
+template <class Mid>
 __device__ __forceinline__ void warp_fft1024(Pts32& P, float* __restrict__ plane, const float4* __restrict__ tw4,
-                                             int lane) {
+                                             int lane, Mid&& mid) {
     fft32_dit(P);                                    // register-index k1 = A[k1] for column n2 = lane
     float* wr = plane + lane;
     const float2* rd = reinterpret_cast<const float2*>(plane + lane * kPlaneStride);
@@ -178,7 +181,12 @@ __device__ __forceinline__ void warp_fft1024(Pts32& P, float* __restrict__ plane
 #pragma unroll
     for (int i = 0; i < 16; ++i) P.I[i] = rd[brev5(i) >> 1];
     __syncwarp();
+    mid();
     fft32_dit_twiddled(P, tw4, lane);                // row k1 = lane: X[lane + 32*k2]
+}
+__device__ __forceinline__ void warp_fft1024(Pts32& P, float* __restrict__ plane, const float4* __restrict__ tw4,
+                                             int lane) {
+    warp_fft1024(P, plane, tw4, lane, [] {});
 }
 
 // Device-wide constant tables (filled once per device by fft_tables_kernel):
