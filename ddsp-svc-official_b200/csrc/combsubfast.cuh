@@ -11,6 +11,8 @@
 //   * per frame one complex FFT-1024 transforms comb (real part) and noise (imag part) together;
 //     the two real spectra are separated with the conjugate-symmetric partner bin, which lives in
 //     lane 32-l and is fetched with warp shuffles;
+//   * the three filter rows of a frame (3 x 513 floats) travel global -> shared by bulk async copies that one lane
+//     issues between the two passes of the frame's FFT, into the then idle transpose plane and the dead ring slot;
 //   * per PAIR one complex inverse FFT-1024 returns both real output frames (V = Y_m + j*Y_{m+1});
 //   * the hop shared by the two frames of a pair is finished in registers; the hop shared with
 //     the next pair is carried in registers; the hop shared with the neighbouring RUN gets one
@@ -33,24 +35,15 @@ constexpr int kCsfCtxInts = 16;                     // cold per-warp scalars par
 // git history): filter bins / hop operands staged by per-lane cp.async (+5 % / +3 % time), L1 prefetch of the first
 // filter lines (+1 %), unvoiced zeroing only on hops that touch a non-positive frame (+6 %: spills), control values of
 // the first 1..6 filter bins or the next hop's operands loaded BEFORE the FFT and held in registers across it (+3 % .. +19 %
-// even without spills: the FFT needs every temporary register it can get, profiles/r02_csf_variants_e_early_loads.txt).
+// even without spills: the FFT needs every temporary register it can get, profiles/r02_csf_variants_e_early_loads.txt);
+// per-lane LDG of the filter rows, software-pipelined 6 bins ahead behind an L2 prefetch (the round-1 form, 178.4 us vs
+// 174.3 us for the bulk copies below; an extra L2 prefetch in front of the bulk copies costs 4..7 us,
+// profiles/r02_csf_variants_f_bulk_rows.txt, _g_bulk_prefetch.txt).
 #ifndef CSF_RED_OLA
 #define CSF_RED_OLA 1        // hop shared with the previous pair finished by RED.ADD instead of load + add + store
 #endif
 #ifndef CSF_INT_PHASE
 #define CSF_INT_PHASE 1      // intra-lane phase in 32-bit fixed point on top of an fp64 lane base
-#endif
-#ifndef CSF_BULK
-#define CSF_BULK 1           // filter rows of a frame travel global -> shared by three bulk async copies issued mid-FFT
-#endif
-#ifndef CSF_L2PF
-#define CSF_L2PF (!CSF_BULK) // rows pulled into L2 one FFT ahead of the per-lane loads; with the bulk copies it only costs issue slots (178.6 -> 174.5 us without; one cp.async.bulk.prefetch.L2 per row instead: 181.5 us)
-#endif
-#ifndef CSF_LOOK
-#define CSF_LOOK 6           // filter bins whose control loads are in flight ahead of their use
-#endif
-#ifndef CSF_NOALLOC
-#define CSF_NOALLOC 1        // control rows are read once: keep them out of L1
 #endif
 #ifndef CSF_DBG_SKIP
 #define CSF_DBG_SKIP 0       // timing experiments only (wrong output): 1 no FFT, 2 no excitation, 4 no filter arithmetic, 8 no framing, 16 no output stores
@@ -106,6 +99,9 @@ __device__ __forceinline__ void csf_gen_hop(const CsfParams& P, int h, const Hop
         return;
     }
     float2 f2[8], rot2[8];
+    // (an opaque copy of the lane index: ptxas otherwise hoists the lane's interpolation weights out of the step loop and
+    // spills them to local memory, whose reloads miss the tiny L1 left beside 224 KB of shared memory)
+    asm volatile("" : "+r"(lane));
 #if CSF_INT_PHASE
     hop_rotation_q32(in.x0, in.x1, in.base, P.inv_sr, lane, f2, rot2);
     const float sr_scale = P.sr * 2.3283064365386963e-10f;      // rot2 holds rot * 2^32
@@ -159,17 +155,6 @@ __device__ __forceinline__ void csf_bulk_row(uint32_t dst, const float* row, uin
                  : "memory");
 }
 __device__ __forceinline__ int csf_row_skew(const float* row) { return (int)((reinterpret_cast<uint64_t>(row) & 15ull) >> 2); }
-
-// control rows are consumed exactly once: bypass L1 so that it keeps serving f0 / prefix / seam lines
-__device__ __forceinline__ float ldg_once(const float* p) {
-#if CSF_NOALLOC
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-#else
-    return __ldg(p);
-#endif
-}
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -296,9 +281,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             const uint64_t k64 = noise_key64(seed, (uint32_t)b0);
             ctx[3] = (int)((uint32_t)k64 + P.key_offset);
             ctx[5] = (int)(uint32_t)(k64 >> 32);
-#if CSF_BULK
             csf_mbar_init(csf_s32(ctx + 6));                    // ctx[6..7]: the warp's mbarrier for the filter-row copies
-#endif
         }
         __syncwarp();
     }
@@ -350,12 +333,6 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                 CTX_STEP = 0; __syncwarp(); continue;
             }
             // @section frame
-            {   // pull this frame's three control rows into L2 while the FFT runs (lanes 0..16: one line each)
-                const int64_t ro = (int64_t)CTX_B * P.cB + (int64_t)min(fm, F - 1) * P.cF + 32 * lane;
-#if CSF_L2PF == 1
-                if (lane <= 16) { prefetch_l2(P.hm + ro); prefetch_l2(P.hp + ro); prefetch_l2(P.nm + ro); }
-#endif
-            }
 #if CSF_DBG_SKIP & 8
             if (fm == -12345)
 #endif
@@ -364,8 +341,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
         // @section fft
         // s == 2: re/im already hold the packed spectrum of the pair (swapped for the inverse)
 
-#if CSF_DBG_SKIP & 1
-#elif CSF_BULK
+#if !(CSF_DBG_SKIP & 1)
         // Between the two passes of the FFT the transpose plane is free (until the next transform) and so is the ring
         // slot of hop fm-1 (until hop fm+1 is generated): lane 0 starts the copies of this frame's three filter rows into
         // them -- hm | hp into the plane, nm into the slot.  They land while the second pass runs; no register is held.
@@ -381,8 +357,6 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
                 csf_bulk_row(csf_s32(ring + ((fr - 1) & 1) * kRingSlot), P.nm + ro, bar);
             }
         });
-#else
-        warp_fft1024(X, plane, tw4, lane);
 #endif
 
         // @section filter
@@ -392,41 +366,17 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             const int64_t ro = (int64_t)CTX_B * P.cB + (int64_t)min(fm, F - 1) * P.cF + lane;
             const int k16 = 512 - lane;                                       // bin 512 (used by lane 0 only): every lane reads that one word
             float yr[17], yi[17];
-#if CSF_BULK
             // the rows were copied into shared memory while the FFT ran (parity of the barrier = step: two copies per pair)
             const float* hm_r = plane + csf_row_skew(P.hm + ro - lane) + lane;
             const float* hp_r = plane + kRowWindowBytes / 4 + csf_row_skew(P.hp + ro - lane) + lane;
             const float* nm_r = ring + ((fm - 1) & 1) * kRingSlot + csf_row_skew(P.nm + ro - lane) + lane;
             csf_mbar_wait(csf_s32(ctx + 6), (uint32_t)(CTX_STEP & 1));
-#else
-            const float* hm_r = P.hm + ro;
-            const float* hp_r = P.hp + ro;
-            const float* nm_r = P.nm + ro;
-#endif
             // control loads run kLook bins ahead of their use (software pipeline over the unrolled loop)
-#if !CSF_BULK
-            constexpr int kLook = CSF_LOOK;
-            float chm[kLook], chp[kLook], cnm[kLook];
-#pragma unroll
-            for (int q = 0; q < kLook; ++q) {
-                const int off = (q < 16) ? 32 * q : k16;
-                chm[q] = ldg_once(hm_r + off); chp[q] = ldg_once(hp_r + off); cnm[q] = ldg_once(nm_r + off);
-            }
-#endif
 #pragma unroll
             for (int q = 0; q < 17; ++q) {
                 float a, bb, c, d;
-#if CSF_BULK
                 const int off = (q < 16) ? 32 * q : k16;                         // bin 512: lane 0 (others: dummy)
                 const float vhm = hm_r[off], vhp = hp_r[off], vnm = nm_r[off];
-#else
-                const int i = q % kLook;
-                const float vhm = chm[i], vhp = chp[i], vnm = cnm[i];
-                if (q + kLook < 17) {
-                    const int off = (q + kLook < 16) ? 32 * (q + kLook) : k16;   // bin 512: lane 0 (others: dummy)
-                    chm[i] = ldg_once(hm_r + off); chp[i] = ldg_once(hp_r + off); cnm[i] = ldg_once(nm_r + off);
-                }
-#endif
                 if (q < 16) {
                     a = DDSP_RE(X, q); bb = DDSP_IM(X, q);
                     c = __shfl_sync(kFullMask, DDSP_RE(X, 31 - q), partner);

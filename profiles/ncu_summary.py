@@ -62,7 +62,7 @@ def main():
             st[op] += int(r[iT])
         S = max(1, sum(st.values()))
         print(f'--- static SASS instructions {len(b)}, dynamic warp instructions {tot}')
-        for k, v in ops.most_common(24):
+        for k, v in ops.most_common(int(sys.argv[3]) if len(sys.argv) > 3 else 24):
             per = f'{v / units:9.1f}/unit' if units else ''
             print(f'{k:10s} {100 * v / tot:5.1f}% {per}  stall-samples {100 * st[k] / S:5.1f}%')
 
