@@ -33,7 +33,7 @@ constexpr int kStashFloat2 = 17 * 32;               // Y_m stash: 16 bins/lane (
 constexpr int kCsfCtxInts = 16;                     // cold per-warp scalars parked in shared memory (+ staged hop operands)
 // Experiment switches; the defaults are the shipped configuration.  Measured and dropped (profiles/r02_csf_variants_*.txt,
 // git history): filter bins / hop operands staged by per-lane cp.async (+5 % / +3 % time), L1 prefetch of the first
-// filter lines (+1 %), unvoiced zeroing only on hops that touch a non-positive frame (+6 %: spills), control values of
+// filter lines (+1 %), the sinc sign flip as a shift-add instead of shift + xor (no change), control values of
 // the first 1..6 filter bins or the next hop's operands loaded BEFORE the FFT and held in registers across it (+3 % .. +19 %
 // even without spills: the FFT needs every temporary register it can get, profiles/r02_csf_variants_e_early_loads.txt);
 // per-lane LDG of the filter rows, software-pipelined 6 bins ahead behind an L2 prefetch (the round-1 form, 178.4 us vs
@@ -41,6 +41,9 @@ constexpr int kCsfCtxInts = 16;                     // cold per-warp scalars par
 // profiles/r02_csf_variants_f_bulk_rows.txt, _g_bulk_prefetch.txt).
 #ifndef CSF_RED_OLA
 #define CSF_RED_OLA 1        // hop shared with the previous pair finished by RED.ADD instead of load + add + store
+#endif
+#ifndef CSF_ZERO_FAST
+#define CSF_ZERO_FAST 1      // unvoiced zeroing (vocoder.py:460) only on hops that touch a non-positive f0 frame (171.2 -> 169.3 us)
 #endif
 #ifndef CSF_INT_PHASE
 #define CSF_INT_PHASE 1      // intra-lane phase in 32-bit fixed point on top of an fp64 lane base
@@ -115,9 +118,24 @@ __device__ __forceinline__ void csf_gen_hop(const CsfParams& P, int h, const Hop
         const float2 den = add2(f2[j], bc2(1e-3f));
         const float2 xs = fma2(mul2(bc2(sr_scale), rot2[j]), make_float2(rcp_approx(den.x), rcp_approx(den.y)), bc2(1e-30f));
         const float2 c = sinc2_xs(xs);
+#if CSF_ZERO_FAST
+        dst[2 * j] = c.x;
+        dst[2 * j + 1] = c.y;
+#else
         dst[2 * j] = (f2[j].x <= 0.0f) ? 0.0f : c.x;       // vocoder.py:460
         dst[2 * j + 1] = (f2[j].y <= 0.0f) ? 0.0f : c.y;
+#endif
     }
+#if CSF_ZERO_FAST
+    // vocoder.py:460 combtooth[f0 <= 0] = 0.  An interpolated sample can only be non-positive when one of the hop's two
+    // frame values is (warp-uniform test): voiced hops skip the per-sample compare + select.
+    if (in.x0 <= 0.0f || in.x1 <= 0.0f) {
+        const float lam0 = (float)(16 * lane) * (1.0f / kHop);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (lerp_torch(in.x0, in.x1, lam0 + (float)i * (1.0f / kHop)) <= 0.0f) dst[i] = 0.0f;
+    }
+#endif
 }
 
 // ---- bulk async copy (TMA engine, no tensor map) of the three filter rows of one frame -------------------------------
