@@ -138,39 +138,14 @@ __device__ __forceinline__ void csf_gen_hop(const CsfParams& P, int h, const Hop
 #endif
 }
 
-// ---- bulk async copy (TMA engine, no tensor map) of the three filter rows of one frame -------------------------------
+// ---- the three filter rows of one frame by bulk async copy (helpers in common.cuh) --------------------------------
 // A row is 513 floats = 2052 B at a 4-byte-aligned address; cp.async.bulk wants 16-byte-aligned addresses and sizes, so
 // the copy covers the 16-byte-aligned window around the row: 2064 B from (address & ~15).  The <= 12 B read in front of /
 // behind the row lie in the same 16-byte granule as valid bytes of the row (never on another page).
 constexpr int kRowWindowBytes = 2064;
-__device__ __forceinline__ uint32_t csf_s32(const volatile void* p) {
-    return (uint32_t)__cvta_generic_to_shared(const_cast<const void*>(p));
-}
-__device__ __forceinline__ void csf_mbar_init(uint32_t bar) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void csf_mbar_expect(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void csf_mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "CSF_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra CSF_DONE_%=;\n\t"
-        "bra CSF_WAIT_%=;\n\t"
-        "CSF_DONE_%=:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
 // row -> shared window; the row's first float sits at window + csf_row_skew(row)
 __device__ __forceinline__ void csf_bulk_row(uint32_t dst, const float* row, uint32_t bar) {
-    const uint64_t src = reinterpret_cast<uint64_t>(row) & ~15ull;
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "n"(kRowWindowBytes), "r"(bar)
-                 : "memory");
+    bulk_copy_g2s(dst, reinterpret_cast<const void*>(reinterpret_cast<uint64_t>(row) & ~15ull), kRowWindowBytes, bar);
 }
 __device__ __forceinline__ int csf_row_skew(const float* row) { return (int)((reinterpret_cast<uint64_t>(row) & 15ull) >> 2); }
 
@@ -299,7 +274,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             const uint64_t k64 = noise_key64(seed, (uint32_t)b0);
             ctx[3] = (int)((uint32_t)k64 + P.key_offset);
             ctx[5] = (int)(uint32_t)(k64 >> 32);
-            csf_mbar_init(csf_s32(ctx + 6));                    // ctx[6..7]: the warp's mbarrier for the filter-row copies
+            bulk_mbar_init(smem_addr(ctx + 6));                    // ctx[6..7]: the warp's mbarrier for the filter-row copies
         }
         __syncwarp();
     }
@@ -365,14 +340,14 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
         // them -- hm | hp into the plane, nm into the slot.  They land while the second pass runs; no register is held.
         warp_fft1024(X, plane, tw4, lane, [&] {
             if (lane0 && CTX_STEP < 2) {
-                const uint32_t bar = csf_s32(ctx + 6);
+                const uint32_t bar = smem_addr(ctx + 6);
                 const int fr = 2 * p + CTX_STEP;
                 const int64_t ro = (int64_t)CTX_B * P.cB + (int64_t)min(fr, F - 1) * P.cF;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the warp's generic accesses before the async writes
-                csf_mbar_expect(bar, 3 * kRowWindowBytes);
-                csf_bulk_row(csf_s32(plane), P.hm + ro, bar);
-                csf_bulk_row(csf_s32(plane) + kRowWindowBytes, P.hp + ro, bar);
-                csf_bulk_row(csf_s32(ring + ((fr - 1) & 1) * kRingSlot), P.nm + ro, bar);
+                fence_proxy_async_smem();                  // the warp's generic accesses before the async writes
+                bulk_mbar_expect(bar, 3 * kRowWindowBytes);
+                csf_bulk_row(smem_addr(plane), P.hm + ro, bar);
+                csf_bulk_row(smem_addr(plane) + kRowWindowBytes, P.hp + ro, bar);
+                csf_bulk_row(smem_addr(ring + ((fr - 1) & 1) * kRingSlot), P.nm + ro, bar);
             }
         });
 #endif
@@ -388,7 +363,7 @@ __global__ void __launch_bounds__(kCsfThreads, 1) combsubfast_kernel(const CsfPa
             const float* hm_r = plane + csf_row_skew(P.hm + ro - lane) + lane;
             const float* hp_r = plane + kRowWindowBytes / 4 + csf_row_skew(P.hp + ro - lane) + lane;
             const float* nm_r = ring + ((fm - 1) & 1) * kRingSlot + csf_row_skew(P.nm + ro - lane) + lane;
-            csf_mbar_wait(csf_s32(ctx + 6), (uint32_t)(CTX_STEP & 1));
+            bulk_mbar_wait(smem_addr(ctx + 6), (uint32_t)(CTX_STEP & 1));
             // control loads run kLook bins ahead of their use (software pipeline over the unrolled loop)
 #pragma unroll
             for (int q = 0; q < 17; ++q) {

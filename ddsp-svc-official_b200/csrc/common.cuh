@@ -41,6 +41,41 @@ __device__ __forceinline__ void slot_to_run(int64_t slot, int B, int R, int rem,
     }
 }
 
+// ---- bulk asynchronous copies global -> shared (cp.async.bulk: the TMA engine without a tensor map) -----------------
+// One lane issues a copy of a 16-byte-aligned range; completion is counted in bytes on an mbarrier the consumers wait on
+// (phase parity = number of completed uses & 1).  No register is held while the data is in flight and no lane spends
+// issue slots on it, which is what the instruction-bound FFT kernels need: the copies are started where the warp's
+// transpose plane falls idle (between the two passes of a transform, fft32.cuh) and land while the second pass runs.
+__device__ __forceinline__ uint32_t smem_addr(const volatile void* p) {
+    return (uint32_t)__cvta_generic_to_shared(const_cast<const void*>(p));
+}
+__device__ __forceinline__ void bulk_mbar_init(uint32_t bar) {         // one arrival (the issuing lane's expect_tx) per phase
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_mbar_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "BULK_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra BULK_DONE_%=;\n\t"
+        "bra BULK_WAIT_%=;\n\t"
+        "BULK_DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// generic-proxy accesses of the warp (made visible to the issuing lane by a __syncwarp) before async-proxy writes
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 // torch upsample_linear1d(align_corners=True) arithmetic for one sample (core.py:17):
 // fma(w0, x0, fl32(w1*x1)) with w1 = j/hop (exact for power-of-two hop), w0 = 1 - w1.
 __device__ __forceinline__ float lerp_torch(float x0, float x1, float w1) {

@@ -472,12 +472,15 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
             const uint64_t k64 = noise_key64(P.seed, (uint32_t)b0);
             ctx[3] = (int)((uint32_t)k64 + P.key_offset);
             ctx[5] = (int)(uint32_t)(k64 >> 32);
+            bulk_mbar_init(smem_addr(ctx + 6));          // ctx[6..7]: mbarrier of the audio copies into the transpose plane
         }
         __syncwarp();
     }
 #define CV_B ctx[0]
 #define CV_MBEGIN ctx[1]
 #define CV_MEND ctx[2]
+#define CV_BAR smem_addr(ctx + 6)                                                  // (recomputed where used: no register
+#define CV_SKEW ((int)((reinterpret_cast<uint64_t>(P.audio) & 15ull) >> 2))       //  is held across the transforms)
     const int F = P.F;
     const int64_t T = (int64_t)F * kHop;
     const int D = P.n_mag - 1;                          // L/2: delay compensation (core.py:177)
@@ -488,6 +491,22 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
     __syncwarp();
     if (P.run_len >= 4) __nanosleep((unsigned)(wid >> 2) * LTV_STAGGER_NS);   // de-phase the warps of a scheduler (see combsubfast.cuh)
     int rs = 0;                                          // ring start (logical sample 0 of the current frame)
+    // The frame's 1024 input samples (amode 0 / 1) arrive in the transpose plane by one bulk copy (common.cuh) that lane 0
+    // starts inside the INVERSE transform of the previous frame (before the loop for the run's first frame), where the
+    // plane falls idle; layout and alignment handling as in ltv_conv510_kernel.  (The 8 KB tap spectrum does not fit
+    // beside it and keeps its software-pipelined loads.)
+    const bool stage_audio = amode != 2;
+    auto start_audio = [&](int mm) {
+        const bool hA = mm >= 1, hB = mm < F;
+        const float* src = P.audio + (int64_t)CV_B * T + (int64_t)(hA ? mm - 1 : 0) * kHop;
+        const uint32_t bytes = (uint32_t)((hA ? 2048 : 0) + (hB ? 2048 : 0) + (CV_SKEW ? 16 : 0));
+        const uint32_t bar = CV_BAR;
+        fence_proxy_async_smem();
+        bulk_mbar_expect(bar, bytes);
+        bulk_copy_g2s(smem_addr(plane) + (hA ? 0 : 2048), reinterpret_cast<const void*>(reinterpret_cast<uint64_t>(src) & ~15ull),
+                      bytes, bar);
+    };
+    if (stage_audio && lane0) start_audio(CV_MBEGIN);
 
     Pts32 X;
     for (int m = CV_MBEGIN; m < CV_MEND; ++m) {
@@ -503,7 +522,8 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                 }
                 // z[n] = a[2n] + j a[2n+1], n = 32 n1 + lane < 512; a = bartlett * frame (core.py:218-222)
                 const bool vA = m >= 1, vB = m < F;
-                const float* src = P.audio + (int64_t)CV_B * T;
+                const float* src = plane + CV_SKEW;                     // the staged frame (see start_audio)
+                if (stage_audio) bulk_mbar_wait(CV_BAR, (uint32_t)((m - CV_MBEGIN) & 1));
                 const uint32_t key = (uint32_t)ctx[3], key2 = (uint32_t)ctx[5];
                 uint32_t stA = noise_seed(key, key2, (uint32_t)(m - 1), (uint32_t)lane);
                 uint32_t stB = noise_seed(key, key2, (uint32_t)m, (uint32_t)lane);
@@ -520,7 +540,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                             v0 = ok ? v0 : 0.0f;
                             v1 = ok ? v1 : 0.0f;
                         } else if (ok) {
-                            const float2 x = __ldg(reinterpret_cast<const float2*>(src + t0 + i));
+                            const float2 x = *reinterpret_cast<const float2*>(src + i);
                             v0 = x.x; v1 = x.y;
                             if (amode == 1) { v0 = fmaf(2.0f, v0, -1.0f); v1 = fmaf(2.0f, v1, -1.0f); }
                         }
@@ -530,9 +550,12 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                     DDSP_RE(X, brev5(n1)) = v0;
                     DDSP_IM(X, brev5(n1)) = v1;
                 }
+                if (stage_audio) __syncwarp();          // every lane has read its samples before the transform reuses the plane
             }
 
-            warp_fft1024(X, plane, tw4, lane);
+            warp_fft1024(X, plane, tw4, lane, [&] {
+                if (lane0 && phase == 1 && stage_audio && m + 1 < CV_MEND) start_audio(m + 1);
+            });
 
             if (phase == 0) {
                 // even/odd-domain product:  Zy = (Ea Eh + W1024^k Oa Oh) + j (Ea Oh + Oa Eh)
@@ -728,17 +751,40 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
             const uint64_t k64 = noise_key64(P.seed, (uint32_t)b0);
             ctx[3] = (int)((uint32_t)k64 + P.key_offset);
             ctx[5] = (int)(uint32_t)(k64 >> 32);
+            bulk_mbar_init(smem_addr(ctx + 6));          // ctx[6..7]: mbarrier of the bulk copies into the transpose plane
         }
         __syncwarp();
     }
     const int F = P.F;
     const int64_t T = (int64_t)F * kHop;
     constexpr int D = 255;                               // L/2: delay compensation (core.py:177)
+    // The transpose plane doubles as the landing zone of two bulk copies per frame (common.cuh), each issued by lane 0
+    // where the plane falls idle -- between the two passes of a transform:
+    //   audio  (amode 0 / 1): the frame's 1024 input samples, started inside the INVERSE transform of the previous frame
+    //          (before the loop for the run's first frame), consumed when the frame is built;
+    //   taps   : bins 0..512 of the frame's tap spectrum (4104 -> 4112 B), started inside the forward transform,
+    //          consumed by the spectral product.
+    // Barrier phase parity: with audio copies the uses alternate audio (0), taps (1); without, taps alone (frame & 1).
+    const bool stage_audio = amode != 2;
+    // frame m covers samples [512 (m-1), 512 (m+1)) of the clip; hop m-1 is absent for m = 0, hop m for m = F.  The
+    // window is laid out frame-relative (sample i of the frame at float `skew + i`), `skew` = the 16-byte misalignment
+    // of the audio pointer in floats (0 or 2: the ABI asks for 8-byte alignment).
+    auto start_audio = [&](int mm) {
+        const bool hA = mm >= 1, hB = mm < F;
+        const float* src = P.audio + (int64_t)CV_B * T + (int64_t)(hA ? mm - 1 : 0) * kHop;
+        const uint32_t bytes = (uint32_t)((hA ? 2048 : 0) + (hB ? 2048 : 0) + (CV_SKEW ? 16 : 0));
+        const uint32_t bar = CV_BAR;
+        fence_proxy_async_smem();
+        bulk_mbar_expect(bar, bytes);
+        bulk_copy_g2s(smem_addr(plane) + (hA ? 0 : 2048), reinterpret_cast<const void*>(reinterpret_cast<uint64_t>(src) & ~15ull),
+                      bytes, bar);
+    };
 
     for (int i = lane; i < kLtvRing; i += 32) ring[i] = 0.0f;
     __syncwarp();
     if (P.run_len >= 4) __nanosleep((unsigned)(wid >> 2) * LTV_STAGGER_NS);   // de-phase the warps of a scheduler (see combsubfast.cuh)
     int rs = 0;
+    if (stage_audio && lane == 0) start_audio(CV_MBEGIN);
 
     Pts32 X;
     for (int m = CV_MBEGIN; m < CV_MEND; ++m) {
@@ -746,16 +792,11 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
 #pragma unroll 1
         for (int phase = 0; phase < 2; ++phase) {
             if (phase == 0) {
-                const float2* zh = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2;
-                {   // pull this frame's tap spectrum (bins 0..512: 4 KB + one line) into L2 while the audio FFT runs
-                    const char* pz = reinterpret_cast<const char*>(zh) + 128 * lane;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pz));
-                    if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pz + 4096));
-                }
                 // z[n] = up[n] + j down[n], n = 32 n1 + lane < 512:
                 //   up[n] = x[t0 + n] * n/512, down[n] = x[t0 + 512 + n] * (512 - n)/512   (core.py:218-222)
                 const bool vA = m >= 1, vB = m < F;
-                const float* src = P.audio + (int64_t)CV_B * T + lane;
+                const float* src = plane + CV_SKEW + lane;              // the staged frame (see start_audio)
+                if (stage_audio) bulk_mbar_wait(CV_BAR, 0u);
                 const uint32_t key = (uint32_t)ctx[3], key2 = (uint32_t)ctx[5];
                 uint32_t stA = noise_seed(key, key2, (uint32_t)(m - 1), (uint32_t)lane);
                 uint32_t stB = noise_seed(key, key2, (uint32_t)m, (uint32_t)lane);
@@ -771,8 +812,8 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
                             v0 = vA ? v0 : 0.0f;
                             v1 = vB ? v1 : 0.0f;
                         } else {
-                            if (vA) v0 = __ldg(src + t0 + 32 * n1);
-                            if (vB) v1 = __ldg(src + t0 + kHop + 32 * n1);
+                            if (vA) v0 = src[32 * n1];
+                            if (vB) v1 = src[kHop + 32 * n1];
                             if (amode == 1) { v0 = vA ? fmaf(2.0f, v0, -1.0f) : 0.0f; v1 = vB ? fmaf(2.0f, v1, -1.0f) : 0.0f; }
                         }
                         v0 *= (float)n * (1.0f / 512.0f);
@@ -781,25 +822,31 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv510_kernel(const LtvPa
                     DDSP_RE(X, brev5(n1)) = v0;
                     DDSP_IM(X, brev5(n1)) = v1;
                 }
+                if (stage_audio) __syncwarp();          // every lane has read its samples before the transform reuses the plane
             }
 
-            warp_fft1024(X, plane, tw4, lane);
+            warp_fft1024(X, plane, tw4, lane, [&] {
+                if (lane != 0) return;
+                if (phase == 0) {                       // last IR repeated (core.py:228)
+                    const uint32_t bar = CV_BAR;
+                    fence_proxy_async_smem();
+                    bulk_mbar_expect(bar, 4112u);
+                    bulk_copy_g2s(smem_addr(plane), P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2, 4112u, bar);
+                } else if (stage_audio && m + 1 < CV_MEND) {
+                    start_audio(m + 1);
+                }
+            });
 
             if (phase == 0) {
                 // last IR repeated (core.py:228).  Only bins 0..512 of the Hermitian tap spectrum are stored:
                 // bin k = lane + 32 q >= 512 is read as conj(H[1024 - k]) (for k = 512 that is H[512] itself, real)
-                const float2* zlo = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2 + lane;
-                const float2* zhi = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2 + (1024 - lane);
-                constexpr int kLook = 8;
-                float2 hq[kLook];
-#pragma unroll
-                for (int q = 0; q < kLook; ++q) hq[q] = __ldg(zlo + 32 * q);
+                const float2* zlo = reinterpret_cast<const float2*>(plane) + lane;
+                const float2* zhi = reinterpret_cast<const float2*>(plane) + (1024 - lane);
+                bulk_mbar_wait(CV_BAR, stage_audio ? 1u : (uint32_t)((m - CV_MBEGIN) & 1));
                 float yr[32], yi[32];
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
-                    const float2 h = hq[q % kLook];
-                    if (q + kLook < 32)
-                        hq[q % kLook] = (q + kLook < 16) ? __ldg(zlo + 32 * (q + kLook)) : __ldg(zhi - 32 * (q + kLook));
+                    const float2 h = (q < 16) ? zlo[32 * q] : zhi[-32 * q];
                     const float ar = DDSP_RE(X, q), ai = DDSP_IM(X, q);
                     if (q < 16) {
                         yr[q] = ar * h.x - ai * h.y;
