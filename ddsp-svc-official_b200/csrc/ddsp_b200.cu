@@ -55,7 +55,9 @@ int sm_count() {
 
 using LtvKernel = void (*)(const ddsp::LtvParams);
 // Specialised instantiations for the combinations the synthesizers use + generic fallbacks.
-LtvKernel ltv_ir_select(int enc, int win) {
+LtvKernel ltv_ir_select(int enc, int win, int n_mag = 0) {
+    if (enc == DDSP_B200_MAG_EXP && win == DDSP_B200_WINDOW_DYNAMIC && n_mag == 512)      // CombSub's harmonic filter (vocoder.py:541)
+        return ddsp::ltv_ir_kernel<DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_DYNAMIC, 512>;
     if (enc == DDSP_B200_MAG_ALLPASS_TANH && win == DDSP_B200_WINDOW_NONE)
         return ddsp::ltv_ir_kernel<DDSP_B200_MAG_ALLPASS_TANH, DDSP_B200_WINDOW_NONE>;
     if (enc == DDSP_B200_MAG_EXP && win == DDSP_B200_WINDOW_DYNAMIC)
@@ -130,7 +132,8 @@ int ensure_device_ready(cudaStream_t st, const float** tables, int level = 2) {
         g_device_level[dev].store(1, std::memory_order_release);
     }
     if (have < level) {
-        for (LtvKernel fn : {ltv_ir_select(DDSP_B200_MAG_ALLPASS_TANH, DDSP_B200_WINDOW_NONE),
+        for (LtvKernel fn : {ltv_ir_select(DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_DYNAMIC, 512),
+                             ltv_ir_select(DDSP_B200_MAG_ALLPASS_TANH, DDSP_B200_WINDOW_NONE),
                              ltv_ir_select(DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_DYNAMIC),
                              ltv_ir_select(DDSP_B200_MAG_EXP, DDSP_B200_WINDOW_HANN), ltv_ir_select(-1, -1)})
             CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ddsp::kLtvIrSmemBytes));
@@ -482,7 +485,7 @@ unsigned ltv_ir_grid(int B, int F) {
 
 // 1) impulse responses -> tap spectra (frames independent)
 int launch_ltv_ir(const ddsp::LtvParams& P, cudaStream_t st) {
-    ltv_ir_select(P.encoding, P.window_mode)<<<ltv_ir_grid(P.B, P.F), ddsp::kLtvThreads, ddsp::kLtvIrSmemBytes, st>>>(P);
+    ltv_ir_select(P.encoding, P.window_mode, P.n_mag)<<<ltv_ir_grid(P.B, P.F), ddsp::kLtvThreads, ddsp::kLtvIrSmemBytes, st>>>(P);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }

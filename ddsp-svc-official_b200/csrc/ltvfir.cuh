@@ -82,7 +82,7 @@ __device__ __forceinline__ float bartlett1024(int i) {      // torch.bartlett_wi
 // Kernel 1: magnitudes -> windowed causal impulse response -> its spectrum.  One warp per frame.
 // ENC / WIN >= 0 fix the magnitude encoding / window mode at compile time (-1: read from P).
 // ---------------------------------------------------------------------------------------------
-template <int ENC, int WIN>
+template <int ENC, int WIN, int NMAG = 0>     // NMAG > 0 fixes n_mag at compile time (drops the per-element range tests)
 __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams P) {
     const int enc = ENC >= 0 ? ENC : P.encoding;
     const int win_mode = WIN >= 0 ? WIN : P.window_mode;
@@ -101,9 +101,9 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_ir_kernel(const LtvParams 
         for (int e = threadIdx.x; e < kLtvChirpBytes / 16; e += kLtvThreads) cdst[e] = __ldg(csrc + e);
         __syncthreads();
     }
-#define IR_NMAG (P.n_mag)
-#define IR_L (2 * (P.n_mag - 1))
-#define IR_D (P.n_mag - 1)
+#define IR_NMAG (NMAG > 0 ? NMAG : P.n_mag)
+#define IR_L (2 * (IR_NMAG - 1))
+#define IR_D (IR_NMAG - 1)
     const int64_t n_frames = (int64_t)P.B * P.F;
 
     __nanosleep((unsigned)(wid >> 2) * LTV_STAGGER_NS);
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
 #define CV_SKEW ((int)((reinterpret_cast<uint64_t>(P.audio) & 15ull) >> 2))       //  is held across the transforms)
     const int F = P.F;
     const int64_t T = (int64_t)F * kHop;
-    const int D = P.n_mag - 1;                          // L/2: delay compensation (core.py:177)
+    constexpr int D = 511;                              // L/2 (this kernel serves n_mag = 512 only): delay compensation (core.py:177)
     const int partner = (32 - lane) & 31;
     const bool lane0 = lane == 0;
 
@@ -508,12 +508,19 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
     };
     if (stage_audio && lane0) start_audio(CV_MBEGIN);
 
+    // The frame counter lives in the per-warp shared-memory context (read where used), like the step counter of
+    // combsubfast_kernel: ptxas otherwise spills it and the addresses derived from it to local memory, whose reloads miss
+    // the tiny L1 left beside the shared memory.
+#define CV_M ctx[4]
+    if (lane0) CV_M = CV_MBEGIN;
+    __syncwarp();
     Pts32 X;
-    for (int m = CV_MBEGIN; m < CV_MEND; ++m) {
-        const int64_t t0 = (int64_t)(m - 1) * kHop;      // first input sample of the frame
+#pragma unroll 1
+    for (;;) {
 #pragma unroll 1
         for (int phase = 0; phase < 2; ++phase) {
             if (phase == 0) {
+                const int m = CV_M;
                 const float2* zh = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2;
                 {   // pull this frame's tap spectrum (8 KB) into L2 while the audio FFT runs
                     const char* pz = reinterpret_cast<const char*>(zh) + 128 * lane;
@@ -554,12 +561,12 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
             }
 
             warp_fft1024(X, plane, tw4, lane, [&] {
-                if (lane0 && phase == 1 && stage_audio && m + 1 < CV_MEND) start_audio(m + 1);
+                if (lane0 && phase == 1 && stage_audio && CV_M + 1 < CV_MEND) start_audio(CV_M + 1);
             });
 
             if (phase == 0) {
                 // even/odd-domain product:  Zy = (Ea Eh + W1024^k Oa Oh) + j (Ea Oh + Oa Eh)
-                const float2* zh = P.spec + ((int64_t)CV_B * F + min(m, F - 1)) * kLtvSpecFloat2;   // last IR repeated (core.py:228)
+                const float2* zh = P.spec + ((int64_t)CV_B * F + min(CV_M, F - 1)) * kLtvSpecFloat2;   // last IR repeated (core.py:228)
                 const float2 wl = make_float2(tw4[lane].y, tw4[lane].w);        // W1024^lane = (cos, -sin)
                 float zr[32], zi[32];
                 // Ey and Oy are spectra of REAL sequences (the even / odd output samples), so
@@ -634,10 +641,10 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                 }
                 __syncwarp();
                 // retire the first 512 samples of the window: output index t = 512(m-1) - D + j  (core.py:238,177-182)
-                const int m_begin = CV_MBEGIN;
+                const int m = CV_M, m_begin = CV_MBEGIN;
                 const bool complete = (m - 3 >= m_begin) || (m_begin == 0);
                 float* ob = P.out + (int64_t)CV_B * T;
-                const int64_t tb = t0 - D;
+                const int64_t tb = (int64_t)(m - 1) * kHop - D;       // frame m starts at input sample 512 (m - 1)
                 const float* blk0 = ring + rs + lane;
                 if (complete && tb >= 0 && tb + kHop <= T) {       // the common case: a whole finished hop inside the clip
                     float* dst = ob + tb + lane;
@@ -658,6 +665,11 @@ __global__ void __launch_bounds__(kLtvThreads, 1) ltv_conv_kernel(const LtvParam
                 rs = (rs + kHop) & (kLtvRing - 1);
             }
         }
+        const int m_next = CV_M + 1;
+        if (m_next >= CV_MEND) break;
+        __syncwarp();
+        if (lane0) CV_M = m_next;
+        __syncwarp();
     }
     // flush the three remaining hops of the ring
     {
