@@ -609,13 +609,7 @@ __global__ void __launch_bounds__(256) glu_dwconv_silu_kernel(const float* __res
 // producing GEMM, csrc/gemm_attn.cuh EPI_GLU).  A thread owns one channel and kDw2Run consecutive frames: the 31 taps and
 // a sliding window of inputs stay in registers, every input is loaded once per thread (lanes = consecutive channels:
 // 128-byte coalesced rows; the 30-frame halo of neighbouring runs comes out of L1 / L2).
-#ifndef DW2_RUN
-#define DW2_RUN 32
-#endif
-#ifndef DW2_PREFETCH
-#define DW2_PREFETCH 0
-#endif
-constexpr int kDw2Run = DW2_RUN;
+constexpr int kDw2Run = 32;
 
 __global__ void __launch_bounds__(256) dwconv_silu_kernel(const float* __restrict__ g, const float* __restrict__ w,
                                                           const float* __restrict__ bias, float* __restrict__ out, int T, int C) {
@@ -629,24 +623,10 @@ __global__ void __launch_bounds__(256) dwconv_silu_kernel(const float* __restric
 #pragma unroll
     for (int o = 0; o < kDw2Run; ++o) acc[o] = bs;
     const float* gb = g + (int64_t)b * T * C + c;
-#if DW2_PREFETCH
-    // all loads of the run in flight before the first use: the kernel is bound by load latency, not by its 31 FMAs per
-    // output (one exposed round trip per thread instead of one per input frame)
-    float v[kDw2Run + kDwTaps - 1];
 #pragma unroll
     for (int i = 0; i < kDw2Run + kDwTaps - 1; ++i) {
-        const int t = t0 + i - kDwPad;
-        v[i] = (t >= 0 && t < T) ? __ldg(gb + (int64_t)t * C) : 0.0f;
-    }
-#endif
-#pragma unroll
-    for (int i = 0; i < kDw2Run + kDwTaps - 1; ++i) {
-#if DW2_PREFETCH
-        const float val = v[i];
-#else
         const int t = t0 + i - kDwPad;
         const float val = (t >= 0 && t < T) ? __ldg(gb + (int64_t)t * C) : 0.0f;
-#endif
 #pragma unroll
         for (int o = 0; o < kDw2Run; ++o) {
             const int j = i - o;

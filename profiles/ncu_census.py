@@ -62,7 +62,7 @@ def main():
     sel = [(n, b) for n, b in zip(names, blocks) if pat is None or pat.search(n)]
     for idx, (name, b) in enumerate(sel):
         iS, iE = shdr.index('Source'), shdr.index('Instructions Executed')
-        slots = inst = 0
+        slots = inst = packed = 0
         for r in b:
             m = re.match(r'\s*(?:@!?U?P\d+\s+)?([A-Z0-9_]+)', r[iS])
             op = m.group(1) if m else '?'
@@ -70,25 +70,31 @@ def main():
             inst += n
             if op in ('FFMA2', 'FMUL2', 'FADD2'):
                 slots += 2 * n
+                packed += n
             elif op in ('FFMA', 'FMUL', 'FADD', 'IMAD'):
                 slots += n
         short = re.sub(r'[<(].*', '', name).replace('void ', '').replace('ddsp::', '')
         k = kernels[idx] if idx < len(kernels) else {}      # raw page and source page list the launches in the same order
         cur = rec['kernels'].get(short)
         if cur is None:
+            # dispatch cycles: a packed fp32x2 instruction holds the scheduler's dispatch port for two cycles
+            # (profiles/ubench/ffma2_issue.cu), every other instruction for one
             rec['kernels'][short] = {'launches': 1, 'instructions_per_unit': inst / units, 'fma_pipe_slots_per_unit': slots / units,
+                                     'dispatch_cycles_per_unit': (inst + packed) / units,
                                      'dram_bytes_per_launch': k.get('dram_bytes'), 'ncu_time_us': k.get('time_us'),
                                      'issue_active_pct': k.get('issue_active_pct')}
         else:       # the same kernel launched again inside the step (e.g. the two L = 510 convolutions): totals per step
             cur['launches'] += 1
             cur['instructions_per_unit'] += inst / units
             cur['fma_pipe_slots_per_unit'] += slots / units
+            cur['dispatch_cycles_per_unit'] += (inst + packed) / units
             cur['dram_bytes_per_launch'] = (cur['dram_bytes_per_launch'] or 0.0) + (k.get('dram_bytes') or 0.0)
             cur['ncu_time_us'] = (cur['ncu_time_us'] or 0.0) + (k.get('time_us') or 0.0)
         tot_dram += k.get('dram_bytes') or 0.0
     rec['dram_bytes_per_launch'] = tot_dram
     rec['instructions_per_unit'] = sum(v['instructions_per_unit'] for v in rec['kernels'].values())
     rec['fma_pipe_slots_per_unit'] = sum(v['fma_pipe_slots_per_unit'] for v in rec['kernels'].values())
+    rec['dispatch_cycles_per_unit'] = sum(v['dispatch_cycles_per_unit'] for v in rec['kernels'].values())
     rec['ncu_time_us'] = sum(v['ncu_time_us'] or 0.0 for v in rec['kernels'].values())
     if model == 'combsubfast' and rec['kernels']:
         k0 = next(iter(rec['kernels'].values()))
