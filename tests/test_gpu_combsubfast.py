@@ -73,6 +73,26 @@ def test_contiguous_and_strided_controls_agree():
     assert np.array_equal(sig_views, sig_sep)
 
 
+def test_control_rows_at_every_alignment():
+    """The kernel copies a filter row as the 16-byte-aligned window around it (cp.async.bulk): three separately
+    allocated control tensors whose rows start 4, 8 and 12 bytes past a 16-byte boundary (row length 2052 B, so every
+    row of each tensor has a different skew as well) must give the bits of the packed (B,F,1539) layout."""
+    d = make_inputs(3, 41, 1539, seed=17, zero_f0_fraction=0.1)
+    packed = dev(d['ctrl'])
+    f0 = dev(d['f0_frames'])[..., None]
+    U = dev(d['U'])
+    pf, prefix, _ = core.phase_stage(f0, 512, 44100)
+    ref = core.combsubfast_stage(*torch.split(packed, 513, dim=-1), f0, prefix, 512, 44100, noise_u=U)
+    views = []
+    for k, off in enumerate((1, 2, 3)):
+        flat = torch.zeros(3 * 41 * 513 + 4, device='cuda')
+        v = flat[off:off + 3 * 41 * 513].view(3, 41, 513)
+        v.copy_(packed[..., 513 * k:513 * (k + 1)])
+        assert v.data_ptr() % 16 == 4 * off and v.is_contiguous()
+        views.append(v)
+    assert torch.equal(ref, core.combsubfast_stage(*views, f0, prefix, 512, 44100, noise_u=U))
+
+
 def test_batch_and_run_partition_invariance():
     """A clip's waveform must not depend on what else is in the batch nor on how frame pairs are
     partitioned into warp runs (different B -> different run length): bitwise identical."""

@@ -84,6 +84,22 @@ def test_frequency_filter_is_linear_and_deterministic():
     assert torch.equal(y1, core.frequency_filter(dev(a1), mags))        # atomics at run seams: two addends -> bitwise stable
 
 
+@pytest.mark.parametrize('n_mag', [256, 512])
+def test_frequency_filter_audio_eight_byte_aligned(n_mag):
+    """The convolution kernels stage a frame's input samples by bulk copies of the 16-byte-aligned window around them:
+    audio that is only 8-byte aligned (the ABI's requirement) takes the skewed path and must give the same bits."""
+    rng = np.random.default_rng(11)
+    B, F = 3, 37
+    a = (rng.random((B, F * 512)) * 2 - 1).astype(np.float32)
+    mags = dev(np.exp(0.57 * rng.standard_normal((B, F, n_mag))).astype(np.float32))
+    aligned = dev(a)
+    flat = torch.zeros(B * F * 512 + 2, device='cuda')
+    skewed = flat[2:].view(B, F * 512)                      # contiguous, data pointer 8 bytes past a 16-byte boundary
+    skewed.copy_(aligned)
+    assert aligned.data_ptr() % 16 == 0 and skewed.data_ptr() % 16 == 8 and skewed.is_contiguous()
+    assert torch.equal(core.frequency_filter(aligned, mags), core.frequency_filter(skewed, mags))
+
+
 def test_frequency_filter_batch_mismatch_raises():
     with pytest.raises(ValueError):
         core.frequency_filter(torch.zeros(2, 1024).cuda(), torch.zeros(3, 2, 256).cuda())
