@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(512, 1) k(float2* out, int iters, float s) {
     float g[8], f2[8];
     float2 b2[8];
     for (int i = 0; i < 4; ++i) w[i] = (unsigned)(s * 1000.f) + i * threadIdx.x;
+    float2 q2[8];                                   // opaque register pairs (loaded, so that nothing folds into immediates)
+    for (int i = 0; i < 8; ++i) q2[i] = out[(threadIdx.x * 8 + i) & 1023];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a[i] = make_float2(threadIdx.x + i, i); f[i] = threadIdx.x * 0.5f + i; u[i] = threadIdx.x + i; v[i] = 3 * threadIdx.x + i; g[i] = f[i] * 0.3f; f2[i] = f[i] * 0.7f; b2[i] = make_float2(1.0f + 1e-6f * i * s, 1.0f - 1e-6f * threadIdx.x * s); }
     const float2 m = make_float2(s, s * 0.5f), c = make_float2(0.25f, 0.125f);
@@ -34,6 +36,13 @@ __global__ void __launch_bounds__(512, 1) k(float2* out, int iters, float s) {
                 if (MODE == 15) { f[i] = fmaf(f[i], g[i], g[(i + 3) & 7]); f2[i] = fmaf(f2[i], g[(i + 1) & 7], g[(i + 5) & 7]); }   // 16 FFMA, three register operands
                 if (MODE == 16) { a[i] = __ffma2_rn(a[i], b2[i], b2[(i + 3) & 7]); }                                   // 8 FFMA2, three register-pair operands
                 if (MODE == 17) { a[i] = __ffma2_rn(a[i], make_float2(1.0001f, 1.0001f), make_float2(0.25f, 0.25f)); }   // 8 FFMA2, broadcast immediates
+                if (MODE == 20) { a[i] = __fadd2_rn(a[i], q2[i]); }                                               // 8 FADD2, two register pairs
+                if (MODE == 21) { a[i] = __ffma2_rn(a[i], q2[i], make_float2(0.25f, 0.25f)); }                    // 8 FFMA2, two register pairs + immediate
+                if (MODE == 22) { a[i] = __ffma2_rn(a[i], q2[i], q2[(i + 3) & 7]); }                              // 8 FFMA2, three register pairs
+                if (MODE == 23) { f[i] = fmaf(f[i], q2[i].x, q2[(i + 3) & 7].y); g[i] = fmaf(g[i], q2[i].y, q2[(i + 5) & 7].x); }   // 16 FFMA, three registers
+                if (MODE == 24) { a[i] = __fmul2_rn(a[i], q2[i]); }                                               // 8 FMUL2, two register pairs
+                if (MODE == 18) { f[i] = fmaf(f[i], g[i], f2[i]); g[i] = fmaf(g[i], f2[i], f[i]); }          // 16 FFMA, three live register operands each
+                if (MODE == 19) { a[i] = __ffma2_rn(a[i], b2[i], a[(i + 1) & 7]); }                               // 8 FFMA2, three live register-pair operands
                 if (MODE == 5) { a[i] = __ffma2_rn(a[i], m, c); u[i] = u[i] + w[i & 3]; v[i] = v[i] + w[(i + 1) & 3]; }   // 8 FFMA2 + 16 IADD
                 if (MODE == 6) { u[i] = u[i] + w[i & 3]; v[i] = v[i] + w[(i + 1) & 3]; }                        // 16 IADD
                 if (MODE == 7) { f[i] = fmaf(f[i], s, 0.25f); g[i] = fmaf(g[i], s, 0.5f); u[i] = u[i] + w[i & 3]; v[i] = v[i] + w[(i + 1) & 3]; }   // 16 FFMA + 16 IADD
@@ -52,6 +61,7 @@ template <int MODE>
 void run(const char* name, int per_iter_note) {
     float2* out;
     cudaMalloc(&out, 148 * 512 * sizeof(float2));
+    cudaMemset(out, 0, 148 * 512 * sizeof(float2));
     const int iters = 20000;
     k<MODE><<<148, 512>>>(out, 100, 1.0001f);
     cudaEvent_t e0, e1;
@@ -82,6 +92,13 @@ int main() {
     run<12>("8 FFMA2 + 16 LOP3", 24);
     run<13>("16 LOP3", 16);
     run<14>("16 FFMA + 16 LOP3", 32);
+    run<20>("8 FADD2 (2 register pairs)", 8);
+    run<21>("8 FFMA2 (2 register pairs + immediate)", 8);
+    run<22>("8 FFMA2 (3 register pairs)", 8);
+    run<23>("16 FFMA (3 registers)", 16);
+    run<24>("8 FMUL2 (2 register pairs)", 8);
+    run<18>("16 FFMA (3 live registers, rotating roles)", 16);
+    run<19>("8 FFMA2 (3 live register pairs)", 8);
     run<15>("16 FFMA (3 registers)", 16);
     run<16>("8 FFMA2 (3 register pairs)", 8);
     run<17>("8 FFMA2 (broadcast immediates)", 8);
