@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kOscThreads) sins_osc_kernel(const float* __re
                                                        int64_t fF, int F, float fmax,
                                                        const float* __restrict__ phase_full,
                                                        float* __restrict__ out) {
-    __shared__ float4 amps[kSinsMaxHarm];      // (A0, A0, dA, dA) per harmonic
+    __shared__ float2 amps[kSinsMaxHarm];      // (A0, dA) per harmonic: broadcast operands of the packed interpolation
     __shared__ int k_live;                      // harmonics below Nyquist in at least one of the hop's two frames
     if (threadIdx.x == 0) k_live = 0;
     __syncthreads();
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kOscThreads) sins_osc_kernel(const float* __re
         const float A0 = __fmul_rn(__fmul_rn(expf(__ldg(ra + k)), 0.0078125f), ma);         // exp()/128 then mask
         const float A1 = __fmul_rn(__fmul_rn(expf(__ldg(rb + k)), 0.0078125f), mb);
         const float dA = A1 - A0;
-        amps[k] = make_float4(A0, A0, dA, dA);
+        amps[k] = make_float2(A0, dA);
 #if SINS_SKIP_MASKED
         if (ma > 0.5f || mb > 0.5f) atomicMax(&k_live, k + 1);
 #endif
@@ -125,13 +125,15 @@ __global__ void __launch_bounds__(kOscThreads) sins_osc_kernel(const float* __re
     }
 #pragma unroll 4
     for (int k = 0; k < n_loop; k += 2) {        // k, k+1 are harmonics k+1 (odd) and k+2 (even); n_harm is even
-        const float4 a = amps[k], a2 = amps[k + 1];
+        // (A0, dA) enter as single-register broadcast operands: a packed FMA with three register-PAIR operands takes
+        // 3 cycles of register reads instead of 2 (profiles/ubench/ffma2_issue.cu)
+        const float4 aa = *reinterpret_cast<const float4*>(&amps[k]);       // harmonics k+1, k+2
 #pragma unroll
         for (int p = 0; p < kOscPairs; ++p) {
-            acc_o[p] = fma2(fma2(lam[p], make_float2(a.z, a.w), make_float2(a.x, a.y)), sk[p], acc_o[p]);
+            acc_o[p] = fma2(fma2(lam[p], bc2(aa.y), bc2(aa.x)), sk[p], acc_o[p]);
             dk[p] = fma2(dl[p], sk[p], dk[p]);
             sk[p] = add2(sk[p], dk[p]);
-            acc_e[p] = fma2(fma2(lam[p], make_float2(a2.z, a2.w), make_float2(a2.x, a2.y)), sk[p], acc_e[p]);
+            acc_e[p] = fma2(fma2(lam[p], bc2(aa.w), bc2(aa.z)), sk[p], acc_e[p]);
             dk[p] = fma2(dl[p], sk[p], dk[p]);
             sk[p] = add2(sk[p], dk[p]);
         }
