@@ -65,3 +65,25 @@ def test_two_rank_gloo_sharding_matches_single_process():
     for idx, sig in gathered:
         out[idx] = sig
     assert np.array_equal(out, ref)          # sharding clips changes nothing: clips are independent
+
+
+def test_host_placement_helpers(tmp_path):
+    """sharding.near_gpu: cpulist parsing, sysfs lookup, affinity restored on exit, no-op without an answer."""
+    import os
+    assert sharding.parse_cpulist('0-3,8,10-11\n') == [0, 1, 2, 3, 8, 10, 11]
+    assert sharding.parse_cpulist('') == []
+    before = os.sched_getaffinity(0)
+    dev = tmp_path / '0000:1b:00.0'
+    dev.mkdir()
+    first = min(before)
+    (dev / 'numa_node').write_text('-1\n')
+    (dev / 'local_cpulist').write_text('%d\n' % first)
+    assert sharding.gpu_locality('0000:1B:00.0', str(tmp_path)) == (None, [first])
+    with sharding.near_gpu(pci_bus_id='0000:1b:00.0', sysfs=str(tmp_path)) as info:
+        assert os.sched_getaffinity(0) == {first}
+        assert info['cpus'] == 1 and info['bound'] == (before != {first})
+    assert os.sched_getaffinity(0) == before
+    with sharding.near_gpu(pci_bus_id='0000:ff:00.0', sysfs=str(tmp_path)) as info:      # unknown device: nothing changes
+        assert os.sched_getaffinity(0) == before and not info['bound']
+    buf = np.ones(1 << 16, np.float32)
+    assert sharding.node_of_address(buf.ctypes.data) in (None, 0, 1, 2, 3, 4, 5, 6, 7)
