@@ -199,6 +199,22 @@ def phase_stage_stream(f0_frames, block_size, sampling_rate, carry=None, initial
     return phase_frames, prefix
 
 
+def combsubfast_synth(harmonic_magnitude, harmonic_phase, noise_magnitude, f0_frames, block_size, sampling_rate,
+                      initial_phase=None, noise_u=None, seed=0, window=None, seed_device=None):
+    """Stage A + stage B of CombSubFast (vocoder.py:449-451, 455-492) in one operator of the extension host, for callers
+    whose control rows do not depend on the phase (rows from outside the module: a streaming plugin, the benchmarks).
+    Returns (signal (B,T), phase_frames (B,F), prefix (B,F) fp64) -- the same tensors as `phase_stage` followed by
+    `combsubfast_stage`."""
+    ops = _torchext.ops()
+    if ops is None:
+        pf, prefix, _ = phase_stage(f0_frames, block_size, sampling_rate, initial_phase)
+        return combsubfast_stage(harmonic_magnitude, harmonic_phase, noise_magnitude, f0_frames, prefix, block_size,
+                                 sampling_rate, noise_u=noise_u, seed=seed, window=window, seed_device=seed_device), pf, prefix
+    ip = None if initial_phase is None else torch.as_tensor(initial_phase, dtype=torch.float32, device=f0_frames.device)
+    return _op(ops.combsubfast_ab, harmonic_magnitude, harmonic_phase, noise_magnitude, f0_frames, int(block_size),
+               float(sampling_rate), ip, None, noise_u, int(seed) % _TWO62, window, seed_device, 0)
+
+
 def _common_views(tensors, names):
     """Control tensors arrive as non-contiguous `torch.split` views of one (B,F,sumK) tensor
     (unit2control.py:10-20).  Pass them through untouched when they share (batch,row) strides and

@@ -144,6 +144,65 @@ Tensor combsubfast(const Tensor& harmonic_magnitude, const Tensor& harmonic_phas
     return signal;
 }
 
+// Stage A + stage B of CombSubFast in ONE operator, for callers whose control rows do not depend on the phase (rows that
+// come from outside, a streaming plugin): one dispatcher crossing and no Python between the two stages.
+// Returns (signal, phase_frames, prefix).
+std::tuple<Tensor, Tensor, Tensor> combsubfast_ab(const Tensor& harmonic_magnitude, const Tensor& harmonic_phase,
+                                                  const Tensor& noise_magnitude, const Tensor& f0_frames, int64_t hop,
+                                                  double sr, const c10::optional<Tensor>& initial_phase,
+                                                  const c10::optional<Tensor>& carry, const c10::optional<Tensor>& noise_u,
+                                                  int64_t seed, const c10::optional<Tensor>& window,
+                                                  const c10::optional<Tensor>& seed_device, int64_t hop_offset) {
+    auto [phase_frames, prefix, unused] = phase(f0_frames, hop, sr, initial_phase, true, false, carry);
+    (void)unused;
+    Tensor signal = combsubfast(harmonic_magnitude, harmonic_phase, noise_magnitude, f0_frames, prefix, hop, sr, noise_u, seed,
+                                window, seed_device, hop_offset, c10::nullopt);
+    return {signal, phase_frames, prefix};
+}
+
+// One block of a carried-state CombSubFast stream (streaming.CombSubFastStream.push) in one operator:
+//   f0_buf (B,cap), rows_buf (B,cap,3K): the stream's linear buffers; frames [end-t, end) are the tail kept from the
+//   previous block.  The k new frames are copied behind the tail, stage A continues from `carry` over the window
+//   [end-t, end+k), stage B synthesises the window with the noise hop index `hop_offset`.
+// Returns (signal of the window (B, (t+k)*hop), phase_frames (B,t+k), prefix (B,t+k)).
+std::tuple<Tensor, Tensor, Tensor> csf_stream_push(Tensor f0_buf, Tensor rows_buf, const Tensor& f0_new,
+                                                   const Tensor& harmonic_magnitude, const Tensor& harmonic_phase,
+                                                   const Tensor& noise_magnitude, int64_t end, int64_t t, int64_t hop,
+                                                   double sr, const c10::optional<Tensor>& initial_phase,
+                                                   const c10::optional<Tensor>& carry, int64_t seed,
+                                                   const c10::optional<Tensor>& window, int64_t hop_offset) {
+    Tensor f0n = f0_2d(f0_new);
+    const int64_t B = f0n.size(0), k = f0n.size(1), K = hop + 1;
+    TORCH_CHECK_VALUE(k >= 1, "a push needs at least one new frame");
+    TORCH_CHECK_VALUE(f0_buf.dim() == 2 && rows_buf.dim() == 3 && f0_buf.size(0) == B && rows_buf.size(0) == B &&
+                          rows_buf.size(2) == 3 * K && f0_buf.size(1) == rows_buf.size(1) && end + k <= f0_buf.size(1) &&
+                          t >= 0 && t <= end,
+                      "stream buffers do not fit the block (B, cap) / (B, cap, 3*(block_size+1))");
+    const Tensor* rows[3] = {&harmonic_magnitude, &harmonic_phase, &noise_magnitude};
+    for (const Tensor* r : rows) {
+        need_f32(*r, "control rows");
+        TORCH_CHECK_VALUE(r->dim() == 3 && r->size(0) == B && r->size(1) == k && r->size(2) == K,
+                          "control rows must be (B, k, block_size + 1)");
+    }
+    c10::cuda::CUDAGuard guard(f0n.device());
+    f0_buf.narrow(1, end, k).copy_(f0n);
+    Tensor dst = rows_buf.narrow(1, end, k);
+    const Tensor &hm = harmonic_magnitude, &hp = harmonic_phase, &nm = noise_magnitude;
+    if (hm.stride(2) == 1 && hm.strides() == hp.strides() && hm.strides() == nm.strides() &&
+        hp.data_ptr<float>() == hm.data_ptr<float>() + K && nm.data_ptr<float>() == hp.data_ptr<float>() + K) {
+        // the split views of one (B,k,3K) tensor: one copy
+        dst.copy_(hm.as_strided({B, k, 3 * K}, hm.strides()));
+    } else {
+        for (int i = 0; i < 3; ++i) dst.narrow(2, i * K, K).copy_(*rows[i]);
+    }
+    Tensor f0_win = f0_buf.narrow(1, end - t, t + k), rows_win = rows_buf.narrow(1, end - t, t + k);
+    auto [phase_frames, prefix, unused] = phase(f0_win, hop, sr, carry.has_value() ? c10::nullopt : initial_phase, true, false, carry);
+    (void)unused;
+    Tensor signal = combsubfast(rows_win.narrow(2, 0, K), rows_win.narrow(2, K, K), rows_win.narrow(2, 2 * K, K), f0_win, prefix,
+                                hop, sr, c10::nullopt, seed, window, c10::nullopt, hop_offset, c10::nullopt);
+    return {signal, phase_frames, prefix};
+}
+
 std::tuple<Tensor, Tensor, Tensor> filter_model(bool is_sins, const Tensor& c0_, const Tensor& c1_, const Tensor& c2_,
                                                 const Tensor& f0_frames, const Tensor& aux, int64_t hop, double sr,
                                                 const c10::optional<Tensor>& noise_u, int64_t seed) {
@@ -206,6 +265,13 @@ TORCH_LIBRARY(ddsp_b200, m) {
     m.def("combsubfast(Tensor harmonic_magnitude, Tensor harmonic_phase, Tensor noise_magnitude, Tensor f0_frames, "
           "Tensor prefix, int block_size, float sampling_rate, Tensor? noise_u=None, int seed=0, Tensor? window=None, "
           "Tensor? seed_device=None, int hop_offset=0, Tensor? out=None) -> Tensor");
+    m.def("combsubfast_ab(Tensor harmonic_magnitude, Tensor harmonic_phase, Tensor noise_magnitude, Tensor f0_frames, "
+          "int block_size, float sampling_rate, Tensor? initial_phase=None, Tensor? carry=None, Tensor? noise_u=None, "
+          "int seed=0, Tensor? window=None, Tensor? seed_device=None, int hop_offset=0) -> (Tensor, Tensor, Tensor)");
+    m.def("csf_stream_push(Tensor(a!) f0_buf, Tensor(b!) rows_buf, Tensor f0_new, Tensor harmonic_magnitude, "
+          "Tensor harmonic_phase, Tensor noise_magnitude, int end, int tail, int block_size, float sampling_rate, "
+          "Tensor? initial_phase=None, Tensor? carry=None, int seed=0, Tensor? window=None, int hop_offset=0) "
+          "-> (Tensor, Tensor, Tensor)");
     m.def("combsub(Tensor group_delay, Tensor harmonic_magnitude, Tensor noise_magnitude, Tensor f0_frames, Tensor prefix, "
           "int block_size, float sampling_rate, Tensor? noise_u=None, int seed=0) -> (Tensor, Tensor, Tensor)");
     m.def("sins(Tensor amplitudes, Tensor group_delay, Tensor noise_magnitude, Tensor f0_frames, Tensor phase_full, "
@@ -216,6 +282,8 @@ TORCH_LIBRARY(ddsp_b200, m) {
 TORCH_LIBRARY_IMPL(ddsp_b200, CUDA, m) {
     m.impl("phase", &phase);
     m.impl("combsubfast", &combsubfast);
+    m.impl("combsubfast_ab", &combsubfast_ab);
+    m.impl("csf_stream_push", &csf_stream_push);
     m.impl("combsub", &combsub);
     m.impl("sins", &sins);
 }

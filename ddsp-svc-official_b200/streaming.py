@@ -155,8 +155,40 @@ class CombSubFastStream:
         return out
 
     def push(self, harmonic_magnitude, harmonic_phase, noise_magnitude, f0_new, noise_u=None):
-        self.begin(f0_new)
-        return self.finish(harmonic_magnitude, harmonic_phase, noise_magnitude, noise_u=noise_u)
+        ops = core._torchext.ops()
+        fast = ops is not None and noise_u is None and self._noise_tail is None and self._pending is None and all(
+            isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32
+            for x in (f0_new, harmonic_magnitude, harmonic_phase, noise_magnitude))
+        if not fast:
+            self.begin(f0_new)
+            return self.finish(harmonic_magnitude, harmonic_phase, noise_magnitude, noise_u=noise_u)
+        # the whole block -- both buffer copies, stage A from the carried prefix, stage B -- in ONE operator of the
+        # extension host (csrc/torch_ext.cpp csf_stream_push); what remains here is the stream's bookkeeping
+        B, k = f0_new.shape[0], f0_new.shape[1]
+        if k < 1:
+            raise ValueError('push() needs at least one new frame')
+        self._room(B, k, f0_new.device)
+        t, end = self._t, self._end
+        first_hop = self.frames_pushed - t
+        ip = None
+        if self._carry is None and self.initial_phase is not None:
+            ip = torch.as_tensor(self.initial_phase, dtype=torch.float32, device=f0_new.device)
+        signal, _, prefix = core._op(ops.csf_stream_push, self._f0_buf, self._rows_buf, f0_new, harmonic_magnitude,
+                                     harmonic_phase, noise_magnitude, end, t, self.hop, self.sr, ip, self._carry,
+                                     self._seed_now, self.window, first_hop)
+        W = t + k
+        lo = self.hops_emitted - first_hop
+        hi = max(lo, W - LATENCY)
+        hop = self.hop
+        out = signal[:, lo * hop:hi * hop]
+        self._last_tail = signal[:, hi * hop:]
+        keep = min(CONTEXT, W)
+        self._end = end + k
+        self._t = keep
+        self._carry = prefix[:, W - keep]
+        self.frames_pushed += k
+        self.hops_emitted += hi - lo
+        return out
 
     def flush(self):
         """The hops still held back (at most LATENCY), ending the way one call over all pushed frames ends

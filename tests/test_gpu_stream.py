@@ -80,6 +80,44 @@ def test_stream_equals_one_call_in_kernel_noise():
     assert not torch.equal(other, ref)
 
 
+def test_push_operator_equals_begin_finish():
+    """`push` runs the whole block in one operator of the extension host (csf_stream_push): bitwise the same stream as
+    begin() + finish(), for split views of one tensor, separately stored rows and (B,k,1) f0."""
+    d = make_inputs(3, 57, 1539, seed=21, zero_f0_fraction=0.1)
+    hm, hp, nm = ctrl_views(d['ctrl'], 'combsubfast')
+    f0 = dev(d['f0_frames'])
+    ip = dev(np.array([0.3, -1.0, 2.0], np.float32))
+    for separate in (False, True):
+        sa = CombSubFastStream(512, 44100, seed=5, initial_phase=ip)
+        sb = CombSubFastStream(512, 44100, seed=5, initial_phase=ip)
+        a = 0
+        for k in (9, 1, 26, 2, 19):
+            b = a + k
+            rows = [t[:, a:b] for t in (hm, hp, nm)]
+            if separate:
+                rows = [r.contiguous() for r in rows]
+            out_a = sa.push(*rows, f0[:, a:b, None] if separate else f0[:, a:b])
+            sb.begin(f0[:, a:b])
+            out_b = sb.finish(*rows)
+            assert torch.equal(out_a, out_b)
+            assert (sa.frames_pushed, sa.hops_emitted, sa._t, sa._end) == (sb.frames_pushed, sb.hops_emitted, sb._t, sb._end)
+            assert torch.equal(sa._carry, sb._carry)
+            a = b
+        assert torch.equal(sa.flush(), sb.flush())
+
+
+def test_fused_stage_a_b_operator_equals_the_two_stages():
+    d = make_inputs(2, 33, 1539, seed=8, zero_f0_fraction=0.2)
+    hm, hp, nm = ctrl_views(d['ctrl'], 'combsubfast')
+    f0 = dev(d['f0_frames'])
+    ip = dev(np.array([1.5, -0.25], np.float32))
+    for U in (None, dev(d['U'])):
+        pf, prefix, _ = core.phase_stage(f0, 512, 44100, ip)
+        ref = core.combsubfast_stage(hm, hp, nm, f0, prefix, 512, 44100, noise_u=U, seed=77)
+        sig, pf2, prefix2 = core.combsubfast_synth(hm, hp, nm, f0, 512, 44100, initial_phase=ip, noise_u=U, seed=77)
+        assert torch.equal(sig, ref) and torch.equal(pf2, pf) and torch.equal(prefix2, prefix)
+
+
 def test_carry_fold_keeps_the_phase_after_hours_of_audio():
     # a carry beyond 2^40 Hz*samples is folded modulo sr in the kernel; the phase only depends on carry mod sr
     f0 = torch.full((1, 8), 441.0, device='cuda')
