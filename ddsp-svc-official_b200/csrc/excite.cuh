@@ -20,13 +20,19 @@ __global__ void __launch_bounds__(256) combtooth_kernel(const float* __restrict_
     const float* row = f0_frames + (int64_t)b * fB;
     const float x0 = __ldg(row + (int64_t)h * fF);
     const float x1 = __ldg(row + (int64_t)min(h + 1, F - 1) * fF);
-    float f[16], rot[16], c[16];
-    hop_rotation(x0, x1, prefix[warp], inv_sr, lane, f, rot);
+    // the arithmetic of the CombSubFast excitation (csf_gen_hop): fixed-point phase inside the lane on top of the exact fp64
+    // hop prefix, packed fp32x2 sinc -- two samples per instruction instead of an fp64 running sum per sample
+    float2 f2[8], rot2[8];
+    float c[16];
+    hop_rotation_q32(x0, x1, prefix[warp], inv_sr, lane, f2, rot2);
+    const float sr_scale = sr * 2.3283064365386963e-10f;      // rot2 holds rot * 2^32
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float x = __fmul_rn(sr, rot[i]) * rcp_approx(__fadd_rn(f[i], 1e-3f));   // vocoder.py:539
-        c[i] = sinc_f(x);
-        if (zero_unvoiced && f[i] <= 0.0f) c[i] = 0.0f;
+    for (int j = 0; j < 8; ++j) {
+        const float2 den = add2(f2[j], bc2(1e-3f));                                   // vocoder.py:539
+        const float2 xs = fma2(mul2(bc2(sr_scale), rot2[j]), make_float2(rcp_approx(den.x), rcp_approx(den.y)), bc2(1e-30f));
+        const float2 v = sinc2_xs(xs);
+        c[2 * j] = (zero_unvoiced && f2[j].x <= 0.0f) ? 0.0f : v.x;
+        c[2 * j + 1] = (zero_unvoiced && f2[j].y <= 0.0f) ? 0.0f : v.y;
     }
     float4* dst = reinterpret_cast<float4*>(out + warp * kHop + 16 * lane);
 #pragma unroll
