@@ -81,6 +81,11 @@ _PROTOS = {
                                           c_f32p, C.c_int, C.c_void_p]),
     'ddsp_b200_sola_splice': (C.c_int, [c_f32p, C.c_int, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p,
                                         C.c_void_p]),
+    'ddsp_b200_pad_frames': (C.c_int, [c_f32p, i64, i64, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
+    'ddsp_b200_groupnorm_leaky': (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p]),
+    'ddsp_b200_embed_sum_ln': (C.c_int, [c_f32p, i64, i64, c_f32p, i64, i64, c_f32p, i64, i64, c_f32p, i64, i64] + [c_f32p] * 7 +
+                               [i64, c_f32p, c_f32p, C.c_float, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, C.c_void_p]),
     'ddsp_b200_frequency_filter_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'ddsp_b200_frequency_filter': (C.c_int, [c_f32p, c_f32p, i64, i64, C.c_int, C.c_int, C.c_float, C.c_int, c_f32p,
                                              i64, i64, C.c_double, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,

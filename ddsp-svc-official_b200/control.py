@@ -307,11 +307,13 @@ class PCmer(nn.Module):
     def forward(self, x):
         return self.net(x)
 
-    def forward_tc(self, x, post_ln):
+    def forward_tc(self, x, post_ln, xn=None):
         """Tensor-core path over all layers; every LayerNorm but the first is produced by the epilogue of the GEMM
-        that finishes its input (pcmer.py:25-37).  Returns post_ln(PCmer(x)); x is overwritten (residual stream)."""
+        that finishes its input (pcmer.py:25-37); the first one arrives as `xn` when the embedding kernel made it.
+        Returns post_ln(PCmer(x)); x is overwritten (residual stream)."""
         layers = list(self.net)
-        xn = F.layer_norm(x, (x.shape[-1],), layers[0].norm.weight, layers[0].norm.bias, layers[0].norm.eps)
+        if xn is None:
+            xn = F.layer_norm(x, (x.shape[-1],), layers[0].norm.weight, layers[0].norm.bias, layers[0].norm.eps)
         for i, layer in enumerate(layers):
             x, xn = layer.attn.forward_tc(xn, x, layer.local_mixer.net[0])
             nxt = layers[i + 1].norm if i + 1 < len(layers) else post_ln
@@ -358,15 +360,41 @@ class Unit2Control(nn.Module):
                 torch.backends.cuda.matmul.allow_tf32 = prev
         return self._forward(units, f0, phase, volume, spk_id, spk_mix_dict)
 
+    def _prenet_tc(self, units):
+        """unit_prenet on the tensor cores, channels last (no transposes): each Conv1d(k=3) is one 3xTF32 GEMM over the
+        zero-padded frames read as overlapping rows (core.conv3_frames); GroupNorm + LeakyReLU in one in-place pass.
+        Returns a (B, N, 256) view (row stride 256, clip stride (N+2)*256)."""
+        from . import core
+        _, conv1, gn, act, conv2, _ = self.unit_prenet
+        B, N, _ = units.shape
+        w1_hi, w1_lo = _split_cached(self, 'pre1', (conv1.weight,), core.conv3_weight)
+        w2_hi, w2_lo = _split_cached(self, 'pre2', (conv2.weight,), core.conv3_weight)
+        xp = core.pad_frames(units)
+        hp = torch.empty((B, N + 2, _DIM), dtype=torch.float32, device=units.device)
+        rows = hp.view(-1, _DIM)
+        core.conv3_frames(xp, w1_hi, conv1.bias, rows[1:rows.shape[0] - 1], weight_lo=w1_lo)       # frame n -> padded frame n + 1
+        core.groupnorm_leaky_(hp, gn.weight, gn.bias, gn.eps, gn.num_groups, act.negative_slope)
+        yp = torch.empty((B, N + 2, _DIM), dtype=torch.float32, device=units.device)
+        core.conv3_frames(hp, w2_hi, conv2.bias, yp.view(-1, _DIM)[:rows.shape[0] - 2], weight_lo=w2_lo)
+        return yp[:, :N]
+
     def _forward(self, units, f0, phase, volume, spk_id, spk_mix_dict=None):
-        x = self.unit_prenet(units)
+        tc_pre = (_fused_ok(units) and not self.causal and units.dim() == 3 and units.shape[0] * units.shape[1] > _ATTENTION_KERNEL_MAX_FRAMES
+                  and units.shape[-1] % 32 == 0 and f0.dtype == torch.float32 and phase.dtype == torch.float32
+                  and volume.dtype == torch.float32 and os.environ.get('DDSP_B200_STOCK_PRENET') != '1')
+        x = self._prenet_tc(units) if tc_pre else self.unit_prenet(units)
         if _fused_ok(x) and f0.dtype == torch.float32 and phase.dtype == torch.float32 and volume.dtype == torch.float32:
             from . import core
             if spk_mix_dict is not None:                 # weighted mix of speaker embeddings (unit2control.py:89-93)
                 spk = sum(v * self.spk_embed.weight[int(k) - 1] for k, v in spk_mix_dict.items()).reshape(1, -1)
             else:
                 spk = self.spk_embed(spk_id - 1)
-            x = core.embed_sum(x, f0, phase, volume, self.f0_embed, self.phase_embed, self.volume_embed, spk)
+            xn = None
+            if tc_pre:                                   # embedding sum + the first LayerNorm of PCmer in one pass
+                x, xn = core.embed_sum_ln(x, f0, phase, volume, self.f0_embed, self.phase_embed, self.volume_embed, spk,
+                                          self.dec_post[0].net[0].norm)
+            else:
+                x = core.embed_sum(x, f0, phase, volume, self.f0_embed, self.phase_embed, self.volume_embed, spk)
             names, sizes = list(self.output_splits), list(self.output_splits.values())
             if _tc_path(x) and not self.causal:
                 # output projection on the tensor cores into a buffer whose row stride is padded to a multiple of 4
@@ -381,7 +409,7 @@ class Unit2Control(nn.Module):
                     w_hi, w_lo = _split_cached(self, 'proj', (proj.weight,))
                 if not x.is_contiguous():
                     x = x.contiguous()
-                e = core.linear_ex(pcmer.forward_tc(x, norm), w_hi, proj.bias, out=buf[..., :n_out], weight_lo=w_lo)
+                e = core.linear_ex(pcmer.forward_tc(x, norm, xn), w_hi, proj.bias, out=buf[..., :n_out], weight_lo=w_lo)
             else:
                 e = self.dec_post(x)
             return dict(zip(names, torch.split(e, sizes, dim=-1)))

@@ -780,6 +780,74 @@ def embed_sum(x, f0, phase, volume, f0_embed, phase_embed, volume_embed, spk_row
     return out
 
 
+def conv3_frames(xp, weight_hi, bias, out_rows, weight_lo=None):
+    """Conv1d(C_in, C_out, 3, padding='same') over channels-last frames on the tensor cores (unit2control.py:40,43).
+    xp (B, N+2, C_in): frames with one zero frame in front of and behind every clip (`pad_frames`); weight_hi [/ weight_lo]:
+    the (C_out, 3*C_in) weight W'[o, t*C_in + c] = W[o, c, t] (`conv3_weight`, split by `split_tf32`); out_rows: the
+    (B*(N+2) - 2, C_out) rows that receive the result -- row b*(N+2) + n is frame n of clip b (the two rows per clip
+    boundary are garbage).  The A operand is xp itself read with row stride C_in and K = 3*C_in (overlapping rows)."""
+    B, Np2, Cin = xp.shape
+    M = B * Np2 - 2
+    a = xp.as_strided((M, 3 * Cin), (Cin, 1))
+    return linear_ex(a, weight_hi, bias, out=out_rows, weight_lo=weight_lo)
+
+
+def conv3_weight(weight):
+    """Conv1d weight (C_out, C_in, 3) -> (C_out, 3*C_in) with the tap as the slow index of a row."""
+    return weight.permute(0, 2, 1).reshape(weight.shape[0], -1).contiguous()
+
+
+def pad_frames(x):
+    """(B, N, C) [unit channel stride] -> contiguous (B, N+2, C) with zero frames 0 and N+1."""
+    x = _need_cuda_f32(x, 'x')
+    B, N, Cc = x.shape
+    if x.stride(2) != 1 or (x.stride(0) & 3) or (x.stride(1) & 3) or (x.data_ptr() & 15):
+        x = x.contiguous()
+    out = torch.empty((B, N + 2, Cc), dtype=torch.float32, device=x.device)
+    with _OnDevice(x.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_pad_frames(x.data_ptr(), x.stride(0), x.stride(1), B, N, Cc, out.data_ptr(), _st))
+    return out
+
+
+def groupnorm_leaky_(hp, gamma, beta, eps, groups, slope=0.01):
+    """In place on a padded (B, N+2, C) buffer: GroupNorm(groups, C) over the N real frames of every clip, LeakyReLU(slope),
+    zeros on the pad frames (unit2control.py:41-42)."""
+    B, Np2, Cc = hp.shape
+    sums = torch.empty((B, groups, 2), dtype=torch.float64, device=hp.device)
+    with _OnDevice(hp.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_groupnorm_leaky(hp.data_ptr(), gamma.detach().contiguous().data_ptr(),
+                                                          beta.detach().contiguous().data_ptr(), float(eps), float(slope),
+                                                          int(groups), B, Np2 - 2, Cc, sums.data_ptr(), _st))
+    return hp
+
+
+def embed_sum_ln(x, f0, phase, volume, f0_embed, phase_embed, volume_embed, spk_rows, ln):
+    """`embed_sum` (unit2control.py:80-95) that also returns the first LayerNorm of PCmer (pcmer.py:25) of the finished
+    rows; C = 256.  x (B,N,256) with unit channel stride.  Returns (x_sum, layer_norm(x_sum)), both contiguous."""
+    x = _need_cuda_f32(x, 'x')
+    B, N, Cc = x.shape
+    f0 = _f0_2d(f0)
+    phase = _need_cuda_f32(phase, 'phase').reshape(B, N)
+    volume = _need_cuda_f32(volume, 'volume').reshape(B, N)
+    spk = _need_cuda_f32(spk_rows, 'spk_rows').reshape(-1, Cc).contiguous()
+    if spk.shape[0] not in (1, B):
+        raise ValueError('spk_rows must have 1 or B rows')
+    ws = []
+    for lin in (f0_embed, phase_embed, volume_embed):
+        ws += [lin.weight.detach().reshape(-1).contiguous(), lin.bias.detach().contiguous()]
+    g, b_ = ln.weight.detach().contiguous(), ln.bias.detach().contiguous()
+    out = torch.empty((B, N, Cc), dtype=torch.float32, device=x.device)
+    out_ln = torch.empty_like(out)
+    with _OnDevice(x.device) as _st:
+        _cabi.check(_cabi.lib().ddsp_b200_embed_sum_ln(
+            x.data_ptr(), x.stride(0), x.stride(1), f0.data_ptr(), f0.stride(0), f0.stride(1),
+            phase.data_ptr(), phase.stride(0), phase.stride(1), volume.data_ptr(), volume.stride(0), volume.stride(1),
+            ws[0].data_ptr(), ws[1].data_ptr(), ws[2].data_ptr(), ws[3].data_ptr(), ws[4].data_ptr(), ws[5].data_ptr(),
+            spk.data_ptr(), 0 if spk.shape[0] == 1 else Cc, g.data_ptr(), b_.data_ptr(), float(ln.eps), B, N, Cc,
+            out.data_ptr(), out_ln.data_ptr(), _st))
+    return out, out_ln
+
+
 def performer_attention(q, k, v, projection, heads, q_bias=None, k_bias=None, v_bias=None, eps=1e-4):
     """Non-causal Performer attention after the q/k/v projections as one kernel (blocks of up to 16 frames)
     or three kernels over 8-frame tiles (pcmer.py:69-78,124-160):

@@ -609,35 +609,197 @@ __global__ void __launch_bounds__(256) glu_dwconv_silu_kernel(const float* __res
 // producing GEMM, csrc/gemm_attn.cuh EPI_GLU).  A thread owns one channel and kDw2Run consecutive frames: the 31 taps and
 // a sliding window of inputs stay in registers, every input is loaded once per thread (lanes = consecutive channels:
 // 128-byte coalesced rows; the 30-frame halo of neighbouring runs comes out of L1 / L2).
-constexpr int kDw2Run = 32;
+#ifndef DW2_RUN
+#define DW2_RUN 24      // measured on B200 at 64 x 862 x 512: 16 -> 77 us, 20 -> 68, 24 -> 65, 32 -> 71, 40 -> 70, 48 -> 82
+#endif
+constexpr int kDw2Run = DW2_RUN;
 
-__global__ void __launch_bounds__(256) dwconv_silu_kernel(const float* __restrict__ g, const float* __restrict__ w,
-                                                          const float* __restrict__ bias, float* __restrict__ out, int T, int C) {
-    const int c = blockIdx.x * 256 + threadIdx.x, t0 = blockIdx.y * kDw2Run, b = blockIdx.z;
-    if (c >= C) return;
-    float wr[kDwTaps];
-#pragma unroll
-    for (int j = 0; j < kDwTaps; ++j) wr[j] = __ldg(w + (int64_t)c * kDwTaps + j);
-    const float bs = __ldg(bias + c);
+// C_T: compile-time channel count (0 = runtime C).  With the shipped width (512) every load / store address is the thread's
+// base pointer plus an immediate offset, and runs that lie inside the clip (all but the first and last one) carry no range
+// tests: the checked form spent 14 address / predicate instructions per load (2420 warp instructions per run for 992 FMAs,
+// ncu), this one ~1.4 k.
+template <int C_T, bool CHECKED>
+__device__ __forceinline__ void dwconv_silu_run(const float* __restrict__ gp, const float (&wr)[kDwTaps], float bs,
+                                                float* __restrict__ op, int t0, int T, int C) {
+    const int64_t Cc = C_T ? C_T : C;
     float acc[kDw2Run];
 #pragma unroll
     for (int o = 0; o < kDw2Run; ++o) acc[o] = bs;
-    const float* gb = g + (int64_t)b * T * C + c;
 #pragma unroll
     for (int i = 0; i < kDw2Run + kDwTaps - 1; ++i) {
-        const int t = t0 + i - kDwPad;
-        const float val = (t >= 0 && t < T) ? __ldg(gb + (int64_t)t * C) : 0.0f;
+        float val;
+        if (CHECKED) {
+            const int t = t0 + i - kDwPad;
+            val = (t >= 0 && t < T) ? __ldg(gp + i * Cc) : 0.0f;
+        } else {
+            val = __ldg(gp + i * Cc);
+        }
 #pragma unroll
         for (int o = 0; o < kDw2Run; ++o) {
             const int j = i - o;
             if (j >= 0 && j < kDwTaps) acc[o] = fmaf(wr[j], val, acc[o]);
         }
     }
-    float* ob = out + (int64_t)b * T * C + c;
 #pragma unroll
     for (int o = 0; o < kDw2Run; ++o) {
-        const int t = t0 + o;
-        if (t < T) ob[(int64_t)t * C] = __fdividef(acc[o], 1.0f + __expf(-acc[o]));
+        if (!CHECKED || t0 + o < T) op[o * Cc] = __fdividef(acc[o], 1.0f + __expf(-acc[o]));
+    }
+}
+
+template <int C_T>
+__global__ void __launch_bounds__(256) dwconv_silu_kernel(const float* __restrict__ g, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ out, int T, int C) {
+    const int Cc = C_T ? C_T : C;
+    const int c = blockIdx.x * 256 + threadIdx.x, t0 = blockIdx.y * kDw2Run, b = blockIdx.z;
+    if (c >= Cc) return;
+    float wr[kDwTaps];
+#pragma unroll
+    for (int j = 0; j < kDwTaps; ++j) wr[j] = __ldg(w + (int64_t)c * kDwTaps + j);
+    const float bs = __ldg(bias + c);
+    // (the pointer of the first window frame may lie in front of the clip: it is only dereferenced where the frame exists)
+    const float* gp = g + ((int64_t)b * T + (t0 - kDwPad)) * Cc + c;
+    float* op = out + ((int64_t)b * T + t0) * Cc + c;
+    if (t0 >= kDwPad && t0 + kDw2Run + kDwPad <= T) dwconv_silu_run<C_T, false>(gp, wr, bs, op, t0, T, C);   // block-uniform
+    else dwconv_silu_run<C_T, true>(gp, wr, bs, op, t0, T, C);
+}
+
+// ---- unit pre-net on the tensor cores (unit2control.py:38-45) -----------------------------------------------------------
+// Conv1d(k=3, 'same') over channels-last frames is a GEMM whose row m is the window of three consecutive frames: with one
+// zero frame in front of and behind every clip the window of frame n is the 3*C contiguous floats that start at padded
+// frame n, so the A operand is the padded buffer itself read with row stride C and K = 3*C (overlapping rows; the two
+// rows per clip that straddle a clip boundary produce garbage that lands exactly on the pad frames of the next buffer).
+
+// (B,N,C) strided -> (B,N+2,C) contiguous with zero frames 0 and N+1.  One thread per float4.
+__global__ void __launch_bounds__(256) pad_frames_kernel(const float* __restrict__ x, int64_t xB, int64_t xN, int B, int N,
+                                                         int C, float4* __restrict__ out) {
+    const int c4 = C >> 2;
+    const int64_t total = (int64_t)B * (N + 2) * c4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4);
+        const int64_t r = i / c4;
+        const int n = (int)(r % (N + 2)) - 1, b = (int)(r / (N + 2));
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n >= 0 && n < N) v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)b * xB + (int64_t)n * xN) + c);
+        out[i] = v;
+    }
+}
+
+// GroupNorm statistics of a padded (B,N+2,C) buffer over the N real frames: sums[b][g] = (sum, sum of squares) in fp64.
+// grid (chunks, B); a thread owns 4 consecutive channels (one group: C/G is a multiple of 4) and strides over the frames.
+constexpr int kGnThreads = 256;
+__global__ void __launch_bounds__(kGnThreads) groupnorm_stats_kernel(const float* __restrict__ hp, int N, int C, int G,
+                                                                      double* __restrict__ sums) {
+    __shared__ double sh[2 * 32];                         // up to 32 groups
+    const int b = blockIdx.y, c4 = C >> 2;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    const int col = threadIdx.x % c4, row0 = threadIdx.x / c4, rows_per_pass = blockDim.x / c4;
+    const int per = (N + gridDim.x - 1) / gridDim.x, n0 = blockIdx.x * per, n1 = min(N, n0 + per);
+    float s = 0.f, q = 0.f;
+    const float4* base = reinterpret_cast<const float4*>(hp + ((int64_t)b * (N + 2) + 1) * C) + col;
+    for (int n = n0 + row0; n < n1; n += rows_per_pass) {
+        const float4 v = __ldg(base + (int64_t)n * c4);
+        s += (v.x + v.y) + (v.z + v.w);
+        q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
+    }
+    const int g = (4 * col) / (C / G);
+    atomicAdd(&sh[2 * g], (double)s);
+    atomicAdd(&sh[2 * g + 1], (double)q);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[(int64_t)b * 2 * G + i], sh[i]);
+}
+
+// In place: hp[b,1+n,c] = leaky_relu(gamma[c] * (h - mean[b,g]) * rstd[b,g] + beta[c]); pad frames 0 and N+1 := 0.
+__global__ void __launch_bounds__(256) groupnorm_leaky_kernel(float4* __restrict__ hp, const double* __restrict__ sums,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              float eps, float slope, int B, int N, int C, int G) {
+    const int c4 = C >> 2;
+    const int64_t total = (int64_t)B * (N + 2) * c4;
+    const double inv_cnt = 1.0 / ((double)N * (C / G));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4) * 4;
+        const int64_t r = i / c4;
+        const int n = (int)(r % (N + 2)) - 1, b = (int)(r / (N + 2));
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n >= 0 && n < N) {
+            const int g = c / (C / G);
+            const double m = sums[((int64_t)b * G + g) * 2] * inv_cnt;
+            const double var = fmax(sums[((int64_t)b * G + g) * 2 + 1] * inv_cnt - m * m, 0.0);      // biased, as GroupNorm
+            const float mean = (float)m, rstd = (float)(1.0 / sqrt(var + (double)eps));
+            const float4 h = hp[i];
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
+            v.x = fmaf((h.x - mean) * rstd, ga.x, be.x); v.y = fmaf((h.y - mean) * rstd, ga.y, be.y);
+            v.z = fmaf((h.z - mean) * rstd, ga.z, be.z); v.w = fmaf((h.w - mean) * rstd, ga.w, be.w);
+            v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+            v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+        }
+        hp[i] = v;
+    }
+}
+
+// Input embedding sum (embed_sum_kernel above) + the first LayerNorm of PCmer (pcmer.py:25) for C = 256: one warp per frame,
+// lane owns channels 4l..4l+3 and 128+4l..128+4l+3 (two 128-bit accesses per tensor); the per-frame scalars
+// log(1 + f0/700), phase/pi, volume are computed once per frame instead of once per channel.
+__global__ void __launch_bounds__(256) embed_sum_ln256_kernel(const float* __restrict__ x, int64_t xB, int64_t xN,
+                                                              const float* __restrict__ f0, int64_t fB, int64_t fN,
+                                                              const float* __restrict__ phase, int64_t pB, int64_t pN,
+                                                              const float* __restrict__ vol, int64_t vB, int64_t vN,
+                                                              const float* __restrict__ wf, const float* __restrict__ bf,
+                                                              const float* __restrict__ wp, const float* __restrict__ bp,
+                                                              const float* __restrict__ wv, const float* __restrict__ bv,
+                                                              const float* __restrict__ spk, int64_t sB,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              float eps, int B, int N, float* __restrict__ out,
+                                                              float* __restrict__ out_ln) {
+    const int lane = threadIdx.x & 31;
+    const int64_t rows = (int64_t)B * N;
+    const int64_t w0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), wstep = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = w0; r < rows; r += wstep) {
+        const int n = (int)(r % N), b = (int)(r / N);
+        const float lf0 = logf(__fadd_rn(1.0f, __fdiv_rn(__ldg(f0 + b * fB + n * fN), 700.0f)));
+        const float ph = __fdiv_rn(__ldg(phase + b * pB + n * pN), 3.14159265358979323846f);
+        const float vv = __ldg(vol + b * vB + n * vN);
+        float v[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = 128 * h + 4 * lane;
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(x + b * xB + n * xN + c));
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(wf + c)), a1 = __ldg(reinterpret_cast<const float4*>(bf + c));
+            const float4 p0 = __ldg(reinterpret_cast<const float4*>(wp + c)), p1 = __ldg(reinterpret_cast<const float4*>(bp + c));
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(wv + c)), v1 = __ldg(reinterpret_cast<const float4*>(bv + c));
+            const float4 sp = __ldg(reinterpret_cast<const float4*>(spk + b * sB + c));
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, wfs[4] = {a0.x, a0.y, a0.z, a0.w}, bfs[4] = {a1.x, a1.y, a1.z, a1.w};
+            const float wps[4] = {p0.x, p0.y, p0.z, p0.w}, bps[4] = {p1.x, p1.y, p1.z, p1.w};
+            const float wvs[4] = {v0.x, v0.y, v0.z, v0.w}, bvs[4] = {v1.x, v1.y, v1.z, v1.w}, sps[4] = {sp.x, sp.y, sp.z, sp.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {                 // the operation order of embed_sum_kernel
+                float t = __fadd_rn(xs[e], fmaf(lf0, wfs[e], bfs[e]));
+                t = __fadd_rn(t, fmaf(ph, wps[e], bps[e]));
+                t = __fadd_rn(t, fmaf(vv, wvs[e], bvs[e]));
+                v[4 * h + e] = __fadd_rn(t, sps[e]);
+            }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += v[e];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / 256.0f);
+        float q = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) q = fmaf(v[e] - mean, v[e] - mean, q);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q * (1.0f / 256.0f) + eps);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = 128 * h + 4 * lane;
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c)), be = __ldg(reinterpret_cast<const float4*>(beta + c));
+            *reinterpret_cast<float4*>(out + r * 256 + c) = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+            *reinterpret_cast<float4*>(out_ln + r * 256 + c) =
+                make_float4(fmaf((v[4 * h] - mean) * rstd, ga.x, be.x), fmaf((v[4 * h + 1] - mean) * rstd, ga.y, be.y),
+                            fmaf((v[4 * h + 2] - mean) * rstd, ga.z, be.z), fmaf((v[4 * h + 3] - mean) * rstd, ga.w, be.w));
+        }
     }
 }
 

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <initializer_list>
@@ -708,7 +709,62 @@ int ddsp_b200_dwconv_silu(const float* g, const float* weight, const float* bias
     if (!g || !weight || !bias || !out || B <= 0 || T <= 0 || C <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
     if (B > 65535) return DDSP_B200_ERR_UNSUPPORTED;
     const dim3 grid((C + 255) / 256, (T + ddsp::kDw2Run - 1) / ddsp::kDw2Run, B);
-    ddsp::dwconv_silu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, weight, bias, out, T, C);
+    if (C == 512) ddsp::dwconv_silu_kernel<512><<<grid, 256, 0, (cudaStream_t)stream>>>(g, weight, bias, out, T, C);
+    else ddsp::dwconv_silu_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(g, weight, bias, out, T, C);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int ddsp_b200_pad_frames(const float* x, int64_t xB, int64_t xN, int B, int N, int C, float* out, void* stream) {
+    g_launches = 0;
+    if (!x || !out || B <= 0 || N <= 0 || C <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if ((C & 3) || (xB & 3) || (xN & 3) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+        return DDSP_B200_ERR_UNSUPPORTED;
+    const int64_t total = (int64_t)B * (N + 2) * (C / 4);
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+    ddsp::pad_frames_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, xB, xN, B, N, C, reinterpret_cast<float4*>(out));
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int ddsp_b200_groupnorm_leaky(float* hp, const float* gamma, const float* beta, float eps, float slope, int groups, int B,
+                              int N, int C, double* sums, void* stream) {
+    g_launches = 0;
+    if (!hp || !gamma || !beta || !sums || B <= 0 || N <= 0 || C <= 0 || groups <= 0) return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (groups > 32 || C % groups || ((C / groups) & 3) || C / 4 > ddsp::kGnThreads || ddsp::kGnThreads % (C / 4) || B > 65535 ||
+        (reinterpret_cast<uintptr_t>(hp) & 15) || (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15))
+        return DDSP_B200_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups * B, st));
+    const int chunks = std::max(1, std::min(32, (sm_count() * 4 + B - 1) / B));
+    ddsp::groupnorm_stats_kernel<<<dim3(chunks, B), ddsp::kGnThreads, 0, st>>>(hp, N, C, groups, sums);
+    LAUNCH_CHECK();
+    const int64_t total = (int64_t)B * (N + 2) * (C / 4);
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+    ddsp::groupnorm_leaky_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<float4*>(hp), sums, gamma, beta, eps, slope, B, N, C, groups);
+    LAUNCH_CHECK();
+    return DDSP_B200_OK;
+}
+
+int ddsp_b200_embed_sum_ln(const float* x, int64_t xB, int64_t xN, const float* f0, int64_t fB, int64_t fN, const float* phase,
+                           int64_t pB, int64_t pN, const float* volume, int64_t vB, int64_t vN, const float* w_f0,
+                           const float* b_f0, const float* w_phase, const float* b_phase, const float* w_volume,
+                           const float* b_volume, const float* spk, int64_t sB, const float* ln_gamma, const float* ln_beta,
+                           float ln_eps, int B, int N, int C, float* out, float* out_ln, void* stream) {
+    g_launches = 0;
+    if (!x || !f0 || !phase || !volume || !w_f0 || !b_f0 || !w_phase || !b_phase || !w_volume || !b_volume || !spk || !ln_gamma ||
+        !ln_beta || !out || !out_ln || B <= 0 || N <= 0)
+        return DDSP_B200_ERR_INVALID_ARGUMENT;
+    if (C != 256 || (xB & 3) || (xN & 3) || (sB & 3)) return DDSP_B200_ERR_UNSUPPORTED;
+    for (const void* p : {(const void*)x, (const void*)w_f0, (const void*)b_f0, (const void*)w_phase, (const void*)b_phase,
+                          (const void*)w_volume, (const void*)b_volume, (const void*)spk, (const void*)ln_gamma,
+                          (const void*)ln_beta, (const void*)out, (const void*)out_ln})
+        if (reinterpret_cast<uintptr_t>(p) & 15) return DDSP_B200_ERR_UNSUPPORTED;
+    const int64_t rows = (int64_t)B * N;
+    const int blocks = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * 8);
+    ddsp::embed_sum_ln256_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, xB, xN, f0, fB, fN, phase, pB, pN, volume, vB, vN,
+                                                                          w_f0, b_f0, w_phase, b_phase, w_volume, b_volume, spk,
+                                                                          sB, ln_gamma, ln_beta, ln_eps, B, N, out, out_ln);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }
@@ -1080,7 +1136,9 @@ int ddsp_b200_linear_tf32x3_ex(const float* A, int64_t lda, const float* W, cons
                                const float* ln_beta, float ln_eps, float* C_ln, int64_t ldc_ln, int M, int N, int K,
                                void* stream) {
     g_launches = 0;
-    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || lda < K || ldw < K || ldc < N || (residual && ldr < N))
+    // lda < K with K a multiple of lda: row m is the window of K/lda consecutive lda-float rows (overlapping rows -- the
+    // im2col view of a Conv1d over channels-last frames, unit2control.py:40-44)
+    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || lda <= 0 || (lda < K && K % lda) || ldw < K || ldc < N || (residual && ldr < N))
         return DDSP_B200_ERR_INVALID_ARGUMENT;
     if ((ln_gamma != nullptr) != (C_ln != nullptr) || (ln_gamma && !ln_beta) || (ln_gamma && ldc_ln < N))
         return DDSP_B200_ERR_INVALID_ARGUMENT;

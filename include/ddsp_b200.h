@@ -294,6 +294,29 @@ int ddsp_b200_embed_sum(const float *x, int64_t xB, int64_t xN, int64_t xC, cons
                         const float *b_volume, const float *spk, int64_t sB, int B, int N, int C,
                         float *out, void *stream);
 
+/* Unit pre-net on the tensor cores                                 unit2control.py:38-45
+ *   Transpose - Conv1d(n_unit,256,3,'same') - GroupNorm(4,256) - LeakyReLU - Conv1d(256,256,3,'same') - Transpose
+ * in channels-last layout without transposes: `ddsp_b200_pad_frames` copies the (B,N,C) frames (element strides xB, xN; unit
+ * channel stride) into a contiguous (B,N+2,C) buffer with one zero frame in front of and behind every clip.  The window of
+ * frame n is then the 3*C contiguous floats starting at padded frame n, so each convolution is ONE call of
+ * `ddsp_b200_linear_tf32x3_ex` with A = the padded buffer, lda = C, K = 3*C, M = B*(N+2) - 2 and the weight laid out as
+ * W'[o][t*C + c] = W[o][c][t]; the output of the first convolution is written one row further down into the next padded
+ * buffer (its two garbage rows per clip boundary land on the pad frames).
+ * `ddsp_b200_groupnorm_leaky` normalises such a padded (B,N+2,C) buffer in place over the N real frames of every clip
+ * (GroupNorm statistics per clip and group in fp64: biased variance, eps inside the root), applies gamma / beta and
+ * LeakyReLU(slope) and writes zeros to the pad frames.  sums: scratch of 2*groups*B doubles.
+ * `ddsp_b200_embed_sum_ln` (C = 256) is `ddsp_b200_embed_sum` (unit2control.py:80-95) that also returns the first
+ * LayerNorm of PCmer (pcmer.py:25) of every finished row: out, out_ln (B,N,256) contiguous. */
+int ddsp_b200_pad_frames(const float *x, int64_t xB, int64_t xN, int B, int N, int C, float *out, void *stream);
+int ddsp_b200_groupnorm_leaky(float *hp, const float *gamma, const float *beta, float eps, float slope, int groups,
+                              int B, int N, int C, double *sums, void *stream);
+int ddsp_b200_embed_sum_ln(const float *x, int64_t xB, int64_t xN, const float *f0, int64_t fB, int64_t fN,
+                           const float *phase, int64_t pB, int64_t pN, const float *volume, int64_t vB, int64_t vN,
+                           const float *w_f0, const float *b_f0, const float *w_phase, const float *b_phase,
+                           const float *w_volume, const float *b_volume, const float *spk, int64_t sB,
+                           const float *ln_gamma, const float *ln_beta, float ln_eps, int B, int N, int C,
+                           float *out, float *out_ln, void *stream);
+
 /* Linear layer on the tensor cores, fp32-faithful ("3xTF32": each operand split into two TF32 terms, three
  * tcgen05.mma per k-step accumulate hi*hi + hi*lo + lo*hi in fp32 TMEM; csrc/gemm_tc.cuh):
  *   C[m,n] = sum_k A[m,k] * W[n,k] (+ bias[n]) (+ residual[m,n])

@@ -140,6 +140,47 @@ def test_merged_qkv_weight_follows_weight_updates():
     assert '_qkv_cache' not in att.state_dict()
 
 
+@pytest.mark.parametrize('B,N,n_unit', [(1, 300, 256), (3, 101, 256), (2, 131, 768), (5, 64, 32)])
+def test_prenet_on_tensor_cores_matches_stock_ops(B, N, n_unit):
+    """unit_prenet as two overlapping-row GEMMs + GroupNorm/LeakyReLU kernel (channels last) against the stock
+    Transpose - Conv1d - GroupNorm - LeakyReLU - Conv1d - Transpose in fp64 (unit2control.py:38-45)."""
+    torch.manual_seed(B * 1000 + N)
+    net = Unit2Control(n_unit, 1, {'a': 8}).cuda().eval()
+    with torch.no_grad():
+        net.unit_prenet[2].weight.uniform_(0.5, 1.5)
+        net.unit_prenet[2].bias.uniform_(-0.5, 0.5)
+    units = torch.randn(B, N, n_unit, device='cuda')
+    units[:, :, ::7] += 3.0                                   # non-zero group means
+    with torch.no_grad():
+        out = net._prenet_tc(units)
+        ref = net.unit_prenet.double()(units.double())
+        net.float()
+    assert out.shape == (B, N, 256) and out.stride(2) == 1
+    assert (out.double() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_embed_sum_with_fused_layer_norm():
+    torch.manual_seed(12)
+    net = Unit2Control(32, 4, {'a': 8}).cuda().eval()
+    B, N = 3, 97
+    xp = torch.randn(B, N + 2, 256, device='cuda')
+    x = xp[:, :N]                                              # the strided view the pre-net hands over
+    f0 = torch.rand(B, N, 1, device='cuda') * 500 + 80
+    f0[1, 5:9] = 0.0
+    ph = (torch.rand(B, N, device='cuda') - 0.5) * 6
+    vol = torch.rand(B, N, device='cuda')
+    ln = net.dec_post[0].net[0].norm
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.5, 0.5)
+        for spk in (net.spk_embed.weight[1:2], net.spk_embed.weight[:3].unsqueeze(1)):
+            a = core.embed_sum(x, f0, ph, vol, net.f0_embed, net.phase_embed, net.volume_embed, spk)
+            b, bn = core.embed_sum_ln(x, f0, ph, vol, net.f0_embed, net.phase_embed, net.volume_embed, spk, ln)
+            assert torch.equal(a, b)
+            ref = torch.nn.functional.layer_norm(a.double(), (256,), ln.weight.double(), ln.bias.double(), ln.eps)
+            assert (bn.double() - ref).abs().max().item() < 5e-6
+
+
 def test_embed_sum_and_speaker_mix():
     torch.manual_seed(9)
     net = Unit2Control(16, 3, {'a': 513, 'b': 513, 'c': 513}).cuda().eval()
