@@ -319,6 +319,13 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 const float* rrow = (P.residual && row_ok) ? P.residual + (int64_t)row * P.ldr : nullptr;
                 const bool ln = P.ln_gamma != nullptr;
                 float sum = 0.0f;
+                // the residual of chunk c+1 is loaded while chunk c is staged and stored (its latency was exposed once per chunk)
+                float4 e[8];
+                auto load_res = [&](int n) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) e[j] = *reinterpret_cast<const float4*>(rrow + n + 4 * j);
+                };
+                if (rrow) load_res(n0);
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     const int n = n0 + c0;
@@ -341,10 +348,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     }
                     if (rrow) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 e = *reinterpret_cast<const float4*>(rrow + n + j);
-                            v[j] += e.x; v[j + 1] += e.y; v[j + 2] += e.z; v[j + 3] += e.w;
+                        for (int j = 0; j < 8; ++j) {
+                            v[4 * j] += e[j].x; v[4 * j + 1] += e[j].y; v[4 * j + 2] += e[j].z; v[4 * j + 3] += e[j].w;
                         }
+                        if (c0 + 32 < BN && n + 32 < P.N) load_res(n + 32);
                     }
                     if (ln) {
 #pragma unroll
