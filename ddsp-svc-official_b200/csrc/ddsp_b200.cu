@@ -1122,6 +1122,12 @@ int launch_gemm3x(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap&
     const int64_t tiles = (int64_t)P.Z * P.tiles_m * P.tiles_n;
     if (tiles > 0x7fffffffLL) return DDSP_B200_ERR_UNSUPPORTED;
     const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+    static const int forced_pf = [] { const char* e = getenv("DDSP_B200_GEMM_PREFETCH"); return e ? atoi(e) : -1; }();   // experiments
+    // the operands streamed once from HBM pass through a 2..3-stage ring: an L2 prefetch cursor 3 k-blocks ahead measured
+    // 219 -> 207 us (context GEMM), 148.5 -> 142 us (output GEMM), 90.4 -> 88.6 us (N = 256 layers), 191 -> 185 us (final
+    // projection); 6 / 12 k-blocks ahead are no better (profiles/r02_gemm_l2_prefetch.txt)
+    P.l2_prefetch = 3;
+    if (forced_pf >= 0) P.l2_prefetch = forced_pf;
     ddsp::tc::gemm3x_kernel<BN, EPI><<<grid, ddsp::tc::kThreads, C::kSmemBytes, st>>>(a, a_lo ? *a_lo : a, w, wlo, c, c2, P);
     LAUNCH_CHECK();
     return DDSP_B200_OK;

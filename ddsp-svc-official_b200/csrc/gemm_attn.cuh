@@ -44,6 +44,7 @@ struct GemmParams {
     const float* ln_gamma;          // LayerNorm over the N columns as second output (tiles_n == 1), or null
     const float* ln_beta;
     float ln_eps;
+    int l2_prefetch;                // > 0: the producer prefetches the DRAM-streamed operand tiles this many k-blocks ahead into L2
     int split_out;                  // EPI_PLAIN: also write the low TF32 term of C through map_c2 (C itself is the high term)
     // EPI_QKV / EPI_OUT
     float* vt;                      // (B, H, 80, Fp)
@@ -58,6 +59,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
         "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
+}
+// the tile a later tma_load_3d will fetch, pulled into L2 now (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
@@ -213,11 +218,30 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx = (P.a_presplit ? 2 : 1) * C::kABytes + (P.w_presplit ? 2 : 1) * C::kWBytes;
+            // The shared-memory ring holds 2..3 k-blocks: less than a DRAM latency of main-loop time for the narrow batched
+            // GEMMs of the attention (K = frames or features, operands streamed once from HBM).  A second cursor runs
+            // `l2_prefetch` k-blocks ahead of the loads and pulls the streamed tiles into L2, so that the ring is refilled at
+            // L2 latency.  Shared weights (not batched) stay L2-resident by themselves and are not prefetched.
+            int ptile = blockIdx.x, pkb = 0;
+            auto prefetch_next = [&]() {
+                if (ptile >= n_tiles) return;
+                const int z = ptile / tiles_per_z, rem = ptile - z * tiles_per_z;
+                const int m0 = (rem / P.tiles_n) * kBM, n0 = (rem % P.tiles_n) * BN;
+                tma_prefetch_3d(&map_a, pkb * kBK, m0, z);
+                if (P.a_presplit) tma_prefetch_3d(&map_a_lo, pkb * kBK, m0, z);
+                if (P.w_batched) {
+                    tma_prefetch_3d(&map_w, pkb * kBK, n0, z);
+                    if (P.w_presplit) tma_prefetch_3d(&map_w_lo, pkb * kBK, n0, z);
+                }
+                if (++pkb == n_kb) { pkb = 0; ptile += gridDim.x; }
+            };
+            for (int i = 0; i < P.l2_prefetch; ++i) prefetch_next();
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int z = tile / tiles_per_z, rem = tile - z * tiles_per_z;
                 const int m0 = (rem / P.tiles_n) * kBM, n0 = (rem % P.tiles_n) * BN;
                 const int wz = P.w_batched ? z : 0;
                 for (int kb = 0; kb < n_kb; ++kb) {
+                    if (P.l2_prefetch > 0) prefetch_next();
                     mbar_wait(s32(empty_bar + stage), phase ^ 1);
                     const uint32_t st = s32(smem + stage * C::kStageBytes);
                     mbar_arrive_expect_tx(s32(full_bar + stage), tx);
