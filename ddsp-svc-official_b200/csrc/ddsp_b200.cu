@@ -1111,12 +1111,12 @@ int set_smem_once(K kernel, int bytes, bool* flags) {
     return 0;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int AM = ddsp::tc::kBM, int SLICES = 2>
 int launch_gemm3x(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& wlo, const CUtensorMap& c, const CUtensorMap& c2,
                   ddsp::tc::GemmParams P, cudaStream_t st, const CUtensorMap* a_lo = nullptr) {
-    using C = ddsp::tc::GCfg<BN>;
+    using C = ddsp::tc::GCfg<BN, AM, SLICES>;
     static bool attr_set[64] = {false};
-    if (int rc = set_smem_once(ddsp::tc::gemm3x_kernel<BN, EPI>, C::kSmemBytes, attr_set)) return rc;
+    if (int rc = set_smem_once(ddsp::tc::gemm3x_kernel<BN, EPI, AM, SLICES>, C::kSmemBytes, attr_set)) return rc;
     P.tiles_m = (P.M + ddsp::tc::kBM - 1) / ddsp::tc::kBM;
     P.tiles_n = (P.N + BN - 1) / BN;
     const int64_t tiles = (int64_t)P.Z * P.tiles_m * P.tiles_n;
@@ -1128,7 +1128,7 @@ int launch_gemm3x(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap&
     // projection); 6 / 12 k-blocks ahead are no better (profiles/r02_gemm_l2_prefetch.txt)
     P.l2_prefetch = 3;
     if (forced_pf >= 0) P.l2_prefetch = forced_pf;
-    ddsp::tc::gemm3x_kernel<BN, EPI><<<grid, ddsp::tc::kThreads, C::kSmemBytes, st>>>(a, a_lo ? *a_lo : a, w, wlo, c, c2, P);
+    ddsp::tc::gemm3x_kernel<BN, EPI, AM, SLICES><<<grid, ddsp::tc::kThreads, C::kSmemBytes, st>>>(a, a_lo ? *a_lo : a, w, wlo, c, c2, P);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }
@@ -1260,7 +1260,7 @@ int ddsp_b200_favor_context(const float* vt, const float* vt_lo, const float* kt
     GemmParams P = {};
     P.Z = Z; P.M = kVtRows; P.N = kFeatPad; P.K = Fp; P.w_batched = 1;
     CUtensorMap ma, mw, mc;
-    if (int rc = make_map_3(&ma, vt, Fp, kVtRows, Z, Fp, (int64_t)kVtRows * Fp, kBM)) return rc;
+    if (int rc = make_map_3(&ma, vt, Fp, kVtRows, Z, Fp, (int64_t)kVtRows * Fp, kVtRows)) return rc;   // 80-row A tiles (GCfg: AM)
     if (int rc = make_map_3(&mw, kt, Fp, kFeatPad, Z, Fp, (int64_t)kFeatPad * Fp, 96)) return rc;
     if (int rc = make_map_3(&mc, ctxT, kFeatPad, kVtRows, Z, kFeatPad, (int64_t)kVtRows * kFeatPad, 32)) return rc;
     CUtensorMap mc2 = mc;
@@ -1270,10 +1270,10 @@ int ddsp_b200_favor_context(const float* vt, const float* vt_lo, const float* kt
     }
     CUtensorMap mal;
     if (vt_lo) {
-        if (int rc = make_map_3(&mal, vt_lo, Fp, kVtRows, Z, Fp, (int64_t)kVtRows * Fp, kBM)) return rc;
+        if (int rc = make_map_3(&mal, vt_lo, Fp, kVtRows, Z, Fp, (int64_t)kVtRows * Fp, kVtRows)) return rc;
         P.a_presplit = 1;
     }
-    return launch_gemm3x<96, EPI_PLAIN>(ma, mw, mw, mc, mc2, P, (cudaStream_t)stream, vt_lo ? &mal : nullptr);   // 3 column tiles of 96 = 288 >= 272
+    return launch_gemm3x<96, EPI_PLAIN, kVtRows>(ma, mw, mw, mc, mc2, P, (cudaStream_t)stream, vt_lo ? &mal : nullptr);   // 3 column tiles of 96 = 288 >= 272
 }
 
 int ddsp_b200_favor_output(const float* qf, const float* ctxT, const float* ctxT_lo, float* out, int B, int H, int F,
@@ -1293,6 +1293,7 @@ int ddsp_b200_favor_output(const float* qf, const float* ctxT, const float* ctxT
         if (int rc = make_map_3(&mwl, ctxT_lo, kFeatPad, kVtRows, Z, kFeatPad, (int64_t)kVtRows * kFeatPad, kVtRows)) return rc;
         P.w_presplit = 1;
     }
+    // (one staging slice per epilogue warp would buy a fourth stage here: measured 142 -> 150 us, not used)
     return launch_gemm3x<kVtRows, EPI_OUT>(ma, mw, mwl, mc, mc, P, (cudaStream_t)stream);
 }
 

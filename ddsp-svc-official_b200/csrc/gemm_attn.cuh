@@ -124,9 +124,13 @@ struct RowStore {
     uint32_t base;      // shared address of this warp's two 4-KB slices (1024-byte aligned)
     int count;
     int lane;
+    int slices;         // 2, or 1 where a fourth pipeline stage is worth more than overlapped stores (attention output GEMM)
     __device__ __forceinline__ uint32_t begin() {
-        const uint32_t buf = base + (count & 1) * 4096;
-        if (lane == 0) bulk_wait_read<1>();
+        const uint32_t buf = base + (slices == 2 ? (count & 1) * 4096 : 0);
+        if (lane == 0) {
+            if (slices == 2) bulk_wait_read<1>();
+            else bulk_wait_read<0>();
+        }
         __syncwarp();
         return buf;
     }
@@ -144,13 +148,18 @@ struct RowStore {
     }
 };
 
-template <int BN>
+// AM = rows of A that exist (and are loaded) per tile.  The MMA always reads 128 rows: with AM < 128 (the 80-row v^T
+// operand of the context GEMM) rows AM..127 alias the start of the next buffer of the same stage -- finite numbers that only
+// reach accumulator rows nobody stores -- and the bytes saved buy a fourth pipeline stage.
+template <int BN, int AM = kBM, int SLICES = 2>
 struct GCfg {
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128: multiple of 16 in [16, 256]");
-    static constexpr int kABytes = kBM * 128;
+    static_assert(AM % 8 == 0 && AM <= kBM && (kBM - AM) <= AM && (kBM - AM) <= BN,
+                  "aliased rows of A_hi stay inside A_lo, those of A_lo inside W_hi (never in a buffer the splitter writes)");
+    static constexpr int kABytes = AM * 128;
     static constexpr int kWBytes = BN * 128;
     static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;   // A_hi | A_lo | W_hi | W_lo
-    static constexpr int kStoreBytes = 4 * 2 * 4096;                // four epilogue warps x two staging slices
+    static constexpr int kStoreBytes = 4 * SLICES * 4096;           // four epilogue warps x staging slices
     static constexpr int kBarBytes = 256;
     static constexpr int kBudget = 227 * 1024 - 1024 - kBarBytes - kStoreBytes;
     static constexpr int kStages = kBudget / kStageBytes < 2 ? 2 : (kBudget / kStageBytes > 6 ? 6 : kBudget / kStageBytes);
@@ -160,12 +169,12 @@ struct GCfg {
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int AM = kBM, int SLICES = 2>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w_lo,
               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2, const GemmParams P) {
-    using C = GCfg<BN>;
+    using C = GCfg<BN, AM, SLICES>;
     static_assert(EPI != EPI_PLAIN || BN % 32 == 0, "the row-store epilogue works in chunks of 32 columns");
     static_assert(EPI != EPI_QKV || BN % 64 == 0, "head-split epilogue: a column tile holds whole heads");
     extern __shared__ unsigned char smem_dyn[];
@@ -322,7 +331,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         const int q = warp & 3;
         const int row_in_tile = q * 32 + lane;
         RowStore rs;
-        rs.base = s32(store_smem + (warp - kEpiWarp0) * 8192);
+        rs.base = s32(store_smem + (warp - kEpiWarp0) * (SLICES * 4096));
+        rs.slices = SLICES;
         rs.count = 0;
         rs.lane = lane;
         int it = 0;
