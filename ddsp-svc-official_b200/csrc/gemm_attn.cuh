@@ -573,6 +573,9 @@ struct FeatParams {
     float eps;
 };
 
+constexpr int kFeatHalf0 = 128;                                              // features of the first accumulator half (N = 128 | 144)
+constexpr int kFeatSlots = 3, kFeatSlotCols = 144;                           // ring of accumulator halves in TMEM (432 of 512 columns)
+static_assert(kFeatPad - kFeatHalf0 <= kFeatSlotCols && kFeatSlots * kFeatSlotCols + 16 <= 512, "TMEM budget");
 constexpr int kFeatWBytes = kFeatPad * 128;                                  // one k-block of W (hi or lo)
 constexpr int kFeatABytes = kBM * 128;
 constexpr int kFeatSmemW = 4 * kFeatWBytes;                                  // hi kb0 | hi kb1 | lo kb0 | lo kb1
@@ -595,9 +598,9 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint64_t* full_bar = bars + 1;     // TMA -> splitter
     uint64_t* split_bar = bars + 2;    // splitter -> MMA
     uint64_t* empty_bar = bars + 3;    // MMA -> TMA
-    uint64_t* acc_full = bars + 4;     // MMA -> epilogue
-    uint64_t* acc_empty = bars + 5;    // epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* acc_full = bars + 4;     // MMA -> epilogue    [kFeatSlots]
+    uint64_t* acc_empty = bars + 7;    // epilogue -> MMA    [kFeatSlots]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = P.Z * P.tiles_m;
@@ -608,8 +611,10 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             mbar_init(s32(full_bar), 1);
             mbar_init(s32(split_bar), 128);
             mbar_init(s32(empty_bar), 1);
-            mbar_init(s32(acc_full), 1);
-            mbar_init(s32(acc_empty), 128);
+            for (int i = 0; i < kFeatSlots; ++i) {
+                mbar_init(s32(acc_full + i), 1);
+                mbar_init(s32(acc_empty + i), 128);
+            }
             fence_barrier_init();
         }
         __syncwarp();
@@ -656,36 +661,41 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc256 = umma_idesc_tf32_n(256), idesc16 = umma_idesc_tf32_n(16);
+        // A tile's 272 features are issued as two halves (features 0..127 with N = 128, 128..271 with N = 144), each into
+        // its own slot of a ring of three 144-column accumulators: while the epilogue drains the halves of tile t, the halves
+        // of tile t+1 are already being computed (one 272-column accumulator would fit TMEM only once, and MMA and epilogue
+        // of a tile then run back to back).
+        constexpr uint32_t idesc_h[2] = {umma_idesc_tf32_n(kFeatHalf0), umma_idesc_tf32_n(kFeatPad - kFeatHalf0)};
         uint32_t phase = 0;
+        uint32_t g = 0;                    // running half index: slot = g % 3, use = g / 3
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            mbar_wait(s32(acc_empty), phase ^ 1);
             mbar_wait(s32(split_bar), phase);
-            tc_fence_after();
-            if (elect_one()) {
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb) {
-                    const uint64_t a_hi = umma_desc_sw128(s32(a_smem + kb * kFeatABytes));
-                    const uint64_t a_lo = umma_desc_sw128(s32(a_smem + (2 + kb) * kFeatABytes));
-                    const uint32_t wh = s32(w_smem + kb * kFeatWBytes), wl = s32(w_smem + (2 + kb) * kFeatWBytes);
+            for (int half = 0; half < 2; ++half, ++g) {
+                const uint32_t slot = g % kFeatSlots, use = g / kFeatSlots;
+                mbar_wait(s32(acc_empty + slot), (use & 1) ^ 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d = tmem_base + slot * kFeatSlotCols;
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const uint32_t idesc = half ? idesc16 : idesc256;
-                        const uint32_t d = tmem_base + half * 256;
-                        const uint64_t w_hi = umma_desc_sw128(wh + half * 256 * 128), w_lo = umma_desc_sw128(wl + half * 256 * 128);
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t a_hi = umma_desc_sw128(s32(a_smem + kb * kFeatABytes));
+                        const uint64_t a_lo = umma_desc_sw128(s32(a_smem + (2 + kb) * kFeatABytes));
+                        const uint32_t wh = s32(w_smem + kb * kFeatWBytes), wl = s32(w_smem + (2 + kb) * kFeatWBytes);
+                        const uint64_t w_hi = umma_desc_sw128(wh + half * kFeatHalf0 * 128), w_lo = umma_desc_sw128(wl + half * kFeatHalf0 * 128);
 #pragma unroll
                         for (int kk = 0; kk < kBK / 8; ++kk) {
                             const uint64_t o = (uint64_t)(2 * kk);
-                            umma_tf32(d, a_lo + o, w_hi + o, idesc, (kb | kk) != 0);
-                            umma_tf32(d, a_hi + o, w_lo + o, idesc, 1);
-                            umma_tf32(d, a_hi + o, w_hi + o, idesc, 1);
+                            umma_tf32(d, a_lo + o, w_hi + o, idesc_h[half], (kb | kk) != 0);
+                            umma_tf32(d, a_hi + o, w_lo + o, idesc_h[half], 1);
+                            umma_tf32(d, a_hi + o, w_hi + o, idesc_h[half], 1);
                         }
                     }
+                    if (half == 1) umma_commit(s32(empty_bar));          // the A tile is free once both halves have read it
+                    umma_commit(s32(acc_full + slot));
                 }
-                umma_commit(s32(empty_bar));
-                umma_commit(s32(acc_full));
+                __syncwarp();
             }
-            __syncwarp();
             phase ^= 1;
         }
     } else if (warp >= kSplitWarp0) {
@@ -705,8 +715,8 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int row_in_tile = q * 32 + lane;
         const uint32_t stage_buf = s32(store_smem + (warp - kEpiWarp0) * 4096);
         const float ratio = rsqrtf((float)kFeat);
-        uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int z = tile / P.tiles_m, m0 = (tile - z * P.tiles_m) * kBM;
             const int f = m0 + row_in_tile;
             const bool ok = f < P.F;
@@ -721,66 +731,86 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 }
             }
             const float diag = 0.0625f * ss;
-            mbar_wait(s32(acc_full), phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-            // TMEM reads are software-pipelined: the load of chunk c+1 is in flight while chunk c is processed
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t g0 = 2 * it, g1 = g0 + 1;
+            const uint32_t slot_h[2] = {g0 % kFeatSlots, g1 % kFeatSlots};
+            const uint32_t par_h[2] = {(g0 / kFeatSlots) & 1, (g1 / kFeatSlots) & 1};
+            // TMEM reads are software-pipelined inside a half: the load of chunk c+1 is in flight while chunk c is processed
             // (tcgen05.wait::ld covers every load issued before it, so the next load is issued right after the wait)
             uint32_t ra[32], rb[32];
-            constexpr int kChunks = (kFeatPad + 31) / 32;      // 9; the last one reads 16 columns beyond the accumulator (ignored)
             constexpr float kLog2e = 1.4426950408889634f;
             float mx = -3.0e38f;
             if (IS_Q) {
-                tmem_ld32(taddr, ra);
+                // pass 1: row maximum over all 266 features (both halves must be complete before anything is written)
 #pragma unroll
-                for (int c = 0; c < kChunks; ++c) {
-                    uint32_t(&cur)[32] = (c & 1) ? rb : ra;
-                    uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
-                    tmem_ld_wait();
-                    tmem_ld32(taddr + (c + 1 < kChunks ? 32 * (c + 1) : 0), nxt);        // last iteration: chunk 0 for the second pass
+                for (int half = 0; half < 2; ++half) {
+                    constexpr int kCh0 = kFeatHalf0 / 32;
+                    const int n_ch = half ? (kFeatPad - kFeatHalf0 + 31) / 32 : kCh0;
+                    mbar_wait(s32(acc_full + slot_h[half]), par_h[half]);
+                    tc_fence_after();
+                    const uint32_t taddr = lane_base + slot_h[half] * kFeatSlotCols;
+                    tmem_ld32(taddr, ra);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (32 * c + j < kFeat) mx = fmaxf(mx, __uint_as_float(cur[j]));
+                    for (int c = 0; c < 5; ++c) {
+                        if (c < n_ch) {
+                            uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+                            uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
+                            tmem_ld_wait();
+                            if (c + 1 < n_ch) tmem_ld32(taddr + 32 * (c + 1), nxt);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (half * kFeatHalf0 + 32 * c + j < kFeat) mx = fmaxf(mx, __uint_as_float(cur[j]));
+                        }
+                    }
                 }
-            } else {
-                tmem_ld32(taddr, (kChunks & 1) ? rb : ra);
             }
             // exp(dash + shift) = 2^(dash * log2e + shift * log2e): one FFMA + one MUFU.EX2 per element, then ratio * (e + eps)
             const float shift2 = (IS_Q ? -(diag + mx) : (P.eps - diag)) * kLog2e;
             const float add = IS_Q ? ratio * P.eps : 0.0f;
 #pragma unroll
-            for (int c = 0; c < kChunks; ++c) {
-                // after the (odd number of) pass-1 iterations chunk 0 sits in the buffer pass 1 would have used next
-                uint32_t(&cur)[32] = ((c + kChunks) & 1) ? rb : ra;
-                uint32_t(&nxt)[32] = ((c + kChunks) & 1) ? ra : rb;
-                tmem_ld_wait();
-                if (c + 1 < kChunks) tmem_ld32(taddr + 32 * (c + 1), nxt);
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float e = ex2_approx(fmaf(__uint_as_float(cur[j]), kLog2e, shift2));
-                    v[j] = (32 * c + j < kFeat) ? fmaf(e, ratio, add) : 0.0f;
+            for (int half = 0; half < 2; ++half) {
+                constexpr int kCh0 = kFeatHalf0 / 32;
+                const int n_ch = half ? (kFeatPad - kFeatHalf0 + 31) / 32 : kCh0;     // 4 | 5 (the last one reads 16 columns past the half: ignored)
+                if (!IS_Q) {
+                    mbar_wait(s32(acc_full + slot_h[half]), par_h[half]);
+                    tc_fence_after();
                 }
-                const int c0 = 32 * c;
-                if (IS_Q) {
-                    if (lane == 0) bulk_wait_read<0>();
-                    __syncwarp();
+                const uint32_t taddr = lane_base + slot_h[half] * kFeatSlotCols;
+                tmem_ld32(taddr, ra);
 #pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4)
-                        st_shared_v4(stage_buf + lane * 128 + ((k4 ^ (lane & 7)) << 4), v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) { tma_store_3d(&map_c, stage_buf, c0, m0 + q * 32, z); bulk_commit(); }
-                } else if (ok) {
-                    float* dst = P.kt + ((int64_t)z * kFeatPad + c0) * P.Fp + f;
+                for (int c = 0; c < 5; ++c) {
+                    if (c < n_ch) {
+                        uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+                        uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
+                        tmem_ld_wait();
+                        if (c + 1 < n_ch) tmem_ld32(taddr + 32 * (c + 1), nxt);
+                        const int c0 = half * kFeatHalf0 + 32 * c;
+                        float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + j < kFeat) dst[(int64_t)j * P.Fp] = v[j];
+                        for (int j = 0; j < 32; ++j) {
+                            const float e = ex2_approx(fmaf(__uint_as_float(cur[j]), kLog2e, shift2));
+                            v[j] = (c0 + j < kFeat) ? fmaf(e, ratio, add) : 0.0f;
+                        }
+                        if (IS_Q) {
+                            if (lane == 0) bulk_wait_read<0>();
+                            __syncwarp();
+#pragma unroll
+                            for (int k4 = 0; k4 < 8; ++k4)
+                                st_shared_v4(stage_buf + lane * 128 + ((k4 ^ (lane & 7)) << 4), v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) { tma_store_3d(&map_c, stage_buf, c0, m0 + q * 32, z); bulk_commit(); }
+                        } else if (ok) {
+                            float* dst = P.kt + ((int64_t)z * kFeatPad + c0) * P.Fp + f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c0 + j < kFeat) dst[(int64_t)j * P.Fp] = v[j];
+                        }
+                    }
                 }
+                tc_fence_before();
+                mbar_arrive(s32(acc_empty + slot_h[half]));      // this half's slot is free for the MMAs of the next tile
             }
-            tc_fence_before();
-            mbar_arrive(s32(acc_empty));
-            phase ^= 1;
         }
         if (IS_Q) {
             if (lane == 0) bulk_wait_all<0>();
