@@ -581,7 +581,8 @@ constexpr int kFeatABytes = kBM * 128;
 constexpr int kFeatSmemW = 4 * kFeatWBytes;                                  // hi kb0 | hi kb1 | lo kb0 | lo kb1
 constexpr int kFeatSmemA = 4 * kFeatABytes;                                  // hi kb0 | hi kb1 | lo kb0 | lo kb1
 constexpr int kFeatStoreBytes = 4 * 4096;                                    // one staging slice per epilogue warp
-constexpr int kFeatSmemBytes = kFeatSmemW + kFeatSmemA + kFeatStoreBytes + 256 + 1024;
+constexpr int kFeatDiagRing = 4;                                             // |x|^2 terms of the tiles in flight between splitter and epilogue
+constexpr int kFeatSmemBytes = kFeatSmemW + kFeatSmemA + kFeatStoreBytes + 256 + kFeatDiagRing * kBM * 4 + 1024;
 static_assert(kFeatSmemBytes <= 227 * 1024, "shared memory budget");
 
 template <bool IS_Q>
@@ -601,6 +602,7 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint64_t* acc_full = bars + 4;     // MMA -> epilogue    [kFeatSlots]
     uint64_t* acc_empty = bars + 7;    // epilogue -> MMA    [kFeatSlots]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    float* diag_ring = reinterpret_cast<float*>(store_smem + kFeatStoreBytes + 256);     // [kFeatDiagRing][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = P.Z * P.tiles_m;
@@ -701,10 +703,39 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     } else if (warp >= kSplitWarp0) {
         // ===== splitter =====
         const int t = threadIdx.x - kSplitWarp0 * 32;
+        // The splitter reads every element of the tile anyway, so it also forms diag = |x|^2 / (2 sqrt(64)) of the 128 rows
+        // (the epilogue used to re-read its row from global memory: a load latency per tile in front of the exponentials).
+        // Thread t holds float4 column-chunks of rows t/8 + 16 n in both k-blocks; the 8 threads of a row add up by shuffles.
+        // The values travel splitter -> split_bar -> MMA -> acc_full -> epilogue; the epilogue runs at most two tiles behind.
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             mbar_wait(s32(full_bar), phase);
-            split_tile_lo(s32(a_smem), s32(a_smem) + 2 * kFeatABytes, 2 * kFeatABytes / 16, t);
+            const uint32_t raw = s32(a_smem), lo = raw + 2 * kFeatABytes;
+            float ssq[8];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const int i = t + 128 * (n + 8 * kb);
+                    const float4 x = ld_shared_v4(raw + 16 * i);
+                    st_shared_v4(lo + 16 * i, tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+                    acc = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, acc))));
+                }
+                ssq[n] = acc;
+            }
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                ssq[n] += __shfl_xor_sync(0xffffffffu, ssq[n], 1);
+                ssq[n] += __shfl_xor_sync(0xffffffffu, ssq[n], 2);
+                ssq[n] += __shfl_xor_sync(0xffffffffu, ssq[n], 4);
+            }
+            if ((t & 7) == 0) {
+                float* dr = diag_ring + (it % kFeatDiagRing) * kBM + (t >> 3);
+#pragma unroll
+                for (int n = 0; n < 8; ++n) dr[16 * n] = 0.0625f * ssq[n];
+            }
             fence_proxy_async();
             mbar_arrive(s32(split_bar));
             phase ^= 1;
@@ -720,21 +751,14 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const int z = tile / P.tiles_m, m0 = (tile - z * P.tiles_m) * kBM;
             const int f = m0 + row_in_tile;
             const bool ok = f < P.F;
-            // diag = |x|^2 * 64^-0.5 / 2 from the fp32 row itself (L2-resident: TMA has just read it)
-            float ss = 0.0f;
-            if (ok) {
-                const float4* xr = reinterpret_cast<const float4*>(P.x + ((int64_t)z * P.F + f) * 64);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float4 t4 = __ldg(xr + i);
-                    ss = fmaf(t4.x, t4.x, fmaf(t4.y, t4.y, fmaf(t4.z, t4.z, fmaf(t4.w, t4.w, ss))));
-                }
-            }
-            const float diag = 0.0625f * ss;
             const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
             const uint32_t g0 = 2 * it, g1 = g0 + 1;
             const uint32_t slot_h[2] = {g0 % kFeatSlots, g1 % kFeatSlots};
             const uint32_t par_h[2] = {(g0 / kFeatSlots) & 1, (g1 / kFeatSlots) & 1};
+            mbar_wait(s32(acc_full + slot_h[0]), par_h[0]);
+            tc_fence_after();
+            // diag = |x|^2 * 64^-0.5 / 2, formed by the splitter from the tile in shared memory
+            const float diag = diag_ring[(it % kFeatDiagRing) * kBM + row_in_tile];
             // TMEM reads are software-pipelined inside a half: the load of chunk c+1 is in flight while chunk c is processed
             // (tcgen05.wait::ld covers every load issued before it, so the next load is issued right after the wait)
             uint32_t ra[32], rb[32];
@@ -746,8 +770,10 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 for (int half = 0; half < 2; ++half) {
                     constexpr int kCh0 = kFeatHalf0 / 32;
                     const int n_ch = half ? (kFeatPad - kFeatHalf0 + 31) / 32 : kCh0;
-                    mbar_wait(s32(acc_full + slot_h[half]), par_h[half]);
-                    tc_fence_after();
+                    if (half) {
+                        mbar_wait(s32(acc_full + slot_h[half]), par_h[half]);
+                        tc_fence_after();
+                    }
                     const uint32_t taddr = lane_base + slot_h[half] * kFeatSlotCols;
                     tmem_ld32(taddr, ra);
 #pragma unroll
@@ -771,7 +797,7 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             for (int half = 0; half < 2; ++half) {
                 constexpr int kCh0 = kFeatHalf0 / 32;
                 const int n_ch = half ? (kFeatPad - kFeatHalf0 + 31) / 32 : kCh0;     // 4 | 5 (the last one reads 16 columns past the half: ignored)
-                if (!IS_Q) {
+                if (!IS_Q && half) {
                     mbar_wait(s32(acc_full + slot_h[half]), par_h[half]);
                     tc_fence_after();
                 }
