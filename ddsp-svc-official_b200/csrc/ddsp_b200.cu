@@ -1242,10 +1242,10 @@ int ddsp_b200_favor_features(const float* x, const float* proj_scaled, int n_fea
     static bool attr_q[64] = {false}, attr_k[64] = {false};
     if (is_query) {
         if (int rc = set_smem_once(ddsp::tc::favor_features_kernel<true>, ddsp::tc::kFeatSmemBytes, attr_q)) return rc;
-        ddsp::tc::favor_features_kernel<true><<<grid, ddsp::tc::kThreads, ddsp::tc::kFeatSmemBytes, st>>>(ma, mw, mc, P);
+        ddsp::tc::favor_features_kernel<true><<<grid, ddsp::tc::feat_threads<true>(), ddsp::tc::kFeatSmemBytes, st>>>(ma, mw, mc, P);
     } else {
         if (int rc = set_smem_once(ddsp::tc::favor_features_kernel<false>, ddsp::tc::kFeatSmemBytes, attr_k)) return rc;
-        ddsp::tc::favor_features_kernel<false><<<grid, ddsp::tc::kThreads, ddsp::tc::kFeatSmemBytes, st>>>(ma, mw, mc, P);
+        ddsp::tc::favor_features_kernel<false><<<grid, ddsp::tc::feat_threads<false>(), ddsp::tc::kFeatSmemBytes, st>>>(ma, mw, mc, P);
     }
     LAUNCH_CHECK();
     return DDSP_B200_OK;

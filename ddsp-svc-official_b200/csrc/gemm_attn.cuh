@@ -585,8 +585,16 @@ constexpr int kFeatDiagRing = 4;                                             // 
 constexpr int kFeatSmemBytes = kFeatSmemW + kFeatSmemA + kFeatStoreBytes + 256 + kFeatDiagRing * kBM * 4 + 1024;
 static_assert(kFeatSmemBytes <= 227 * 1024, "shared memory budget");
 
+// Eight splitter warps (6..13): load -> split -> MMA of consecutive tiles is a serial chain through the single A buffer and
+// sets the time per tile (the epilogue warps wait about half of the time), so the split is spread over 256 threads and the
+// MMA issuer starts the products that need no low term of A (hi*hi, hi*lo(W): two thirds of the work) as soon as TMA has
+// landed.  Measured and dropped: a second epilogue warp group for k' (126 -> 128 us).
 template <bool IS_Q>
-__global__ void __launch_bounds__(kThreads, 1)
+__host__ __device__ constexpr int feat_threads() { return kThreads + 128; }
+constexpr int kFeatSplitThreads = 256;
+
+template <bool IS_Q>
+__global__ void __launch_bounds__(feat_threads<IS_Q>(), 1)
 favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                       const __grid_constant__ CUtensorMap map_c, const FeatParams P) {
     extern __shared__ unsigned char smem_dyn[];
@@ -611,7 +619,7 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (lane == 0) {
             mbar_init(s32(w_bar), 1);
             mbar_init(s32(full_bar), 1);
-            mbar_init(s32(split_bar), 128);
+            mbar_init(s32(split_bar), kFeatSplitThreads);
             mbar_init(s32(empty_bar), 1);
             for (int i = 0; i < kFeatSlots; ++i) {
                 mbar_init(s32(acc_full + i), 1);
@@ -640,7 +648,7 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     mbar_wait(s32(w_bar), 0);
     {
         const uint32_t hi = s32(w_smem), lo = hi + 2 * kFeatWBytes;
-        for (int i = threadIdx.x; i < 2 * kFeatWBytes / 16; i += kThreads) {
+        for (int i = threadIdx.x; i < 2 * kFeatWBytes / 16; i += feat_threads<IS_Q>()) {
             const float4 x = ld_shared_v4(hi + 16 * i);
             st_shared_v4(lo + 16 * i, tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
         }
@@ -654,6 +662,15 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int z = tile / P.tiles_m, m0 = (tile - z * P.tiles_m) * kBM;
+                // The single A buffer makes load -> split -> MMA of consecutive tiles a serial chain (it, not the epilogue,
+                // sets the time per tile): the next tile is pulled into L2 while this one is in flight, so that its load
+                // costs an L2 instead of an HBM latency.
+                const int nt = tile + gridDim.x;
+                if (nt < n_tiles) {
+                    const int nz = nt / P.tiles_m, nm0 = (nt - nz * P.tiles_m) * kBM;
+                    tma_prefetch_3d(&map_a, 0, nm0, nz);
+                    tma_prefetch_3d(&map_a, kBK, nm0, nz);
+                }
                 mbar_wait(s32(empty_bar), phase ^ 1);
                 mbar_arrive_expect_tx(s32(full_bar), 2 * kFeatABytes);
                 tma_load_3d(s32(a_smem), &map_a, 0, m0, z, s32(full_bar));
@@ -671,26 +688,41 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         uint32_t phase = 0;
         uint32_t g = 0;                    // running half index: slot = g % 3, use = g / 3
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            mbar_wait(s32(split_bar), phase);
+            mbar_wait(s32(full_bar), phase);                           // the raw tile (= high term of A) has landed
 #pragma unroll
             for (int half = 0; half < 2; ++half, ++g) {
                 const uint32_t slot = g % kFeatSlots, use = g / kFeatSlots;
                 mbar_wait(s32(acc_empty + slot), (use & 1) ^ 1);
                 tc_fence_after();
+                const uint32_t d = tmem_base + slot * kFeatSlotCols;
                 if (elect_one()) {
-                    const uint32_t d = tmem_base + slot * kFeatSlotCols;
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb) {
                         const uint64_t a_hi = umma_desc_sw128(s32(a_smem + kb * kFeatABytes));
-                        const uint64_t a_lo = umma_desc_sw128(s32(a_smem + (2 + kb) * kFeatABytes));
                         const uint32_t wh = s32(w_smem + kb * kFeatWBytes), wl = s32(w_smem + (2 + kb) * kFeatWBytes);
                         const uint64_t w_hi = umma_desc_sw128(wh + half * kFeatHalf0 * 128), w_lo = umma_desc_sw128(wl + half * kFeatHalf0 * 128);
 #pragma unroll
                         for (int kk = 0; kk < kBK / 8; ++kk) {
                             const uint64_t o = (uint64_t)(2 * kk);
-                            umma_tf32(d, a_lo + o, w_hi + o, idesc_h[half], (kb | kk) != 0);
-                            umma_tf32(d, a_hi + o, w_lo + o, idesc_h[half], 1);
+                            umma_tf32(d, a_hi + o, w_lo + o, idesc_h[half], (kb | kk) != 0);
                             umma_tf32(d, a_hi + o, w_hi + o, idesc_h[half], 1);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (half == 0) {
+                    mbar_wait(s32(split_bar), phase);                  // the low term of A is in place
+                    tc_fence_after();
+                }
+                if (elect_one()) {
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t a_lo = umma_desc_sw128(s32(a_smem + (2 + kb) * kFeatABytes));
+                        const uint64_t w_hi = umma_desc_sw128(s32(w_smem + kb * kFeatWBytes) + half * kFeatHalf0 * 128);
+#pragma unroll
+                        for (int kk = 0; kk < kBK / 8; ++kk) {
+                            const uint64_t o = (uint64_t)(2 * kk);
+                            umma_tf32(d, a_lo + o, w_hi + o, idesc_h[half], 1);
                         }
                     }
                     if (half == 1) umma_commit(s32(empty_bar));          // the A tile is free once both halves have read it
@@ -705,36 +737,36 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int t = threadIdx.x - kSplitWarp0 * 32;
         // The splitter reads every element of the tile anyway, so it also forms diag = |x|^2 / (2 sqrt(64)) of the 128 rows
         // (the epilogue used to re-read its row from global memory: a load latency per tile in front of the exponentials).
-        // Thread t holds float4 column-chunks of rows t/8 + 16 n in both k-blocks; the 8 threads of a row add up by shuffles.
+        // Thread t holds float4 column-chunks of rows t/8 + 32 m in both k-blocks; the 8 threads of a row add up by shuffles.
         // The values travel splitter -> split_bar -> MMA -> acc_full -> epilogue; the epilogue runs at most two tiles behind.
         uint32_t phase = 0;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             mbar_wait(s32(full_bar), phase);
             const uint32_t raw = s32(a_smem), lo = raw + 2 * kFeatABytes;
-            float ssq[8];
+            float ssq[4];
 #pragma unroll
-            for (int n = 0; n < 8; ++n) {
+            for (int m = 0; m < 4; ++m) {
                 float acc = 0.0f;
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
-                    const int i = t + 128 * (n + 8 * kb);
+                    const int i = t + kFeatSplitThreads * (m + 4 * kb);     // 1024 float4 per k-block: row (i % 1024) / 8
                     const float4 x = ld_shared_v4(raw + 16 * i);
                     st_shared_v4(lo + 16 * i, tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
                     acc = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, acc))));
                 }
-                ssq[n] = acc;
+                ssq[m] = acc;
             }
 #pragma unroll
-            for (int n = 0; n < 8; ++n) {
-                ssq[n] += __shfl_xor_sync(0xffffffffu, ssq[n], 1);
-                ssq[n] += __shfl_xor_sync(0xffffffffu, ssq[n], 2);
-                ssq[n] += __shfl_xor_sync(0xffffffffu, ssq[n], 4);
+            for (int m = 0; m < 4; ++m) {
+                ssq[m] += __shfl_xor_sync(0xffffffffu, ssq[m], 1);
+                ssq[m] += __shfl_xor_sync(0xffffffffu, ssq[m], 2);
+                ssq[m] += __shfl_xor_sync(0xffffffffu, ssq[m], 4);
             }
             if ((t & 7) == 0) {
                 float* dr = diag_ring + (it % kFeatDiagRing) * kBM + (t >> 3);
 #pragma unroll
-                for (int n = 0; n < 8; ++n) dr[16 * n] = 0.0625f * ssq[n];
+                for (int m = 0; m < 4; ++m) dr[32 * m] = 0.0625f * ssq[m];
             }
             fence_proxy_async();
             mbar_arrive(s32(split_bar));
@@ -744,7 +776,7 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // ===== epilogue =====
         const int q = warp & 3;
         const int row_in_tile = q * 32 + lane;
-        const uint32_t stage_buf = s32(store_smem + (warp - kEpiWarp0) * 4096);
+        const uint32_t stage_buf = s32(store_smem + (warp - kEpiWarp0) * 4096);            // q' only
         const float ratio = rsqrtf((float)kFeat);
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -790,17 +822,18 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     }
                 }
             }
-            // exp(dash + shift) = 2^(dash * log2e + shift * log2e): one FFMA + one MUFU.EX2 per element, then ratio * (e + eps)
-            const float shift2 = (IS_Q ? -(diag + mx) : (P.eps - diag)) * kLog2e;
-            const float add = IS_Q ? ratio * P.eps : 0.0f;
+            // exp(dash + shift) = 2^(dash * log2e + shift * log2e): one FFMA + one MUFU.EX2 per element, then ratio * (e + eps);
+            // k' has no additive term, so its ratio is folded into the exponent
+            const float shift2 = IS_Q ? -(diag + mx) * kLog2e : fmaf(P.eps - diag, kLog2e, -0.5f * log2f((float)kFeat));
+            const float add = ratio * P.eps;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                constexpr int kCh0 = kFeatHalf0 / 32;
-                const int n_ch = half ? (kFeatPad - kFeatHalf0 + 31) / 32 : kCh0;     // 4 | 5 (the last one reads 16 columns past the half: ignored)
                 if (!IS_Q && half) {
                     mbar_wait(s32(acc_full + slot_h[half]), par_h[half]);
                     tc_fence_after();
                 }
+                constexpr int kCh0 = kFeatHalf0 / 32;
+                const int n_ch = half ? (kFeatPad - kFeatHalf0 + 31) / 32 : kCh0;     // 4 | 5 (the last one reads 16 columns past the half: ignored)
                 const uint32_t taddr = lane_base + slot_h[half] * kFeatSlotCols;
                 tmem_ld32(taddr, ra);
 #pragma unroll
@@ -815,7 +848,7 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float e = ex2_approx(fmaf(__uint_as_float(cur[j]), kLog2e, shift2));
-                            v[j] = (c0 + j < kFeat) ? fmaf(e, ratio, add) : 0.0f;
+                            v[j] = !IS_Q ? e : (c0 + j < kFeat) ? fmaf(e, ratio, add) : 0.0f;
                         }
                         if (IS_Q) {
                             if (lane == 0) bulk_wait_read<0>();
@@ -828,9 +861,10 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                             if (lane == 0) { tma_store_3d(&map_c, stage_buf, c0, m0 + q * 32, z); bulk_commit(); }
                         } else if (ok) {
                             float* dst = P.kt + ((int64_t)z * kFeatPad + c0) * P.Fp + f;
+                            const uint32_t ld = (uint32_t)P.Fp;                  // 32-bit row offsets: one address instruction per store
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (c0 + j < kFeat) dst[(int64_t)j * P.Fp] = v[j];
+                                if (c0 + j < kFeat) dst[(uint32_t)j * ld] = v[j];
                         }
                     }
                 }
