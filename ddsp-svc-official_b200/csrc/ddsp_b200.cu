@@ -1069,12 +1069,13 @@ int ddsp_b200_tc_microbench(const float* A, const float* W, float* C, int N, int
 namespace {
 
 // fp32 tensor of rank 3 or 4 (innermost dimension contiguous), box = 32 floats (one 128-byte swizzle row) x box_rows x 1 (x 1)
-int make_map_nd(CUtensorMap* m, const float* base, int rank, const int64_t* dims, const int64_t* strides_elems, int box_rows) {
+int make_map_nd(CUtensorMap* m, const float* base, int rank, const int64_t* dims, const int64_t* strides_elems, int box_rows,
+                int box_cols = ddsp::tc::kBK) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return DDSP_B200_ERR_UNSUPPORTED;
     cuuint64_t d[4];
     cuuint64_t sb[3];
-    cuuint32_t box[4] = {(cuuint32_t)ddsp::tc::kBK, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1, 1};      // 32 columns: 128-byte swizzle rows, 16: 64-byte
     cuuint32_t es[4] = {1, 1, 1, 1};
     for (int i = 0; i < rank; ++i) d[i] = (cuuint64_t)dims[i];
     for (int i = 0; i + 1 < rank; ++i) {
@@ -1083,7 +1084,8 @@ int make_map_nd(CUtensorMap* m, const float* base, int rank, const int64_t* dims
     }
     if (reinterpret_cast<uintptr_t>(base) & 15) return DDSP_B200_ERR_UNSUPPORTED;
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), d, sb, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         g_last_cuda_error = (int)r;
@@ -1093,10 +1095,10 @@ int make_map_nd(CUtensorMap* m, const float* base, int rank, const int64_t* dims
 }
 // (rows x cols) matrices with row stride ld, Z of them batch_stride apart
 int make_map_3(CUtensorMap* m, const float* base, int64_t cols, int64_t rows, int64_t Z, int64_t ld, int64_t batch_stride,
-               int box_rows) {
+               int box_rows, int box_cols = ddsp::tc::kBK) {
     const int64_t dims[3] = {cols, rows, Z};
     const int64_t strides[2] = {ld, Z > 1 ? batch_stride : ld * rows};
-    return make_map_nd(m, base, 3, dims, strides, box_rows);
+    return make_map_nd(m, base, 3, dims, strides, box_rows, box_cols);
 }
 
 template <typename K>
@@ -1111,12 +1113,12 @@ int set_smem_once(K kernel, int bytes, bool* flags) {
     return 0;
 }
 
-template <int BN, int EPI, int AM = ddsp::tc::kBM, int SLICES = 2>
+template <int BN, int EPI, int AM = ddsp::tc::kBM, int SLICES = 2, int BK = ddsp::tc::kBK>
 int launch_gemm3x(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& wlo, const CUtensorMap& c, const CUtensorMap& c2,
                   ddsp::tc::GemmParams P, cudaStream_t st, const CUtensorMap* a_lo = nullptr) {
-    using C = ddsp::tc::GCfg<BN, AM, SLICES>;
+    using C = ddsp::tc::GCfg<BN, AM, SLICES, BK>;
     static bool attr_set[64] = {false};
-    if (int rc = set_smem_once(ddsp::tc::gemm3x_kernel<BN, EPI, AM, SLICES>, C::kSmemBytes, attr_set)) return rc;
+    if (int rc = set_smem_once(ddsp::tc::gemm3x_kernel<BN, EPI, AM, SLICES, BK>, C::kSmemBytes, attr_set)) return rc;
     P.tiles_m = (P.M + ddsp::tc::kBM - 1) / ddsp::tc::kBM;
     P.tiles_n = (P.N + BN - 1) / BN;
     const int64_t tiles = (int64_t)P.Z * P.tiles_m * P.tiles_n;
@@ -1128,7 +1130,7 @@ int launch_gemm3x(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap&
     // projection); 6 / 12 k-blocks ahead are no better (profiles/r02_gemm_l2_prefetch.txt)
     P.l2_prefetch = 3;
     if (forced_pf >= 0) P.l2_prefetch = forced_pf;
-    ddsp::tc::gemm3x_kernel<BN, EPI, AM, SLICES><<<grid, ddsp::tc::kThreads, C::kSmemBytes, st>>>(a, a_lo ? *a_lo : a, w, wlo, c, c2, P);
+    ddsp::tc::gemm3x_kernel<BN, EPI, AM, SLICES, BK><<<grid, ddsp::tc::kThreads, C::kSmemBytes, st>>>(a, a_lo ? *a_lo : a, w, wlo, c, c2, P);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }
@@ -1166,15 +1168,19 @@ int ddsp_b200_linear_tf32x3_ex(const float* A, int64_t lda, const float* W, cons
             if (cost < best_cost) { best_cost = cost; bn = cand; }
         }
     }
+    static const int forced_bk = [] { const char* e = getenv("DDSP_B200_GEMM_BK"); return e ? atoi(e) : 0; }();   // experiments
+    const int bk = (bn == 256 && forced_bk == 16) ? 16 : 32;
     CUtensorMap ma, mw, mwl, mc, mc2;
-    if (int rc = make_map_3(&ma, A, K, M, 1, lda, 0, ddsp::tc::kBM)) return rc;
-    if (int rc = make_map_3(&mw, W, K, N, 1, ldw, 0, bn)) return rc;
-    if (int rc = make_map_3(&mwl, W_lo ? W_lo : W, K, N, 1, ldw, 0, bn)) return rc;
+    if (int rc = make_map_3(&ma, A, K, M, 1, lda, 0, ddsp::tc::kBM, bk)) return rc;
+    if (int rc = make_map_3(&mw, W, K, N, 1, ldw, 0, bn, bk)) return rc;
+    if (int rc = make_map_3(&mwl, W_lo ? W_lo : W, K, N, 1, ldw, 0, bn, bk)) return rc;
     if (int rc = make_map_3(&mc, C, N, M, 1, ldc, 0, 32)) return rc;
     if (int rc = make_map_3(&mc2, C_ln ? C_ln : C, N, M, 1, C_ln ? ldc_ln : ldc, 0, 32)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     switch (bn) {
-        case 256: return launch_gemm3x<256, ddsp::tc::EPI_PLAIN>(ma, mw, mwl, mc, mc2, P, st);
+        case 256:
+            if (bk == 16) return launch_gemm3x<256, ddsp::tc::EPI_PLAIN, ddsp::tc::kBM, 2, 16>(ma, mw, mwl, mc, mc2, P, st);
+            return launch_gemm3x<256, ddsp::tc::EPI_PLAIN>(ma, mw, mwl, mc, mc2, P, st);
         case 224: return launch_gemm3x<224, ddsp::tc::EPI_PLAIN>(ma, mw, mwl, mc, mc2, P, st);
         default: return launch_gemm3x<128, ddsp::tc::EPI_PLAIN>(ma, mw, mwl, mc, mc2, P, st);
     }

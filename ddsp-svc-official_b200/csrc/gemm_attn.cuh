@@ -117,6 +117,15 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32_n(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 }
 
+// 64-byte-swizzled K-major tile (rows of 16 fp32, 8-row groups of 512 B): layout type SWIZZLE_64B = 4, stride byte offset 512
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+template <int BK>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
+    return BK == 32 ? umma_desc_sw128(smem_addr) : umma_desc_sw64(smem_addr);
+}
+
 // One warp's 32 rows x 32 columns (a row per lane) leave through a 128-byte-swizzled staging slice and one TMA
 // store: coalesced 128-byte rows in global memory, rows / columns beyond the tensor edge are clipped by the TMA
 // unit.  Two slices per warp alternate; `wait_read<1>` makes sure the store that last read this slice is done.
@@ -151,30 +160,34 @@ struct RowStore {
 // AM = rows of A that exist (and are loaded) per tile.  The MMA always reads 128 rows: with AM < 128 (the 80-row v^T
 // operand of the context GEMM) rows AM..127 alias the start of the next buffer of the same stage -- finite numbers that only
 // reach accumulator rows nobody stores -- and the bytes saved buy a fourth pipeline stage.
-template <int BN, int AM = kBM, int SLICES = 2>
+// BK = fp32 elements of one k-block (32: 128-byte swizzle rows; 16: 64-byte rows -- half-sized stages, twice as many of them
+// in the same shared memory, for the tiles whose two 96-KB stages leave the ring empty half of the time).
+template <int BN, int AM = kBM, int SLICES = 2, int BK = kBK>
 struct GCfg {
+    static_assert(BK == 32 || BK == 16, "k-block = one 128-byte or 64-byte swizzle row");
+    static constexpr int kRowBytes = BK * 4;
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128: multiple of 16 in [16, 256]");
     static_assert(AM % 8 == 0 && AM <= kBM && (kBM - AM) <= AM && (kBM - AM) <= BN,
                   "aliased rows of A_hi stay inside A_lo, those of A_lo inside W_hi (never in a buffer the splitter writes)");
-    static constexpr int kABytes = AM * 128;
-    static constexpr int kWBytes = BN * 128;
+    static constexpr int kABytes = AM * kRowBytes;
+    static constexpr int kWBytes = BN * kRowBytes;
     static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;   // A_hi | A_lo | W_hi | W_lo
     static constexpr int kStoreBytes = 4 * SLICES * 4096;           // four epilogue warps x staging slices
     static constexpr int kBarBytes = 256;
     static constexpr int kBudget = 227 * 1024 - 1024 - kBarBytes - kStoreBytes;
-    static constexpr int kStages = kBudget / kStageBytes < 2 ? 2 : (kBudget / kStageBytes > 6 ? 6 : kBudget / kStageBytes);
+    static constexpr int kStages = kBudget / kStageBytes < 2 ? 2 : (kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes);
     static constexpr int kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     static constexpr int kTmemCols = 2 * kAccCols;
     static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + kBarBytes + 1024;
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int EPI, int AM = kBM, int SLICES = 2>
+template <int BN, int EPI, int AM = kBM, int SLICES = 2, int BK = kBK>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w_lo,
               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2, const GemmParams P) {
-    using C = GCfg<BN, AM, SLICES>;
+    using C = GCfg<BN, AM, SLICES, BK>;
     static_assert(EPI != EPI_PLAIN || BN % 32 == 0, "the row-store epilogue works in chunks of 32 columns");
     static_assert(EPI != EPI_QKV || BN % 64 == 0, "head-split epilogue: a column tile holds whole heads");
     extern __shared__ unsigned char smem_dyn[];
@@ -190,7 +203,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     static_assert((3 * C::kStages + 4) * 8 + 4 <= C::kBarBytes, "barrier block too small");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_kb = (P.K + kBK - 1) / kBK;
+    const int n_kb = (P.K + BK - 1) / BK;
     const int tiles_per_z = P.tiles_m * P.tiles_n;
     const int n_tiles = P.Z * tiles_per_z;
 
@@ -236,11 +249,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 if (ptile >= n_tiles) return;
                 const int z = ptile / tiles_per_z, rem = ptile - z * tiles_per_z;
                 const int m0 = (rem / P.tiles_n) * kBM, n0 = (rem % P.tiles_n) * BN;
-                tma_prefetch_3d(&map_a, pkb * kBK, m0, z);
-                if (P.a_presplit) tma_prefetch_3d(&map_a_lo, pkb * kBK, m0, z);
+                tma_prefetch_3d(&map_a, pkb * BK, m0, z);
+                if (P.a_presplit) tma_prefetch_3d(&map_a_lo, pkb * BK, m0, z);
                 if (P.w_batched) {
-                    tma_prefetch_3d(&map_w, pkb * kBK, n0, z);
-                    if (P.w_presplit) tma_prefetch_3d(&map_w_lo, pkb * kBK, n0, z);
+                    tma_prefetch_3d(&map_w, pkb * BK, n0, z);
+                    if (P.w_presplit) tma_prefetch_3d(&map_w_lo, pkb * BK, n0, z);
                 }
                 if (++pkb == n_kb) { pkb = 0; ptile += gridDim.x; }
             };
@@ -254,11 +267,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     mbar_wait(s32(empty_bar + stage), phase ^ 1);
                     const uint32_t st = s32(smem + stage * C::kStageBytes);
                     mbar_arrive_expect_tx(s32(full_bar + stage), tx);
-                    tma_load_3d(st, &map_a, kb * kBK, m0, z, s32(full_bar + stage));
-                    if (P.a_presplit) tma_load_3d(st + C::kABytes, &map_a_lo, kb * kBK, m0, z, s32(full_bar + stage));
-                    tma_load_3d(st + 2 * C::kABytes, &map_w, kb * kBK, n0, wz, s32(full_bar + stage));
+                    tma_load_3d(st, &map_a, kb * BK, m0, z, s32(full_bar + stage));
+                    if (P.a_presplit) tma_load_3d(st + C::kABytes, &map_a_lo, kb * BK, m0, z, s32(full_bar + stage));
+                    tma_load_3d(st + 2 * C::kABytes, &map_w, kb * BK, n0, wz, s32(full_bar + stage));
                     if (P.w_presplit)
-                        tma_load_3d(st + 2 * C::kABytes + C::kWBytes, &map_w_lo, kb * kBK, n0, wz, s32(full_bar + stage));
+                        tma_load_3d(st + 2 * C::kABytes + C::kWBytes, &map_w_lo, kb * BK, n0, wz, s32(full_bar + stage));
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -277,8 +290,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             const uint32_t d = tmem_base + acc * C::kAccCols;
             for (int kb = 0; kb < n_kb; ++kb) {
                 const uint32_t st = s32(smem + stage * C::kStageBytes);
-                const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + C::kABytes);
-                const uint64_t w_hi = umma_desc_sw128(st + 2 * C::kABytes), w_lo = umma_desc_sw128(st + 2 * C::kABytes + C::kWBytes);
+                const uint64_t a_hi = umma_desc_kmajor<BK>(st), a_lo = umma_desc_kmajor<BK>(st + C::kABytes);
+                const uint64_t w_hi = umma_desc_kmajor<BK>(st + 2 * C::kABytes), w_lo = umma_desc_kmajor<BK>(st + 2 * C::kABytes + C::kWBytes);
                 // The raw tile is the high term: hi*hi -- and every product whose low operand arrived pre-split -- can start
                 // the moment TMA has landed; only the products that need a low term from the splitter wait for it, so the
                 // splitter's latency hides behind the early MMAs.
@@ -286,7 +299,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < kBK / 8; ++kk) {
+                    for (int kk = 0; kk < BK / 8; ++kk) {
                         const uint64_t o = (uint64_t)(2 * kk);
                         umma_tf32(d, a_hi + o, w_hi + o, idesc, (kb | kk) != 0);
                         if (P.w_presplit) umma_tf32(d, a_hi + o, w_lo + o, idesc, 1);
@@ -298,7 +311,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < kBK / 8; ++kk) {
+                    for (int kk = 0; kk < BK / 8; ++kk) {
                         const uint64_t o = (uint64_t)(2 * kk);
                         if (!P.w_presplit) umma_tf32(d, a_hi + o, w_lo + o, idesc, 1);
                         if (!P.a_presplit) umma_tf32(d, a_lo + o, w_hi + o, idesc, 1);
