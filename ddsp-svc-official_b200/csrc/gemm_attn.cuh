@@ -623,6 +623,7 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint64_t* acc_full = bars + 4;     // MMA -> epilogue    [kFeatSlots]
     uint64_t* acc_empty = bars + 7;    // epilogue -> MMA    [kFeatSlots]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* lo_empty = bars + 11;    // MMA -> splitter (the low-term buffer of A is free)
     float* diag_ring = reinterpret_cast<float*>(store_smem + kFeatStoreBytes + 256);     // [kFeatDiagRing][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -634,6 +635,7 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             mbar_init(s32(full_bar), 1);
             mbar_init(s32(split_bar), kFeatSplitThreads);
             mbar_init(s32(empty_bar), 1);
+            mbar_init(s32(lo_empty), 1);
             for (int i = 0; i < kFeatSlots; ++i) {
                 mbar_init(s32(acc_full + i), 1);
                 mbar_init(s32(acc_empty + i), 128);
@@ -701,13 +703,18 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         uint32_t phase = 0;
         uint32_t g = 0;                    // running half index: slot = g % 3, use = g / 3
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            mbar_wait(s32(full_bar), phase);                           // the raw tile (= high term of A) has landed
+            // Two thirds of the products need only the raw tile (= high term of A): they are issued for both halves as soon as
+            // TMA has landed, and the raw buffer is handed back to the producer behind them -- the next tile's load then
+            // overlaps the low-term products of this one instead of waiting for the whole tile.
+            mbar_wait(s32(full_bar), phase);
+            uint32_t d_h[2], slot_h[2];
 #pragma unroll
             for (int half = 0; half < 2; ++half, ++g) {
                 const uint32_t slot = g % kFeatSlots, use = g / kFeatSlots;
+                slot_h[half] = slot;
+                d_h[half] = tmem_base + slot * kFeatSlotCols;
                 mbar_wait(s32(acc_empty + slot), (use & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d = tmem_base + slot * kFeatSlotCols;
                 if (elect_one()) {
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb) {
@@ -717,17 +724,19 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
                         for (int kk = 0; kk < kBK / 8; ++kk) {
                             const uint64_t o = (uint64_t)(2 * kk);
-                            umma_tf32(d, a_hi + o, w_lo + o, idesc_h[half], (kb | kk) != 0);
-                            umma_tf32(d, a_hi + o, w_hi + o, idesc_h[half], 1);
+                            umma_tf32(d_h[half], a_hi + o, w_lo + o, idesc_h[half], (kb | kk) != 0);
+                            umma_tf32(d_h[half], a_hi + o, w_hi + o, idesc_h[half], 1);
                         }
                     }
                 }
                 __syncwarp();
-                if (half == 0) {
-                    mbar_wait(s32(split_bar), phase);                  // the low term of A is in place
-                    tc_fence_after();
-                }
-                if (elect_one()) {
+            }
+            mbar_wait(s32(split_bar), phase);                          // the low term is in place, and the splitter has read the raw tile
+            tc_fence_after();
+            if (elect_one()) {
+                umma_commit(s32(empty_bar));                           // raw buffer free once the products above have read it
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb) {
                         const uint64_t a_lo = umma_desc_sw128(s32(a_smem + (2 + kb) * kFeatABytes));
@@ -735,14 +744,14 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
                         for (int kk = 0; kk < kBK / 8; ++kk) {
                             const uint64_t o = (uint64_t)(2 * kk);
-                            umma_tf32(d, a_lo + o, w_hi + o, idesc_h[half], 1);
+                            umma_tf32(d_h[half], a_lo + o, w_hi + o, idesc_h[half], 1);
                         }
                     }
-                    if (half == 1) umma_commit(s32(empty_bar));          // the A tile is free once both halves have read it
-                    umma_commit(s32(acc_full + slot));
+                    umma_commit(s32(acc_full + slot_h[half]));
                 }
-                __syncwarp();
+                umma_commit(s32(lo_empty));
             }
+            __syncwarp();
             phase ^= 1;
         }
     } else if (warp >= kSplitWarp0) {
@@ -756,6 +765,7 @@ favor_features_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             mbar_wait(s32(full_bar), phase);
+            mbar_wait(s32(lo_empty), phase ^ 1);                       // the low-term products of the previous tile are done
             const uint32_t raw = s32(a_smem), lo = raw + 2 * kFeatABytes;
             float ssq[4];
 #pragma unroll
