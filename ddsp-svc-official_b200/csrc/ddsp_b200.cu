@@ -1279,6 +1279,9 @@ int ddsp_b200_favor_context(const float* vt, const float* vt_lo, const float* kt
         if (int rc = make_map_3(&mal, vt_lo, Fp, kVtRows, Z, Fp, (int64_t)kVtRows * Fp, kVtRows)) return rc;
         P.a_presplit = 1;
     }
+    // measured and dropped: eight instead of four splitter warps for the two attention GEMMs (197.6 -> 197.4 us, 142.4 -> 140.7 us;
+    // profiles/r02_gemm_splitw.txt); the output product transposed so that the frames are the wide N of the MMAs
+    // (out^T = ctxT q'^T, 224 frames per tile, two 76-KB stages: 142 -> 210 us; profiles/r02_gemm_output_transposed.txt)
     return launch_gemm3x<96, EPI_PLAIN, kVtRows>(ma, mw, mw, mc, mc2, P, (cudaStream_t)stream, vt_lo ? &mal : nullptr);   // 3 column tiles of 96 = 288 >= 272
 }
 
