@@ -91,7 +91,8 @@ def _favor_reference(x, wq, wk, wv, bq, bk, bv, proj, heads, eps=1e-4):
     return out.transpose(1, 2).reshape(b, n, heads * 64)
 
 
-@pytest.mark.parametrize('B,F', [(1, 300), (3, 862), (2, 129), (5, 37)])
+# (12, 862): 672 feature tiles = 4..5 per CTA, every slot of the accumulator ring and both barrier parities come round
+@pytest.mark.parametrize('B,F', [(1, 300), (3, 862), (2, 129), (5, 37), (12, 862)])
 @pytest.mark.parametrize('presplit', [False, True])
 def test_favor_attention_matches_fp64(B, F, presplit):
     from ddsp_b200 import core
