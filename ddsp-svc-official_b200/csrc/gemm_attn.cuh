@@ -572,14 +572,14 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 
 // ---- FAVOR+ feature map as a GEMM epilogue ---------------------------------------------------------------------------
 // x: (Z, F, 64) rows of one head (q or k with its Linear bias already added), W = 64^-0.25 * projection (266 x 64),
-// resident in shared memory as hi | lo, both k-blocks.  Per 128-row tile: dash = x W^T in TMEM (272 columns, two
-// MMAs of N = 256 and N = 16 per k-step), then
+// resident in shared memory as hi | lo, both k-blocks.  Per 128-row tile: dash = x W^T in TMEM (272 columns as two halves,
+// N = 128 and N = 144 per k-step, through a ring of three accumulator slots), then
 //   q: ratio * (exp(dash - diag - max_j dash) + eps)      -> (Z, F, 272) row-major through TMA stores
 //   k: ratio * exp(dash - diag + eps)                     -> (Z, 272, Fp) transposed, lanes = consecutive frames
 // with diag = |x|^2 / (2 sqrt(64)), ratio = 266^-0.5 (pcmer.py:124-160).  Columns 266..271 of q' are written as
 // zeros; rows 266..271 of k'^T are never written (the buffer is zero-initialised once by the host side).
 struct FeatParams {
-    const float* x;             // (Z, F, 64)
+    const float* x;             // (Z, F, 64) (the kernels read it through map_a only)
     float* kt;                  // k: (Z, 272, Fp)
     int Z, F, Fp;
     int tiles_m;                // per batch
