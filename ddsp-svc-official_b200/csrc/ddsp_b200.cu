@@ -1113,12 +1113,12 @@ int set_smem_once(K kernel, int bytes, bool* flags) {
     return 0;
 }
 
-template <int BN, int EPI, int AM = ddsp::tc::kBM, int SLICES = 2, int BK = ddsp::tc::kBK>
+template <int BN, int EPI, int AM = ddsp::tc::kBM, int SLICES = 2, int BK = ddsp::tc::kBK, bool NSTACK = false>
 int launch_gemm3x(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& wlo, const CUtensorMap& c, const CUtensorMap& c2,
                   ddsp::tc::GemmParams P, cudaStream_t st, const CUtensorMap* a_lo = nullptr) {
-    using C = ddsp::tc::GCfg<BN, AM, SLICES, BK>;
+    using C = ddsp::tc::GCfg<BN, AM, SLICES, BK, NSTACK>;
     static bool attr_set[64] = {false};
-    if (int rc = set_smem_once(ddsp::tc::gemm3x_kernel<BN, EPI, AM, SLICES, BK>, C::kSmemBytes, attr_set)) return rc;
+    if (int rc = set_smem_once(ddsp::tc::gemm3x_kernel<BN, EPI, AM, SLICES, BK, NSTACK>, C::kSmemBytes, attr_set)) return rc;
     P.tiles_m = (P.M + ddsp::tc::kBM - 1) / ddsp::tc::kBM;
     P.tiles_n = (P.N + BN - 1) / BN;
     const int64_t tiles = (int64_t)P.Z * P.tiles_m * P.tiles_n;
@@ -1130,7 +1130,7 @@ int launch_gemm3x(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap&
     // projection); 6 / 12 k-blocks ahead are no better (profiles/r02_gemm_l2_prefetch.txt)
     P.l2_prefetch = 3;
     if (forced_pf >= 0) P.l2_prefetch = forced_pf;
-    ddsp::tc::gemm3x_kernel<BN, EPI, AM, SLICES, BK><<<grid, ddsp::tc::kThreads, C::kSmemBytes, st>>>(a, a_lo ? *a_lo : a, w, wlo, c, c2, P);
+    ddsp::tc::gemm3x_kernel<BN, EPI, AM, SLICES, BK, NSTACK><<<grid, ddsp::tc::kThreads, C::kSmemBytes, st>>>(a, a_lo ? *a_lo : a, w, wlo, c, c2, P);
     LAUNCH_CHECK();
     return DDSP_B200_OK;
 }
@@ -1282,6 +1282,11 @@ int ddsp_b200_favor_context(const float* vt, const float* vt_lo, const float* kt
     // measured and dropped: eight instead of four splitter warps for the two attention GEMMs (197.6 -> 197.4 us, 142.4 -> 140.7 us;
     // profiles/r02_gemm_splitw.txt); the output product transposed so that the frames are the wide N of the MMAs
     // (out^T = ctxT q'^T, 224 frames per tile, two 76-KB stages: 142 -> 210 us; profiles/r02_gemm_output_transposed.txt)
+    // hi*hi and hi*lo(k') as one MMA of N = 192 over the adjacent k'_hi | k'_lo tiles: two instead of three reads of the A tile
+    // per k-step through the shared-memory port, 197.9 -> 183.6 us (profiles/r02_gemm_nstack.txt)
+    static const int nstack = [] { const char* e = getenv("DDSP_B200_ATTN_NSTACK"); return e ? atoi(e) : 1; }();   // experiments
+    if (nstack && !vt_lo)
+        return launch_gemm3x<96, EPI_PLAIN, kVtRows, 2, kBK, true>(ma, mw, mw, mc, mc2, P, (cudaStream_t)stream);
     return launch_gemm3x<96, EPI_PLAIN, kVtRows>(ma, mw, mw, mc, mc2, P, (cudaStream_t)stream, vt_lo ? &mal : nullptr);   // 3 column tiles of 96 = 288 >= 272
 }
 
@@ -1303,6 +1308,9 @@ int ddsp_b200_favor_output(const float* qf, const float* ctxT, const float* ctxT
         P.w_presplit = 1;
     }
     // (one staging slice per epilogue warp would buy a fourth stage here: measured 142 -> 150 us, not used)
+    // (the stacked hi | lo form of the context GEMM measured here too: 142.0 -> 141.1 us, not used; profiles/r02_gemm_nstack.txt)
+    static const int nstack = [] { const char* e = getenv("DDSP_B200_ATTN_NSTACK"); return e ? atoi(e) : 0; }();   // experiments
+    if (nstack == 2) return launch_gemm3x<kVtRows, EPI_OUT, kBM, 2, kBK, true>(ma, mw, mwl, mc, mc, P, (cudaStream_t)stream);
     return launch_gemm3x<kVtRows, EPI_OUT>(ma, mw, mwl, mc, mc, P, (cudaStream_t)stream);
 }
 

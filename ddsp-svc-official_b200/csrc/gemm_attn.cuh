@@ -162,8 +162,13 @@ struct RowStore {
 // reach accumulator rows nobody stores -- and the bytes saved buy a fourth pipeline stage.
 // BK = fp32 elements of one k-block (32: 128-byte swizzle rows; 16: 64-byte rows -- half-sized stages, twice as many of them
 // in the same shared memory, for the tiles whose two 96-KB stages leave the ring empty half of the time).
-template <int BN, int AM = kBM, int SLICES = 2, int BK = kBK>
+// NSTACK: the products hi*hi and hi*lo(W) as ONE MMA of N = 2 BN over the adjacent W_hi | W_lo tiles of a stage (two
+// accumulator column ranges, added in the epilogue), lo(A)*hi as a second MMA of N = BN.  The 3xTF32 GEMMs are bound by the
+// shared-memory port (every MMA re-reads its (128 + N) x 32 bytes of operands, profiles/ubench/umma_issue.cu): two MMAs
+// instead of three read the A tile twice instead of three times per k-step -- for the narrow attention GEMMs (BN <= 128).
+template <int BN, int AM = kBM, int SLICES = 2, int BK = kBK, bool NSTACK = false>
 struct GCfg {
+    static_assert(!NSTACK || 2 * BN <= 256, "stacked W_hi | W_lo operand: one MMA of N = 2 BN");
     static_assert(BK == 32 || BK == 16, "k-block = one 128-byte or 64-byte swizzle row");
     static constexpr int kRowBytes = BK * 4;
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128: multiple of 16 in [16, 256]");
@@ -176,18 +181,19 @@ struct GCfg {
     static constexpr int kBarBytes = 256;
     static constexpr int kBudget = 227 * 1024 - 1024 - kBarBytes - kStoreBytes;
     static constexpr int kStages = kBudget / kStageBytes < 2 ? 2 : (kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes);
-    static constexpr int kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static constexpr int kAccN = NSTACK ? 2 * BN : BN;               // accumulator columns in use
+    static constexpr int kAccCols = kAccN <= 32 ? 32 : kAccN <= 64 ? 64 : kAccN <= 128 ? 128 : 256;
     static constexpr int kTmemCols = 2 * kAccCols;
     static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + kBarBytes + 1024;
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int EPI, int AM = kBM, int SLICES = 2, int BK = kBK>
+template <int BN, int EPI, int AM = kBM, int SLICES = 2, int BK = kBK, bool NSTACK = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w_lo,
               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2, const GemmParams P) {
-    using C = GCfg<BN, AM, SLICES, BK>;
+    using C = GCfg<BN, AM, SLICES, BK, NSTACK>;
     static_assert(EPI != EPI_PLAIN || BN % 32 == 0, "the row-store epilogue works in chunks of 32 columns");
     static_assert(EPI != EPI_QKV || BN % 64 == 0, "head-split epilogue: a column tile holds whole heads");
     extern __shared__ unsigned char smem_dyn[];
@@ -297,6 +303,31 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 // splitter's latency hides behind the early MMAs.
                 mbar_wait(s32(full_bar + stage), phase);
                 tc_fence_after();
+                if constexpr (NSTACK) {
+                    constexpr uint32_t idesc2 = umma_idesc_tf32_n(2 * BN);       // W_hi | W_lo: 2 BN adjacent rows of the stage
+                    if (P.w_presplit) {
+                        if (elect_one()) {
+#pragma unroll
+                            for (int kk = 0; kk < BK / 8; ++kk) umma_tf32(d, a_hi + (uint64_t)(2 * kk), w_hi + (uint64_t)(2 * kk), idesc2, (kb | kk) != 0);
+                        }
+                        __syncwarp();
+                    }
+                    mbar_wait(s32(split_bar + stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < BK / 8; ++kk) {
+                            const uint64_t o = (uint64_t)(2 * kk);
+                            if (!P.w_presplit) umma_tf32(d, a_hi + o, w_hi + o, idesc2, (kb | kk) != 0);
+                            umma_tf32(d, a_lo + o, w_hi + o, idesc, 1);
+                        }
+                        umma_commit(s32(empty_bar + stage));
+                        if (kb == n_kb - 1) umma_commit(s32(acc_full + acc));
+                    }
+                    __syncwarp();
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    continue;
+                }
                 if (elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < BK / 8; ++kk) {
@@ -378,9 +409,17 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     const int n = n0 + c0;
                     if (n >= P.N) break;
                     tmem_ld32(taddr + c0, r);
-                    tmem_ld_wait();
+                    if constexpr (NSTACK) {
+                        uint32_t r2[32];
+                        tmem_ld32(taddr + BN + c0, r2);            // the hi*lo(W) column range
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                    } else {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    }
                     if (P.bias) {
                         if (n + 32 <= P.N) {
 #pragma unroll
@@ -545,15 +584,24 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 // batch z = (clip, head); accumulator columns 0..63 = sum_j q'_j ctx_j, column 64 = q' . k_sum
                 const int H = P.heads;
                 const int b = z / H, h = z - b * H;
+                uint32_t r2[32];
                 tmem_ld32(taddr + 64, r);
+                if constexpr (NSTACK) tmem_ld32(taddr + BN + 64, r2);
                 tmem_ld_wait();
-                const float d_inv = 1.0f / (__uint_as_float(r[0]) + 1e-8f);           // pcmer.py:72
+                float den = __uint_as_float(r[0]);
+                if constexpr (NSTACK) den += __uint_as_float(r2[0]);
+                const float d_inv = 1.0f / (den + 1e-8f);                             // pcmer.py:72
 #pragma unroll 1
                 for (int c0 = 0; c0 < 64; c0 += 32) {
                     tmem_ld32(taddr + c0, r);
+                    if constexpr (NSTACK) tmem_ld32(taddr + BN + c0, r2);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * d_inv;
+                    for (int j = 0; j < 32; ++j) {
+                        float x = __uint_as_float(r[j]);
+                        if constexpr (NSTACK) x += __uint_as_float(r2[j]);
+                        v[j] = x * d_inv;
+                    }
                     const uint32_t buf = rs.begin();
                     rs.fill(buf, v);
                     if (lane == 0) { tma_store_3d(&map_c, buf, h * 64 + c0, m0 + q * 32, b); bulk_commit(); }
