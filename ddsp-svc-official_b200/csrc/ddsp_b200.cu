@@ -1285,8 +1285,8 @@ int ddsp_b200_favor_context(const float* vt, const float* vt_lo, const float* kt
     // hi*hi and hi*lo(k') as one MMA of N = 192 over the adjacent k'_hi | k'_lo tiles: two instead of three reads of the A tile
     // per k-step through the shared-memory port, 197.9 -> 183.6 us (profiles/r02_gemm_nstack.txt)
     static const int nstack = [] { const char* e = getenv("DDSP_B200_ATTN_NSTACK"); return e ? atoi(e) : 1; }();   // experiments
-    if (nstack && !vt_lo)
-        return launch_gemm3x<96, EPI_PLAIN, kVtRows, 2, kBK, true>(ma, mw, mw, mc, mc2, P, (cudaStream_t)stream);
+    if (nstack)
+        return launch_gemm3x<96, EPI_PLAIN, kVtRows, 2, kBK, true>(ma, mw, mw, mc, mc2, P, (cudaStream_t)stream, vt_lo ? &mal : nullptr);
     return launch_gemm3x<96, EPI_PLAIN, kVtRows>(ma, mw, mw, mc, mc2, P, (cudaStream_t)stream, vt_lo ? &mal : nullptr);   // 3 column tiles of 96 = 288 >= 272
 }
 
