@@ -68,7 +68,8 @@ def test_glu_dwconv_silu(B, T, C):
     assert (out.double() - ref.transpose(1, 2)).abs().max().item() < 5e-6
 
 
-@pytest.mark.parametrize('B,F_', [(1, 9), (2, 130), (3, 77), (16, 520)])       # the last one takes the fused projection
+# (16, 520) takes the fused projection; (24, 862): 10-second clips, every tensor-core kernel runs several tiles per CTA
+@pytest.mark.parametrize('B,F_', [(1, 9), (2, 130), (3, 77), (16, 520), (24, 862)])
 def test_unit2control_fused_matches_plain_ops(B, F_):
     """no_grad on CUDA takes the fused stages; under enable_grad the same module runs stock ops."""
     torch.manual_seed(7)
